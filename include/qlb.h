@@ -1,0 +1,210 @@
+/*
+ * qlb.h - C ABI of the B200-native batched contact-force-distribution solver.
+ *
+ * One call solves B independent robot states.  For every state the library runs,
+ * fused in one sm_100a kernel, the hot path of the reference's balance_controller:
+ *
+ *   leg forward kinematics + foot Jacobians + gravity torques
+ *        (reference: quadruped_model/src/quadrupedkinematics.cpp:143-278,485-552)
+ *   -> assembly of the virtual-model contact-force QP
+ *        (reference: balance_controller/src/contact_force_distribution/
+ *                    ContactForceDistribution.cpp:138-336)
+ *   -> its solution (reference: ...ContactForceDistribution.cpp:385-514, the call
+ *        ooqpei::QuadraticProblemFormulation::solve at :490)
+ *   -> joint torques tau = J^T(-x) + G(q)      (reference: ...:516-578)
+ *   -> achieved net wrench A x                  (reference: ...:614-625)
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  Every function returns
+ * QLB_OK (0) or a negative qlb_status and never throws.  There is no CPU fallback:
+ * if no CUDA device is usable the calls fail with QLB_ERR_CUDA.
+ *
+ * Conventions (all fixed by the reference):
+ *   - legs and joints are ordered LF(0), RF(1), RH(2), LH(3); joint slot = 3*leg + j
+ *     (reference: quadruped_model/include/quadruped_model/QuadrupedModel.hpp:47-53,97-109)
+ *   - quaternions are (w, x, y, z), Hamilton, rotating base-frame coordinates into the
+ *     world frame (reference: balance_controller/src/ros_controller/
+ *     gazebo_state_hardware_interface.cpp:327-330; quadruped_state.cpp:127)
+ *   - wrench = desired net force (3) and torque (3) on the base, in base frame
+ *   - batch arrays are SoA, component-major / batch-minor: element (c, i) of an array
+ *     with C components lives at ptr[c * B + i]
+ */
+#ifndef QLB_H
+#define QLB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QLB_NUM_LEGS 4
+#define QLB_NUM_JOINTS 12
+#define QLB_ABI_VERSION 1
+
+typedef enum qlb_status {
+  QLB_OK = 0,
+  QLB_ERR_INVALID_ARGUMENT = -1,
+  QLB_ERR_CUDA = -2,
+  QLB_ERR_BATCH_TOO_LARGE = -3,
+  QLB_ERR_NOT_INITIALISED = -4,
+  QLB_ERR_ALLOC = -5
+} qlb_status;
+
+/* One leg: base_link -> (joint1) link1 -> (joint2) link2 -> (joint3) link3 -> (fixed) foot link.
+ * Row k of joint_xyz / joint_rpy is the URDF <origin xyz rpy> of joint k (k = 3: the fixed foot
+ * joint); all revolute axes are the local z axis.  link_mass / link_com are the <inertial> mass and
+ * origin xyz of the child link of joint k.  Replaces the KDL chains built in
+ * quadrupedkinematics.cpp:54-108.  Ready-made tables: include/qlb_models.h. */
+typedef struct qlb_leg_model {
+  double joint_xyz[4][3];
+  double joint_rpy[4][3];
+  double link_mass[4];
+  double link_com[4][3];
+} qlb_leg_model;
+
+/* Controller parameters; defaults (qlb_default_params) are the reference's
+ * balance_controller/config/controller_gains.yaml:2-41 and quadruped_state.cpp:28-41,83-97. */
+typedef struct qlb_params {
+  double wrench_weights[6];   /* S: virtualForceWeights_ (heading, lateral, vertical, roll, pitch, yaw) */
+  double ground_force_weight; /* W: groundForceWeight_ (1e-4) */
+  double min_normal_force;    /* F_min: minimalNormalGroundForce_ (10 N) */
+  double friction_default;    /* mu used where the per-leg mu array is NULL (0.6) */
+  double gravity;             /* |g|, 9.8 (ContactForceDistribution.cpp:518) */
+  /* virtual-model controller (VirtualModelController.cpp:104-268) */
+  double kp_translation[3], kd_translation[3], kff_translation[3];
+  double kp_rotation[3], kd_rotation[3], kff_rotation[3];
+  double torso_mass;                   /* 27.0 */
+  double leg_mass[QLB_NUM_LEGS];       /* 6.0 each */
+  double leg_base_position[QLB_NUM_LEGS][3]; /* (+-0.42, +-0.075, 0) */
+  double com_in_base[3];               /* (0,0,0) */
+  double gravity_compensation_percentage; /* 1.0 */
+  /* interior-point solver */
+  double ipm_tolerance;       /* stop when complementarity gap and residuals <= tol * scale (1e-9) */
+  int32_t ipm_max_iterations; /* 30 */
+  int32_t reserved;
+} qlb_params;
+
+/* Per-state result word, written to flags[i].
+ *   bits 0..3   contact bit per leg = leg was part of the force distribution
+ *               (isPartOfForceDistribution_, ContactForceDistribution.cpp:147)
+ *   bits 4..23  active-set bits, 5 per leg at bit 4 + 5*leg + r, rows r in the reference's
+ *               order: 0 = n.f >= F_min (ContactForceDistribution.cpp:241-247),
+ *               1 = (mu n + t1).f >= 0, 2 = (mu n - t1).f >= 0, 3 = (mu n + t2).f >= 0,
+ *               4 = (mu n - t2).f >= 0 (:315-325); set when the row is tight at the optimum
+ *               with a positive multiplier
+ *   bits 24..26 status code (qlb_state_status)
+ *   bits 27..31 interior-point iterations used (saturates at 31)
+ */
+#define QLB_FLAG_CONTACT_MASK 0x0000000Fu
+#define QLB_FLAG_ACTIVE_SHIFT 4
+#define QLB_FLAG_ACTIVE_MASK 0x00FFFFF0u
+#define QLB_FLAG_STATUS_SHIFT 24
+#define QLB_FLAG_STATUS_MASK 0x07000000u
+#define QLB_FLAG_ITER_SHIFT 27
+#define QLB_FLAG_PARITY_MASK 0x00FFFFFFu /* contact + active bits: what is compared with the oracle */
+
+typedef enum qlb_state_status {
+  QLB_STATE_OK = 0,            /* optimum found, KKT-verified active set */
+  QLB_STATE_NO_STANCE = 1,     /* no leg in stance: nothing solved, outputs zero (CFD.cpp:127-132) */
+  QLB_STATE_MAX_ITER = 2,      /* iteration limit hit; forces are the last iterate */
+  QLB_STATE_UNVERIFIED = 3,    /* converged, but the active-set polish failed its KKT check */
+  QLB_STATE_BAD_INPUT = 4      /* NaN/Inf input or degenerate surface normal; outputs zero */
+} qlb_state_status;
+
+/* Batch statistics (device-side reduction; all-reduced over ranks by the caller, sum / max as noted). */
+typedef struct qlb_stats {
+  double count;              /* sum: states */
+  double count_status[5];    /* sum: per qlb_state_status */
+  double sum_iterations;     /* sum */
+  double sum_wrench_err;     /* sum of sqrt((Ax-b)' S (Ax-b)) */
+  double active_hist[20];    /* sum: how often each (leg,row) was active */
+  double max_wrench_err;     /* max */
+  double max_iterations;     /* max */
+} qlb_stats;
+#define QLB_STATS_NUM_SUM 28 /* leading doubles that all-reduce with SUM; the rest with MAX */
+#define QLB_STATS_NUM 30
+
+typedef struct qlb_context qlb_context;
+
+/* Fill *p with the reference's gains, weights and solver defaults. */
+int qlb_default_params(qlb_params* p);
+
+/* Create a solver context on CUDA device `device`; max_batch sizes the staging buffers that the
+ * *_host entry points use (0 = grow on demand).  Replaces the construction of
+ * ContactForceDistribution + QuadrupedKinematics (ros_balance_controller.cpp:73-74). */
+int qlb_create(qlb_context** ctx, const qlb_leg_model legs[QLB_NUM_LEGS], const qlb_params* params,
+               int device, size_t max_batch);
+int qlb_destroy(qlb_context* ctx);
+/* Replaces ContactForceDistribution::loadParameters / VirtualModelController::loadParameters
+ * (ContactForceDistribution.cpp:818-886, VirtualModelController.cpp:429-548). */
+int qlb_set_params(qlb_context* ctx, const qlb_params* params);
+int qlb_get_params(const qlb_context* ctx, qlb_params* params);
+
+/* Wrench mode, DEVICE pointers, asynchronous on `stream` (a cudaStream_t, NULL = default stream).
+ * Replaces ContactForceDistribution::computeForceDistribution(Force, Torque)
+ * (ContactForceDistribution.cpp:99-136) for B states at once.
+ *   in : q[12][B] joint positions; quat_wxyz[4][B]; wrench[6][B] (F then T, base frame);
+ *        stance_mask[B] bit k = leg k is a support leg (State::isSupportLeg);
+ *        mu[4][B] per-leg friction coefficient, or NULL -> params.friction_default;
+ *        normals_world[12][B] per-leg surface normal (leg-major), or NULL -> (0,0,1)
+ *   out: grf[12][B] ground-reaction forces x in base frame, zero for swing legs
+ *        (the reference's desiredContactForce_ is -x, CFD.cpp:502-503);
+ *        tau[12][B] joint torques J^T(-x) + G(q) for stance legs, zero for swing legs
+ *        (the reference leaves swing slots unwritten, CFD.cpp:530);
+ *        flags[B] result word (see above);
+ *        netwrench[6][B] achieved A x (getNetForceAndTorqueOnBase), or NULL. */
+int qlb_solve_wrench(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz,
+                     const double* wrench, const uint8_t* stance_mask, const double* mu,
+                     const double* normals_world, double* grf, double* tau, uint32_t* flags,
+                     double* netwrench, void* stream);
+
+/* Same, HOST pointers: copies in, solves, copies out, synchronises.  This is what a batch-of-1
+ * controller tick calls. */
+int qlb_solve_wrench_host(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz,
+                          const double* wrench, const uint8_t* stance_mask, const double* mu,
+                          const double* normals_world, double* grf, double* tau, uint32_t* flags,
+                          double* netwrench);
+
+/* State mode: the virtual-model-controller prologue (VirtualModelController::compute,
+ * VirtualModelController.cpp:89-268) runs in the same kernel and produces the wrench.
+ *   base_pose[7][B]  = position world->base (3) + quat_wxyz (4), feedback
+ *   base_twist[6][B] = linear velocity in world (3) + angular velocity in base (3), feedback
+ *   target_pose[7][B], target_twist[6][B] = the desired counterparts
+ *   wrench_out[6][B] = the virtual force/torque that was distributed, or NULL */
+int qlb_solve_state(qlb_context* ctx, size_t B, const double* q, const double* base_pose,
+                    const double* base_twist, const double* target_pose, const double* target_twist,
+                    const uint8_t* stance_mask, const double* mu, const double* normals_world,
+                    double* grf, double* tau, uint32_t* flags, double* netwrench, double* wrench_out,
+                    void* stream);
+int qlb_solve_state_host(qlb_context* ctx, size_t B, const double* q, const double* base_pose,
+                         const double* base_twist, const double* target_pose,
+                         const double* target_twist, const uint8_t* stance_mask, const double* mu,
+                         const double* normals_world, double* grf, double* tau, uint32_t* flags,
+                         double* netwrench, double* wrench_out);
+
+/* Kinematics only (DEVICE pointers): foot positions, translational Jacobians (row-major 3x3 per leg)
+ * and gravity torques for all four legs.  Replaces QuadrupedKinematics::FowardKinematicsSolve /
+ * AnalysticJacobian / getGravityCompensationForLimb (quadrupedkinematics.cpp:143-278,485-552).
+ *   foot[12][B], jac[36][B] (slot = 9*leg + 3*row + col), gravity_tau[12][B]; any output may be NULL.
+ *   quat_wxyz may be NULL (identity: gravity along -z of the base frame). */
+int qlb_leg_kinematics(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz,
+                       double* foot, double* jac, double* gravity_tau, void* stream);
+
+/* Device-side statistics over a solved batch (DEVICE pointers; stats_out is a HOST pointer,
+ * the call synchronises the stream).  wrench/netwrench may be NULL (error terms then zero). */
+int qlb_batch_stats(qlb_context* ctx, size_t B, const uint32_t* flags, const double* wrench,
+                    const double* netwrench, qlb_stats* stats_out, void* stream);
+
+/* How many kernels this context has launched so far (bench.py reports it as gpu_launches). */
+uint64_t qlb_launch_count(const qlb_context* ctx);
+
+const char* qlb_strerror(int status);
+/* Text of the last CUDA error seen by this context ("" if none). */
+const char* qlb_last_cuda_error(const qlb_context* ctx);
+int qlb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QLB_H */

@@ -1,0 +1,216 @@
+"""ctypes face of the CPU oracle.  TEST INFRASTRUCTURE ONLY.
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs, and by nothing under quadruped_locomotion_b200/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import build_oracle  # noqa: E402
+
+SOLVER_GI, SOLVER_IPM, SOLVER_REF = 0, 1, 2
+MAX_N, MAX_M = 12, 24
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class QoParams(C.Structure):
+    _fields_ = [("S", C.c_double * 6), ("W", C.c_double), ("fmin", C.c_double), ("gravity", C.c_double)]
+
+
+class QoVmcParams(C.Structure):
+    _fields_ = [("kp_t", C.c_double * 3), ("kd_t", C.c_double * 3), ("kff_t", C.c_double * 3),
+                ("kp_r", C.c_double * 3), ("kd_r", C.c_double * 3), ("kff_r", C.c_double * 3),
+                ("torso_mass", C.c_double), ("leg_mass", C.c_double * 4),
+                ("leg_base_position", (C.c_double * 3) * 4), ("com", C.c_double * 3),
+                ("gravity_pct", C.c_double), ("gravity", C.c_double)]
+
+
+class QoQp(C.Structure):
+    _fields_ = [("ns", C.c_int), ("n", C.c_int), ("m", C.c_int), ("leg_of_slot", C.c_int * 4),
+                ("G", C.c_double * (MAX_N * MAX_N)), ("g0", C.c_double * MAX_N),
+                ("D", C.c_double * (MAX_M * MAX_N)), ("d", C.c_double * MAX_M),
+                ("A", C.c_double * (6 * MAX_N)), ("b", C.c_double * 6),
+                ("foot", C.c_double * 12), ("jac", C.c_double * 36), ("gtau", C.c_double * 12),
+                ("bad_input", C.c_int)]
+
+
+_lib = None
+_ref = None
+EXT_FN = C.CFUNCTYPE(C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp)
+
+
+def _as(a):
+    return a.ctypes.data_as(_dp)
+
+
+def lib():
+    global _lib, _ref
+    if _lib is None:
+        so, ref = build_oracle.build()
+        _lib = C.CDLL(so)
+        _lib.qo_goldfarb_idnani.restype = C.c_double
+        _lib.qo_goldfarb_idnani.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _ip]
+        _lib.qo_ipm.restype = C.c_int
+        _lib.qo_ipm.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_int, _dp, _ip, _dp, _ip]
+        _lib.qo_solve_wrench_batch.restype = C.c_int
+        _lib.qo_leg_kinematics.restype = None
+        _lib.qo_assemble.restype = None
+        _lib.qo_vmc_wrench.restype = None
+        if ref:
+            _ref = C.CDLL(ref)
+            _ref.qref_solve_quadprog.restype = C.c_double
+            _ref.qref_solve_quadprog.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
+            _ref.qref_solve_quadprog_eq.restype = C.c_double
+            _ref.qref_solve_quadprog_eq.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+    return _lib
+
+
+def have_ref() -> bool:
+    lib()
+    return _ref is not None
+
+
+def default_params() -> QoParams:
+    p = QoParams()
+    lib().qo_default_params(C.byref(p))
+    return p
+
+
+def default_vmc_params() -> QoVmcParams:
+    p = QoVmcParams()
+    lib().qo_default_vmc_params(C.byref(p))
+    return p
+
+
+def model_array(model: dict) -> np.ndarray:
+    """dict from legmodel.load_model -> (4,40) float64 in qo_leg_model layout."""
+    out = np.zeros((4, 40))
+    for i, leg in enumerate(model["legs"]):
+        out[i, 0:12] = np.asarray(leg["joint_xyz"], dtype=np.float64).ravel()
+        out[i, 12:24] = np.asarray(leg["joint_rpy"], dtype=np.float64).ravel()
+        out[i, 24:28] = np.asarray(leg["link_mass"], dtype=np.float64)
+        out[i, 28:40] = np.asarray(leg["link_com"], dtype=np.float64).ravel()
+    return np.ascontiguousarray(out)
+
+
+def leg_kinematics(model_arr, leg: int, q, grav=(0.0, 0.0, -9.8)):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    g = np.ascontiguousarray(grav, dtype=np.float64)
+    foot, jac, gt = np.zeros(3), np.zeros(9), np.zeros(3)
+    lib().qo_leg_kinematics(_as(model_arr[leg]), _as(q), _as(g), _as(foot), _as(jac), _as(gt))
+    return foot, jac.reshape(3, 3), gt
+
+
+def solve_qp_gi(G, g0, D, d, CE=None, ce0=None):
+    """Goldfarb-Idnani port.  Returns dict(x, f, active, u, iterations)."""
+    G = np.ascontiguousarray(G, dtype=np.float64); g0 = np.ascontiguousarray(g0, dtype=np.float64)
+    n = g0.size
+    D = np.ascontiguousarray(D, dtype=np.float64).reshape(-1, n) if np.size(D) else np.zeros((0, n))
+    d = np.ascontiguousarray(d, dtype=np.float64)
+    m = d.size
+    p = 0
+    cep = cp = None
+    if CE is not None and np.size(CE):
+        CE = np.ascontiguousarray(CE, dtype=np.float64); ce0 = np.ascontiguousarray(ce0, dtype=np.float64)
+        p = ce0.size
+        cep, cp = _as(CE), _as(ce0)
+    x = np.zeros(n); u = np.zeros(max(m, 1)); act = np.zeros(max(m, 1), dtype=np.int32); it = C.c_int(0)
+    f = lib().qo_goldfarb_idnani(n, m, p, _as(G), _as(g0), cep, cp, _as(D), _as(d), _as(x),
+                                 act.ctypes.data_as(_ip), _as(u), C.byref(it))
+    return dict(x=x, f=f, active=act[:m].astype(bool), u=u[:m], iterations=it.value)
+
+
+def solve_qp_ipm(G, g0, D, d, tol=1e-9, max_iter=30):
+    G = np.ascontiguousarray(G, dtype=np.float64); g0 = np.ascontiguousarray(g0, dtype=np.float64)
+    n = g0.size
+    D = np.ascontiguousarray(D, dtype=np.float64).reshape(-1, n); d = np.ascontiguousarray(d, dtype=np.float64)
+    m = d.size
+    x = np.zeros(n); u = np.zeros(m); act = np.zeros(m, dtype=np.int32); it = C.c_int(0)
+    st = lib().qo_ipm(n, m, _as(G), _as(g0), _as(D), _as(d), tol, max_iter, _as(x),
+                      act.ctypes.data_as(_ip), _as(u), C.byref(it))
+    return dict(x=x, status=st, active=act.astype(bool), u=u, iterations=it.value)
+
+
+def solve_qp_ref(G, g0, D, d, CE=None, ce0=None):
+    """The reference's own QuadProg++ (oracle/_ref).  Returns dict(x, f)."""
+    lib()
+    if _ref is None:
+        raise RuntimeError("oracle/_ref/libquadprog_ref.so not built (needs /root/reference)")
+    G = np.ascontiguousarray(G, dtype=np.float64); g0 = np.ascontiguousarray(g0, dtype=np.float64)
+    n = g0.size
+    D = np.ascontiguousarray(D, dtype=np.float64).reshape(-1, n) if np.size(D) else np.zeros((0, n))
+    d = np.ascontiguousarray(d, dtype=np.float64)
+    x = np.zeros(n)
+    if CE is not None and np.size(CE):
+        CE = np.ascontiguousarray(CE, dtype=np.float64); ce0 = np.ascontiguousarray(ce0, dtype=np.float64)
+        f = _ref.qref_solve_quadprog_eq(n, d.size, ce0.size, _as(G), _as(g0), _as(CE), _as(ce0), _as(D), _as(d), _as(x))
+    else:
+        f = _ref.qref_solve_quadprog(n, d.size, _as(G), _as(g0), _as(D), _as(d), _as(x))
+    return dict(x=x, f=f)
+
+
+def assemble(model_arr, q, quat, wrench, mask, mu=None, normals=None, params=None, mu_default=0.6):
+    """One state -> dict with the packed QP (G, g0, D, d, A, b) and kinematics."""
+    prm = params or default_params()
+    q = np.ascontiguousarray(q, dtype=np.float64); quat = np.ascontiguousarray(quat, dtype=np.float64)
+    wrench = np.ascontiguousarray(wrench, dtype=np.float64)
+    mup = _as(np.ascontiguousarray(mu, dtype=np.float64)) if mu is not None else None
+    nrp = _as(np.ascontiguousarray(normals, dtype=np.float64)) if normals is not None else None
+    qp = QoQp()
+    lib().qo_assemble(_as(model_arr), C.byref(prm), _as(q), _as(quat), _as(wrench), C.c_uint(int(mask)),
+                      mup, C.c_double(mu_default), nrp, C.byref(qp))
+    n, m = qp.n, qp.m
+    return dict(ns=qp.ns, n=n, m=m, legs=list(qp.leg_of_slot)[:qp.ns],
+                G=np.array(qp.G[:n * n]).reshape(n, n), g0=np.array(qp.g0[:n]),
+                D=np.array(qp.D[:m * n]).reshape(m, n), d=np.array(qp.d[:m]),
+                A=np.array(qp.A[:6 * n]).reshape(6, n), b=np.array(qp.b[:]),
+                foot=np.array(qp.foot[:]).reshape(4, 3), jac=np.array(qp.jac[:]).reshape(4, 3, 3),
+                gtau=np.array(qp.gtau[:]).reshape(4, 3), bad_input=qp.bad_input)
+
+
+def solve_wrench_batch(model_arr, q, quat, wrench, mask, mu=None, normals=None, params=None,
+                       mu_default=0.6, solver=SOLVER_GI, nsolves=1, threads=0, want_margin=False):
+    """Whole pipeline over a batch (SoA arrays [C,B]).  Returns dict(grf, tau, flags, netwrench[, margin])."""
+    prm = params or default_params()
+    q = np.ascontiguousarray(q, dtype=np.float64); B = q.shape[1]
+    quat = np.ascontiguousarray(quat, dtype=np.float64); wrench = np.ascontiguousarray(wrench, dtype=np.float64)
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    mu_a = np.ascontiguousarray(mu, dtype=np.float64) if mu is not None else None
+    nr_a = np.ascontiguousarray(normals, dtype=np.float64) if normals is not None else None
+    grf = np.zeros((12, B)); tau = np.zeros((12, B)); nw = np.zeros((6, B)); flags = np.zeros(B, dtype=np.uint32)
+    margin = np.zeros(B) if want_margin else None
+    ext = None
+    if solver == SOLVER_REF:
+        lib()
+        if _ref is None:
+            raise RuntimeError("oracle/_ref not built")
+        ext = C.cast(_ref.qref_solve_quadprog, C.c_void_p)
+    rc = lib().qo_solve_wrench_batch(
+        _as(model_arr), C.byref(prm), C.c_long(B), _as(q), _as(quat), _as(wrench),
+        mask.ctypes.data_as(C.POINTER(C.c_uint8)), _as(mu_a) if mu_a is not None else None,
+        C.c_double(mu_default), _as(nr_a) if nr_a is not None else None, C.c_int(solver), ext,
+        C.c_int(nsolves), C.c_int(threads), _as(grf), _as(tau), flags.ctypes.data_as(C.POINTER(C.c_uint32)),
+        _as(nw), _as(margin) if margin is not None else None)
+    if rc != 0:
+        raise RuntimeError(f"qo_solve_wrench_batch failed: {rc}")
+    out = dict(grf=grf, tau=tau, flags=flags, netwrench=nw)
+    if want_margin:
+        out["margin"] = margin
+    return out
+
+
+def vmc_wrench(pose, twist, tpose, ttwist, params=None):
+    p = params or default_vmc_params()
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (pose, twist, tpose, ttwist)]
+    w = np.zeros(6)
+    lib().qo_vmc_wrench(C.byref(p), _as(a[0]), _as(a[1]), _as(a[2]), _as(a[3]), _as(w))
+    return w
