@@ -1,0 +1,222 @@
+"""ctypes binding of the C ABI in include/qlb.h (libqlb.so, built in-tree by build.py).
+
+This is harness plumbing: torch supplies device memory and streams, the product is the shared
+library.  There is no fallback: if libqlb.so is missing or CUDA is unavailable the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import legmodel
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libqlb.so")
+
+NUM_LEGS = 4
+STATS_NUM = 30
+STATS_NUM_SUM = 28
+FLAG_PARITY_MASK = 0x00FFFFFF
+STATUS_NAMES = ("ok", "no_stance", "max_iter", "unverified", "bad_input")
+
+
+class LegModel(C.Structure):
+    _fields_ = [("joint_xyz", (C.c_double * 3) * 4), ("joint_rpy", (C.c_double * 3) * 4),
+                ("link_mass", C.c_double * 4), ("link_com", (C.c_double * 3) * 4)]
+
+
+class Params(C.Structure):
+    _fields_ = [("wrench_weights", C.c_double * 6), ("ground_force_weight", C.c_double),
+                ("min_normal_force", C.c_double), ("friction_default", C.c_double), ("gravity", C.c_double),
+                ("kp_translation", C.c_double * 3), ("kd_translation", C.c_double * 3),
+                ("kff_translation", C.c_double * 3), ("kp_rotation", C.c_double * 3),
+                ("kd_rotation", C.c_double * 3), ("kff_rotation", C.c_double * 3),
+                ("torso_mass", C.c_double), ("leg_mass", C.c_double * 4),
+                ("leg_base_position", (C.c_double * 3) * 4), ("com_in_base", C.c_double * 3),
+                ("gravity_compensation_percentage", C.c_double), ("ipm_tolerance", C.c_double),
+                ("ipm_max_iterations", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("count", C.c_double), ("count_status", C.c_double * 5), ("sum_iterations", C.c_double),
+                ("sum_wrench_err", C.c_double), ("active_hist", C.c_double * 20),
+                ("max_wrench_err", C.c_double), ("max_iterations", C.c_double)]
+
+
+EXPORTS = (
+    "qlb_default_params", "qlb_create", "qlb_destroy", "qlb_set_params", "qlb_get_params",
+    "qlb_solve_wrench", "qlb_solve_wrench_host", "qlb_solve_state", "qlb_solve_state_host",
+    "qlb_leg_kinematics", "qlb_batch_stats", "qlb_launch_count", "qlb_strerror",
+    "qlb_last_cuda_error", "qlb_abi_version",
+)
+
+_lib = None
+_vp = C.c_void_p
+
+
+def load() -> C.CDLL:
+    """dlopen libqlb.so and declare the signatures.  Raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: run `python -m quadruped_locomotion_b200.build` "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.qlb_default_params.argtypes = [C.POINTER(Params)]
+    lib.qlb_create.argtypes = [C.POINTER(_vp), C.POINTER(LegModel), C.POINTER(Params), C.c_int, C.c_size_t]
+    lib.qlb_destroy.argtypes = [_vp]
+    lib.qlb_set_params.argtypes = [_vp, C.POINTER(Params)]
+    lib.qlb_get_params.argtypes = [_vp, C.POINTER(Params)]
+    lib.qlb_solve_wrench.argtypes = [_vp, C.c_size_t] + [_vp] * 11
+    lib.qlb_solve_wrench_host.argtypes = [_vp, C.c_size_t] + [_vp] * 10
+    lib.qlb_solve_state.argtypes = [_vp, C.c_size_t] + [_vp] * 14
+    lib.qlb_solve_state_host.argtypes = [_vp, C.c_size_t] + [_vp] * 13
+    lib.qlb_leg_kinematics.argtypes = [_vp, C.c_size_t] + [_vp] * 6
+    lib.qlb_batch_stats.argtypes = [_vp, C.c_size_t, _vp, _vp, _vp, C.POINTER(Stats), _vp]
+    lib.qlb_launch_count.argtypes = [_vp]
+    lib.qlb_launch_count.restype = C.c_uint64
+    lib.qlb_strerror.argtypes = [C.c_int]
+    lib.qlb_strerror.restype = C.c_char_p
+    lib.qlb_last_cuda_error.argtypes = [_vp]
+    lib.qlb_last_cuda_error.restype = C.c_char_p
+    lib.qlb_abi_version.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def default_params() -> Params:
+    p = Params()
+    rc = load().qlb_default_params(C.byref(p))
+    if rc != 0:
+        raise RuntimeError("qlb_default_params failed")
+    return p
+
+
+def leg_models(model: dict | str = "quadruped_model"):
+    if isinstance(model, str):
+        model = legmodel.load_model(model)
+    arr = (LegModel * NUM_LEGS)()
+    for i, leg in enumerate(model["legs"]):
+        for k in range(4):
+            for a in range(3):
+                arr[i].joint_xyz[k][a] = leg["joint_xyz"][k][a]
+                arr[i].joint_rpy[k][a] = leg["joint_rpy"][k][a]
+                arr[i].link_com[k][a] = leg["link_com"][k][a]
+            arr[i].link_mass[k] = leg["link_mass"][k]
+    return arr
+
+
+def _ptr(t):
+    """device/host pointer of a torch tensor or numpy array, or None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+class Solver:
+    """One context = one GPU.  Mirrors the call shape of ContactForceDistribution
+    (computeForceDistribution / getNetForceAndTorqueOnBase) for a whole batch."""
+
+    def __init__(self, model: dict | str = "quadruped_model", params: Params | None = None, device: int = 0,
+                 max_batch: int = 0):
+        self.lib = load()
+        self._ctx = _vp()
+        legs = leg_models(model)
+        rc = self.lib.qlb_create(C.byref(self._ctx), legs, C.byref(params) if params is not None else None,
+                                 int(device), int(max_batch))
+        if rc != 0:
+            self._ctx = _vp()
+            raise RuntimeError(f"qlb_create failed: {self.lib.qlb_strerror(rc).decode()} (no CPU fallback)")
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.qlb_destroy(self._ctx)
+            self._ctx = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            detail = self.lib.qlb_last_cuda_error(self._ctx).decode()
+            raise RuntimeError(f"{what} failed: {self.lib.qlb_strerror(rc).decode()} {detail}")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.qlb_launch_count(self._ctx))
+
+    def set_params(self, p: Params):
+        self._check(self.lib.qlb_set_params(self._ctx, C.byref(p)), "qlb_set_params")
+
+    def get_params(self) -> Params:
+        p = Params()
+        self._check(self.lib.qlb_get_params(self._ctx, C.byref(p)), "qlb_get_params")
+        return p
+
+    # -- device-pointer entry points (torch CUDA tensors, SoA [C, B] contiguous float64)
+    def solve_wrench(self, q, quat, wrench, mask, mu=None, normals=None, grf=None, tau=None, flags=None,
+                     netwrench=None, stream=None):
+        B = q.shape[1]
+        rc = self.lib.qlb_solve_wrench(self._ctx, B, _ptr(q), _ptr(quat), _ptr(wrench), _ptr(mask), _ptr(mu),
+                                       _ptr(normals), _ptr(grf), _ptr(tau), _ptr(flags), _ptr(netwrench),
+                                       stream if stream is not None else None)
+        self._check(rc, "qlb_solve_wrench")
+
+    def solve_state(self, q, pose, twist, tpose, ttwist, mask, mu=None, normals=None, grf=None, tau=None,
+                    flags=None, netwrench=None, wrench_out=None, stream=None):
+        B = q.shape[1]
+        rc = self.lib.qlb_solve_state(self._ctx, B, _ptr(q), _ptr(pose), _ptr(twist), _ptr(tpose), _ptr(ttwist),
+                                      _ptr(mask), _ptr(mu), _ptr(normals), _ptr(grf), _ptr(tau), _ptr(flags),
+                                      _ptr(netwrench), _ptr(wrench_out), stream if stream is not None else None)
+        self._check(rc, "qlb_solve_state")
+
+    def leg_kinematics(self, q, quat=None, foot=None, jac=None, gtau=None, stream=None):
+        B = q.shape[1]
+        rc = self.lib.qlb_leg_kinematics(self._ctx, B, _ptr(q), _ptr(quat), _ptr(foot), _ptr(jac), _ptr(gtau),
+                                         stream if stream is not None else None)
+        self._check(rc, "qlb_leg_kinematics")
+
+    def batch_stats(self, flags, wrench=None, netwrench=None, stream=None) -> np.ndarray:
+        st = Stats()
+        B = flags.shape[0]
+        rc = self.lib.qlb_batch_stats(self._ctx, B, _ptr(flags), _ptr(wrench), _ptr(netwrench), C.byref(st),
+                                      stream if stream is not None else None)
+        self._check(rc, "qlb_batch_stats")
+        return np.frombuffer(bytes(st), dtype=np.float64).copy()
+
+    # -- host-pointer entry points (numpy arrays or pinned torch CPU tensors)
+    def solve_wrench_host(self, q, quat, wrench, mask, mu=None, normals=None, grf=None, tau=None, flags=None,
+                          netwrench=None):
+        B = q.shape[1]
+        rc = self.lib.qlb_solve_wrench_host(self._ctx, B, _ptr(q), _ptr(quat), _ptr(wrench), _ptr(mask), _ptr(mu),
+                                            _ptr(normals), _ptr(grf), _ptr(tau), _ptr(flags), _ptr(netwrench))
+        self._check(rc, "qlb_solve_wrench_host")
+
+    def solve_state_host(self, q, pose, twist, tpose, ttwist, mask, mu=None, normals=None, grf=None, tau=None,
+                         flags=None, netwrench=None, wrench_out=None):
+        B = q.shape[1]
+        rc = self.lib.qlb_solve_state_host(self._ctx, B, _ptr(q), _ptr(pose), _ptr(twist), _ptr(tpose),
+                                           _ptr(ttwist), _ptr(mask), _ptr(mu), _ptr(normals), _ptr(grf), _ptr(tau),
+                                           _ptr(flags), _ptr(netwrench), _ptr(wrench_out))
+        self._check(rc, "qlb_solve_state_host")
+
+    def solve_wrench_numpy(self, states: dict, with_net=True) -> dict:
+        """Convenience for tests: numpy SoA in, numpy SoA out, through the host entry point."""
+        B = states["q"].shape[1]
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        q, quat, wr = f64(states["q"]), f64(states["quat"]), f64(states["wrench"])
+        mu, nr = f64(states.get("mu")), f64(states.get("normals"))
+        mask = np.ascontiguousarray(states["mask"], dtype=np.uint8)
+        grf = np.zeros((12, B)); tau = np.zeros((12, B)); flags = np.zeros(B, dtype=np.uint32)
+        net = np.zeros((6, B)) if with_net else None
+        self.solve_wrench_host(q, quat, wr, mask, mu, nr, grf, tau, flags, net)
+        return dict(grf=grf, tau=tau, flags=flags, netwrench=net)

@@ -1,0 +1,442 @@
+// qlb_api.cu - the C ABI declared in include/qlb.h: context management and kernel launches.
+// No CPU fallback lives here: every compute entry point launches sm_100a kernels or returns an error.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "qlb.h"
+#include "qlb_aux.cuh"
+#include "qlb_solve.cuh"
+
+using namespace qlb;
+
+struct qlb_context {
+  int device = 0;
+  int sm_count = 0;
+  int blocks_per_sm[2] = {0, 0};
+  qlb_params params;
+  qlb_leg_model legs[QLB_NUM_LEGS];
+  DeviceModel* d_model = nullptr;
+  DeviceParams* d_params = nullptr;
+  unsigned long long* d_counter = nullptr;
+  double* d_stats = nullptr;
+  cudaStream_t stream = nullptr;  // used by the *_host entry points
+  // device staging for the *_host entry points
+  double* d_in = nullptr;
+  double* d_out = nullptr;
+  uint8_t* d_mask = nullptr;
+  uint32_t* d_flags = nullptr;
+  size_t cap = 0;
+  uint64_t launches = 0;
+  char last_error[256] = {0};
+};
+
+namespace {
+
+constexpr int kHostInRows = 12 + 7 + 6 + 7 + 6 + 4 + 12;  // state mode is the larger one (54)
+constexpr int kHostOutRows = 12 + 12 + 6 + 6;
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int cuda_fail(qlb_context* ctx, cudaError_t e, const char* what) {
+  if (ctx) std::snprintf(ctx->last_error, sizeof ctx->last_error, "%s: %s", what, cudaGetErrorString(e));
+  return QLB_ERR_CUDA;
+}
+#define QLB_CUDA(ctx, call)                                   \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+  } while (0)
+
+// URDF <origin rpy> -> rotation matrix, through the quaternion like urdfdom + KDL do.
+void rpy_to_rot(const double rpy[3], double R[9]) {
+  const double hr = 0.5 * rpy[0], hp = 0.5 * rpy[1], hy = 0.5 * rpy[2];
+  double x = std::sin(hr) * std::cos(hp) * std::cos(hy) - std::cos(hr) * std::sin(hp) * std::sin(hy);
+  double y = std::cos(hr) * std::sin(hp) * std::cos(hy) + std::sin(hr) * std::cos(hp) * std::sin(hy);
+  double z = std::cos(hr) * std::cos(hp) * std::sin(hy) - std::sin(hr) * std::sin(hp) * std::cos(hy);
+  double w = std::cos(hr) * std::cos(hp) * std::cos(hy) + std::sin(hr) * std::sin(hp) * std::sin(hy);
+  const double n = std::sqrt(x * x + y * y + z * z + w * w);
+  x /= n; y /= n; z /= n; w /= n;
+  R[0] = w * w + x * x - y * y - z * z; R[1] = 2.0 * (x * y - w * z); R[2] = 2.0 * (x * z + w * y);
+  R[3] = 2.0 * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = 2.0 * (y * z - w * x);
+  R[6] = 2.0 * (x * z - w * y); R[7] = 2.0 * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
+}
+
+void build_device_model(const qlb_leg_model legs[QLB_NUM_LEGS], DeviceModel* m) {
+  std::memset(m, 0, sizeof *m);
+  for (int l = 0; l < 4; l++) {
+    for (int j = 0; j < 4; j++) {
+      rpy_to_rot(legs[l].joint_rpy[j], m->rot[l][j]);
+      for (int a = 0; a < 3; a++) m->xyz[l][j][a] = legs[l].joint_xyz[j][a];
+      m->mass[l][j] = legs[l].link_mass[j];
+      for (int a = 0; a < 3; a++) m->com[l][j][a] = legs[l].link_com[j][a];
+    }
+    // the foot frame is never rotated in the kernel: fold its fixed rotation into the foot link's COM
+    const double* R3 = m->rot[l][3];
+    const double* c3 = legs[l].link_com[3];
+    for (int a = 0; a < 3; a++) m->com[l][3][a] = R3[3 * a] * c3[0] + R3[3 * a + 1] * c3[1] + R3[3 * a + 2] * c3[2];
+    double acc = 0.0;
+    for (int j = 3; j >= 0; j--) { acc += legs[l].link_mass[j]; m->msuf[l][j] = acc; }
+  }
+}
+
+void build_device_params(const qlb_params* p, DeviceParams* d) {
+  std::memset(d, 0, sizeof *d);
+  for (int i = 0; i < 6; i++) d->S[i] = p->wrench_weights[i];
+  d->W = p->ground_force_weight;
+  d->fmin = p->min_normal_force;
+  d->mu_default = p->friction_default;
+  d->gravity = p->gravity;
+  d->tol = p->ipm_tolerance;
+  d->max_iter = p->ipm_max_iterations;
+  for (int i = 0; i < 3; i++) {
+    d->kp_t[i] = p->kp_translation[i]; d->kd_t[i] = p->kd_translation[i]; d->kff_t[i] = p->kff_translation[i];
+    d->kp_r[i] = p->kp_rotation[i]; d->kd_r[i] = p->kd_rotation[i]; d->kff_r[i] = p->kff_rotation[i];
+    d->com[i] = p->com_in_base[i];
+  }
+  d->torso_mass = p->torso_mass;
+  for (int l = 0; l < 4; l++) {
+    d->leg_mass[l] = p->leg_mass[l];
+    for (int a = 0; a < 3; a++) d->leg_pos[l][a] = p->leg_base_position[l][a];
+  }
+  d->grav_pct = p->gravity_compensation_percentage;
+}
+
+bool params_ok(const qlb_params* p) {
+  if (!(p->ground_force_weight > 0.0) || !(p->ipm_tolerance > 0.0) || p->ipm_max_iterations < 1) return false;
+  for (int i = 0; i < 6; i++)
+    if (!(p->wrench_weights[i] >= 0.0)) return false;
+  return std::isfinite(p->min_normal_force) && std::isfinite(p->friction_default) && std::isfinite(p->gravity);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <int MODE>
+int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
+  constexpr int ROWS = (MODE == 1) ? kInRowsState : kInRows;
+  const size_t smem = sizeof(CtaSmem<ROWS>);
+  const unsigned long long nbatch = (a.B + kBatch - 1) / kBatch;
+  unsigned long long want = (nbatch + kWarpsPerCta - 1) / kWarpsPerCta;
+  unsigned long long cap = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm[MODE];
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  QLB_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st));
+  qlb_solve_kernel<MODE><<<grid, kThreads, smem, st>>>(a);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return QLB_OK;
+}
+
+int ensure_capacity(qlb_context* ctx, size_t B) {
+  if (B <= ctx->cap) return QLB_OK;
+  size_t cap = ctx->cap ? ctx->cap : 1024;
+  while (cap < B) cap *= 2;
+  cap = (cap + 15) & ~size_t(15);
+  cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags);
+  ctx->d_in = ctx->d_out = nullptr; ctx->d_mask = nullptr; ctx->d_flags = nullptr; ctx->cap = 0;
+  if (cudaMalloc(&ctx->d_in, cap * kHostInRows * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_out, cap * kHostOutRows * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_mask, cap) != cudaSuccess || cudaMalloc(&ctx->d_flags, cap * sizeof(uint32_t)) != cudaSuccess) {
+    cudaGetLastError();
+    return QLB_ERR_ALLOC;
+  }
+  ctx->cap = cap;
+  return QLB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qlb_abi_version(void) { return QLB_ABI_VERSION; }
+
+const char* qlb_strerror(int status) {
+  switch (status) {
+    case QLB_OK: return "ok";
+    case QLB_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case QLB_ERR_CUDA: return "CUDA error (see qlb_last_cuda_error)";
+    case QLB_ERR_BATCH_TOO_LARGE: return "batch too large";
+    case QLB_ERR_NOT_INITIALISED: return "context not initialised";
+    case QLB_ERR_ALLOC: return "device allocation failed";
+    default: return "unknown status";
+  }
+}
+
+const char* qlb_last_cuda_error(const qlb_context* ctx) { return ctx ? ctx->last_error : ""; }
+
+int qlb_default_params(qlb_params* p) {
+  if (!p) return QLB_ERR_INVALID_ARGUMENT;
+  std::memset(p, 0, sizeof *p);
+  // balance_controller/config/controller_gains.yaml:27-41
+  const double S[6] = {1.0, 5.0, 1.0, 10.0, 10.0, 5.0};
+  for (int i = 0; i < 6; i++) p->wrench_weights[i] = S[i];
+  p->ground_force_weight = 0.0001;
+  p->min_normal_force = 10.0;
+  p->friction_default = 0.6;
+  p->gravity = 9.8;  // ContactForceDistribution.cpp:518, VirtualModelController.cpp:165
+  // controller_gains.yaml:3-26 (heading, lateral, vertical / roll, pitch, yaw)
+  const double kp_t[3] = {5000, 5000, 10000}, kd_t[3] = {5000, 4000, 5000}, kff_t[3] = {10, 10, 100};
+  const double kp_r[3] = {10000, 10000, 4000}, kd_r[3] = {1000, 1000, 1000}, kff_r[3] = {0.2, 0.2, 1000};
+  for (int i = 0; i < 3; i++) {
+    p->kp_translation[i] = kp_t[i]; p->kd_translation[i] = kd_t[i]; p->kff_translation[i] = kff_t[i];
+    p->kp_rotation[i] = kp_r[i]; p->kd_rotation[i] = kd_r[i]; p->kff_rotation[i] = kff_r[i];
+    p->com_in_base[i] = 0.0;
+  }
+  p->torso_mass = 27.0;  // quadruped_state.cpp:28
+  // quadruped_state.cpp:83-97, LF RF RH LH
+  const double pos[4][3] = {{0.42, 0.075, 0.0}, {0.42, -0.075, 0.0}, {-0.42, -0.075, 0.0}, {-0.42, 0.075, 0.0}};
+  for (int l = 0; l < 4; l++) {
+    p->leg_mass[l] = 6.0;  // quadruped_state.cpp:36-41
+    for (int a = 0; a < 3; a++) p->leg_base_position[l][a] = pos[l][a];
+  }
+  p->gravity_compensation_percentage = 1.0;  // VirtualModelController.cpp:57
+  p->ipm_tolerance = 1e-9;
+  p->ipm_max_iterations = 30;
+  return QLB_OK;
+}
+
+int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const qlb_params* params, int device,
+               size_t max_batch) {
+  if (!out || !legs) return QLB_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  qlb_params defaults;
+  qlb_default_params(&defaults);
+  const qlb_params* p = params ? params : &defaults;
+  if (!params_ok(p)) return QLB_ERR_INVALID_ARGUMENT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return QLB_ERR_CUDA;
+  }
+  qlb_context* ctx = new (std::nothrow) qlb_context();
+  if (!ctx) return QLB_ERR_ALLOC;
+  ctx->device = device;
+  ctx->params = *p;
+  std::memcpy(ctx->legs, legs, sizeof ctx->legs);
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete ctx; return QLB_ERR_CUDA; }
+  ctx->sm_count = prop.multiProcessorCount;
+  auto fail = [&](int code) { qlb_destroy(ctx); return code; };
+  if (cudaMalloc(&ctx->d_model, sizeof(DeviceModel)) != cudaSuccess || cudaMalloc(&ctx->d_params, sizeof(DeviceParams)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_counter, sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_stats, QLB_STATS_NUM * sizeof(double)) != cudaSuccess)
+    return fail(QLB_ERR_ALLOC);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(QLB_ERR_CUDA);
+  DeviceModel hm;
+  build_device_model(legs, &hm);
+  if (cudaMemcpy(ctx->d_model, &hm, sizeof hm, cudaMemcpyHostToDevice) != cudaSuccess) return fail(QLB_ERR_CUDA);
+  if (qlb_set_params(ctx, p) != QLB_OK) return fail(QLB_ERR_CUDA);
+  // the fused kernels need more than the default 48 KB of dynamic shared memory
+  if (cudaFuncSetAttribute(qlb_solve_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem<kInRows>)) != cudaSuccess ||
+      cudaFuncSetAttribute(qlb_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem<kInRowsState>)) != cudaSuccess)
+    return fail(QLB_ERR_CUDA);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], qlb_solve_kernel<0>, kThreads, sizeof(CtaSmem<kInRows>)) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], qlb_solve_kernel<1>, kThreads, sizeof(CtaSmem<kInRowsState>)) != cudaSuccess)
+    return fail(QLB_ERR_CUDA);
+  if (ctx->blocks_per_sm[0] < 1 || ctx->blocks_per_sm[1] < 1) return fail(QLB_ERR_CUDA);
+  if (max_batch > 0 && ensure_capacity(ctx, max_batch) != QLB_OK) return fail(QLB_ERR_ALLOC);
+  *out = ctx;
+  return QLB_OK;
+}
+
+int qlb_destroy(qlb_context* ctx) {
+  if (!ctx) return QLB_OK;
+  DeviceGuard guard(ctx->device);
+  if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  cudaFree(ctx->d_model); cudaFree(ctx->d_params); cudaFree(ctx->d_counter); cudaFree(ctx->d_stats);
+  cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags);
+  cudaGetLastError();
+  delete ctx;
+  return QLB_OK;
+}
+
+int qlb_set_params(qlb_context* ctx, const qlb_params* params) {
+  if (!ctx || !params) return QLB_ERR_INVALID_ARGUMENT;
+  if (!params_ok(params)) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  DeviceParams hp;
+  build_device_params(params, &hp);
+  // ordered after any solve already queued on the context stream
+  QLB_CUDA(ctx, cudaDeviceSynchronize());
+  QLB_CUDA(ctx, cudaMemcpy(ctx->d_params, &hp, sizeof hp, cudaMemcpyHostToDevice));
+  ctx->params = *params;
+  return QLB_OK;
+}
+
+int qlb_get_params(const qlb_context* ctx, qlb_params* params) {
+  if (!ctx || !params) return QLB_ERR_INVALID_ARGUMENT;
+  *params = ctx->params;
+  return QLB_OK;
+}
+
+uint64_t qlb_launch_count(const qlb_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int qlb_solve_wrench(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz, const double* wrench,
+                     const uint8_t* stance_mask, const double* mu, const double* normals_world, double* grf,
+                     double* tau, uint32_t* flags, double* netwrench, void* stream) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!q || !quat_wxyz || !wrench || !stance_mask || !grf || !tau || !flags) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  SolveArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.B = B; a.q = q; a.quat = quat_wxyz; a.wrench = wrench; a.mask = stance_mask; a.mu = mu; a.normals = normals_world;
+  a.grf = grf; a.tau = tau; a.flags = flags; a.netwrench = netwrench;
+  a.counter = ctx->d_counter; a.model = ctx->d_model; a.params = ctx->d_params;
+  a.vec_ok = (B % 2 == 0) && aligned16(q) && aligned16(quat_wxyz) && aligned16(wrench) && aligned16(grf) && aligned16(tau) &&
+             (!mu || aligned16(mu)) && (!normals_world || aligned16(normals_world)) && (!netwrench || aligned16(netwrench));
+  return launch_solve<0>(ctx, a, static_cast<cudaStream_t>(stream));
+}
+
+int qlb_solve_state(qlb_context* ctx, size_t B, const double* q, const double* base_pose, const double* base_twist,
+                    const double* target_pose, const double* target_twist, const uint8_t* stance_mask,
+                    const double* mu, const double* normals_world, double* grf, double* tau, uint32_t* flags,
+                    double* netwrench, double* wrench_out, void* stream) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!q || !base_pose || !base_twist || !target_pose || !target_twist || !stance_mask || !grf || !tau || !flags)
+    return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  SolveArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.B = B; a.q = q; a.pose = base_pose; a.twist = base_twist; a.tpose = target_pose; a.ttwist = target_twist;
+  a.mask = stance_mask; a.mu = mu; a.normals = normals_world;
+  a.grf = grf; a.tau = tau; a.flags = flags; a.netwrench = netwrench; a.wrench_out = wrench_out;
+  a.counter = ctx->d_counter; a.model = ctx->d_model; a.params = ctx->d_params;
+  a.vec_ok = (B % 2 == 0) && aligned16(q) && aligned16(base_pose) && aligned16(base_twist) && aligned16(target_pose) &&
+             aligned16(target_twist) && aligned16(grf) && aligned16(tau) && (!mu || aligned16(mu)) &&
+             (!normals_world || aligned16(normals_world)) && (!netwrench || aligned16(netwrench)) &&
+             (!wrench_out || aligned16(wrench_out));
+  return launch_solve<1>(ctx, a, static_cast<cudaStream_t>(stream));
+}
+
+// ---- host-pointer entry points: copy in, solve, copy out, synchronise
+int qlb_solve_wrench_host(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz, const double* wrench,
+                          const uint8_t* stance_mask, const double* mu, const double* normals_world, double* grf,
+                          double* tau, uint32_t* flags, double* netwrench) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!q || !quat_wxyz || !wrench || !stance_mask || !grf || !tau || !flags) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  int rc = ensure_capacity(ctx, B);
+  if (rc != QLB_OK) return rc;
+  const size_t cap = ctx->cap;  // row pitch of the staging buffers: keeps every row 16-byte aligned
+  cudaStream_t st = ctx->stream;
+  double* din = ctx->d_in;
+  double* d_q = din; double* d_quat = din + 12 * cap; double* d_wr = din + 16 * cap;
+  double* d_mu = din + 22 * cap; double* d_nr = din + 26 * cap;
+  double* dout = ctx->d_out;
+  double* d_grf = dout; double* d_tau = dout + 12 * cap; double* d_net = dout + 24 * cap;
+  // the kernel indexes rows with pitch B, so stage contiguous [C][B] blocks
+  QLB_CUDA(ctx, cudaMemcpyAsync(d_q, q, 12 * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  QLB_CUDA(ctx, cudaMemcpyAsync(d_quat, quat_wxyz, 4 * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  QLB_CUDA(ctx, cudaMemcpyAsync(d_wr, wrench, 6 * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (mu) QLB_CUDA(ctx, cudaMemcpyAsync(d_mu, mu, 4 * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (normals_world) QLB_CUDA(ctx, cudaMemcpyAsync(d_nr, normals_world, 12 * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  QLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, stance_mask, B, cudaMemcpyHostToDevice, st));
+  rc = qlb_solve_wrench(ctx, B, d_q, d_quat, d_wr, ctx->d_mask, mu ? d_mu : nullptr, normals_world ? d_nr : nullptr,
+                        d_grf, d_tau, ctx->d_flags, netwrench ? d_net : nullptr, st);
+  if (rc != QLB_OK) return rc;
+  QLB_CUDA(ctx, cudaMemcpyAsync(grf, d_grf, 12 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  QLB_CUDA(ctx, cudaMemcpyAsync(tau, d_tau, 12 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  QLB_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (netwrench) QLB_CUDA(ctx, cudaMemcpyAsync(netwrench, d_net, 6 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  QLB_CUDA(ctx, cudaStreamSynchronize(st));
+  return QLB_OK;
+}
+
+int qlb_solve_state_host(qlb_context* ctx, size_t B, const double* q, const double* base_pose, const double* base_twist,
+                         const double* target_pose, const double* target_twist, const uint8_t* stance_mask,
+                         const double* mu, const double* normals_world, double* grf, double* tau, uint32_t* flags,
+                         double* netwrench, double* wrench_out) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!q || !base_pose || !base_twist || !target_pose || !target_twist || !stance_mask || !grf || !tau || !flags)
+    return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  int rc = ensure_capacity(ctx, B);
+  if (rc != QLB_OK) return rc;
+  const size_t cap = ctx->cap;
+  cudaStream_t st = ctx->stream;
+  double* din = ctx->d_in;
+  double* d_q = din; double* d_pose = din + 12 * cap; double* d_tw = din + 19 * cap; double* d_tp = din + 25 * cap;
+  double* d_tt = din + 32 * cap; double* d_mu = din + 38 * cap; double* d_nr = din + 42 * cap;
+  double* dout = ctx->d_out;
+  double* d_grf = dout; double* d_tau = dout + 12 * cap; double* d_net = dout + 24 * cap; double* d_wo = dout + 30 * cap;
+  QLB_CUDA(ctx, cudaMemcpyAsync(d_q, q, 12 * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  QLB_CUDA(ctx, cudaMemcpyAsync(d_pose, base_pose, 7 * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  QLB_CUDA(ctx, cudaMemcpyAsync(d_tw, base_twist, 6 * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  QLB_CUDA(ctx, cudaMemcpyAsync(d_tp, target_pose, 7 * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  QLB_CUDA(ctx, cudaMemcpyAsync(d_tt, target_twist, 6 * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (mu) QLB_CUDA(ctx, cudaMemcpyAsync(d_mu, mu, 4 * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (normals_world) QLB_CUDA(ctx, cudaMemcpyAsync(d_nr, normals_world, 12 * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  QLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, stance_mask, B, cudaMemcpyHostToDevice, st));
+  rc = qlb_solve_state(ctx, B, d_q, d_pose, d_tw, d_tp, d_tt, ctx->d_mask, mu ? d_mu : nullptr,
+                       normals_world ? d_nr : nullptr, d_grf, d_tau, ctx->d_flags, netwrench ? d_net : nullptr,
+                       wrench_out ? d_wo : nullptr, st);
+  if (rc != QLB_OK) return rc;
+  QLB_CUDA(ctx, cudaMemcpyAsync(grf, d_grf, 12 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  QLB_CUDA(ctx, cudaMemcpyAsync(tau, d_tau, 12 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  QLB_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (netwrench) QLB_CUDA(ctx, cudaMemcpyAsync(netwrench, d_net, 6 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (wrench_out) QLB_CUDA(ctx, cudaMemcpyAsync(wrench_out, d_wo, 6 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  QLB_CUDA(ctx, cudaStreamSynchronize(st));
+  return QLB_OK;
+}
+
+int qlb_leg_kinematics(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz, double* foot, double* jac,
+                       double* gravity_tau, void* stream) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!q) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  const unsigned long long total = (unsigned long long)B * 4ull;
+  const unsigned threads = 128;
+  const unsigned long long blocks = (total + threads - 1) / threads;
+  if (blocks > 0x7fffffffull) return QLB_ERR_BATCH_TOO_LARGE;
+  qlb_kinematics_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      B, q, quat_wxyz, foot, jac, gravity_tau, ctx->d_model, ctx->d_params);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return QLB_OK;
+}
+
+int qlb_batch_stats(qlb_context* ctx, size_t B, const uint32_t* flags, const double* wrench, const double* netwrench,
+                    qlb_stats* stats_out, void* stream) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (!flags || !stats_out) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  QLB_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, QLB_STATS_NUM * sizeof(double), st));
+  if (B > 0) {
+    const unsigned threads = 256;
+    unsigned long long blocks = (B + threads - 1) / threads;
+    const unsigned long long cap = (unsigned long long)ctx->sm_count * 8ull;
+    if (blocks > cap) blocks = cap;
+    qlb_stats_kernel<<<(unsigned)blocks, threads, 0, st>>>(B, flags, wrench, netwrench, ctx->d_params, ctx->d_stats);
+    QLB_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+  }
+  double h[QLB_STATS_NUM];
+  QLB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost, st));
+  QLB_CUDA(ctx, cudaStreamSynchronize(st));
+  std::memcpy(stats_out, h, sizeof h);
+  return QLB_OK;
+}
+
+}  // extern "C"

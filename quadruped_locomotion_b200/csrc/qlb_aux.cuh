@@ -1,0 +1,148 @@
+// qlb_aux.cuh - small companion kernels: stand-alone leg kinematics and batch statistics.
+#pragma once
+
+#include "qlb.h"
+#include "qlb_device.cuh"
+
+namespace qlb {
+
+// One thread per (state, leg): foot position, translational Jacobian, gravity torques.
+// Replaces QuadrupedKinematics::FowardKinematicsSolve / AnalysticJacobian /
+// getGravityCompensationForLimb (quadruped_model/src/quadrupedkinematics.cpp:143-278,485-552).
+// Consecutive threads handle consecutive states of the same leg, so all global accesses coalesce.
+__global__ void __launch_bounds__(128) qlb_kinematics_kernel(unsigned long long B, const double* __restrict__ q,
+                                                             const double* __restrict__ quat, double* __restrict__ foot,
+                                                             double* __restrict__ jac, double* __restrict__ gtau,
+                                                             const DeviceModel* __restrict__ mdl,
+                                                             const DeviceParams* __restrict__ prm) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 4ull * B) return;
+  const int leg = (int)(t / B);
+  const unsigned long long i = t - (unsigned long long)leg * B;
+  double gb[3] = {0.0, 0.0, -prm->gravity};
+  if (quat) {
+    const double w = quat[i], x = quat[B + i], y = quat[2 * B + i], z = quat[3 * B + i];
+    // third row of R_bw = R_wb * e_z
+    gb[0] = -prm->gravity * 2.0 * (x * z - w * y);
+    gb[1] = -prm->gravity * 2.0 * (y * z + w * x);
+    gb[2] = -prm->gravity * (w * w - x * x - y * y + z * z);
+  }
+  double R[9], p[3], zax[3][3], pj[3][3], com[4][3];
+#pragma unroll
+  for (int e = 0; e < 9; e++) R[e] = mdl->rot[leg][0][e];
+#pragma unroll
+  for (int a = 0; a < 3; a++) p[a] = mdl->xyz[leg][0][a];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (j > 0) {
+      const double* xj = mdl->xyz[leg][j];
+#pragma unroll
+      for (int a = 0; a < 3; a++) p[a] += R[3 * a] * xj[0] + R[3 * a + 1] * xj[1] + R[3 * a + 2] * xj[2];
+      if (j < 3) {
+        const double* Rj = mdl->rot[leg][j];
+        double T[9];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int s = 0; s < 3; s++) T[3 * r + s] = R[3 * r] * Rj[s] + R[3 * r + 1] * Rj[3 + s] + R[3 * r + 2] * Rj[6 + s];
+#pragma unroll
+        for (int e = 0; e < 9; e++) R[e] = T[e];
+      }
+    }
+    if (j < 3) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) { zax[j][a] = R[3 * a + 2]; pj[j][a] = p[a]; }
+      double sj, cj;
+      sincos(q[(size_t)(3 * leg + j) * B + i], &sj, &cj);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const double a0 = R[3 * r], a1 = R[3 * r + 1];
+        R[3 * r] = cj * a0 + sj * a1;
+        R[3 * r + 1] = cj * a1 - sj * a0;
+      }
+    }
+    const double* cm = mdl->com[leg][j];
+#pragma unroll
+    for (int a = 0; a < 3; a++) com[j][a] = p[a] + R[3 * a] * cm[0] + R[3 * a + 1] * cm[1] + R[3 * a + 2] * cm[2];
+  }
+  if (foot) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) foot[(size_t)(3 * leg + a) * B + i] = p[a];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double dv[3] = {p[0] - pj[k][0], p[1] - pj[k][1], p[2] - pj[k][2]};
+    const double col[3] = {zax[k][1] * dv[2] - zax[k][2] * dv[1], zax[k][2] * dv[0] - zax[k][0] * dv[2],
+                           zax[k][0] * dv[1] - zax[k][1] * dv[0]};
+    if (jac) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) jac[(size_t)(9 * leg + 3 * a + k) * B + i] = col[a];
+    }
+    if (gtau) {
+      double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        if (l < k) continue;
+        const double m = mdl->mass[leg][l];
+        const double arm[3] = {com[l][0] - pj[k][0], com[l][1] - pj[k][1], com[l][2] - pj[k][2]};
+        acc[0] += m * (arm[1] * gb[2] - arm[2] * gb[1]);
+        acc[1] += m * (arm[2] * gb[0] - arm[0] * gb[2]);
+        acc[2] += m * (arm[0] * gb[1] - arm[1] * gb[0]);
+      }
+      gtau[(size_t)(3 * leg + k) * B + i] = -(zax[k][0] * acc[0] + zax[k][1] * acc[1] + zax[k][2] * acc[2]);
+    }
+  }
+}
+
+// Batch statistics: counts per status, iteration sum/max, weighted wrench error sum/max, active-row
+// histogram.  Block-level shared-memory reduction, one atomic per block and statistic.
+__global__ void __launch_bounds__(256) qlb_stats_kernel(unsigned long long B, const uint32_t* __restrict__ flags,
+                                                        const double* __restrict__ wrench,
+                                                        const double* __restrict__ netwrench,
+                                                        const DeviceParams* __restrict__ prm, double* __restrict__ out) {
+  __shared__ double sh[QLB_STATS_NUM];
+  if (threadIdx.x < QLB_STATS_NUM) sh[threadIdx.x] = 0.0;
+  __syncthreads();
+  double loc_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // count, status[5], iters, err
+  double max_err = 0.0, max_it = 0.0;
+  unsigned hist_local[20];
+#pragma unroll
+  for (int k = 0; k < 20; k++) hist_local[k] = 0u;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < B;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t f = flags[i];
+    const unsigned st = (f >> QLB_FLAG_STATUS_SHIFT) & 7u;
+    const double it = (double)(f >> QLB_FLAG_ITER_SHIFT);
+    loc_sum[0] += 1.0;
+    if (st < 5) loc_sum[1 + st] += 1.0;
+    loc_sum[6] += it;
+    max_it = fmax(max_it, it);
+    const unsigned act = (f & QLB_FLAG_ACTIVE_MASK) >> QLB_FLAG_ACTIVE_SHIFT;
+#pragma unroll
+    for (int k = 0; k < 20; k++) hist_local[k] += (act >> k) & 1u;
+    if (wrench && netwrench && (st == 0 || st == 2 || st == 3)) {
+      double e2 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        const double d = netwrench[(size_t)r * B + i] - wrench[(size_t)r * B + i];
+        e2 += prm->S[r] * d * d;
+      }
+      const double e = sqrt(e2);
+      loc_sum[7] += e;
+      max_err = fmax(max_err, e);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) atomicAdd(&sh[k], loc_sum[k]);
+#pragma unroll
+  for (int k = 0; k < 20; k++) atomicAdd(&sh[8 + k], (double)hist_local[k]);
+  // max via atomicMax on the bit pattern (values are non-negative)
+  atomicMax(reinterpret_cast<unsigned long long*>(&sh[28]), (unsigned long long)__double_as_longlong(max_err));
+  atomicMax(reinterpret_cast<unsigned long long*>(&sh[29]), (unsigned long long)__double_as_longlong(max_it));
+  __syncthreads();
+  if (threadIdx.x < QLB_STATS_NUM_SUM) atomicAdd(&out[threadIdx.x], sh[threadIdx.x]);
+  else if (threadIdx.x < QLB_STATS_NUM)
+    atomicMax(reinterpret_cast<unsigned long long*>(&out[threadIdx.x]), (unsigned long long)__double_as_longlong(sh[threadIdx.x]));
+}
+
+}  // namespace qlb

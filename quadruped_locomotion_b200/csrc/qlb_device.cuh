@@ -1,0 +1,128 @@
+// qlb_device.cuh - device-side building blocks of the fused contact-force-distribution kernel.
+//
+// Mapping: one QP per HALF-WARP ("group" of 16 lanes, two QPs per warp).  Lane gl < 12 of a group owns
+// variable gl = 3*leg + c of the 12-slot problem and row gl of every 12x12 matrix; lanes 12..15 carry
+// zeros.  All linear algebra is register-resident; rows are exchanged with width-16 warp shuffles.
+//
+// The problem is solved in per-leg contact coordinates y = (y_n, y_1, y_2) = Q_leg^T f_leg with
+// Q_leg = [n t1 t2] the friction-pyramid frame the reference builds in
+// ContactForceDistribution.cpp:286-309.  In these coordinates the five rows of a leg
+// (ContactForceDistribution.cpp:241-247,315-325) are
+//     y_n >= F_min,  mu y_n + y_1 >= 0,  mu y_n - y_1 >= 0,  mu y_n + y_2 >= 0,  mu y_n - y_2 >= 0
+// so the constraint matrix never has to be stored.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qlb {
+
+constexpr int kGroup = 16;        // lanes per QP
+constexpr int kVars = 12;         // variable slots (4 legs x 3)
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------- shuffles / reductions in a group
+// Always full-mask: callers keep the whole warp converged around every exchange (a partial, run-time
+// mask makes nvcc emit WARPSYNC + a convergence barrier per shuffle - measured 30x slower).
+__device__ __forceinline__ double gshfl(double v, int src) { return __shfl_sync(kFull, v, src, kGroup); }
+__device__ __forceinline__ float gshfl(float v, int src) { return __shfl_sync(kFull, v, src, kGroup); }
+__device__ __forceinline__ int gshfl(int v, int src) { return __shfl_sync(kFull, v, src, kGroup); }
+
+// per-leg value (replicated on the three lanes of a leg) -> sum / max / min over the four legs
+__device__ __forceinline__ double leg_sum(double v) {
+  return (gshfl(v, 0) + gshfl(v, 3)) + (gshfl(v, 6) + gshfl(v, 9));
+}
+__device__ __forceinline__ float leg_max(float v) {
+  return fmaxf(fmaxf(gshfl(v, 0), gshfl(v, 3)), fmaxf(gshfl(v, 6), gshfl(v, 9)));
+}
+__device__ __forceinline__ double leg_min(double v) {
+  return fmin(fmin(gshfl(v, 0), gshfl(v, 3)), fmin(gshfl(v, 6), gshfl(v, 9)));
+}
+// max over the 16 lanes of a group (butterfly)
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o, kGroup));
+  return v;
+}
+
+// single MUFU.RCP (no denormal / range slow path)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// 1/x to ~1e-13 relative: FP32 seed + two Newton steps in FP64 (x must be in FP32 normal range)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r = (double)rcp_approx((float)x);
+  r = r * fma(-x, r, 2.0);
+  return r * fma(-x, r, 2.0);
+}
+
+// ---------------------------------------------------------------- 12x12 Cholesky through shuffles
+// In : H[j] = entry (gl, j) of a symmetric positive definite matrix (full row; lanes >= 12: zeros).
+// Out: H[j<gl] = L[gl][j], H[gl] = L[gl][gl], H[j>gl] = L[j][gl] (row gl of L^T), rdiag = 1/L[gl][gl].
+// Right-looking; at step k the scaled column k is broadcast entry by entry and every lane below
+// updates its whole trailing row, so the trailing matrix stays symmetric and lane k can keep the
+// broadcast values as its row of L^T (needed by the backward substitution).
+// Returns false (group-uniform) when a pivot is not positive.
+__device__ __forceinline__ bool group_cholesky(double (&H)[kVars], double& rdiag, const int gl) {
+  bool ok = true;
+  rdiag = 1.0;
+#pragma unroll
+  for (int k = 0; k < kVars; k++) {
+    const double dkk = gshfl(H[k], k);
+    ok = ok && (dkk > 0.0);
+    const double rinv = rsqrt(dkk);
+    if (gl >= k) H[k] *= rinv;
+    if (gl == k) rdiag = rinv;
+    const double a = (gl > k) ? -H[k] : 0.0;
+#pragma unroll
+    for (int j = k + 1; j < kVars; j++) {
+      const double v = gshfl(H[k], j);  // L[j][k]
+      H[j] = (gl == k) ? v : fma(a, v, H[j]);
+    }
+  }
+  return ok;
+}
+
+// Solve L L^T x = b with the factor layout above; lane gl passes b[gl] and receives x[gl].
+__device__ __forceinline__ double group_solve(const double (&H)[kVars], const double rdiag,
+                                              const double b, const int gl) {
+  double acc = b;
+#pragma unroll
+  for (int j = 0; j < kVars; j++) {
+    const double zj = gshfl(acc * rdiag, j);
+    const double a = (gl > j) ? H[j] : 0.0;
+    acc = fma(-a, zj, acc);
+  }
+  acc *= rdiag;
+#pragma unroll
+  for (int j = kVars - 1; j >= 0; j--) {
+    const double xj = gshfl(acc * rdiag, j);
+    const double a = (gl < j) ? H[j] : 0.0;
+    acc = fma(-a, xj, acc);
+  }
+  return acc * rdiag;
+}
+
+// ---------------------------------------------------------------- model / parameters in device memory
+struct DeviceModel {
+  double rot[4][4][9];   // [leg][joint] rotation of <origin rpy>, row-major
+  double xyz[4][4][3];   // [leg][joint] <origin xyz>
+  double mass[4][4];     // link masses
+  double com[4][4][3];   // link COM in link frame (the foot link's is pre-rotated by rot[leg][3])
+  double msuf[4][4];     // suffix sums of mass: msuf[leg][c] = sum_{l>=c} mass[leg][l]
+};
+
+struct DeviceParams {
+  double S[6];
+  double W, fmin, mu_default, gravity;
+  double tol;
+  int max_iter;
+  int pad;
+  // virtual model controller
+  double kp_t[3], kd_t[3], kff_t[3], kp_r[3], kd_r[3], kff_r[3];
+  double torso_mass, leg_mass[4], leg_pos[4][3], com[3], grav_pct;
+};
+
+}  // namespace qlb

@@ -1,0 +1,756 @@
+// qlb_solve.cuh - the fused kernel: state -> leg kinematics -> QP assembly -> interior-point solve with
+// active-set polish -> joint torques.  Nothing between the input state and the outputs touches HBM.
+//
+// Reference path being replaced (per state): ContactForceDistribution::computeForceDistribution
+// (balance_controller/src/contact_force_distribution/ContactForceDistribution.cpp:99-136) with
+// QuadrupedKinematics FK / Jacobian / gravity (quadruped_model/src/quadrupedkinematics.cpp:143-278,
+// 485-552) underneath and, in state mode, VirtualModelController::compute
+// (balance_controller/src/motion_control/VirtualModelController.cpp:89-268) in front.
+#pragma once
+
+#include "qlb_device.cuh"
+
+namespace qlb {
+
+constexpr int kBatch = 16;        // QPs staged per warp batch (one 128-byte line per component row)
+constexpr int kWarpsPerCta = 4;
+constexpr int kThreads = 32 * kWarpsPerCta;
+
+// input staging rows
+constexpr int kRowQ = 0, kRowQuat = 12, kRowWrench = 16, kRowMu = 22, kRowNormal = 26, kInRows = 38;
+// state mode adds: pose(7) twist(6) target pose(7) target twist(6) -> quat/wrench rows are derived
+constexpr int kRowPose = 38, kRowTwist = 45, kRowTPose = 51, kRowTTwist = 58, kInRowsState = 64;
+// output staging rows
+constexpr int kRowGrf = 0, kRowTau = 12, kRowNet = 24, kRowWout = 30, kOutRows = 36;
+
+constexpr int kModePolish = 0, kModeIpm = 1, kModeDone = 2;
+constexpr int kPdasFirst = 1;      // active-set passes tried right after the unconstrained solve
+constexpr int kPolishPasses = 8;   // passes per polish attempt
+constexpr double kNeighbourhood = 1e-2;
+
+struct SolveArgs {
+  unsigned long long B;
+  const double* q;
+  const double* quat;
+  const double* wrench;
+  const uint8_t* mask;
+  const double* mu;       // may be null
+  const double* normals;  // may be null
+  // state mode
+  const double* pose;
+  const double* twist;
+  const double* tpose;
+  const double* ttwist;
+  double* grf;
+  double* tau;
+  uint32_t* flags;
+  double* netwrench;      // may be null
+  double* wrench_out;     // may be null (state mode)
+  unsigned long long* counter;  // work counter, zeroed before launch
+  const DeviceModel* model;
+  const DeviceParams* params;
+  int vec_ok;             // all row pointers 16-byte aligned and B even
+};
+
+template <int ROWS>
+struct alignas(16) WarpSmem {
+  double in[ROWS][kBatch];
+  double out[kOutRows][kBatch];
+  double atl[2][kVars][6];   // per group: wrench-map column of every slot, [e; r x e]
+  double col[2][kVars][6];   // per group: reduced columns of the current polish pass
+  double fix[2][4][6];       // per group, per leg: contribution of a pinned normal force
+  double grow[kVars][32];    // row of G~ of every lane (lane-minor: conflict-free)
+  double tail[7][32];        // per lane: slot direction e (3), Jacobian column (3), gravity torque
+  double bw[2][6];           // per group: the wrench b
+  uint32_t flags[kBatch];
+  uint8_t mask[kBatch];
+};
+
+template <int ROWS>
+struct alignas(16) CtaSmem {
+  WarpSmem<ROWS> w[kWarpsPerCta];
+  DeviceModel model;
+  DeviceParams prm;
+};
+
+// ---------------------------------------------------------------- staging (coalesced 16-byte accesses)
+template <int ROWS>
+__device__ __forceinline__ void stage_in(double (*dst)[kBatch], const double* __restrict__ src, int rows,
+                                         unsigned long long B, unsigned long long b0, int nvalid, int lane,
+                                         bool vec) {
+  if (vec && nvalid == kBatch) {
+    const int chunks = rows * (kBatch / 2);
+    for (int ch = lane; ch < chunks; ch += 32) {
+      const int r = ch / (kBatch / 2), o = ch % (kBatch / 2);
+      const double2 v = __ldg(reinterpret_cast<const double2*>(src + (size_t)r * B + b0) + o);
+      *reinterpret_cast<double2*>(&dst[r][2 * o]) = v;
+    }
+  } else {
+    for (int e = lane; e < rows * kBatch; e += 32) {
+      const int r = e / kBatch, o = e % kBatch;
+      dst[r][o] = (o < nvalid) ? __ldg(src + (size_t)r * B + b0 + o) : 0.0;
+    }
+  }
+}
+__device__ __forceinline__ void stage_out(double* __restrict__ dst, const double (*src)[kBatch], int rows,
+                                          unsigned long long B, unsigned long long b0, int nvalid, int lane,
+                                          bool vec) {
+  if (vec && nvalid == kBatch) {
+    const int chunks = rows * (kBatch / 2);
+    for (int ch = lane; ch < chunks; ch += 32) {
+      const int r = ch / (kBatch / 2), o = ch % (kBatch / 2);
+      reinterpret_cast<double2*>(dst + (size_t)r * B + b0)[o] = *reinterpret_cast<const double2*>(&src[r][2 * o]);
+    }
+  } else {
+    for (int e = lane; e < rows * kBatch; e += 32) {
+      const int r = e / kBatch, o = e % kBatch;
+      if (o < nvalid) dst[(size_t)r * B + b0 + o] = src[r][o];
+    }
+  }
+}
+
+// D~^T v for the five rows of a leg, component c of the leg's triple
+__device__ __forceinline__ double dt_apply(const double (&v)[5], double mu, int c) {
+  const double n = fma(mu, (v[1] + v[2]) + (v[3] + v[4]), v[0]);
+  return c == 0 ? n : (c == 1 ? v[1] - v[2] : v[3] - v[4]);
+}
+// D~ y for a leg
+__device__ __forceinline__ void d_apply(double yn, double y1, double y2, double mu, double (&e)[5]) {
+  const double m = mu * yn;
+  e[0] = yn; e[1] = m + y1; e[2] = m - y1; e[3] = m + y2; e[4] = m - y2;
+}
+
+// kindr logarithmic map of (q_t^-1 * q): see VirtualModelController.cpp:120,124
+__device__ __forceinline__ void quat_rel_log(const double* qt, const double* q, double (&v)[3]) {
+  // rel = conj(qt) * q
+  const double aw = qt[0], ax = -qt[1], ay = -qt[2], az = -qt[3];
+  double w = aw * q[0] - ax * q[1] - ay * q[2] - az * q[3];
+  double x = aw * q[1] + ax * q[0] + ay * q[3] - az * q[2];
+  double y = aw * q[2] - ax * q[3] + ay * q[0] + az * q[1];
+  double z = aw * q[3] + ax * q[2] - ay * q[1] + az * q[0];
+  if (w < 0.0) { w = -w; x = -x; y = -y; z = -z; }
+  const double n = sqrt(x * x + y * y + z * z);
+  double k = 2.0;
+  if (n >= 1e-12) k = 2.0 * atan2(n, w) / n;
+  v[0] = k * x; v[1] = k * y; v[2] = k * z;
+}
+
+// ---------------------------------------------------------------- one QP per group
+// Every lane of the warp calls this (two QPs side by side).  qi = index of this group's QP in the batch.
+template <int MODE, int ROWS>
+__device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceModel& mdl, const DeviceParams& prm,
+                                            const int qi, const int lane, const bool have_mu,
+                                            const bool have_normals, const bool want_net) {
+  const int grp = lane >> 4, gl = lane & 15;
+  const bool var_lane = gl < kVars;
+  const int leg = var_lane ? gl / 3 : 3;
+  const int c = var_lane ? gl - 3 * leg : 0;
+  const int l0 = 3 * leg;
+
+  // ---------------- inputs
+  const unsigned mask = ws.mask[qi] & 0xFu;
+  const bool alive = var_lane && ((mask >> leg) & 1u);
+  const double alive_d = alive ? 1.0 : 0.0;
+  const int ns = __popc(mask);
+  const double qv = ws.in[kRowQ + l0 + c][qi];
+  double quat[4], b[6];
+  bool bad = !isfinite(qv);
+  if (MODE == 1) {
+    // virtual model controller prologue (VirtualModelController.cpp:104-268)
+    double pose[7], tw[6], tp[7], tt[6];
+#pragma unroll
+    for (int r = 0; r < 7; r++) { pose[r] = ws.in[kRowPose + r][qi]; tp[r] = ws.in[kRowTPose + r][qi]; bad |= !isfinite(pose[r]) || !isfinite(tp[r]); }
+#pragma unroll
+    for (int r = 0; r < 6; r++) { tw[r] = ws.in[kRowTwist + r][qi]; tt[r] = ws.in[kRowTTwist + r][qi]; bad |= !isfinite(tw[r]) || !isfinite(tt[r]); }
+#pragma unroll
+    for (int r = 0; r < 4; r++) quat[r] = pose[3 + r];
+    const double w = quat[0], x = quat[1], y = quat[2], z = quat[3];
+    double R[9];
+    R[0] = w * w + x * x - y * y - z * z; R[1] = 2.0 * (x * y - w * z); R[2] = 2.0 * (x * z + w * y);
+    R[3] = 2.0 * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = 2.0 * (y * z - w * x);
+    R[6] = 2.0 * (x * z - w * y); R[7] = 2.0 * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
+    double ep[3], ev[3], ew[3], eR[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) { ep[a] = tp[a] - pose[a]; ev[a] = tt[a] - tw[a]; ew[a] = tt[3 + a] - tw[3 + a]; }
+    quat_rel_log(tp + 3, quat, eR);
+#pragma unroll
+    for (int a = 0; a < 3; a++) eR[a] = -eR[a];
+    // gravity compensation (VMC.cpp:162-188): g_b = R^T (0,0,-g)
+    double gb[3], Fg[3], Tg[3], ft[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) { gb[a] = -prm.gravity * R[6 + a]; ft[a] = -prm.grav_pct * prm.torso_mass * gb[a]; Fg[a] = ft[a]; }
+    Tg[0] = prm.com[1] * ft[2] - prm.com[2] * ft[1];
+    Tg[1] = prm.com[2] * ft[0] - prm.com[0] * ft[2];
+    Tg[2] = prm.com[0] * ft[1] - prm.com[1] * ft[0];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      double fl[3], r[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) { fl[a] = -prm.grav_pct * prm.leg_mass[l] * gb[a]; Fg[a] += fl[a]; r[a] = prm.leg_pos[l][a] - prm.com[a]; }
+      Tg[0] += r[1] * fl[2] - r[2] * fl[1];
+      Tg[1] += r[2] * fl[0] - r[0] * fl[2];
+      Tg[2] += r[0] * fl[1] - r[1] * fl[0];
+    }
+    const double ffx = tt[0], ffy = tt[1];
+    const double gfz = prm.kp_t[2] * ep[2], gdz = prm.kd_t[2] * ev[2];
+    const double dwv[3] = {prm.kd_r[0] * ew[0], prm.kd_r[1] * ew[1], prm.kd_r[2] * ew[2]};
+    const double fwz = prm.kff_r[2] * tt[5];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      // R^T v, component a = column a of R dotted with v
+      const double epb = R[a] * ep[0] + R[3 + a] * ep[1] + R[6 + a] * ep[2];
+      const double evb = R[a] * ev[0] + R[3 + a] * ev[1] + R[6 + a] * ev[2];
+      const double ffb = R[a] * ffx + R[3 + a] * ffy;
+      b[a] = prm.kp_t[a] * epb + prm.kd_t[a] * evb + prm.kff_t[a] * ffb + Fg[a] + R[6 + a] * gfz + R[6 + a] * gdz;
+      const double dwb = R[a] * dwv[0] + R[3 + a] * dwv[1] + R[6 + a] * dwv[2];
+      b[3 + a] = prm.kp_r[a] * eR[a] + dwb + R[6 + a] * fwz + Tg[a];
+    }
+    if (gl < 6) ws.out[kRowWout + gl][qi] = b[gl];
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; r++) { quat[r] = ws.in[kRowQuat + r][qi]; bad |= !isfinite(quat[r]); }
+#pragma unroll
+    for (int r = 0; r < 6; r++) { b[r] = ws.in[kRowWrench + r][qi]; bad |= !isfinite(b[r]); }
+  }
+  const double mu = have_mu ? ws.in[kRowMu + leg][qi] : prm.mu_default;
+  double nw[3] = {0.0, 0.0, 1.0};
+  if (have_normals) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) nw[a] = ws.in[kRowNormal + l0 + a][qi];
+  }
+
+  // ---------------- base rotation, friction frame (CFD.cpp:223,237,286-309), gravity in base frame (:518-519)
+  double nb[3], t1[3], t2[3], gb[3];
+  {
+    const double w = quat[0], x = quat[1], y = quat[2], z = quat[3];
+    double R[9];
+    R[0] = w * w + x * x - y * y - z * z; R[1] = 2.0 * (x * y - w * z); R[2] = 2.0 * (x * z + w * y);
+    R[3] = 2.0 * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = 2.0 * (y * z - w * x);
+    R[6] = 2.0 * (x * z - w * y); R[7] = 2.0 * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      nb[a] = R[a] * nw[0] + R[3 + a] * nw[1] + R[6 + a] * nw[2];  // R^T n_world
+      gb[a] = -prm.gravity * R[6 + a];
+    }
+    const double ey[3] = {R[3], R[4], R[5]};  // R^T e_y
+    t1[0] = nb[1] * ey[2] - nb[2] * ey[1];
+    t1[1] = nb[2] * ey[0] - nb[0] * ey[2];
+    t1[2] = nb[0] * ey[1] - nb[1] * ey[0];
+    double rn = rsqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+#pragma unroll
+    for (int a = 0; a < 3; a++) t1[a] *= rn;
+    t2[0] = nb[1] * t1[2] - nb[2] * t1[1];
+    t2[1] = nb[2] * t1[0] - nb[0] * t1[2];
+    t2[2] = nb[0] * t1[1] - nb[1] * t1[0];
+    rn = rsqrt(t2[0] * t2[0] + t2[1] * t2[1] + t2[2] * t2[2]);
+#pragma unroll
+    for (int a = 0; a < 3; a++) t2[a] *= rn;
+    if (alive) {
+      bad |= !isfinite(mu);
+#pragma unroll
+      for (int a = 0; a < 3; a++) bad |= !isfinite(nb[a]) || !isfinite(t1[a]) || !isfinite(t2[a]);
+    }
+  }
+  // group-wide verdict on the inputs
+  const unsigned badbits = (__ballot_sync(kFull, bad) >> (16 * grp)) & 0xFFFFu;
+
+  // ---------------- leg forward kinematics, Jacobian column c, gravity torque c (QK.cpp:143-278,485-552)
+  double foot[3], jcol[3], gtau;
+  {
+    double sn, cs;
+    sincos(qv, &sn, &cs);
+    double R[9], p[3], zc[3] = {0, 0, 0}, pjc[3] = {0, 0, 0}, mcs[3] = {0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 9; e++) R[e] = mdl.rot[leg][0][e];
+#pragma unroll
+    for (int a = 0; a < 3; a++) p[a] = mdl.xyz[leg][0][a];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (j > 0) {
+        const double* xj = mdl.xyz[leg][j];
+#pragma unroll
+        for (int a = 0; a < 3; a++) p[a] += R[3 * a] * xj[0] + R[3 * a + 1] * xj[1] + R[3 * a + 2] * xj[2];
+        if (j < 3) {
+          const double* Rj = mdl.rot[leg][j];
+          double T[9];
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int s = 0; s < 3; s++) T[3 * r + s] = R[3 * r] * Rj[s] + R[3 * r + 1] * Rj[3 + s] + R[3 * r + 2] * Rj[6 + s];
+#pragma unroll
+          for (int e = 0; e < 9; e++) R[e] = T[e];
+        }
+      }
+      if (j < 3) {
+        if (c == j) {
+#pragma unroll
+          for (int a = 0; a < 3; a++) { zc[a] = R[3 * a + 2]; pjc[a] = p[a]; }
+        }
+        const double cj = gshfl(cs, l0 + j), sj = gshfl(sn, l0 + j);
+#pragma unroll
+        for (int r = 0; r < 3; r++) {  // R = R * Rz(q_j)
+          const double a0 = R[3 * r], a1 = R[3 * r + 1];
+          R[3 * r] = cj * a0 + sj * a1;
+          R[3 * r + 1] = cj * a1 - sj * a0;
+        }
+      }
+      const double* cm = mdl.com[leg][j];
+      const double mj = (j >= c) ? mdl.mass[leg][j] : 0.0;
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+        mcs[a] += mj * (p[a] + R[3 * a] * cm[0] + R[3 * a + 1] * cm[1] + R[3 * a + 2] * cm[2]);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) foot[a] = p[a];
+    const double dv[3] = {foot[0] - pjc[0], foot[1] - pjc[1], foot[2] - pjc[2]};
+    jcol[0] = zc[1] * dv[2] - zc[2] * dv[1];
+    jcol[1] = zc[2] * dv[0] - zc[0] * dv[2];
+    jcol[2] = zc[0] * dv[1] - zc[1] * dv[0];
+    const double ms = mdl.msuf[leg][c];
+    const double arm[3] = {mcs[0] - ms * pjc[0], mcs[1] - ms * pjc[1], mcs[2] - ms * pjc[2]};
+    gtau = -(zc[0] * (arm[1] * gb[2] - arm[2] * gb[1]) + zc[1] * (arm[2] * gb[0] - arm[0] * gb[2]) +
+             zc[2] * (arm[0] * gb[1] - arm[1] * gb[0]));
+  }
+
+  // ---------------- wrench-map column of this slot: [e; r x e], e = column c of Q_leg (CFD.cpp:186-200)
+  double ev[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) ev[a] = (c == 0) ? nb[a] : (c == 1 ? t1[a] : t2[a]);
+  {
+    double at[6];
+    at[0] = ev[0]; at[1] = ev[1]; at[2] = ev[2];
+    at[3] = foot[1] * ev[2] - foot[2] * ev[1];
+    at[4] = foot[2] * ev[0] - foot[0] * ev[2];
+    at[5] = foot[0] * ev[1] - foot[1] * ev[0];
+    if (var_lane) {
+#pragma unroll
+      for (int r = 0; r < 6; r++) ws.atl[grp][gl][r] = alive ? at[r] : 0.0;
+    }
+  }
+  __syncwarp();
+
+  // ---------------- solver state
+  // Everything that contains a shuffle is executed by the whole warp with the full mask; a group that
+  // is not in the corresponding mode just computes values it never commits.  (Shuffles under a
+  // per-group mask cost a WARPSYNC each and were 30x slower.)
+  if (var_lane) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) { ws.tail[a][lane] = ev[a]; ws.tail[3 + a][lane] = jcol[a]; }
+    ws.tail[6][lane] = gtau;
+  }
+  if (gl < 6) ws.bw[grp][gl] = b[gl];
+  __syncwarp();
+
+  double H[kVars];
+  double gt = 0.0;             // g~ of this slot
+  double y = 0.0;              // interior-point iterate / final solution of this slot
+  double s[5], lam[5];
+  int a0 = 0, sg1 = 0, sg2 = 0;  // active pattern of this leg: y_n pinned; y_1 = sg1*mu*y_n; y_2 = sg2*mu*y_n
+  int mode = kModePolish, it = 0, pass = 0, status = 0, next_polish = 2;
+  bool first = true, converged = false, have_G = false;
+#pragma unroll
+  for (int r = 0; r < 5; r++) { s[r] = 1.0; lam[r] = 0.0; }
+  if (badbits != 0u) { mode = kModeDone; status = 4; }
+  else if (ns == 0) { mode = kModeDone; status = 1; }
+  const double rm = ns > 0 ? 1.0 / (5.0 * ns) : 0.0;
+
+  // ---------------- rounds: every round is one factorisation + one or two solves, shared by both groups
+  int rounds = 0;
+#pragma unroll 1
+  for (;;) {
+    if (__all_sync(kFull, mode == kModeDone)) break;
+    if (++rounds > 160 && mode != kModeDone) { mode = kModeDone; status = 2; }  // hard stop, never reached in practice
+    double rd = 0.0, rp[5], rs[5], rhs = 0.0, mu_c = 0.0;
+#pragma unroll
+    for (int r = 0; r < 5; r++) { rp[r] = 0.0; rs[r] = 1.0; }
+    bool ipm_round = false;
+
+    // ---- A. residuals of the interior-point iterate, convergence test, decision to polish
+    if (__any_sync(kFull, mode == kModeIpm)) {
+      double gy = 0.0;
+#pragma unroll
+      for (int j = 0; j < kVars; j++) gy = fma(ws.grow[j][lane], gshfl(y, j), gy);
+      const double yn = gshfl(y, l0), y1 = gshfl(y, l0 + 1), y2 = gshfl(y, l0 + 2);
+      double e[5];
+      d_apply(yn, y1, y2, mu, e);
+      e[0] -= prm.fmin;
+      double sl = 0.0;
+      float nrp = 0.f;
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        rp[r] = (s[r] - e[r]) * alive_d;
+        rs[r] = fast_rcp(s[r]);
+        sl = fma(s[r], lam[r], sl);
+        nrp = fmaxf(nrp, fabsf((float)rp[r]));
+      }
+      rd = gy + gt - dt_apply(lam, mu, c);
+      mu_c = leg_sum(sl) * rm;
+      const float nrd = group_max(var_lane ? fabsf((float)rd) : 0.f);
+      nrp = leg_max(nrp);
+      const float scale = fmaxf(1.f, group_max(fabsf((float)y)));
+      if (mode == kModeIpm) {
+        converged = (mu_c <= prm.tol * scale) && (nrp <= (float)prm.tol * scale) && (nrd <= 100.f * (float)prm.tol * scale);
+        const bool out_of_iters = it >= prm.max_iter;
+        if (converged || out_of_iters || (it >= next_polish && mu_c <= 1e-3 * scale)) {
+          mode = kModePolish;
+          pass = 0;
+          a0 = lam[0] > s[0];
+          sg1 = (lam[1] > s[1]) ? -1 : ((lam[2] > s[2]) ? 1 : 0);
+          sg2 = (lam[3] > s[3]) ? -1 : ((lam[4] > s[4]) ? 1 : 0);
+          if (!alive) { a0 = 0; sg1 = 0; sg2 = 0; }
+          if (out_of_iters && !converged) status = 2;
+        }
+        ipm_round = (mode == kModeIpm);
+      }
+    }
+
+    // ---- B. system of this round
+    const bool any_pol = __any_sync(kFull, mode == kModePolish);
+    if (any_pol) {
+      // reduced system of the equality-constrained QP for the current pattern
+      double mycol[6];
+      const bool free_slot = alive && ((c == 0) ? (a0 == 0) : (c == 1 ? (sg1 == 0) : (sg2 == 0)));
+      if (mode == kModePolish) {
+        const double* an = ws.atl[grp][l0];
+        const double* a1 = ws.atl[grp][l0 + 1];
+        const double* a2 = ws.atl[grp][l0 + 2];
+        const double k1 = sg1 * mu, k2 = sg2 * mu;
+        const double f = (a0 != 0 && alive) ? prm.fmin : 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          const double cn = fma(k2, a2[r], fma(k1, a1[r], an[r]));
+          const double own = (c == 0) ? cn : (c == 1 ? a1[r] : a2[r]);
+          mycol[r] = (free_slot && var_lane) ? own : 0.0;
+          if (var_lane) ws.col[grp][gl][r] = mycol[r];
+          if (var_lane && c == 0) ws.fix[grp][leg][r] = f * cn;
+        }
+      }
+      __syncwarp();
+      if (mode == kModePolish) {
+        const double wd = free_slot ? ((c == 0) ? prm.W * fma(mu * mu, (double)(sg1 * sg1 + sg2 * sg2), 1.0) : prm.W) : 1.0;
+        double sc[6];
+        rhs = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          const double bp = ws.bw[grp][r] - ((ws.fix[grp][0][r] + ws.fix[grp][1][r]) + (ws.fix[grp][2][r] + ws.fix[grp][3][r]));
+          sc[r] = prm.S[r] * mycol[r];
+          rhs = fma(sc[r], bp, rhs);
+        }
+#pragma unroll
+        for (int j = 0; j < kVars; j++) {
+          const double* cj = ws.col[grp][j];
+          double acc = 0.0;
+#pragma unroll
+          for (int r = 0; r < 6; r++) acc = fma(sc[r], cj[r], acc);
+          H[j] = acc + ((j == gl) ? wd : 0.0);
+        }
+        if (!have_G) {  // first pass (empty pattern): this is G~ and -g~
+#pragma unroll
+          for (int j = 0; j < kVars; j++) ws.grow[j][lane] = H[j];
+          gt = -rhs;
+          have_G = true;
+        }
+      }
+      __syncwarp();
+    }
+    if (ipm_round) {
+      // H = G~ + D~' diag(lam/s) D~ (3x3 block on the diagonal), predictor right-hand side
+      double th[5], v[5];
+#pragma unroll
+      for (int r = 0; r < 5; r++) { th[r] = lam[r] * rs[r]; v[r] = fma(-th[r], rp[r], lam[r]); }
+      const double t12 = th[1] + th[2], t34 = th[3] + th[4];
+      const double d12 = mu * (th[1] - th[2]), d34 = mu * (th[3] - th[4]);
+      double blk[3];
+      blk[0] = (c == 0) ? fma(mu * mu, t12 + t34, th[0]) : (c == 1 ? d12 : d34);
+      blk[1] = (c == 0) ? d12 : (c == 1 ? t12 : 0.0);
+      blk[2] = (c == 0) ? d34 : (c == 1 ? 0.0 : t34);
+#pragma unroll
+      for (int j = 0; j < kVars; j++) H[j] = ws.grow[j][lane] + ((j / 3 == leg && var_lane) ? blk[j % 3] : 0.0);
+      rhs = var_lane ? -rd - dt_apply(v, mu, c) : 0.0;
+    } else if (mode == kModeDone) {
+#pragma unroll
+      for (int j = 0; j < kVars; j++) H[j] = (j == gl) ? 1.0 : 0.0;
+      rhs = 0.0;
+    }
+
+    // ---- C. factorise and solve (both groups, converged)
+    double rdiag;
+    const bool pd = group_cholesky(H, rdiag, gl);
+    const double sol = group_solve(H, rdiag, rhs, gl);
+    if (!pd && mode != kModeDone) { mode = kModeDone; status = 4; y = 0.0; ipm_round = false; }
+
+    // ---- D. polish: recover y, multipliers, slacks; verify the KKT signs; repair the pattern
+    if (any_pol) {
+      const double zn = gshfl(sol, l0);
+      const double ynp = (a0 != 0) ? prm.fmin : zn;
+      double yp = (c == 0) ? ynp : (c == 1 ? (sg1 != 0 ? sg1 * mu * ynp : sol) : (sg2 != 0 ? sg2 * mu * ynp : sol));
+      if (!alive) yp = 0.0;
+      double gam = gt;
+#pragma unroll
+      for (int j = 0; j < kVars; j++) gam = fma(ws.grow[j][lane], gshfl(yp, j), gam);
+      const double yn = gshfl(yp, l0), y1 = gshfl(yp, l0 + 1), y2 = gshfl(yp, l0 + 2);
+      const double gn = gshfl(gam, l0), g1 = gshfl(gam, l0 + 1), g2 = gshfl(gam, l0 + 2);
+      double e[5], u[5];
+      d_apply(yn, y1, y2, mu, e);
+      e[0] -= prm.fmin;
+      u[1] = (sg1 == -1) ? g1 : 0.0;
+      u[2] = (sg1 == 1) ? -g1 : 0.0;
+      u[3] = (sg2 == -1) ? g2 : 0.0;
+      u[4] = (sg2 == 1) ? -g2 : 0.0;
+      u[0] = (a0 != 0) ? gn - mu * ((u[1] + u[2]) + (u[3] + u[4])) : 0.0;
+      const bool act[5] = {a0 != 0, sg1 == -1, sg1 == 1, sg2 == -1, sg2 == 1};
+      const float scale = fmaxf(1.f, group_max(fabsf((float)yp)));
+      const float gscale = fmaxf(1.f, group_max(fabsf((float)gt)));
+      const double tol_u = 1e-13 * (double)gscale, tol_s = 1e-10 * (double)scale;
+      // worst violations of this leg
+      double wd_v = -tol_u, wp_v = -tol_s;
+      int wd_r = -1, wp_r = -1;
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        if (alive && act[r] && u[r] < wd_v) { wd_v = u[r]; wd_r = r; }
+        if (alive && !act[r] && e[r] < wp_v) { wp_v = e[r]; wp_r = r; }
+      }
+      const bool leg_viol = (wd_r >= 0) || (wp_r >= 0);
+      const bool any_viol = ((__ballot_sync(kFull, leg_viol) >> (16 * grp)) & 0xFFFu) != 0u;
+      // globally worst leg (used after the first passes, prevents cycling); duals before primals
+      const double key = (wd_r >= 0) ? wd_v * 1e6 : ((wp_r >= 0) ? wp_v : 0.0);
+      const double best = leg_min(key);
+      const unsigned tie = (__ballot_sync(kFull, key == best && leg_viol) >> (16 * grp)) & 0xFFFu;
+      // start values of the interior-point iteration, should this group need them
+      double smin = fmin(fmin(fmin(e[0], e[1]), fmin(e[2], e[3])), e[4]);
+      smin = alive ? smin : 0.0;
+      const double gmin = leg_min(smin);
+      const double shift = fmax(-1.5 * gmin, 1e-2 * (double)scale);
+      double s0[5], ssum = 0.0;
+#pragma unroll
+      for (int r = 0; r < 5; r++) { s0[r] = fmax(e[r], 0.0) + shift; ssum += s0[r]; }
+      const double mu0 = leg_sum(alive ? ssum : 0.0) * rm;
+
+      if (mode == kModePolish) {
+        if (!any_viol) {
+          y = yp;
+          mode = kModeDone;
+          if (status == 2) status = 0;  // iteration limit hit but the polish verified the optimum
+        } else {
+          pass++;
+          const bool give_up = first ? (pass > kPdasFirst) : (pass >= kPolishPasses);
+          if (!give_up) {
+            // repair: per leg, drop the most negative multiplier, else add the most violated row;
+            // after the first passes only the globally worst leg moves
+            bool mine = true;
+            if (pass > 2) mine = leg_viol && (tie != 0u) && ((__ffs(tie) - 1) / 3 == leg);
+            if (mine && alive) {
+              if (wd_r >= 0) {
+                if (wd_r == 0) a0 = 0; else if (wd_r <= 2) sg1 = 0; else sg2 = 0;
+              } else if (wp_r >= 0) {
+                if (wp_r == 0) a0 = 1; else if (wp_r == 1) sg1 = -1; else if (wp_r == 2) sg1 = 1; else if (wp_r == 3) sg2 = -1; else sg2 = 1;
+              }
+            }
+          } else if (first) {
+            // start the interior-point iteration from the last active-set solution
+            first = false;
+            mode = kModeIpm;
+            y = yp;
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+              lam[r] = alive ? mu0 * fast_rcp(s0[r]) : 0.0;
+              s[r] = alive ? s0[r] : 1.0;
+            }
+            a0 = 0; sg1 = 0; sg2 = 0;
+          } else if (converged || status == 2) {
+            // interior-point iterate is final but the polish could not certify an active set
+            mode = kModeDone;
+            if (status == 0) status = 3;
+          } else {
+            mode = kModeIpm;  // keep iterating, try again later
+            next_polish = it + 2;
+          }
+        }
+      }
+    }
+
+    // ---- E. second solve of the round: Mehrotra corrector (groups in interior-point mode)
+    if (__any_sync(kFull, ipm_round)) {
+      double dsa[5], dla[5], de[5], v[5];
+      {
+        const double dyn = gshfl(sol, l0), dy1 = gshfl(sol, l0 + 1), dy2 = gshfl(sol, l0 + 2);
+        d_apply(dyn, dy1, dy2, mu, de);
+      }
+      float ratio = 0.f;
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        dsa[r] = de[r] * alive_d - rp[r];
+        dla[r] = -fma(lam[r] * rs[r], dsa[r], lam[r]);
+        const float rl = (alive && ipm_round) ? rcp_approx((float)lam[r]) : 0.f;
+        ratio = fmaxf(ratio, fmaxf(-(float)dsa[r] * (float)rs[r], -(float)dla[r] * rl));
+      }
+      ratio = leg_max(ratio);
+      const double ala = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
+      double pa = 0.0;
+#pragma unroll
+      for (int r = 0; r < 5; r++) pa = fma(fma(ala, dsa[r], s[r]), fma(ala, dla[r], lam[r]), pa);
+      const double mua = leg_sum(pa) * rm;
+      const double q3 = ipm_round ? mua / mu_c : 0.0;
+      const double sigmu = q3 * q3 * q3 * mu_c;
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        const double rc = fma(dsa[r], dla[r], s[r] * lam[r]) - sigmu;
+        dsa[r] = rc;  // keep the complementarity right-hand side, the affine steps are no longer needed
+        v[r] = (rc - lam[r] * rp[r]) * rs[r] * alive_d;
+      }
+      const double rhs2 = (var_lane && ipm_round) ? -rd - dt_apply(v, mu, c) : 0.0;
+      const double dy = group_solve(H, rdiag, rhs2, gl);
+      {
+        const double dyn = gshfl(dy, l0), dy1 = gshfl(dy, l0 + 1), dy2 = gshfl(dy, l0 + 2);
+        d_apply(dyn, dy1, dy2, mu, de);
+      }
+      double dl[5];
+      ratio = 0.f;
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        de[r] = de[r] * alive_d - rp[r];  // ds
+        dl[r] = -(dsa[r] + lam[r] * de[r]) * rs[r] * alive_d;
+        const float rl = (alive && ipm_round) ? rcp_approx((float)lam[r]) : 0.f;
+        ratio = fmaxf(ratio, fmaxf(-(float)de[r] * (float)rs[r], -(float)dl[r] * rl));
+      }
+      ratio = leg_max(ratio);
+      double al = (ratio > 0.995f) ? 0.995 / (double)ratio : 1.0;
+      // stay inside the neighbourhood min_i s_i lam_i >= gamma * mu (both groups loop together)
+#pragma unroll 1
+      for (int tries = 0; tries < 12; tries++) {
+        double ps = 0.0, pm = 1e300;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          const double pr = fma(al, de[r], s[r]) * fma(al, dl[r], lam[r]);
+          ps += pr;
+          pm = fmin(pm, pr);
+        }
+        ps = leg_sum(alive ? ps : 0.0) * rm;
+        pm = leg_min(alive ? pm : 1e300);
+        const bool ok = !ipm_round || (pm >= kNeighbourhood * ps && pm > 0.0);
+        if (__all_sync(kFull, ok)) break;
+        if (!ok) al *= 0.7;
+      }
+      if (ipm_round) {
+        y = fma(al, dy, y);
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          s[r] = fma(al, de[r], s[r]);
+          lam[r] = fma(al, dl[r], lam[r]);
+        }
+        it++;
+      }
+    }
+  }
+
+  // ---------------- outputs: forces in base frame, torques, net wrench, flags
+  const bool solved = (status == 0 || status == 2 || status == 3);
+  if (!solved) { y = 0.0; a0 = 0; sg1 = 0; sg2 = 0; }
+  // f_leg = y_n n + y_1 t1 + y_2 t2 : sum of the three lanes' contributions y * e
+  double f[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const double w = var_lane ? y * ws.tail[a][lane] * alive_d : 0.0;
+    f[a] = (gshfl(w, l0) + gshfl(w, l0 + 1)) + gshfl(w, l0 + 2);
+  }
+  const double fx = (c == 0) ? f[0] : (c == 1 ? f[1] : f[2]);
+  if (var_lane) {
+    // tau_c = column c of J dotted with (-f) + G_c (CFD.cpp:535-559); swing legs report zero
+    const double tq = (alive && solved)
+                          ? ws.tail[6][lane] - (ws.tail[3][lane] * f[0] + ws.tail[4][lane] * f[1] + ws.tail[5][lane] * f[2])
+                          : 0.0;
+    ws.out[kRowGrf + gl][qi] = fx;
+    ws.out[kRowTau + gl][qi] = tq;
+  }
+  if (want_net) {
+    // A x = sum over slots of column * y (CFD.cpp:614-625)
+    if (var_lane) {
+#pragma unroll
+      for (int r = 0; r < 6; r++) ws.col[grp][gl][r] = ws.atl[grp][gl][r] * y;
+    }
+    __syncwarp();
+    if (gl < 6) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < kVars; j++) acc += ws.col[grp][j][gl];
+      ws.out[kRowNet + gl][qi] = acc;
+    }
+    __syncwarp();
+  }
+  {
+    unsigned bits = 0u;
+    if (alive && c == 0 && solved) {
+      bits = (a0 != 0 ? 1u : 0u) | (sg1 == -1 ? 2u : 0u) | (sg1 == 1 ? 4u : 0u) | (sg2 == -1 ? 8u : 0u) | (sg2 == 1 ? 16u : 0u);
+      bits <<= (4 + 5 * leg);
+    }
+    // OR over the group
+    bits |= __shfl_xor_sync(kFull, bits, 1, kGroup);
+    bits |= __shfl_xor_sync(kFull, bits, 2, kGroup);
+    bits |= __shfl_xor_sync(kFull, bits, 4, kGroup);
+    bits |= __shfl_xor_sync(kFull, bits, 8, kGroup);
+    if (gl == 0) {
+      const unsigned itc = it > 31 ? 31u : (unsigned)it;
+      ws.flags[qi] = mask | bits | ((unsigned)status << 24) | (itc << 27);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- kernel
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 3) qlb_solve_kernel(const SolveArgs a) {
+  constexpr int ROWS = (MODE == 1) ? kInRowsState : kInRows;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CtaSmem<ROWS>& sm = *reinterpret_cast<CtaSmem<ROWS>*>(smem_raw);
+  {
+    const double* src = reinterpret_cast<const double*>(a.model);
+    double* dst = reinterpret_cast<double*>(&sm.model);
+    for (int i = threadIdx.x; i < (int)(sizeof(DeviceModel) / 8); i += blockDim.x) dst[i] = src[i];
+    src = reinterpret_cast<const double*>(a.params);
+    dst = reinterpret_cast<double*>(&sm.prm);
+    for (int i = threadIdx.x; i < (int)(sizeof(DeviceParams) / 8); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpSmem<ROWS>& ws = sm.w[warp];
+  const unsigned long long nbatch = (a.B + kBatch - 1) / kBatch;
+  const bool vec = a.vec_ok != 0;
+  const bool have_mu = a.mu != nullptr, have_normals = a.normals != nullptr, want_net = a.netwrench != nullptr;
+
+  for (;;) {
+    unsigned long long bi = 0;
+    if (lane == 0) bi = atomicAdd(a.counter, 1ull);
+    bi = __shfl_sync(kFull, bi, 0);
+    if (bi >= nbatch) break;
+    const unsigned long long b0 = bi * kBatch;
+    const int nvalid = (int)((a.B - b0 < (unsigned long long)kBatch) ? (a.B - b0) : kBatch);
+
+    stage_in<ROWS>(&ws.in[kRowQ], a.q, 12, a.B, b0, nvalid, lane, vec);
+    if (MODE == 1) {
+      stage_in<ROWS>(&ws.in[kRowPose], a.pose, 7, a.B, b0, nvalid, lane, vec);
+      stage_in<ROWS>(&ws.in[kRowTwist], a.twist, 6, a.B, b0, nvalid, lane, vec);
+      stage_in<ROWS>(&ws.in[kRowTPose], a.tpose, 7, a.B, b0, nvalid, lane, vec);
+      stage_in<ROWS>(&ws.in[kRowTTwist], a.ttwist, 6, a.B, b0, nvalid, lane, vec);
+    } else {
+      stage_in<ROWS>(&ws.in[kRowQuat], a.quat, 4, a.B, b0, nvalid, lane, vec);
+      stage_in<ROWS>(&ws.in[kRowWrench], a.wrench, 6, a.B, b0, nvalid, lane, vec);
+    }
+    if (have_mu) stage_in<ROWS>(&ws.in[kRowMu], a.mu, 4, a.B, b0, nvalid, lane, vec);
+    if (have_normals) stage_in<ROWS>(&ws.in[kRowNormal], a.normals, 12, a.B, b0, nvalid, lane, vec);
+    if (lane < kBatch) ws.mask[lane] = (lane < nvalid) ? a.mask[b0 + lane] : (uint8_t)0;
+    __syncwarp();
+
+#pragma unroll 1
+    for (int pair = 0; 2 * pair < nvalid; pair++)
+      solve_group<MODE, ROWS>(ws, sm.model, sm.prm, 2 * pair + (lane >> 4), lane, have_mu, have_normals, want_net);
+    __syncwarp();
+
+    stage_out(a.grf, &ws.out[kRowGrf], 12, a.B, b0, nvalid, lane, vec);
+    stage_out(a.tau, &ws.out[kRowTau], 12, a.B, b0, nvalid, lane, vec);
+    if (want_net) stage_out(a.netwrench, &ws.out[kRowNet], 6, a.B, b0, nvalid, lane, vec);
+    if (MODE == 1 && a.wrench_out) stage_out(a.wrench_out, &ws.out[kRowWout], 6, a.B, b0, nvalid, lane, vec);
+    if (lane < nvalid) a.flags[b0 + lane] = ws.flags[lane];
+    __syncwarp();
+  }
+}
+
+}  // namespace qlb
