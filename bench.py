@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py - contact-force QPs solved per second (BASELINE.json metric).
+
+Workload = BASELINE config C3: the fused FK + Jacobian + QP + J^T f torque pipeline on 2^20 randomised
+states per GPU, FP64 (weak scaling: every rank owns its own 2^20-state slice of the counter-based
+synthetic batch; no collective on the solve path, one tiny NCCL all-reduce of statistics at the end).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  `value` = whole-job QP/s with inputs resident in HBM; `e2e` = the same
+through the C ABI's host-pointer entry (pinned host buffers, H2D + D2H inside the timed region);
+`roofline` = algorithmic FP64 FLOP/s of the fused kernel against the FP64 FMA peak measured on the box;
+`cpu_baseline` = the reference's own QuadProg++ (oracle/_ref) or the oracle port on the host cores.
+--impl reference times that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "contact-force QPs solved/sec"
+UNIT = "QP/s"
+BATCH_PER_GPU = 1 << 20
+MODEL = "quadruped_model"   # the URDF the reference's kinematics class actually loads (quadrupedkinematics.cpp:21)
+# fixed accounting constants of SURVEY.md 8d: algorithmic FP64 FLOP per QP by stance count
+FLOP_PER_QP = {0: 0.0, 1: 6000.0, 2: 12000.0, 3: 21000.0, 4: 30000.0}
+WORKLOAD = ("C3: fused FK+Jacobian+QP+J^T.f torque pipeline, 2^20 randomised states per GPU "
+            "(60% four-stance, 25% diagonal pairs, 15% three-stance), FP64, model quadruped_model.urdf")
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference(st, steps: int, warmup: int, sample: int):
+    """The reference's CPU implementation of the path on the host cores: QP assembly per
+    ContactForceDistribution.cpp + the reference's own QuadProg++ (oracle/_ref) when it was built,
+    else the oracle port.  Returns (QP/s, dict)."""
+    from oracle import oracle as O
+    from quadruped_locomotion_b200 import legmodel
+    M = O.model_array(legmodel.load_model(MODEL))
+    kind = "reference" if O.have_ref() else "port"
+    solver = O.SOLVER_REF if kind == "reference" else O.SOLVER_GI
+    cores = os.cpu_count() or 1
+    sub = {k: np.ascontiguousarray(v[..., :sample]) for k, v in st.items()}
+
+    def run(nsolves):
+        t0 = time.perf_counter()
+        O.solve_wrench_batch(M, sub["q"], sub["quat"], sub["wrench"], sub["mask"], mu=sub["mu"], normals=None,
+                             solver=solver, nsolves=nsolves, threads=cores)
+        return time.perf_counter() - t0
+
+    for _ in range(max(1, warmup)):
+        run(1)
+    times = [run(1) for _ in range(max(1, steps))]
+    t1 = float(np.mean(times))
+    t2 = run(2) if kind == "port" else 2.0 * t1   # the reference solves twice per tick (CFD.cpp:367,120)
+    info = {"value": sample / t1, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"first {sample} states of the same workload, {max(1, steps)} passes, one solve per state; "
+                      f"solver = {'reference QuadProg++ (qp_solver/src/QuadProg++.cc compiled in place)' if kind == 'reference' else 'oracle Goldfarb-Idnani port'}; "
+                      "real OOQP+MA27 is not vendored and cannot run here",
+            "value_two_solves_per_state": sample / t2, "ms_per_pass": t1 * 1e3}
+    return sample / t1, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="states per GPU (default 2^20)")
+    ap.add_argument("--config", default="C3")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 19)
+    args = ap.parse_args()
+    warmup = max(3, args.warmup)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    from quadruped_locomotion_b200 import synth
+    B = args.batch
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        st = synth.make_states(args.config, min(B, args.cpu_sample))
+        sample = st["q"].shape[1]
+        v, info = cpu_reference(st, args.steps, min(warmup, 3), sample)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": warmup, "ms_per_step": info["ms_per_pass"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": WORKLOAD, "states_per_step": sample},
+                "cpu_baseline": info, "gpu_launches": 0,
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from quadruped_locomotion_b200 import capi, dist as qdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- inputs: this rank's contiguous slice of the global synthetic batch (no inter-GPU traffic)
+    st = synth.make_states(args.config, B, start=rank * B)
+    keys = ("q", "quat", "wrench", "mask", "mu")
+    d = {k: torch.from_numpy(np.ascontiguousarray(st[k])).to(dev) for k in keys}
+    grf = torch.empty((12, B), dtype=torch.float64, device=dev)
+    tau = torch.empty_like(grf)
+    net = torch.empty((6, B), dtype=torch.float64, device=dev)
+    flags = torch.empty(B, dtype=torch.int32, device=dev)
+    solver = capi.Solver(MODEL, device=local_rank, max_batch=B)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        solver.solve_wrench(d["q"], d["quat"], d["wrench"], d["mask"], d["mu"], None, grf, tau, flags, net,
+                            stream=stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = solver.measure_fp64_peak()
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = solver.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    launches = solver.launches - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+
+    # ---- statistics: device reduction + the only collective of the design (NCCL all-reduce, ~240 B)
+    stats = torch.from_numpy(solver.batch_stats(flags, d["wrench"], net, stream=stream.cuda_stream)).to(dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    qdist.allreduce_stats(stats)
+    torch.cuda.synchronize()
+    allreduce_ms = (time.perf_counter() - t0) * 1e3
+    sd = qdist.stats_dict(stats.cpu().numpy())
+
+    # ---- end to end through the C ABI host entry: pinned host buffers, H2D + D2H inside the timed region
+    h = {k: torch.from_numpy(np.ascontiguousarray(st[k])).pin_memory() for k in keys}
+    h_grf = torch.empty((12, B), dtype=torch.float64).pin_memory()
+    h_tau = torch.empty((12, B), dtype=torch.float64).pin_memory()
+    h_net = torch.empty((6, B), dtype=torch.float64).pin_memory()
+    h_flags = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        solver.solve_wrench_host(h["q"], h["quat"], h["wrench"], h["mask"], h["mu"], None, h_grf, h_tau, h_flags, h_net)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    h2d = B * ((12 + 4 + 6 + 4) * 8 + 1)
+    d2h = B * ((12 + 12 + 6) * 8 + 4)
+    # the e2e result must be the device result
+    assert torch.equal(h_grf, grf.cpu()) and torch.equal(h_flags, flags.cpu())
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline: FP64 pipe (not HBM-, not tensor-bound), algorithmic FLOP by stance count
+    ns = np.array([bin(int(m)).count("1") for m in range(16)])[st["mask"]]
+    flop_local = float(sum(FLOP_PER_QP[int(k)] * int((ns == k).sum()) for k in range(5)))
+    ft = torch.tensor([flop_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ft, op=dist.ReduceOp.SUM)
+    flop_total = float(ft.item())
+    peaks, peak_src = load_peaks()
+    achieved_tf = flop_local / (ms_step * 1e-3) * 1e-12       # per GPU (the kernel of this rank)
+    bytes_per_qp = ((12 + 4 + 6 + 4) * 8 + 1) + ((12 + 12 + 6) * 8 + 4)
+    hbm_gbs = B * bytes_per_qp / (ms_step * 1e-3) * 1e-9
+
+    if rank == 0:
+        value = world * B / (ms_step * 1e-3)
+        cpu_v, cpu_info = (None, None)
+        if world == 1:
+            cpu_v, cpu_info = cpu_reference(st, 3, 1, min(B, args.cpu_sample))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "states_per_gpu": B, "global_batch": world * B,
+                       "parallelism": f"instance-sharded x{world}, no data-path collective",
+                       "l2_policy": f"inputs+outputs {B * bytes_per_qp / 1e6:.0f} MB per step exceed the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "qlb_solve_wrench_host (pinned host buffers, copies inside the timed region)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                         "kernel": "qlb_solve_kernel<0>",
+                         "note": "algorithmic FP64 FLOP (30k/21k/12k per 4/3/2-stance QP, SURVEY 8d) / CUDA-event time "
+                                 "of the launch, per GPU; peak = DFMA probe measured in this run (qlb_measure_fp64_peak)",
+                         "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                 "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src,
+                                 "bytes_per_qp": bytes_per_qp}},
+            "cpu_baseline": cpu_info,
+            "stats": {"ok": sd["ok"], "max_iter": sd["max_iter"], "unverified": sd["unverified"],
+                      "mean_ipm_iterations": sd["mean_iterations"], "max_ipm_iterations": sd["max_iterations"],
+                      "mean_wrench_err": sd["mean_wrench_err"], "allreduce_ms": allreduce_ms,
+                      "algorithmic_flop_total": flop_total},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

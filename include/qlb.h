@@ -81,7 +81,7 @@ typedef struct qlb_params {
   double gravity_compensation_percentage; /* 1.0 */
   /* interior-point solver */
   double ipm_tolerance;       /* stop when complementarity gap and residuals <= tol * scale (1e-9) */
-  int32_t ipm_max_iterations; /* 30 */
+  int32_t ipm_max_iterations; /* 40 */
   int32_t reserved;
 } qlb_params;
 
@@ -195,6 +195,10 @@ int qlb_leg_kinematics(qlb_context* ctx, size_t B, const double* q, const double
  * the call synchronises the stream).  wrench/netwrench may be NULL (error terms then zero). */
 int qlb_batch_stats(qlb_context* ctx, size_t B, const uint32_t* flags, const double* wrench,
                     const double* netwrench, qlb_stats* stats_out, void* stream);
+
+/* Measure the FP64 FMA throughput of the context's device (TFLOP/s, best of 4 runs of a register-only
+ * DFMA kernel): the denominator of the FP64-pipe roofline this path is bound by.  Synchronous. */
+int qlb_measure_fp64_peak(qlb_context* ctx, double* tflops_out);
 
 /* How many kernels this context has launched so far (bench.py reports it as gpu_launches). */
 uint64_t qlb_launch_count(const qlb_context* ctx);

@@ -60,7 +60,7 @@ def lib():
         _lib.qo_goldfarb_idnani.restype = C.c_double
         _lib.qo_goldfarb_idnani.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _ip]
         _lib.qo_ipm.restype = C.c_int
-        _lib.qo_ipm.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_int, _dp, _ip, _dp, _ip]
+        _lib.qo_ipm.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_int, _dp, _dp, _ip, _dp, _ip]
         _lib.qo_solve_wrench_batch.restype = C.c_int
         _lib.qo_leg_kinematics.restype = None
         _lib.qo_assemble.restype = None
@@ -129,13 +129,14 @@ def solve_qp_gi(G, g0, D, d, CE=None, ce0=None):
     return dict(x=x, f=f, active=act[:m].astype(bool), u=u[:m], iterations=it.value)
 
 
-def solve_qp_ipm(G, g0, D, d, tol=1e-9, max_iter=30):
+def solve_qp_ipm(G, g0, D, d, tol=1e-9, max_iter=40, x0=None):
     G = np.ascontiguousarray(G, dtype=np.float64); g0 = np.ascontiguousarray(g0, dtype=np.float64)
     n = g0.size
     D = np.ascontiguousarray(D, dtype=np.float64).reshape(-1, n); d = np.ascontiguousarray(d, dtype=np.float64)
     m = d.size
     x = np.zeros(n); u = np.zeros(m); act = np.zeros(m, dtype=np.int32); it = C.c_int(0)
-    st = lib().qo_ipm(n, m, _as(G), _as(g0), _as(D), _as(d), tol, max_iter, _as(x),
+    x0p = _as(np.ascontiguousarray(x0, dtype=np.float64)) if x0 is not None else None
+    st = lib().qo_ipm(n, m, _as(G), _as(g0), _as(D), _as(d), tol, max_iter, x0p, _as(x),
                       act.ctypes.data_as(_ip), _as(u), C.byref(it))
     return dict(x=x, status=st, active=act.astype(bool), u=u, iterations=it.value)
 

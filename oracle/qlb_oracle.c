@@ -530,16 +530,18 @@ void qo_finish(const qo_qp* qp, const double* x, const int* active, int status, 
   *flags = fl;
 }
 
-/* non-degeneracy margin of a solution: min over rows of max(|slack|, |multiplier|)-style gap, i.e.
- * how far the closest row is from flipping between active and inactive; relative to the force scale */
-static double qo_margin(const qo_qp* qp, const double* x, const int* active, const double* u) {
+/* non-degeneracy margin of a solution: how far the closest row is from flipping between active and
+ * inactive.  Inactive rows: slack relative to the force scale.  Active rows: multiplier relative to
+ * W * force scale - releasing a row with multiplier u moves x by up to u / lambda_min(G) = u / W, so
+ * this is the same "relative change of x" unit. */
+static double qo_margin(const qo_qp* qp, const double* x, const int* active, const double* u, double W) {
   const int n = qp->n, m = qp->m;
   double scale = 1.0, best = INFINITY;
   for (int j = 0; j < n; j++) if (fabs(x[j]) > scale) scale = fabs(x[j]);
   for (int i = 0; i < m; i++) {
     double s = -qp->d[i];
     for (int j = 0; j < n; j++) s += qp->D[i * n + j] * x[j];
-    const double v = active[i] ? fabs(u[i]) : fabs(s);
+    const double v = active[i] ? fabs(u[i]) / W : fabs(s);
     if (v < best) best = v;
   }
   return best / scale;
@@ -575,10 +577,18 @@ static int qo_solve_one(const qo_qp* qp, int solver, qo_external_solver ext, int
       if (isfinite(f2)) memcpy(x, x2, n * sizeof(double));
     }
   } else if (solver == QO_SOLVER_IPM) {
-    status = qo_ipm(n, m, qp->G, qp->g0, qp->D, qp->d, 1e-9, 30, x, active, u, iters);
+    /* strictly feasible start: every stance leg pushes c along its normal (rows 0..ns-1 of D) */
+    double x0[QO_MAX_N], fn = 0.0;
+    for (int a = 0; a < 3; a++) fn += qp->b[a] * qp->D[a];
+    const double c = fmax(2.0 * qp->d[0], fn / qp->ns);
+    for (int j = 0; j < n; j++) {
+      x0[j] = 0.0;
+      for (int k = 0; k < qp->ns; k++) x0[j] += c * qp->D[k * n + j];
+    }
+    status = qo_ipm(n, m, qp->G, qp->g0, qp->D, qp->d, 1e-9, 40, x0, x, active, u, iters);
     if (nsolves == 2) {
       double x2[QO_MAX_N], u2[QO_MAX_M]; int a2[QO_MAX_M], it2;
-      qo_ipm(n, m, qp->G, qp->g0, qp->D, qp->d, 1e-9, 30, x2, a2, u2, &it2);
+      qo_ipm(n, m, qp->G, qp->g0, qp->D, qp->d, 1e-9, 40, x0, x2, a2, u2, &it2);
     }
   } else {
     for (int rep = 0; rep < nsolves; rep++) {
@@ -623,7 +633,7 @@ int qo_solve_wrench_batch(const qo_leg_model legs[4], const qo_params* prm, long
     for (int c = 0; c < 12; c++) { grf[c * B + i] = g[c]; tau[c * B + i] = t[c]; }
     if (netwrench) for (int c = 0; c < 6; c++) netwrench[c * B + i] = nw[c];
     flags[i] = fl;
-    if (margin) margin[i] = (status == 0 && qp.ns > 0) ? qo_margin(&qp, x, active, u) : INFINITY;
+    if (margin) margin[i] = (status == 0 && qp.ns > 0) ? qo_margin(&qp, x, active, u, prm->W) : INFINITY;
   }
   return 0;
 }

@@ -80,9 +80,10 @@ double qo_goldfarb_idnani(int n, int m, int p, const double* G, const double* g0
                           int* active, double* u, int* iterations);
 
 /* Dense Mehrotra predictor-corrector interior point + exact active-set polish: the CPU mirror of the
- * GPU algorithm and the "OOQP-style" stand-in for timing.  Returns 0 ok, 2 max-iter, 3 unverified. */
+ * GPU algorithm and the "OOQP-style" stand-in for timing.  x0 = optional strictly feasible start
+ * (NULL: start from the unconstrained minimiser).  Returns 0 ok, 2 max-iter, 3 unverified. */
 int qo_ipm(int n, int m, const double* G, const double* g0, const double* D, const double* d,
-           double tol, int max_iter, double* x, int* active, double* u, int* iterations);
+           double tol, int max_iter, const double* x0, double* x, int* active, double* u, int* iterations);
 
 /* Assemble one state.  mu may be NULL (-> mu_default); normals_world may be NULL (-> (0,0,1)). */
 void qo_assemble(const qo_leg_model legs[4], const qo_params* prm, const double q[12],

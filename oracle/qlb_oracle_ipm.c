@@ -122,7 +122,7 @@ static int polish(int n, int m, const double* LG, const double* g0, const double
 }
 
 int qo_ipm(int n, int m, const double* G, const double* g0, const double* D, const double* d,
-           double tol, int max_iter, double* x, int* active, double* u, int* iterations) {
+           double tol, int max_iter, const double* x0, double* x, int* active, double* u, int* iterations) {
   double LG[NMAX * NMAX], H[NMAX * NMAX];
   double s[MMAX], lam[MMAX], rd[NMAX], rp[MMAX], rhs[NMAX], dx[NMAX], ds[MMAX], dl[MMAX];
   double dxa[NMAX], dsa[MMAX], dla[MMAX];
@@ -142,17 +142,42 @@ int qo_ipm(int n, int m, const double* G, const double* g0, const double* D, con
     if (v < smin) smin = v;
   }
   if (smin >= 0.0) return 0;
-  /* 2. start: keep x, push the slacks inside, centre the multipliers */
-  {
+  /* 2. start.  With a strictly feasible x0 (the contact-force QP always has one: every stance leg
+   * pushing along its normal): s = D x0 - d > 0, multipliers centred at the scale of the gradient.
+   * Without one: keep the unconstrained minimiser, push the slacks inside, centre the multipliers. */
+  int feasible_start = 0;
+  if (x0) {
+    feasible_start = 1;
+    for (int i = 0; i < m; i++) {
+      double v = -d[i];
+      for (int j = 0; j < n; j++) v += D[i * n + j] * x0[j];
+      s[i] = v;
+      if (!(v > 0.0)) feasible_start = 0;
+    }
+  }
+  if (feasible_start) {
+    double gmax = 1.0;
+    for (int i = 0; i < n; i++) {
+      double v = g0[i];
+      for (int j = 0; j < n; j++) v += G[i * n + j] * x0[j];
+      if (fabs(v) > gmax) gmax = fabs(v);
+    }
+    memcpy(x, x0, n * sizeof(double));
+    for (int i = 0; i < m; i++) lam[i] = gmax / s[i];
+  } else {
+    for (int i = 0; i < m; i++) {
+      double v = -d[i];
+      for (int j = 0; j < n; j++) v += D[i * n + j] * x[j];
+      s[i] = v;
+    }
     const double shift = fmax(-1.5 * smin, 1e-2 * scale);
     double mu0 = 0.0;
     for (int i = 0; i < m; i++) { s[i] = fmax(s[i], 0.0) + shift; }
-    /* multiplier scale from the gradient of the violated rows */
-    for (int i = 0; i < m; i++) lam[i] = 1.0;
-    for (int i = 0; i < m; i++) mu0 += s[i] * lam[i];
+    for (int i = 0; i < m; i++) mu0 += s[i];
     mu0 /= m;
     for (int i = 0; i < m; i++) lam[i] = mu0 / s[i];
   }
+  double alpha_prev = 1.0;
   int status = 2;
   for (int it = 0; it < max_iter; it++) {
     double mu = 0.0, nrd = 0.0, nrp = 0.0;
@@ -217,7 +242,8 @@ int qo_ipm(int n, int m, const double* G, const double* g0, const double* D, con
     double mua = 0.0;
     for (int k = 0; k < m; k++) mua += (s[k] + alpha * dsa[k]) * (lam[k] + alpha * dla[k]);
     mua /= m;
-    const double sigma = pow(mua / mu, 3.0);
+    double sigma = pow(mua / mu, 3.0);
+    if (alpha_prev < 0.1 && sigma < 0.5) sigma = 0.5; /* short step last time: re-centre */
     /* corrector */
     for (int i = 0; i < n; i++) {
       double v = -rd[i];
@@ -241,6 +267,17 @@ int qo_ipm(int n, int m, const double* G, const double* g0, const double* D, con
       if (dl[k] < 0.0) amax = fmin(amax, -lam[k] / dl[k]);
     }
     alpha = fmin(1.0, 0.995 * amax);
+    for (int tries = 0; tries < 20; tries++) { /* stay in the neighbourhood min s_i lam_i >= 1e-3 mu */
+      double ps = 0.0, pm = INFINITY;
+      for (int k = 0; k < m; k++) {
+        const double pr = (s[k] + alpha * ds[k]) * (lam[k] + alpha * dl[k]);
+        ps += pr;
+        if (pr < pm) pm = pr;
+      }
+      if (pm >= 1e-3 * ps / m && pm > 0.0) break;
+      alpha *= 0.7;
+    }
+    alpha_prev = alpha;
     for (int j = 0; j < n; j++) x[j] += alpha * dx[j];
     for (int k = 0; k < m; k++) { s[k] += alpha * ds[k]; lam[k] += alpha * dl[k]; }
   }

@@ -48,7 +48,7 @@ class Stats(C.Structure):
 EXPORTS = (
     "qlb_default_params", "qlb_create", "qlb_destroy", "qlb_set_params", "qlb_get_params",
     "qlb_solve_wrench", "qlb_solve_wrench_host", "qlb_solve_state", "qlb_solve_state_host",
-    "qlb_leg_kinematics", "qlb_batch_stats", "qlb_launch_count", "qlb_strerror",
+    "qlb_leg_kinematics", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
     "qlb_last_cuda_error", "qlb_abi_version",
 )
 
@@ -76,6 +76,7 @@ def load() -> C.CDLL:
     lib.qlb_solve_state_host.argtypes = [_vp, C.c_size_t] + [_vp] * 13
     lib.qlb_leg_kinematics.argtypes = [_vp, C.c_size_t] + [_vp] * 6
     lib.qlb_batch_stats.argtypes = [_vp, C.c_size_t, _vp, _vp, _vp, C.POINTER(Stats), _vp]
+    lib.qlb_measure_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
     lib.qlb_launch_count.argtypes = [_vp]
     lib.qlb_launch_count.restype = C.c_uint64
     lib.qlb_strerror.argtypes = [C.c_int]
@@ -153,6 +154,11 @@ class Solver:
     @property
     def launches(self) -> int:
         return int(self.lib.qlb_launch_count(self._ctx))
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double(0.0)
+        self._check(self.lib.qlb_measure_fp64_peak(self._ctx, C.byref(v)), "qlb_measure_fp64_peak")
+        return float(v.value)
 
     def set_params(self, p: Params):
         self._check(self.lib.qlb_set_params(self._ctx, C.byref(p)), "qlb_set_params")

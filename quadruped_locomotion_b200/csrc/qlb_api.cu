@@ -204,7 +204,7 @@ int qlb_default_params(qlb_params* p) {
   }
   p->gravity_compensation_percentage = 1.0;  // VirtualModelController.cpp:57
   p->ipm_tolerance = 1e-9;
-  p->ipm_max_iterations = 30;
+  p->ipm_max_iterations = 40;
   return QLB_OK;
 }
 
@@ -436,6 +436,34 @@ int qlb_batch_stats(qlb_context* ctx, size_t B, const uint32_t* flags, const dou
   QLB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost, st));
   QLB_CUDA(ctx, cudaStreamSynchronize(st));
   std::memcpy(stats_out, h, sizeof h);
+  return QLB_OK;
+}
+
+int qlb_measure_fp64_peak(qlb_context* ctx, double* tflops_out) {
+  if (!ctx || !tflops_out) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t e0, e1;
+  QLB_CUDA(ctx, cudaEventCreate(&e0));
+  QLB_CUDA(ctx, cudaEventCreate(&e1));
+  const int iters = 4096, threads = 256;
+  const int blocks = ctx->sm_count * 8;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    QLB_CUDA(ctx, cudaEventRecord(e0, st));
+    qlb_fp64_peak_kernel<<<blocks, threads, 0, st>>>(ctx->d_stats, iters, 1.0 + rep);
+    QLB_CUDA(ctx, cudaGetLastError());
+    QLB_CUDA(ctx, cudaEventRecord(e1, st));
+    QLB_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    QLB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)threads * (double)blocks;
+    const double tf = flops / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops_out = best;
   return QLB_OK;
 }
 

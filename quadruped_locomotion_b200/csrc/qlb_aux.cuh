@@ -145,4 +145,21 @@ __global__ void __launch_bounds__(256) qlb_stats_kernel(unsigned long long B, co
     atomicMax(reinterpret_cast<unsigned long long*>(&out[threadIdx.x]), (unsigned long long)__double_as_longlong(sh[threadIdx.x]));
 }
 
+// FP64 FMA throughput probe: the roofline denominator for this path (SURVEY.md 8d asks for a measured
+// figure; MEASURED_PEAKS.json only has HBM and bf16).  8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) qlb_fp64_peak_kernel(double* __restrict__ sink, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 1.0000001, c = 1e-9;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 12345.678) sink[0] = r;  // never true; keeps the chains alive
+}
+
 }  // namespace qlb

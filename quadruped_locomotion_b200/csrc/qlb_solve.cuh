@@ -25,8 +25,8 @@ constexpr int kRowGrf = 0, kRowTau = 12, kRowNet = 24, kRowWout = 30, kOutRows =
 
 constexpr int kModePolish = 0, kModeIpm = 1, kModeDone = 2;
 constexpr int kPdasFirst = 1;      // active-set passes tried right after the unconstrained solve
-constexpr int kPolishPasses = 8;   // passes per polish attempt
-constexpr double kNeighbourhood = 1e-2;
+constexpr int kPolishPasses = 10;  // passes per polish attempt
+constexpr double kNeighbourhood = 1e-3;
 
 struct SolveArgs {
   unsigned long long B;
@@ -348,6 +348,7 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
   int a0 = 0, sg1 = 0, sg2 = 0;  // active pattern of this leg: y_n pinned; y_1 = sg1*mu*y_n; y_2 = sg2*mu*y_n
   int mode = kModePolish, it = 0, pass = 0, status = 0, next_polish = 2;
   bool first = true, converged = false, have_G = false;
+  double alpha_prev = 1.0;
 #pragma unroll
   for (int r = 0; r < 5; r++) { s[r] = 1.0; lam[r] = 0.0; }
   if (badbits != 0u) { mode = kModeDone; status = 4; }
@@ -516,15 +517,15 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
       const double key = (wd_r >= 0) ? wd_v * 1e6 : ((wp_r >= 0) ? wp_v : 0.0);
       const double best = leg_min(key);
       const unsigned tie = (__ballot_sync(kFull, key == best && leg_viol) >> (16 * grp)) & 0xFFFu;
-      // start values of the interior-point iteration, should this group need them
-      double smin = fmin(fmin(fmin(e[0], e[1]), fmin(e[2], e[3])), e[4]);
-      smin = alive ? smin : 0.0;
-      const double gmin = leg_min(smin);
-      const double shift = fmax(-1.5 * gmin, 1e-2 * (double)scale);
-      double s0[5], ssum = 0.0;
+      // start of the interior-point iteration, should this group need it: strictly feasible point
+      // (every stance leg pushes c along its normal), multipliers centred at the gradient scale
+      const double fn_leg = ws.bw[grp][0] * nb[0] + ws.bw[grp][1] * nb[1] + ws.bw[grp][2] * nb[2];
+      const double c0 = fmax(fmax(2.0 * prm.fmin, fn_leg * (ns > 0 ? 1.0 / ns : 0.0)), prm.fmin + 1.0);
+      const double y0 = (alive && c == 0) ? c0 : 0.0;
+      double gam0 = gt;
 #pragma unroll
-      for (int r = 0; r < 5; r++) { s0[r] = fmax(e[r], 0.0) + shift; ssum += s0[r]; }
-      const double mu0 = leg_sum(alive ? ssum : 0.0) * rm;
+      for (int j = 0; j < kVars; j++) gam0 = fma(ws.grow[j][lane], gshfl(y0, j), gam0);
+      const double gmax = (double)fmaxf(1.f, group_max(var_lane ? fabsf((float)gam0) : 0.f));
 
       if (mode == kModePolish) {
         if (!any_viol) {
@@ -547,14 +548,17 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
               }
             }
           } else if (first) {
-            // start the interior-point iteration from the last active-set solution
             first = false;
             mode = kModeIpm;
-            y = yp;
+            y = y0;
+            double e0[5];
+            d_apply(c0, 0.0, 0.0, mu, e0);
+            e0[0] -= prm.fmin;
 #pragma unroll
             for (int r = 0; r < 5; r++) {
-              lam[r] = alive ? mu0 * fast_rcp(s0[r]) : 0.0;
-              s[r] = alive ? s0[r] : 1.0;
+              const double sr = fmax(e0[r], 1e-3 * c0);  // mu <= 0 would make the friction rows non-positive
+              s[r] = alive ? sr : 1.0;
+              lam[r] = alive ? gmax * fast_rcp(sr) : 0.0;
             }
             a0 = 0; sg1 = 0; sg2 = 0;
           } else if (converged || status == 2) {
@@ -563,7 +567,7 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
             if (status == 0) status = 3;
           } else {
             mode = kModeIpm;  // keep iterating, try again later
-            next_polish = it + 2;
+            next_polish = it + 1;
           }
         }
       }
@@ -591,7 +595,9 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
       for (int r = 0; r < 5; r++) pa = fma(fma(ala, dsa[r], s[r]), fma(ala, dla[r], lam[r]), pa);
       const double mua = leg_sum(pa) * rm;
       const double q3 = ipm_round ? mua / mu_c : 0.0;
-      const double sigmu = q3 * q3 * q3 * mu_c;
+      double sigma = q3 * q3 * q3;
+      if (alpha_prev < 0.1 && sigma < 0.5) sigma = 0.5;  // short step last time: re-centre
+      const double sigmu = sigma * mu_c;
 #pragma unroll
       for (int r = 0; r < 5; r++) {
         const double rc = fma(dsa[r], dla[r], s[r] * lam[r]) - sigmu;
@@ -617,7 +623,7 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
       double al = (ratio > 0.995f) ? 0.995 / (double)ratio : 1.0;
       // stay inside the neighbourhood min_i s_i lam_i >= gamma * mu (both groups loop together)
 #pragma unroll 1
-      for (int tries = 0; tries < 12; tries++) {
+      for (int tries = 0; tries < 20; tries++) {
         double ps = 0.0, pm = 1e300;
 #pragma unroll
         for (int r = 0; r < 5; r++) {
@@ -632,6 +638,7 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
         if (!ok) al *= 0.7;
       }
       if (ipm_round) {
+        alpha_prev = al;
         y = fma(al, dy, y);
 #pragma unroll
         for (int r = 0; r < 5; r++) {
@@ -650,7 +657,7 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
   double f[3];
 #pragma unroll
   for (int a = 0; a < 3; a++) {
-    const double w = var_lane ? y * ws.tail[a][lane] * alive_d : 0.0;
+    const double w = (alive && solved) ? y * ws.tail[a][lane] : 0.0;
     f[a] = (gshfl(w, l0) + gshfl(w, l0 + 1)) + gshfl(w, l0 + 2);
   }
   const double fx = (c == 0) ? f[0] : (c == 1 ? f[1] : f[2]);
@@ -666,7 +673,7 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
     // A x = sum over slots of column * y (CFD.cpp:614-625)
     if (var_lane) {
 #pragma unroll
-      for (int r = 0; r < 6; r++) ws.col[grp][gl][r] = ws.atl[grp][gl][r] * y;
+      for (int r = 0; r < 6; r++) ws.col[grp][gl][r] = solved ? ws.atl[grp][gl][r] * y : 0.0;
     }
     __syncwarp();
     if (gl < 6) {

@@ -1,0 +1,324 @@
+"""GPU parity tests (run on the B200 box): the fused sm_100a path, called through the C ABI, against the
+CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star / SURVEY.md 8d):
+  forces and torques: max_i |x_gpu - x_oracle|_inf / max(1, |x_oracle|_inf) <= 1e-6 in FP64
+  contact + active-set bits: bit-exact on non-degenerate instances; degenerate ones counted
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from quadruped_locomotion_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6          # the north-star bar
+TIGHT = 1e-9        # what the kernel actually delivers; a regression guard
+STATE_KEYS = ("q", "quat", "wrench", "mask", "mu", "normals")
+
+
+@pytest.fixture(scope="module")
+def solver(qlb_built):
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device: the product path has no CPU fallback")
+    s = capi.Solver("quadruped_model")
+    yield s
+    s.close()
+
+
+@pytest.fixture(scope="module")
+def solver_sd(qlb_built):
+    s = capi.Solver("simpledog")
+    yield s
+    s.close()
+
+
+def _oracle(O, M, st, **kw):
+    return O.solve_wrench_batch(M, st["q"], st["quat"], st["wrench"], st["mask"], mu=st.get("mu"),
+                                normals=st.get("normals"), want_margin=True, **kw)
+
+
+def _compare(out, ref, tol=TIGHT, max_degenerate=1e-4):
+    assert np.isfinite(out["grf"]).all() and np.isfinite(out["tau"]).all()
+    assert rel_err(out["grf"], ref["grf"]).max() <= tol
+    assert rel_err(out["tau"], ref["tau"]).max() <= tol
+    if out.get("netwrench") is not None:
+        assert rel_err(out["netwrench"], ref["netwrench"]).max() <= tol
+    mism = ((out["flags"] ^ ref["flags"]) & capi.FLAG_PARITY_MASK) != 0
+    # contact bits always exact
+    assert np.array_equal(out["flags"] & 0xF, ref["flags"] & 0xF)
+    # status must agree on ok / no-stance / bad-input
+    so, sr = (out["flags"] >> 24) & 7, (ref["flags"] >> 24) & 7
+    assert np.array_equal(so == 1, sr == 1) and np.array_equal(so == 4, sr == 4)
+    assert (so[(sr == 0)] == 0).all()
+    # active bits: exact except on (counted) near-degenerate instances
+    assert mism.mean() <= max_degenerate
+    if mism.any():
+        assert (ref["margin"][mism] < 1e-6).all(), "active-set mismatch on a non-degenerate instance"
+    return int(mism.sum())
+
+
+def test_survey_known_answers(solver, oracle, models, kats):
+    for k in kats["kats"]:
+        st = dict(q=np.array(k["q"], float)[:, None], quat=np.array(k["quat"], float)[:, None],
+                  wrench=np.array(k["wrench"], float)[:, None], mask=np.array([k["mask"]], np.uint8),
+                  mu=np.full((4, 1), k["mu"]), normals=None)
+        out = solver.solve_wrench_numpy(st)
+        legs = [l for l in range(4) if (k["mask"] >> l) & 1]
+        x = np.concatenate([out["grf"][3 * l:3 * l + 3, 0] for l in legs])
+        np.testing.assert_allclose(x, k["x"], rtol=0, atol=1e-9 * max(1.0, np.abs(k["x"]).max()))
+        np.testing.assert_allclose(x, k["survey_x"], rtol=0, atol=5e-8)
+        # active rows in the reference's D-row numbering: ns F_min rows, then 4 per stance leg
+        ns = len(legs)
+        rows = []
+        for slot, l in enumerate(legs):
+            bits = (int(out["flags"][0]) >> (4 + 5 * l)) & 31
+            if bits & 1:
+                rows.append(slot)
+            rows += [ns + 4 * slot + r for r in range(4) if bits & (2 << r)]
+        assert sorted(rows) == k["survey_active_rows"]
+        assert (int(out["flags"][0]) >> 24) & 7 == 0
+
+
+def test_golden_fixture(solver, solver_sd, golden):
+    st = {k: golden[k] for k in STATE_KEYS}
+    for name, s in (("quadruped_model", solver), ("simpledog", solver_sd)):
+        out = s.solve_wrench_numpy(st)
+        assert rel_err(out["grf"], golden[name + "_grf"]).max() <= TIGHT
+        assert rel_err(out["tau"], golden[name + "_tau"]).max() <= TIGHT
+        assert rel_err(out["netwrench"], golden[name + "_net"]).max() <= TIGHT
+        assert np.array_equal(out["flags"] & capi.FLAG_PARITY_MASK, golden[name + "_flags"] & capi.FLAG_PARITY_MASK)
+
+
+@pytest.mark.parametrize("cfg,B", [("C1", 1), ("C2", 65536), ("C3", 131072), ("C5", 131072)])
+def test_parity_with_oracle(solver, oracle, models, cfg, B):
+    st = synth.make_states(cfg, B)
+    ref = _oracle(oracle, models["quadruped_model"], st)
+    out = solver.solve_wrench_numpy(st)
+    _compare(out, ref)
+    assert rel_err(out["grf"], ref["grf"]).max() <= TOL  # the stated bar, for the record
+
+
+def test_parity_simpledog(solver_sd, oracle, models):
+    st = synth.make_states("C3", 32768, start=1 << 21)
+    ref = _oracle(oracle, models["simpledog"], st)
+    _compare(solver_sd.solve_wrench_numpy(st), ref)
+
+
+def test_parity_with_reference_solver(solver, oracle, models):
+    """Same check against the reference's own QuadProg++ (oracle/_ref), where it was built."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not present")
+    st = synth.make_states("C5", 32768, start=99)
+    ref = oracle.solve_wrench_batch(models["quadruped_model"], st["q"], st["quat"], st["wrench"], st["mask"],
+                                    mu=st["mu"], normals=st["normals"], solver=oracle.SOLVER_REF)
+    out = solver.solve_wrench_numpy(st)
+    assert rel_err(out["grf"], ref["grf"]).max() <= TIGHT
+    assert rel_err(out["tau"], ref["tau"]).max() <= TIGHT
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 15, 16, 17, 31, 33, 1000, 1001])
+def test_ragged_batch_sizes(solver, oracle, models, B):
+    st = synth.make_states("C5", B, start=31337)
+    _compare(solver.solve_wrench_numpy(st), _oracle(oracle, models["quadruped_model"], st), max_degenerate=0.0)
+
+
+def test_empty_batch(solver):
+    z = np.zeros((12, 0))
+    solver.solve_wrench_host(z, np.zeros((4, 0)), np.zeros((6, 0)), np.zeros(0, np.uint8), None, None,
+                             z.copy(), z.copy(), np.zeros(0, np.uint32), None)
+
+
+def test_all_stance_masks_and_defaults(solver, oracle, models):
+    st = synth.make_states("C3", 64)
+    st["mask"] = (np.arange(64) % 16).astype(np.uint8)
+    st["mu"] = None
+    st["normals"] = None
+    ref = _oracle(oracle, models["quadruped_model"], st)
+    out = solver.solve_wrench_numpy(st)
+    _compare(out, ref, max_degenerate=0.0)
+    nos = st["mask"] == 0
+    assert (((out["flags"][nos] >> 24) & 7) == 1).all() and not out["grf"][:, nos].any() and not out["tau"][:, nos].any()
+    for leg in range(4):
+        swing = ((st["mask"] >> leg) & 1) == 0
+        assert not out["grf"][3 * leg:3 * leg + 3, swing].any()
+        assert not out["tau"][3 * leg:3 * leg + 3, swing].any()
+
+
+def test_tilted_normals_and_per_leg_friction(solver, oracle, models):
+    st = synth.make_states("C5", 4096, start=777777)
+    rng = np.random.default_rng(5)
+    n = rng.normal(0, 0.12, (4, 3, 4096))
+    n[:, 2] = 1.0
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    st["normals"] = n.reshape(12, 4096)
+    _compare(solver.solve_wrench_numpy(st), _oracle(oracle, models["quadruped_model"], st))
+
+
+def test_friction_limited(solver, oracle, models):
+    st = synth.make_states("C3", 8192, start=5)
+    st["wrench"][0] += 350.0   # heavy heading force: most legs sit on the friction pyramid
+    ref = _oracle(oracle, models["quadruped_model"], st)
+    out = solver.solve_wrench_numpy(st)
+    _compare(out, ref)
+    nact = np.array([bin(int(f) >> 4 & 0xFFFFF).count("1") for f in out["flags"]])
+    assert (nact >= 1).mean() > 0.8
+
+
+def test_bad_inputs_are_flagged_and_isolated(solver, oracle, models):
+    st = synth.make_states("C3", 64, start=11)
+    clean = solver.solve_wrench_numpy(st)
+    st["q"][4, 3] = np.nan
+    st["quat"][1, 10] = np.inf
+    st["wrench"][5, 20] = np.nan
+    st["normals"][:, 30] = np.tile([0.0, 1.0, 0.0], 4)  # normal along base y for identity yaw? degenerate only if parallel
+    st["quat"][:, 30] = [1.0, 0.0, 0.0, 0.0]            # identity attitude: n x e_y = 0 -> NaN tangent (CFD.cpp:303)
+    ref = _oracle(oracle, models["quadruped_model"], st)
+    out = solver.solve_wrench_numpy(st)
+    status = (out["flags"] >> 24) & 7
+    for i in (3, 10, 20, 30):
+        assert status[i] == 4 and ((ref["flags"][i] >> 24) & 7) == 4
+        assert not out["grf"][:, i].any() and not out["tau"][:, i].any()
+    ok = np.ones(64, bool); ok[[3, 10, 20, 30]] = False
+    assert np.array_equal(out["grf"][:, ok], clean["grf"][:, ok])
+    assert np.array_equal(out["flags"][ok], clean["flags"][ok])
+
+
+def test_full_size_properties(solver, oracle, models):
+    """BASELINE size (2^20): size-independent properties on the whole batch + oracle parity on a slice."""
+    B = 1 << 20
+    st = synth.make_states("C3", B)
+    out = solver.solve_wrench_numpy(st)
+    flags = out["flags"]
+    status = (flags >> 24) & 7
+    assert (status == 0).mean() > 0.99999
+    ok = status == 0
+    # (1) determinism / idempotence: a second run is bit-identical
+    again = solver.solve_wrench_numpy(st)
+    assert np.array_equal(out["grf"], again["grf"]) and np.array_equal(flags, again["flags"])
+    # (2) batch-split invariance: solving a slice alone gives the same bits
+    lo, hi = 333333, 333333 + 4097
+    part = solver.solve_wrench_numpy({k: (None if v is None else np.ascontiguousarray(v[..., lo:hi])) for k, v in st.items()})
+    assert np.array_equal(part["grf"], out["grf"][:, lo:hi]) and np.array_equal(part["flags"], flags[lo:hi])
+    # (3) primal feasibility of every constraint in the reference's form, from the outputs alone
+    R = synth.rot_from_quat(st["quat"])                 # (3,3,B) base->world
+    n = R[2]                                            # R^T e_z : rows of R_bw -> third row
+    ey = R[1]
+    t1 = np.cross(n, ey, axis=0); t1 /= np.linalg.norm(t1, axis=0)
+    t2 = np.cross(n, t1, axis=0); t2 /= np.linalg.norm(t2, axis=0)
+    for leg in range(4):
+        f = out["grf"][3 * leg:3 * leg + 3]
+        stance = ((st["mask"] >> leg) & 1).astype(bool) & ok
+        fn = (n * f).sum(0); f1 = (t1 * f).sum(0); f2 = (t2 * f).sum(0)
+        scale = np.maximum(1.0, np.abs(out["grf"]).max(0))
+        rows = np.stack([fn - 10.0, 0.6 * fn + f1, 0.6 * fn - f1, 0.6 * fn + f2, 0.6 * fn - f2])
+        assert (rows[:, stance] >= -1e-9 * scale[stance]).all()
+        # (4) an active bit means the row is tight
+        for r in range(5):
+            bit = ((flags >> (4 + 5 * leg + r)) & 1).astype(bool) & stance
+            assert (np.abs(rows[r, bit]) <= 1e-8 * scale[bit]).all()
+    # (5) net wrench output equals sum f and sum r x f recomputed from the force output
+    net_f = out["grf"][0:3] + out["grf"][3:6] + out["grf"][6:9] + out["grf"][9:12]
+    assert np.abs(net_f - out["netwrench"][:3]).max() <= 1e-9 * np.abs(net_f).max()
+    # (6) oracle parity on a slice of the same batch
+    sl = slice(500000, 500000 + 65536)
+    sub = {k: (None if v is None else np.ascontiguousarray(v[..., sl])) for k, v in st.items()}
+    ref = _oracle(oracle, models["quadruped_model"], sub)
+    _compare({k: (None if v is None else v[..., sl]) for k, v in out.items()}, ref)
+
+
+def test_device_pointer_api_and_stream(solver, oracle, models):
+    B = 50000
+    st = synth.make_states("C3", B, start=42)
+    dev = torch.device("cuda:0")
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in st.items()}
+    grf = torch.full((12, B), float("nan"), dtype=torch.float64, device=dev)
+    tau = torch.full((12, B), float("nan"), dtype=torch.float64, device=dev)
+    flags = torch.zeros(B, dtype=torch.int32, device=dev)
+    net = torch.zeros((6, B), dtype=torch.float64, device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    before = solver.launches
+    with torch.cuda.stream(side):
+        solver.solve_wrench(d["q"], d["quat"], d["wrench"], d["mask"], d["mu"], d["normals"], grf, tau, flags, net,
+                            stream=side.cuda_stream)
+    side.synchronize()
+    assert solver.launches == before + 1
+    out = dict(grf=grf.cpu().numpy(), tau=tau.cpu().numpy(), flags=flags.cpu().numpy().view(np.uint32),
+               netwrench=net.cpu().numpy())
+    ref = _oracle(oracle, models["quadruped_model"], st)
+    _compare(out, ref)
+    # statistics kernel against numpy
+    s = solver.batch_stats(flags, d["wrench"], net)
+    assert s[0] == B and s[1] == ((out["flags"] >> 24) & 7 == 0).sum()
+    err = np.sqrt((np.array([1, 5, 1, 10, 10, 5.])[:, None] * (out["netwrench"] - st["wrench"]) ** 2).sum(0))
+    assert abs(s[7] - err.sum()) <= 1e-9 * err.sum() and abs(s[28] - err.max()) <= 1e-12 * err.max()
+    assert s[6] == (out["flags"] >> 27).sum() and s[29] == (out["flags"] >> 27).max()
+    for leg in range(4):
+        for r in range(5):
+            assert s[8 + 5 * leg + r] == ((out["flags"] >> (4 + 5 * leg + r)) & 1).sum()
+
+
+def test_leg_kinematics_kernel(solver, solver_sd, oracle, models):
+    B = 4097
+    st = synth.make_states("C3", B, start=9)
+    dev = torch.device("cuda:0")
+    q = torch.from_numpy(st["q"]).to(dev); quat = torch.from_numpy(st["quat"]).to(dev)
+    for name, s in (("quadruped_model", solver), ("simpledog", solver_sd)):
+        foot = torch.empty((12, B), dtype=torch.float64, device=dev)
+        jac = torch.empty((36, B), dtype=torch.float64, device=dev)
+        gt = torch.empty((12, B), dtype=torch.float64, device=dev)
+        s.leg_kinematics(q, quat, foot, jac, gt)
+        torch.cuda.synchronize()
+        foot, jac, gt = foot.cpu().numpy(), jac.cpu().numpy(), gt.cpu().numpy()
+        for i in range(0, B, 97):
+            R = synth.rot_from_quat(st["quat"][:, i])
+            g = R.T @ np.array([0, 0, -9.8])
+            for leg in range(4):
+                f, J, G = oracle.leg_kinematics(models[name], leg, st["q"][3 * leg:3 * leg + 3, i], grav=g)
+                np.testing.assert_allclose(foot[3 * leg:3 * leg + 3, i], f, atol=1e-13)
+                np.testing.assert_allclose(jac[9 * leg:9 * leg + 9, i].reshape(3, 3), J, atol=1e-13)
+                np.testing.assert_allclose(gt[3 * leg:3 * leg + 3, i], G, atol=1e-11)
+
+
+def test_state_mode_runs_the_vmc_prologue(solver, oracle, models):
+    """qlb_solve_state = VirtualModelController::compute + computeForceDistribution in one kernel."""
+    B = 20000
+    st = synth.make_states("C3", B, start=2024)
+    rng = np.random.default_rng(3)
+    pose = np.concatenate([rng.normal(0, 0.05, (3, B)) + np.array([[0], [0], [0.45]]), st["quat"]])
+    twist = rng.normal(0, 0.05, (6, B))
+    tq = synth.quat_from_ypr(*(rng.normal(0, 0.02, (3, B)) + np.stack([
+        np.arctan2(2 * (st["quat"][0] * st["quat"][3] + st["quat"][1] * st["quat"][2]),
+                   1 - 2 * (st["quat"][2] ** 2 + st["quat"][3] ** 2)), np.zeros(B), np.zeros(B)])))
+    tpose = np.concatenate([pose[:3] + rng.normal(0, 0.004, (3, B)), tq])
+    ttwist = rng.normal(0, 0.05, (6, B))
+    wref = np.stack([oracle.vmc_wrench(pose[:, i], twist[:, i], tpose[:, i], ttwist[:, i]) for i in range(B)], axis=1)
+    grf = np.zeros((12, B)); tau = np.zeros((12, B)); flags = np.zeros(B, np.uint32); net = np.zeros((6, B)); wout = np.zeros((6, B))
+    solver.solve_state_host(st["q"], pose, twist, tpose, ttwist, st["mask"], st["mu"], st["normals"], grf, tau, flags, net, wout)
+    assert rel_err(wout, wref).max() <= 1e-11
+    st2 = dict(st); st2["wrench"] = wref
+    ref = _oracle(oracle, models["quadruped_model"], st2)
+    _compare(dict(grf=grf, tau=tau, flags=flags, netwrench=net), ref)
+
+
+def test_parameters_can_be_changed(solver, oracle, models):
+    st = synth.make_states("C3", 4096, start=77)
+    p = solver.get_params()
+    try:
+        p2 = solver.get_params()
+        p2.min_normal_force = 25.0
+        p2.ground_force_weight = 1e-3
+        for i, v in enumerate((2, 3, 1, 8, 12, 4)):
+            p2.wrench_weights[i] = v
+        solver.set_params(p2)
+        op = oracle.default_params()
+        op.fmin = 25.0; op.W = 1e-3
+        for i, v in enumerate((2, 3, 1, 8, 12, 4)):
+            op.S[i] = v
+        ref = _oracle(oracle, models["quadruped_model"], st, params=op)
+        _compare(solver.solve_wrench_numpy(st), ref)
+    finally:
+        solver.set_params(p)
