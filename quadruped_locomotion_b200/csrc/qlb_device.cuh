@@ -58,6 +58,43 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return r * fma(-x, r, 2.0);
 }
 
+// 1/sqrt(x) to FP64 rounding: FP32 seed (one MUFU.RSQ) + two Newton steps in FP64.  x must be a
+// normal FP32-range number (pivots of the KKT matrices are 1e-4 .. 1e16); x <= 0 gives NaN.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  float xf = (float)x, rf;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(xf));
+  double r = (double)rf;
+  const double hx = 0.5 * x;
+  r = r * fma(-hx * r, r, 1.5);
+  return r * fma(-hx * r, r, 1.5);
+}
+
+// sin and cos for joint angles (|x| up to ~1e4 rad; URDF limits are +-3 rad): two-constant Cody-Waite
+// reduction by pi/2 and the fdlibm kernel polynomials.  No slow path, no local memory.
+__device__ __forceinline__ void sincos_small(double x, double* sn, double* cs) {
+  const double kd = rint(x * 6.36619772367581382433e-01);  // x * 2/pi
+  const int k = (int)kd;
+  double r = fma(-kd, 1.57079632673412561417e+00, x);
+  r = fma(-kd, 6.07710050650619224932e-11, r);
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double sr = fma(z * r, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const double s0 = (k & 1) ? cr : sr;
+  const double c0 = (k & 1) ? sr : cr;
+  *sn = (k & 2) ? -s0 : s0;
+  *cs = ((k + 1) & 2) ? -c0 : c0;
+}
+
 // ---------------------------------------------------------------- 12x12 Cholesky through shuffles
 // In : H[j] = entry (gl, j) of a symmetric positive definite matrix (full row; lanes >= 12: zeros).
 // Out: H[j<gl] = L[gl][j], H[gl] = L[gl][gl], H[j>gl] = L[j][gl] (row gl of L^T), rdiag = 1/L[gl][gl].
@@ -72,35 +109,34 @@ __device__ __forceinline__ bool group_cholesky(double (&H)[kVars], double& rdiag
   for (int k = 0; k < kVars; k++) {
     const double dkk = gshfl(H[k], k);
     ok = ok && (dkk > 0.0);
-    const double rinv = rsqrt(dkk);
+    const double rinv = fast_rsqrt(dkk);
     if (gl >= k) H[k] *= rinv;
     if (gl == k) rdiag = rinv;
-    const double a = (gl > k) ? -H[k] : 0.0;
+    const double a = (gl > k) ? -H[k] : 0.0;  // rows above k are finished: multiplier 0 leaves them alone
 #pragma unroll
     for (int j = k + 1; j < kVars; j++) {
       const double v = gshfl(H[k], j);  // L[j][k]
-      H[j] = (gl == k) ? v : fma(a, v, H[j]);
+      H[j] = fma(a, v, H[j]);
+      if (gl == k) H[j] *= rinv;        // row k of L^T = own trailing row scaled (the trailing matrix is symmetric)
     }
   }
   return ok;
 }
 
 // Solve L L^T x = b with the factor layout above; lane gl passes b[gl] and receives x[gl].
-__device__ __forceinline__ double group_solve(const double (&H)[kVars], const double rdiag,
-                                              const double b, const int gl) {
+__device__ __forceinline__ double group_solve(const double (&H)[kVars], const double rdiag, const double b,
+                                              const int gl) {
   double acc = b;
 #pragma unroll
   for (int j = 0; j < kVars; j++) {
     const double zj = gshfl(acc * rdiag, j);
-    const double a = (gl > j) ? H[j] : 0.0;
-    acc = fma(-a, zj, acc);
+    if (gl > j) acc = fma(-H[j], zj, acc);
   }
   acc *= rdiag;
 #pragma unroll
   for (int j = kVars - 1; j >= 0; j--) {
     const double xj = gshfl(acc * rdiag, j);
-    const double a = (gl < j) ? H[j] : 0.0;
-    acc = fma(-a, xj, acc);
+    if (gl < j) acc = fma(-H[j], xj, acc);
   }
   return acc * rdiag;
 }

@@ -258,7 +258,7 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
   double foot[3], jcol[3], gtau;
   {
     double sn, cs;
-    sincos(qv, &sn, &cs);
+    sincos_small(qv, &sn, &cs);
     double R[9], p[3], zc[3] = {0, 0, 0}, pjc[3] = {0, 0, 0}, mcs[3] = {0, 0, 0};
 #pragma unroll
     for (int e = 0; e < 9; e++) R[e] = mdl.rot[leg][0][e];
@@ -331,79 +331,44 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
 
   // ---------------- solver state
   // Everything that contains a shuffle is executed by the whole warp with the full mask; a group that
-  // is not in the corresponding mode just computes values it never commits.  (Shuffles under a
-  // per-group mask cost a WARPSYNC each and were 30x slower.)
+  // is not in the corresponding mode just computes values it never commits.  The loop body is kept
+  // small (one factorisation site, one substitution site, one mat-vec site): with a dozen warps per SM
+  // at different program counters the instruction cache is the first bottleneck of this kernel.
   if (var_lane) {
 #pragma unroll
     for (int a = 0; a < 3; a++) { ws.tail[a][lane] = ev[a]; ws.tail[3 + a][lane] = jcol[a]; }
     ws.tail[6][lane] = gtau;
   }
   if (gl < 6) ws.bw[grp][gl] = b[gl];
+  // strictly feasible interior-point start for this leg: push c0 along the normal
+  const double c0 = fmax(fmax(2.0 * prm.fmin, (b[0] * nb[0] + b[1] * nb[1] + b[2] * nb[2]) * (ns > 0 ? 1.0 / ns : 0.0)),
+                         prm.fmin + 1.0);
   __syncwarp();
 
   double H[kVars];
   double gt = 0.0;             // g~ of this slot
   double y = 0.0;              // interior-point iterate / final solution of this slot
-  double s[5], lam[5];
+  double rd = 0.0;             // dual residual of this slot, kept up to date incrementally
+  double s[5], lam[5], rp[5];  // slacks, multipliers, primal residual of this leg's five rows
   int a0 = 0, sg1 = 0, sg2 = 0;  // active pattern of this leg: y_n pinned; y_1 = sg1*mu*y_n; y_2 = sg2*mu*y_n
-  int mode = kModePolish, it = 0, pass = 0, status = 0, next_polish = 2;
-  bool first = true, converged = false, have_G = false;
+  int mode = kModePolish, it = 0, pass = 0, status = 0;
+  bool first = true, converged = false, have_G = false, want_polish = false;
   double alpha_prev = 1.0;
 #pragma unroll
-  for (int r = 0; r < 5; r++) { s[r] = 1.0; lam[r] = 0.0; }
+  for (int r = 0; r < 5; r++) { s[r] = 1.0; lam[r] = 0.0; rp[r] = 0.0; }
   if (badbits != 0u) { mode = kModeDone; status = 4; }
   else if (ns == 0) { mode = kModeDone; status = 1; }
   const double rm = ns > 0 ? 1.0 / (5.0 * ns) : 0.0;
 
-  // ---------------- rounds: every round is one factorisation + one or two solves, shared by both groups
+  // ---------------- rounds: one factorisation + one or two substitutions, shared by both groups
   int rounds = 0;
 #pragma unroll 1
   for (;;) {
     if (__all_sync(kFull, mode == kModeDone)) break;
-    if (++rounds > 160 && mode != kModeDone) { mode = kModeDone; status = 2; }  // hard stop, never reached in practice
-    double rd = 0.0, rp[5], rs[5], rhs = 0.0, mu_c = 0.0;
+    if (++rounds > 200 && mode != kModeDone) { mode = kModeDone; status = 2; }  // hard stop, never reached in practice
+    double rhs = 0.0, rs[5];
 #pragma unroll
-    for (int r = 0; r < 5; r++) { rp[r] = 0.0; rs[r] = 1.0; }
-    bool ipm_round = false;
-
-    // ---- A. residuals of the interior-point iterate, convergence test, decision to polish
-    if (__any_sync(kFull, mode == kModeIpm)) {
-      double gy = 0.0;
-#pragma unroll
-      for (int j = 0; j < kVars; j++) gy = fma(ws.grow[j][lane], gshfl(y, j), gy);
-      const double yn = gshfl(y, l0), y1 = gshfl(y, l0 + 1), y2 = gshfl(y, l0 + 2);
-      double e[5];
-      d_apply(yn, y1, y2, mu, e);
-      e[0] -= prm.fmin;
-      double sl = 0.0;
-      float nrp = 0.f;
-#pragma unroll
-      for (int r = 0; r < 5; r++) {
-        rp[r] = (s[r] - e[r]) * alive_d;
-        rs[r] = fast_rcp(s[r]);
-        sl = fma(s[r], lam[r], sl);
-        nrp = fmaxf(nrp, fabsf((float)rp[r]));
-      }
-      rd = gy + gt - dt_apply(lam, mu, c);
-      mu_c = leg_sum(sl) * rm;
-      const float nrd = group_max(var_lane ? fabsf((float)rd) : 0.f);
-      nrp = leg_max(nrp);
-      const float scale = fmaxf(1.f, group_max(fabsf((float)y)));
-      if (mode == kModeIpm) {
-        converged = (mu_c <= prm.tol * scale) && (nrp <= (float)prm.tol * scale) && (nrd <= 100.f * (float)prm.tol * scale);
-        const bool out_of_iters = it >= prm.max_iter;
-        if (converged || out_of_iters || (it >= next_polish && mu_c <= 1e-3 * scale)) {
-          mode = kModePolish;
-          pass = 0;
-          a0 = lam[0] > s[0];
-          sg1 = (lam[1] > s[1]) ? -1 : ((lam[2] > s[2]) ? 1 : 0);
-          sg2 = (lam[3] > s[3]) ? -1 : ((lam[4] > s[4]) ? 1 : 0);
-          if (!alive) { a0 = 0; sg1 = 0; sg2 = 0; }
-          if (out_of_iters && !converged) status = 2;
-        }
-        ipm_round = (mode == kModeIpm);
-      }
-    }
+    for (int r = 0; r < 5; r++) rs[r] = 1.0;
 
     // ---- B. system of this round
     const bool any_pol = __any_sync(kFull, mode == kModePolish);
@@ -454,11 +419,11 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
       }
       __syncwarp();
     }
-    if (ipm_round) {
+    if (mode == kModeIpm) {
       // H = G~ + D~' diag(lam/s) D~ (3x3 block on the diagonal), predictor right-hand side
       double th[5], v[5];
 #pragma unroll
-      for (int r = 0; r < 5; r++) { th[r] = lam[r] * rs[r]; v[r] = fma(-th[r], rp[r], lam[r]); }
+      for (int r = 0; r < 5; r++) { rs[r] = fast_rcp(s[r]); th[r] = lam[r] * rs[r]; v[r] = fma(-th[r], rp[r], lam[r]); }
       const double t12 = th[1] + th[2], t34 = th[3] + th[4];
       const double d12 = mu * (th[1] - th[2]), d34 = mu * (th[3] - th[4]);
       double blk[3];
@@ -474,83 +439,128 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
       rhs = 0.0;
     }
 
-    // ---- C. factorise and solve (both groups, converged)
+    // ---- C. factorise (both groups, converged)
     double rdiag;
     const bool pd = group_cholesky(H, rdiag, gl);
-    const double sol = group_solve(H, rdiag, rhs, gl);
-    if (!pd && mode != kModeDone) { mode = kModeDone; status = 4; y = 0.0; ipm_round = false; }
+    if (!pd && mode != kModeDone) { mode = kModeDone; status = 4; y = 0.0; }
 
-    // ---- D. polish: recover y, multipliers, slacks; verify the KKT signs; repair the pattern
+    // ---- S. substitutions: phase 0 = polish solution / Mehrotra predictor, phase 1 = corrector
+    const bool any_ipm = __any_sync(kFull, mode == kModeIpm);
+    const bool ipm_round = (mode == kModeIpm);
+    double sol = 0.0, rcv[5], sigmu = 0.0, mu_c = 0.0;
+#pragma unroll
+    for (int r = 0; r < 5; r++) rcv[r] = 0.0;
+#pragma unroll 1
+    for (int ph = 0; ph < (any_ipm ? 2 : 1); ph++) {
+      const double x = group_solve(H, rdiag, rhs, gl);
+      if (ph == 0) sol = x;
+      double de[5];
+      {
+        const double dyn = gshfl(x, l0), dy1 = gshfl(x, l0 + 1), dy2 = gshfl(x, l0 + 2);
+        d_apply(dyn, dy1, dy2, mu, de);
+      }
+      // step of the five rows of this leg for the direction x: ds = D~ dy - rp, dl = -(rc + lam ds)/s
+      // (phase 0: rc = s lam, phase 1: rc = s lam + dsa dla - sigma mu)
+      double ds[5], dl[5], pa = 0.0;
+      float ratio = 0.f;
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        ds[r] = de[r] * alive_d - rp[r];
+        const double rc = (ph == 0) ? s[r] * lam[r] : rcv[r];
+        dl[r] = -fma(lam[r], ds[r], rc) * rs[r] * alive_d;
+        const float rl = (alive && ipm_round) ? rcp_approx((float)lam[r]) : 0.f;
+        ratio = fmaxf(ratio, fmaxf(-(float)ds[r] * (float)rs[r], -(float)dl[r] * rl));
+        pa = fma(s[r], lam[r], pa);
+      }
+      ratio = leg_max(ipm_round ? ratio : 0.f);
+      if (ph == 0) {
+        // affine step length, centring parameter, corrector right-hand side
+        mu_c = leg_sum(ipm_round ? pa : 0.0) * rm;
+        const double ala = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
+        double pb = 0.0;
+#pragma unroll
+        for (int r = 0; r < 5; r++) pb = fma(fma(ala, ds[r], s[r]), fma(ala, dl[r], lam[r]), pb);
+        const double mua = leg_sum(ipm_round ? pb : 0.0) * rm;
+        const double q3 = (ipm_round && mu_c > 0.0) ? mua / mu_c : 0.0;
+        double sigma = q3 * q3 * q3;
+        if (alpha_prev < 0.1 && sigma < 0.5) sigma = 0.5;  // short step last time: re-centre
+        sigmu = sigma * mu_c;
+        double v[5];
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          rcv[r] = fma(ds[r], dl[r], s[r] * lam[r]) - sigmu;
+          v[r] = (rcv[r] - lam[r] * rp[r]) * rs[r] * alive_d;
+        }
+        rhs = (var_lane && ipm_round) ? -rd - dt_apply(v, mu, c) : 0.0;
+      } else {
+        double al = (ratio > 0.995f) ? 0.995 / (double)ratio : 1.0;
+        // stay inside the neighbourhood min_i s_i lam_i >= gamma * mu (both groups loop together)
+#pragma unroll 1
+        for (int tries = 0; tries < 20; tries++) {
+          double ps = 0.0, pm = 1e300;
+#pragma unroll
+          for (int r = 0; r < 5; r++) {
+            const double pr = fma(al, ds[r], s[r]) * fma(al, dl[r], lam[r]);
+            ps += pr;
+            pm = fmin(pm, pr);
+          }
+          ps = leg_sum(alive ? ps : 0.0) * rm;
+          pm = leg_min(alive ? pm : 1e300);
+          const bool ok = !ipm_round || (pm >= kNeighbourhood * ps && pm > 0.0);
+          if (__all_sync(kFull, ok)) break;
+          if (!ok) al *= 0.7;
+        }
+        // take the step; the residuals follow without a mat-vec:
+        //   G~ dy = rhs - D~' diag(lam/s) D~ dy   =>   rd += al (rhs - D~'(theta .* de + dl)),   rp *= (1 - al)
+        double w5[5], pn = 0.0;
+        float nrp = 0.f;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          w5[r] = fma(lam[r] * rs[r], de[r] * alive_d, dl[r]);
+          const double sn = fma(al, ds[r], s[r]), ln = fma(al, dl[r], lam[r]);
+          pn = fma(sn, ln, pn);
+          if (ipm_round) { s[r] = sn; lam[r] = ln; rp[r] *= (1.0 - al); }
+          nrp = fmaxf(nrp, fabsf((float)rp[r]));
+        }
+        if (ipm_round) {
+          rd = fma(al, rhs - dt_apply(w5, mu, c), rd);
+          y = fma(al, x, y);
+          alpha_prev = al;
+          it++;
+        }
+        // convergence test and decision to polish, on the new iterate
+        const double mu_n = leg_sum(ipm_round ? pn : 0.0) * rm;
+        const float nrd = group_max((var_lane && ipm_round) ? fabsf((float)rd) : 0.f);
+        nrp = leg_max(ipm_round ? nrp : 0.f);
+        const float scale = fmaxf(1.f, group_max(fabsf((float)y)));
+        if (ipm_round) {
+          converged = (mu_n <= prm.tol * scale) && (nrp <= (float)prm.tol * scale) && (nrd <= 100.f * (float)prm.tol * scale);
+          const bool out_of_iters = it >= prm.max_iter;
+          want_polish = converged || out_of_iters || (it >= 2 && mu_n <= 1e-3 * scale);
+          if (out_of_iters && !converged) status = 2;
+        }
+      }
+    }
+
+    // ---- M. polish: recover y, multipliers, slacks; verify the KKT signs; repair the pattern.
+    //         One mat-vec site: pass 0 multiplies the polished point, pass 1 (only when a group starts
+    //         its interior-point iteration) the strictly feasible start.
     if (any_pol) {
       const double zn = gshfl(sol, l0);
       const double ynp = (a0 != 0) ? prm.fmin : zn;
       double yp = (c == 0) ? ynp : (c == 1 ? (sg1 != 0 ? sg1 * mu * ynp : sol) : (sg2 != 0 ? sg2 * mu * ynp : sol));
       if (!alive) yp = 0.0;
-      double gam = gt;
+      bool start_ipm = false;
+#pragma unroll 1
+      for (int rep = 0; rep < 2; rep++) {
+        const double vv = (rep == 0) ? yp : ((alive && c == 0) ? c0 : 0.0);
+        double gam = gt;
 #pragma unroll
-      for (int j = 0; j < kVars; j++) gam = fma(ws.grow[j][lane], gshfl(yp, j), gam);
-      const double yn = gshfl(yp, l0), y1 = gshfl(yp, l0 + 1), y2 = gshfl(yp, l0 + 2);
-      const double gn = gshfl(gam, l0), g1 = gshfl(gam, l0 + 1), g2 = gshfl(gam, l0 + 2);
-      double e[5], u[5];
-      d_apply(yn, y1, y2, mu, e);
-      e[0] -= prm.fmin;
-      u[1] = (sg1 == -1) ? g1 : 0.0;
-      u[2] = (sg1 == 1) ? -g1 : 0.0;
-      u[3] = (sg2 == -1) ? g2 : 0.0;
-      u[4] = (sg2 == 1) ? -g2 : 0.0;
-      u[0] = (a0 != 0) ? gn - mu * ((u[1] + u[2]) + (u[3] + u[4])) : 0.0;
-      const bool act[5] = {a0 != 0, sg1 == -1, sg1 == 1, sg2 == -1, sg2 == 1};
-      const float scale = fmaxf(1.f, group_max(fabsf((float)yp)));
-      const float gscale = fmaxf(1.f, group_max(fabsf((float)gt)));
-      const double tol_u = 1e-13 * (double)gscale, tol_s = 1e-10 * (double)scale;
-      // worst violations of this leg
-      double wd_v = -tol_u, wp_v = -tol_s;
-      int wd_r = -1, wp_r = -1;
-#pragma unroll
-      for (int r = 0; r < 5; r++) {
-        if (alive && act[r] && u[r] < wd_v) { wd_v = u[r]; wd_r = r; }
-        if (alive && !act[r] && e[r] < wp_v) { wp_v = e[r]; wp_r = r; }
-      }
-      const bool leg_viol = (wd_r >= 0) || (wp_r >= 0);
-      const bool any_viol = ((__ballot_sync(kFull, leg_viol) >> (16 * grp)) & 0xFFFu) != 0u;
-      // globally worst leg (used after the first passes, prevents cycling); duals before primals
-      const double key = (wd_r >= 0) ? wd_v * 1e6 : ((wp_r >= 0) ? wp_v : 0.0);
-      const double best = leg_min(key);
-      const unsigned tie = (__ballot_sync(kFull, key == best && leg_viol) >> (16 * grp)) & 0xFFFu;
-      // start of the interior-point iteration, should this group need it: strictly feasible point
-      // (every stance leg pushes c along its normal), multipliers centred at the gradient scale
-      const double fn_leg = ws.bw[grp][0] * nb[0] + ws.bw[grp][1] * nb[1] + ws.bw[grp][2] * nb[2];
-      const double c0 = fmax(fmax(2.0 * prm.fmin, fn_leg * (ns > 0 ? 1.0 / ns : 0.0)), prm.fmin + 1.0);
-      const double y0 = (alive && c == 0) ? c0 : 0.0;
-      double gam0 = gt;
-#pragma unroll
-      for (int j = 0; j < kVars; j++) gam0 = fma(ws.grow[j][lane], gshfl(y0, j), gam0);
-      const double gmax = (double)fmaxf(1.f, group_max(var_lane ? fabsf((float)gam0) : 0.f));
-
-      if (mode == kModePolish) {
-        if (!any_viol) {
-          y = yp;
-          mode = kModeDone;
-          if (status == 2) status = 0;  // iteration limit hit but the polish verified the optimum
-        } else {
-          pass++;
-          const bool give_up = first ? (pass > kPdasFirst) : (pass >= kPolishPasses);
-          if (!give_up) {
-            // repair: per leg, drop the most negative multiplier, else add the most violated row;
-            // after the first passes only the globally worst leg moves
-            bool mine = true;
-            if (pass > 2) mine = leg_viol && (tie != 0u) && ((__ffs(tie) - 1) / 3 == leg);
-            if (mine && alive) {
-              if (wd_r >= 0) {
-                if (wd_r == 0) a0 = 0; else if (wd_r <= 2) sg1 = 0; else sg2 = 0;
-              } else if (wp_r >= 0) {
-                if (wp_r == 0) a0 = 1; else if (wp_r == 1) sg1 = -1; else if (wp_r == 2) sg1 = 1; else if (wp_r == 3) sg2 = -1; else sg2 = 1;
-              }
-            }
-          } else if (first) {
-            first = false;
-            mode = kModeIpm;
-            y = y0;
+        for (int j = 0; j < kVars; j++) gam = fma(ws.grow[j][lane], gshfl(vv, j), gam);
+        if (rep == 1) {
+          // interior-point start: multipliers centred at the gradient scale, residuals of the start
+          const double gmax = (double)fmaxf(1.f, group_max(var_lane ? fabsf((float)gam) : 0.f));
+          if (start_ipm) {
             double e0[5];
             d_apply(c0, 0.0, 0.0, mu, e0);
             e0[0] -= prm.fmin;
@@ -559,94 +569,88 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
               const double sr = fmax(e0[r], 1e-3 * c0);  // mu <= 0 would make the friction rows non-positive
               s[r] = alive ? sr : 1.0;
               lam[r] = alive ? gmax * fast_rcp(sr) : 0.0;
+              rp[r] = alive ? sr - e0[r] : 0.0;
             }
-            a0 = 0; sg1 = 0; sg2 = 0;
-          } else if (converged || status == 2) {
-            // interior-point iterate is final but the polish could not certify an active set
+            y = vv;
+            rd = var_lane ? gam - dt_apply(lam, mu, c) : 0.0;
+          }
+          break;
+        }
+        const double yn = gshfl(yp, l0), y1 = gshfl(yp, l0 + 1), y2 = gshfl(yp, l0 + 2);
+        const double gn = gshfl(gam, l0), g1 = gshfl(gam, l0 + 1), g2 = gshfl(gam, l0 + 2);
+        double e[5], u[5];
+        d_apply(yn, y1, y2, mu, e);
+        e[0] -= prm.fmin;
+        u[1] = (sg1 == -1) ? g1 : 0.0;
+        u[2] = (sg1 == 1) ? -g1 : 0.0;
+        u[3] = (sg2 == -1) ? g2 : 0.0;
+        u[4] = (sg2 == 1) ? -g2 : 0.0;
+        u[0] = (a0 != 0) ? gn - mu * ((u[1] + u[2]) + (u[3] + u[4])) : 0.0;
+        const bool act[5] = {a0 != 0, sg1 == -1, sg1 == 1, sg2 == -1, sg2 == 1};
+        const float scale = fmaxf(1.f, group_max(fabsf((float)yp)));
+        const float gscale = fmaxf(1.f, group_max(fabsf((float)gt)));
+        const double tol_u = 1e-13 * (double)gscale, tol_s = 1e-10 * (double)scale;
+        // worst violations of this leg
+        double wd_v = -tol_u, wp_v = -tol_s;
+        int wd_r = -1, wp_r = -1;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          if (alive && act[r] && u[r] < wd_v) { wd_v = u[r]; wd_r = r; }
+          if (alive && !act[r] && e[r] < wp_v) { wp_v = e[r]; wp_r = r; }
+        }
+        const bool leg_viol = (wd_r >= 0) || (wp_r >= 0);
+        const bool any_viol = ((__ballot_sync(kFull, leg_viol) >> (16 * grp)) & 0xFFFu) != 0u;
+        // globally worst leg (used after the first passes, prevents cycling); duals before primals
+        const double key = (wd_r >= 0) ? wd_v * 1e6 : ((wp_r >= 0) ? wp_v : 0.0);
+        const double best = leg_min(key);
+        const unsigned tie = (__ballot_sync(kFull, key == best && leg_viol) >> (16 * grp)) & 0xFFFu;
+
+        if (mode == kModePolish) {
+          if (!any_viol) {
+            y = yp;
             mode = kModeDone;
-            if (status == 0) status = 3;
+            if (status == 2) status = 0;  // iteration limit hit but the polish verified the optimum
           } else {
-            mode = kModeIpm;  // keep iterating, try again later
-            next_polish = it + 1;
+            pass++;
+            const bool give_up = first ? (pass > kPdasFirst) : (pass >= kPolishPasses);
+            if (!give_up) {
+              // repair: per leg, drop the most negative multiplier, else add the most violated row;
+              // after the first passes only the globally worst leg moves
+              bool mine = true;
+              if (pass > 2) mine = leg_viol && (tie != 0u) && ((__ffs(tie) - 1) / 3 == leg);
+              if (mine && alive) {
+                if (wd_r >= 0) {
+                  if (wd_r == 0) a0 = 0; else if (wd_r <= 2) sg1 = 0; else sg2 = 0;
+                } else if (wp_r >= 0) {
+                  if (wp_r == 0) a0 = 1; else if (wp_r == 1) sg1 = -1; else if (wp_r == 2) sg1 = 1; else if (wp_r == 3) sg2 = -1; else sg2 = 1;
+                }
+              }
+            } else if (first) {
+              first = false;
+              mode = kModeIpm;
+              start_ipm = true;
+              a0 = 0; sg1 = 0; sg2 = 0;
+            } else if (converged || status == 2) {
+              // interior-point iterate is final but the polish could not certify an active set
+              mode = kModeDone;
+              if (status == 0) status = 3;
+            } else {
+              mode = kModeIpm;  // keep iterating, try again after the next iteration
+            }
           }
         }
+        if (!__any_sync(kFull, start_ipm)) break;
       }
     }
-
-    // ---- E. second solve of the round: Mehrotra corrector (groups in interior-point mode)
-    if (__any_sync(kFull, ipm_round)) {
-      double dsa[5], dla[5], de[5], v[5];
-      {
-        const double dyn = gshfl(sol, l0), dy1 = gshfl(sol, l0 + 1), dy2 = gshfl(sol, l0 + 2);
-        d_apply(dyn, dy1, dy2, mu, de);
-      }
-      float ratio = 0.f;
-#pragma unroll
-      for (int r = 0; r < 5; r++) {
-        dsa[r] = de[r] * alive_d - rp[r];
-        dla[r] = -fma(lam[r] * rs[r], dsa[r], lam[r]);
-        const float rl = (alive && ipm_round) ? rcp_approx((float)lam[r]) : 0.f;
-        ratio = fmaxf(ratio, fmaxf(-(float)dsa[r] * (float)rs[r], -(float)dla[r] * rl));
-      }
-      ratio = leg_max(ratio);
-      const double ala = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
-      double pa = 0.0;
-#pragma unroll
-      for (int r = 0; r < 5; r++) pa = fma(fma(ala, dsa[r], s[r]), fma(ala, dla[r], lam[r]), pa);
-      const double mua = leg_sum(pa) * rm;
-      const double q3 = ipm_round ? mua / mu_c : 0.0;
-      double sigma = q3 * q3 * q3;
-      if (alpha_prev < 0.1 && sigma < 0.5) sigma = 0.5;  // short step last time: re-centre
-      const double sigmu = sigma * mu_c;
-#pragma unroll
-      for (int r = 0; r < 5; r++) {
-        const double rc = fma(dsa[r], dla[r], s[r] * lam[r]) - sigmu;
-        dsa[r] = rc;  // keep the complementarity right-hand side, the affine steps are no longer needed
-        v[r] = (rc - lam[r] * rp[r]) * rs[r] * alive_d;
-      }
-      const double rhs2 = (var_lane && ipm_round) ? -rd - dt_apply(v, mu, c) : 0.0;
-      const double dy = group_solve(H, rdiag, rhs2, gl);
-      {
-        const double dyn = gshfl(dy, l0), dy1 = gshfl(dy, l0 + 1), dy2 = gshfl(dy, l0 + 2);
-        d_apply(dyn, dy1, dy2, mu, de);
-      }
-      double dl[5];
-      ratio = 0.f;
-#pragma unroll
-      for (int r = 0; r < 5; r++) {
-        de[r] = de[r] * alive_d - rp[r];  // ds
-        dl[r] = -(dsa[r] + lam[r] * de[r]) * rs[r] * alive_d;
-        const float rl = (alive && ipm_round) ? rcp_approx((float)lam[r]) : 0.f;
-        ratio = fmaxf(ratio, fmaxf(-(float)de[r] * (float)rs[r], -(float)dl[r] * rl));
-      }
-      ratio = leg_max(ratio);
-      double al = (ratio > 0.995f) ? 0.995 / (double)ratio : 1.0;
-      // stay inside the neighbourhood min_i s_i lam_i >= gamma * mu (both groups loop together)
-#pragma unroll 1
-      for (int tries = 0; tries < 20; tries++) {
-        double ps = 0.0, pm = 1e300;
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-          const double pr = fma(al, de[r], s[r]) * fma(al, dl[r], lam[r]);
-          ps += pr;
-          pm = fmin(pm, pr);
-        }
-        ps = leg_sum(alive ? ps : 0.0) * rm;
-        pm = leg_min(alive ? pm : 1e300);
-        const bool ok = !ipm_round || (pm >= kNeighbourhood * ps && pm > 0.0);
-        if (__all_sync(kFull, ok)) break;
-        if (!ok) al *= 0.7;
-      }
-      if (ipm_round) {
-        alpha_prev = al;
-        y = fma(al, dy, y);
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-          s[r] = fma(al, de[r], s[r]);
-          lam[r] = fma(al, dl[r], lam[r]);
-        }
-        it++;
-      }
+    // an interior-point group that asked for a polish switches now (its iterate stays untouched)
+    if (mode == kModeIpm && want_polish) {
+      want_polish = false;
+      mode = kModePolish;
+      pass = 0;
+      a0 = lam[0] > s[0];
+      sg1 = (lam[1] > s[1]) ? -1 : ((lam[2] > s[2]) ? 1 : 0);
+      sg2 = (lam[3] > s[3]) ? -1 : ((lam[4] > s[4]) ? 1 : 0);
+      if (!alive) { a0 = 0; sg1 = 0; sg2 = 0; }
     }
   }
 
