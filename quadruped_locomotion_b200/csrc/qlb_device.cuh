@@ -38,6 +38,12 @@ __device__ __forceinline__ float leg_max(float v) {
 __device__ __forceinline__ double leg_min(double v) {
   return fmin(fmin(gshfl(v, 0), gshfl(v, 3)), fmin(gshfl(v, 6), gshfl(v, 9)));
 }
+__device__ __forceinline__ float leg_sum(float v) {
+  return (gshfl(v, 0) + gshfl(v, 3)) + (gshfl(v, 6) + gshfl(v, 9));
+}
+__device__ __forceinline__ float leg_min(float v) {
+  return fminf(fminf(gshfl(v, 0), gshfl(v, 3)), fminf(gshfl(v, 6), gshfl(v, 9)));
+}
 // max over the 16 lanes of a group (butterfly)
 __device__ __forceinline__ float group_max(float v) {
 #pragma unroll
@@ -123,16 +129,73 @@ __device__ __forceinline__ bool group_cholesky(double (&H)[kVars], double& rdiag
   return ok;
 }
 
-// Solve L L^T x = b with the factor layout above; lane gl passes b[gl] and receives x[gl].
-__device__ __forceinline__ double group_solve(const double (&H)[kVars], const double rdiag, const double b,
-                                              const int gl) {
+// Same factorisation with the column broadcast going through shared memory (one 8-byte store per lane,
+// one __syncwarp and a handful of 16-byte broadcast loads per step instead of 2 x (11-k) shuffles) and
+// the forward substitution L z = rhs fused in.  xb = this warp's exchange buffer [2][2][16] (double
+// buffered by step parity, one row per group); lt = this group's 12 x 13 transposition buffer.
+// In: acc = rhs[gl].  Out: acc = z[gl].
+__device__ __forceinline__ bool group_cholesky_fwd(double (&H)[kVars], double& rdiag, double& acc,
+                                                   double (*xb)[2][16], double* lt, const int grp, const int gl) {
+  bool ok = true;
+  rdiag = 1.0;
+#pragma unroll
+  for (int k = 0; k < kVars; k++) {
+    double* buf = xb[k & 1][grp];
+    if (gl >= k && gl < kVars) buf[gl] = H[k];
+    if (gl == k) buf[12] = acc;
+    __syncwarp();
+    double bcol[kVars];
+#pragma unroll
+    for (int p2 = 0; p2 < kVars / 2; p2++) {
+      if (2 * p2 + 1 >= k) {  // 16-byte broadcast loads of the part of the column that is still needed
+        const double2 t = *reinterpret_cast<const double2*>(buf + 2 * p2);
+        bcol[2 * p2] = t.x;
+        bcol[2 * p2 + 1] = t.y;
+      }
+    }
+    const double dkk = bcol[k];
+    const double rk = buf[12];
+    ok = ok && (dkk > 0.0);
+    const double rinv = fast_rsqrt(dkk);
+    const double zk = rk * rinv;
+    const double a = (gl > k) ? -H[k] * (rinv * rinv) : 0.0;  // rows above k are finished
+    if (gl >= k) H[k] *= rinv;                                // L[i][k]
+    if (gl == k) { rdiag = rinv; acc = zk; }
+    if (gl > k) acc = fma(-H[k], zk, acc);
+#pragma unroll
+    for (int j = k + 1; j < kVars; j++) {
+      const double bj = bcol[j];           // raw H[j][k]
+      H[j] = fma(a, bj, H[j]);             // H[i][j] -= H[i][k] H[j][k] / d
+    }
+  }
+  // rows of L^T for the backward substitution: transpose L through shared memory
+  // (row pitch 13 doubles: both the row writes and the column reads are bank-conflict free)
+#pragma unroll
+  for (int j = 0; j < kVars; j++)
+    if (gl < kVars) lt[gl * 13 + j] = H[j];
+  __syncwarp();
+#pragma unroll
+  for (int j = 1; j < kVars; j++)
+    if (gl < j) H[j] = lt[j * 13 + gl];
+  __syncwarp();
+  return ok;
+}
+
+// forward substitution L z = b (shuffles): lane gl passes b[gl], receives z[gl]
+__device__ __forceinline__ double group_forward(const double (&H)[kVars], const double rdiag, const double b,
+                                                const int gl) {
   double acc = b;
 #pragma unroll
   for (int j = 0; j < kVars; j++) {
     const double zj = gshfl(acc * rdiag, j);
     if (gl > j) acc = fma(-H[j], zj, acc);
   }
-  acc *= rdiag;
+  return acc * rdiag;
+}
+// backward substitution L^T x = z (shuffles)
+__device__ __forceinline__ double group_backward(const double (&H)[kVars], const double rdiag, const double z,
+                                                 const int gl) {
+  double acc = z;
 #pragma unroll
   for (int j = kVars - 1; j >= 0; j--) {
     const double xj = gshfl(acc * rdiag, j);

@@ -12,7 +12,7 @@
 
 namespace qlb {
 
-constexpr int kBatch = 16;        // QPs staged per warp batch (one 128-byte line per component row)
+constexpr int kBatch = 8;         // QPs staged per warp batch (64 bytes = two sectors per component row)
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = 32 * kWarpsPerCta;
 
@@ -62,6 +62,9 @@ struct alignas(16) WarpSmem {
   double grow[kVars][32];    // row of G~ of every lane (lane-minor: conflict-free)
   double tail[7][32];        // per lane: slot direction e (3), Jacobian column (3), gravity torque
   double bw[2][6];           // per group: the wrench b
+  double xb[2][2][16];       // exchange buffer of the factorisation (double buffered, one row per group)
+  double vb[2][2][16];       // vector exchange: [which][group][slot]
+  double lt[2][kVars * 13];  // per group: transposition buffer for the rows of L^T
   uint32_t flags[kBatch];
   uint8_t mask[kBatch];
 };
@@ -439,30 +442,32 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
       rhs = 0.0;
     }
 
-    // ---- C. factorise (both groups, converged)
-    double rdiag;
-    const bool pd = group_cholesky(H, rdiag, gl);
+    // ---- C. factorise; the forward substitution of this round's first right-hand side is fused in
+    double rdiag, zf = rhs;
+    const bool pd = group_cholesky_fwd(H, rdiag, zf, ws.xb, ws.lt[grp], grp, gl);
     if (!pd && mode != kModeDone) { mode = kModeDone; status = 4; y = 0.0; }
 
     // ---- S. substitutions: phase 0 = polish solution / Mehrotra predictor, phase 1 = corrector
     const bool any_ipm = __any_sync(kFull, mode == kModeIpm);
     const bool ipm_round = (mode == kModeIpm);
-    double sol = 0.0, rcv[5], sigmu = 0.0, mu_c = 0.0;
+    double sol = 0.0, rcv[5];
 #pragma unroll
     for (int r = 0; r < 5; r++) rcv[r] = 0.0;
 #pragma unroll 1
     for (int ph = 0; ph < (any_ipm ? 2 : 1); ph++) {
-      const double x = group_solve(H, rdiag, rhs, gl);
+      if (ph == 1) zf = group_forward(H, rdiag, rhs, gl);
+      const double x = group_backward(H, rdiag, zf, gl);
       if (ph == 0) sol = x;
-      double de[5];
-      {
-        const double dyn = gshfl(x, l0), dy1 = gshfl(x, l0 + 1), dy2 = gshfl(x, l0 + 2);
-        d_apply(dyn, dy1, dy2, mu, de);
-      }
-      // step of the five rows of this leg for the direction x: ds = D~ dy - rp, dl = -(rc + lam ds)/s
+      if (!any_ipm) break;
+      // direction of the five rows of this leg: ds = D~ dy - rp, dl = -(rc + lam ds)/s
       // (phase 0: rc = s lam, phase 1: rc = s lam + dsa dla - sigma mu)
-      double ds[5], dl[5], pa = 0.0;
-      float ratio = 0.f;
+      if (var_lane) ws.vb[0][grp][gl] = x;
+      __syncwarp();
+      double de[5];
+      d_apply(ws.vb[0][grp][l0], ws.vb[0][grp][l0 + 1], ws.vb[0][grp][l0 + 2], mu, de);
+      __syncwarp();
+      double ds[5], dl[5];
+      float ratio = 0.f, pa = 0.f;
 #pragma unroll
       for (int r = 0; r < 5; r++) {
         ds[r] = de[r] * alive_d - rp[r];
@@ -470,21 +475,21 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
         dl[r] = -fma(lam[r], ds[r], rc) * rs[r] * alive_d;
         const float rl = (alive && ipm_round) ? rcp_approx((float)lam[r]) : 0.f;
         ratio = fmaxf(ratio, fmaxf(-(float)ds[r] * (float)rs[r], -(float)dl[r] * rl));
-        pa = fma(s[r], lam[r], pa);
+        pa += (float)(s[r] * lam[r]);
       }
       ratio = leg_max(ipm_round ? ratio : 0.f);
       if (ph == 0) {
         // affine step length, centring parameter, corrector right-hand side
-        mu_c = leg_sum(ipm_round ? pa : 0.0) * rm;
+        const float mu_c = leg_sum(ipm_round ? pa : 0.f) * (float)rm;
         const double ala = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
-        double pb = 0.0;
+        float pb = 0.f;
 #pragma unroll
-        for (int r = 0; r < 5; r++) pb = fma(fma(ala, ds[r], s[r]), fma(ala, dl[r], lam[r]), pb);
-        const double mua = leg_sum(ipm_round ? pb : 0.0) * rm;
-        const double q3 = (ipm_round && mu_c > 0.0) ? mua / mu_c : 0.0;
-        double sigma = q3 * q3 * q3;
-        if (alpha_prev < 0.1 && sigma < 0.5) sigma = 0.5;  // short step last time: re-centre
-        sigmu = sigma * mu_c;
+        for (int r = 0; r < 5; r++) pb += (float)(fma(ala, ds[r], s[r]) * fma(ala, dl[r], lam[r]));
+        const float mua = leg_sum(ipm_round ? pb : 0.f) * (float)rm;
+        const float q3 = (ipm_round && mu_c > 0.f) ? mua / mu_c : 0.f;
+        float sigma = q3 * q3 * q3;
+        if (alpha_prev < 0.1 && sigma < 0.5f) sigma = 0.5f;  // short step last time: re-centre
+        const double sigmu = (double)sigma * (double)mu_c;
         double v[5];
 #pragma unroll
         for (int r = 0; r < 5; r++) {
@@ -497,28 +502,28 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
         // stay inside the neighbourhood min_i s_i lam_i >= gamma * mu (both groups loop together)
 #pragma unroll 1
         for (int tries = 0; tries < 20; tries++) {
-          double ps = 0.0, pm = 1e300;
+          float ps = 0.f, pm = 3e38f;
 #pragma unroll
           for (int r = 0; r < 5; r++) {
-            const double pr = fma(al, ds[r], s[r]) * fma(al, dl[r], lam[r]);
+            const float pr = (float)(fma(al, ds[r], s[r]) * fma(al, dl[r], lam[r]));
             ps += pr;
-            pm = fmin(pm, pr);
+            pm = fminf(pm, pr);
           }
-          ps = leg_sum(alive ? ps : 0.0) * rm;
-          pm = leg_min(alive ? pm : 1e300);
-          const bool ok = !ipm_round || (pm >= kNeighbourhood * ps && pm > 0.0);
+          ps = leg_sum(alive ? ps : 0.f) * (float)rm;
+          pm = leg_min(alive ? pm : 3e38f);
+          const bool ok = !ipm_round || (pm >= (float)kNeighbourhood * ps && pm > 0.f);
           if (__all_sync(kFull, ok)) break;
           if (!ok) al *= 0.7;
         }
         // take the step; the residuals follow without a mat-vec:
         //   G~ dy = rhs - D~' diag(lam/s) D~ dy   =>   rd += al (rhs - D~'(theta .* de + dl)),   rp *= (1 - al)
-        double w5[5], pn = 0.0;
-        float nrp = 0.f;
+        double w5[5];
+        float nrp = 0.f, pn = 0.f;
 #pragma unroll
         for (int r = 0; r < 5; r++) {
           w5[r] = fma(lam[r] * rs[r], de[r] * alive_d, dl[r]);
           const double sn = fma(al, ds[r], s[r]), ln = fma(al, dl[r], lam[r]);
-          pn = fma(sn, ln, pn);
+          pn += (float)(sn * ln);
           if (ipm_round) { s[r] = sn; lam[r] = ln; rp[r] *= (1.0 - al); }
           nrp = fmaxf(nrp, fabsf((float)rp[r]));
         }
@@ -529,14 +534,15 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
           it++;
         }
         // convergence test and decision to polish, on the new iterate
-        const double mu_n = leg_sum(ipm_round ? pn : 0.0) * rm;
+        const float mu_n = leg_sum(ipm_round ? pn : 0.f) * (float)rm;
         const float nrd = group_max((var_lane && ipm_round) ? fabsf((float)rd) : 0.f);
         nrp = leg_max(ipm_round ? nrp : 0.f);
         const float scale = fmaxf(1.f, group_max(fabsf((float)y)));
         if (ipm_round) {
-          converged = (mu_n <= prm.tol * scale) && (nrp <= (float)prm.tol * scale) && (nrd <= 100.f * (float)prm.tol * scale);
+          const float tolf = (float)prm.tol * scale;
+          converged = (mu_n <= tolf) && (nrp <= tolf) && (nrd <= 100.f * tolf);
           const bool out_of_iters = it >= prm.max_iter;
-          want_polish = converged || out_of_iters || (it >= 2 && mu_n <= 1e-3 * scale);
+          want_polish = converged || out_of_iters || (it >= 2 && mu_n <= 1e-3f * scale);
           if (out_of_iters && !converged) status = 2;
         }
       }
@@ -546,7 +552,10 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
     //         One mat-vec site: pass 0 multiplies the polished point, pass 1 (only when a group starts
     //         its interior-point iteration) the strictly feasible start.
     if (any_pol) {
-      const double zn = gshfl(sol, l0);
+      if (var_lane) ws.vb[0][grp][gl] = sol;
+      __syncwarp();
+      const double zn = ws.vb[0][grp][l0];
+      __syncwarp();
       const double ynp = (a0 != 0) ? prm.fmin : zn;
       double yp = (c == 0) ? ynp : (c == 1 ? (sg1 != 0 ? sg1 * mu * ynp : sol) : (sg2 != 0 ? sg2 * mu * ynp : sol));
       if (!alive) yp = 0.0;
@@ -554,12 +563,17 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
 #pragma unroll 1
       for (int rep = 0; rep < 2; rep++) {
         const double vv = (rep == 0) ? yp : ((alive && c == 0) ? c0 : 0.0);
+        if (var_lane) ws.vb[0][grp][gl] = vv;
+        __syncwarp();
         double gam = gt;
 #pragma unroll
-        for (int j = 0; j < kVars; j++) gam = fma(ws.grow[j][lane], gshfl(vv, j), gam);
+        for (int j = 0; j < kVars; j++) gam = fma(ws.grow[j][lane], ws.vb[0][grp][j], gam);
+        if (var_lane) ws.vb[1][grp][gl] = gam;
+        const float gmaxf = group_max(var_lane ? fabsf((float)gam) : 0.f);
+        __syncwarp();
         if (rep == 1) {
           // interior-point start: multipliers centred at the gradient scale, residuals of the start
-          const double gmax = (double)fmaxf(1.f, group_max(var_lane ? fabsf((float)gam) : 0.f));
+          const double gmax = (double)fmaxf(1.f, gmaxf);
           if (start_ipm) {
             double e0[5];
             d_apply(c0, 0.0, 0.0, mu, e0);
@@ -576,8 +590,8 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
           }
           break;
         }
-        const double yn = gshfl(yp, l0), y1 = gshfl(yp, l0 + 1), y2 = gshfl(yp, l0 + 2);
-        const double gn = gshfl(gam, l0), g1 = gshfl(gam, l0 + 1), g2 = gshfl(gam, l0 + 2);
+        const double yn = ws.vb[0][grp][l0], y1 = ws.vb[0][grp][l0 + 1], y2 = ws.vb[0][grp][l0 + 2];
+        const double gn = ws.vb[1][grp][l0], g1 = ws.vb[1][grp][l0 + 1], g2 = ws.vb[1][grp][l0 + 2];
         double e[5], u[5];
         d_apply(yn, y1, y2, mu, e);
         e[0] -= prm.fmin;
