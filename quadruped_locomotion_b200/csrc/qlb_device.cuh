@@ -204,6 +204,76 @@ __device__ __forceinline__ double group_backward(const double (&H)[kVars], const
   return acc * rdiag;
 }
 
+// ---------------------------------------------------------------- rolled variants, matrix in shared memory
+// The unrolled register-resident routines above are ~1.5k instructions per round; with a dozen warps
+// per SM at different program counters the kernel then streams its instructions from L2 (ncu:
+// stall_no_instruction > 50 % of all samples, profiles/r1_v4_ncu_summary.txt).  These versions keep row
+// gl of the matrix in shared memory, hs[j * kPitch + lane] = entry (gl, j), and are plain loops: a few
+// dozen instructions that stay in the instruction cache.  kPitch = 33 makes both the row accesses
+// (lane varies) and the transposed accesses of the backward substitution bank-conflict free.
+constexpr int kPitch = 33;
+
+// Cholesky with the forward substitution of one right-hand side fused in.
+// In: acc = rhs[gl].  Out: hs = L (entry (gl, j), j <= gl), rdiag = 1/L[gl][gl], acc = z[gl] with L z = rhs.
+__device__ __forceinline__ bool smem_cholesky_fwd(double* __restrict__ hs, double (*xb)[2][16], double& rdiag,
+                                                  double& acc, const int grp, const int gl, const int lane) {
+  bool ok = true;
+  rdiag = 1.0;
+#pragma unroll 1
+  for (int k = 0; k < kVars; k++) {
+    double* buf = xb[k & 1][grp];
+    const double hk = hs[k * kPitch + lane];
+    if (gl >= k && gl < kVars) buf[gl] = hk;   // publish the raw column k
+    if (gl == k) buf[12] = acc;                // and the pivot row's right-hand side
+    __syncwarp();
+    const double dkk = buf[k];
+    const double rk = buf[12];
+    ok = ok && (dkk > 0.0);
+    const double rinv = fast_rsqrt(dkk);
+    const double zk = rk * rinv;
+    const double lik = hk * rinv;
+    const double a = (gl > k) ? -lik * rinv : 0.0;  // finished rows: multiplier 0
+    if (gl >= k) hs[k * kPitch + lane] = lik;
+    if (gl == k) { rdiag = rinv; acc = zk; }
+    if (gl > k) acc = fma(-lik, zk, acc);
+#pragma unroll 4
+    for (int j = k + 1; j < kVars; j++) hs[j * kPitch + lane] = fma(a, buf[j], hs[j * kPitch + lane]);
+  }
+  return ok;
+}
+
+// forward substitution L z = b: lane gl passes b[gl], receives z[gl]
+__device__ __forceinline__ double smem_forward(const double* __restrict__ hs, double (*xb)[2][16], const double rdiag,
+                                               const double b, const int grp, const int gl, const int lane) {
+  double acc = b, z = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < kVars; j++) {
+    double* buf = xb[j & 1][grp];
+    if (gl == j) buf[13] = acc * rdiag;
+    __syncwarp();
+    const double zj = buf[13];
+    if (gl == j) z = zj;
+    if (gl > j) acc = fma(-hs[j * kPitch + lane], zj, acc);
+  }
+  return z;
+}
+
+// backward substitution L^T x = z; L[j][gl] is read transposed from row j's lane
+__device__ __forceinline__ double smem_backward(const double* __restrict__ hs, double (*xb)[2][16], const double rdiag,
+                                                const double z, const int grp, const int gl) {
+  double acc = z, x = 0.0;
+#pragma unroll 1
+  for (int j = kVars - 1; j >= 0; j--) {
+    double* buf = xb[j & 1][grp];
+    if (gl == j) buf[13] = acc * rdiag;
+    __syncwarp();
+    const double xj = buf[13];
+    if (gl == j) x = xj;
+    if (gl < j) acc = fma(-hs[gl * kPitch + 16 * grp + j], xj, acc);
+  }
+  return x;
+}
+
 // ---------------------------------------------------------------- model / parameters in device memory
 struct DeviceModel {
   double rot[4][4][9];   // [leg][joint] rotation of <origin rpy>, row-major

@@ -64,7 +64,7 @@ struct alignas(16) WarpSmem {
   double bw[2][6];           // per group: the wrench b
   double xb[2][2][16];       // exchange buffer of the factorisation (double buffered, one row per group)
   double vb[2][2][16];       // vector exchange: [which][group][slot]
-  double lt[2][kVars * 13];  // per group: transposition buffer for the rows of L^T
+  double hs[kVars * kPitch]; // the round's matrix / its Cholesky factor, one row per lane
   uint32_t flags[kBatch];
   uint8_t mask[kBatch];
 };
@@ -112,15 +112,31 @@ __device__ __forceinline__ void stage_out(double* __restrict__ dst, const double
   }
 }
 
-// D~^T v for the five rows of a leg, component c of the leg's triple
-__device__ __forceinline__ double dt_apply(const double (&v)[5], double mu, int c) {
-  const double n = fma(mu, (v[1] + v[2]) + (v[3] + v[4]), v[0]);
-  return c == 0 ? n : (c == 1 ? v[1] - v[2] : v[3] - v[4]);
+// The five rows of a leg are spread over its three lanes: the lane of the normal component (c = 0)
+// owns row 0 (y_n >= F_min), the lane of y_1 owns rows 1, 2 (mu y_n +- y_1 >= 0), the lane of y_2 rows
+// 3, 4.  Every lane therefore carries at most two rows, "A" and "B" (B is void on the normal lane).
+//
+// D~ x restricted to this lane's rows: xn = the leg's normal component, x = this lane's component
+__device__ __forceinline__ void rows_apply(double xn, double x, double mu, int c, double& eA, double& eB) {
+  const double m = mu * xn;
+  eA = (c == 0) ? xn : m + x;
+  eB = m - x;
 }
-// D~ y for a leg
-__device__ __forceinline__ void d_apply(double yn, double y1, double y2, double mu, double (&e)[5]) {
-  const double m = mu * yn;
-  e[0] = yn; e[1] = m + y1; e[2] = m - y1; e[3] = m + y2; e[4] = m - y2;
+// (D~' v)_lane: the normal lane needs the sums vA + vB of its two leg-mates (full-warp shuffles)
+__device__ __forceinline__ double dt_lane(double vA, double vB, double mu, int c, int l0) {
+  const double sv = vA + vB;
+  const double S = gshfl(sv, l0 + 1) + gshfl(sv, l0 + 2);
+  return (c == 0) ? fma(mu, S, vA) : vA - vB;
+}
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) v += __shfl_xor_sync(kFull, v, o, kGroup);
+  return v;
+}
+__device__ __forceinline__ float group_min(float v) {
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) v = fminf(v, __shfl_xor_sync(kFull, v, o, kGroup));
+  return v;
 }
 
 // kindr logarithmic map of (q_t^-1 * q): see VirtualModelController.cpp:120,124
@@ -348,20 +364,20 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
                          prm.fmin + 1.0);
   __syncwarp();
 
-  double H[kVars];
-  double gt = 0.0;             // g~ of this slot
-  double y = 0.0;              // interior-point iterate / final solution of this slot
-  double rd = 0.0;             // dual residual of this slot, kept up to date incrementally
-  double s[5], lam[5], rp[5];  // slacks, multipliers, primal residual of this leg's five rows
-  int a0 = 0, sg1 = 0, sg2 = 0;  // active pattern of this leg: y_n pinned; y_1 = sg1*mu*y_n; y_2 = sg2*mu*y_n
+  double* const hs = ws.hs;
+  const bool rowB = alive && c > 0;  // this lane owns a second row
+  double gt = 0.0;                   // g~ of this slot
+  double y = 0.0;                    // interior-point iterate / final solution of this slot
+  double rd = 0.0;                   // dual residual of this slot, kept up to date incrementally
+  double sA = 1.0, sB = 1.0, lamA = 0.0, lamB = 0.0, rpA = 0.0, rpB = 0.0;  // slack, multiplier, primal residual
+  int pat = 0;  // active pattern of this lane's rows: normal lane 1 = pinned at F_min; tangential lanes
+                // -1 = row A active (y_c = -mu y_n), +1 = row B active (y_c = +mu y_n)
   int mode = kModePolish, it = 0, pass = 0, status = 0;
   bool first = true, converged = false, have_G = false, want_polish = false;
   double alpha_prev = 1.0;
-#pragma unroll
-  for (int r = 0; r < 5; r++) { s[r] = 1.0; lam[r] = 0.0; rp[r] = 0.0; }
   if (badbits != 0u) { mode = kModeDone; status = 4; }
   else if (ns == 0) { mode = kModeDone; status = 1; }
-  const double rm = ns > 0 ? 1.0 / (5.0 * ns) : 0.0;
+  const float rm = ns > 0 ? 1.f / (5.f * ns) : 0.f;
 
   // ---------------- rounds: one factorisation + one or two substitutions, shared by both groups
   int rounds = 0;
@@ -369,22 +385,21 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
   for (;;) {
     if (__all_sync(kFull, mode == kModeDone)) break;
     if (++rounds > 200 && mode != kModeDone) { mode = kModeDone; status = 2; }  // hard stop, never reached in practice
-    double rhs = 0.0, rs[5];
-#pragma unroll
-    for (int r = 0; r < 5; r++) rs[r] = 1.0;
+    double rhs = 0.0, rsA = 1.0, rsB = 1.0;
 
     // ---- B. system of this round
     const bool any_pol = __any_sync(kFull, mode == kModePolish);
     if (any_pol) {
       // reduced system of the equality-constrained QP for the current pattern
+      const int p1 = gshfl(pat, l0 + 1), p2 = gshfl(pat, l0 + 2);
       double mycol[6];
-      const bool free_slot = alive && ((c == 0) ? (a0 == 0) : (c == 1 ? (sg1 == 0) : (sg2 == 0)));
+      const bool free_slot = alive && (pat == 0);
       if (mode == kModePolish) {
         const double* an = ws.atl[grp][l0];
         const double* a1 = ws.atl[grp][l0 + 1];
         const double* a2 = ws.atl[grp][l0 + 2];
-        const double k1 = sg1 * mu, k2 = sg2 * mu;
-        const double f = (a0 != 0 && alive) ? prm.fmin : 0.0;
+        const double k1 = p1 * mu, k2 = p2 * mu;
+        const double f = (c == 0 && pat != 0 && alive) ? prm.fmin : 0.0;
 #pragma unroll
         for (int r = 0; r < 6; r++) {
           const double cn = fma(k2, a2[r], fma(k1, a1[r], an[r]));
@@ -396,7 +411,7 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
       }
       __syncwarp();
       if (mode == kModePolish) {
-        const double wd = free_slot ? ((c == 0) ? prm.W * fma(mu * mu, (double)(sg1 * sg1 + sg2 * sg2), 1.0) : prm.W) : 1.0;
+        const double wd = free_slot ? ((c == 0) ? prm.W * fma(mu * mu, (double)(p1 * p1 + p2 * p2), 1.0) : prm.W) : 1.0;
         double sc[6];
         rhs = 0.0;
 #pragma unroll
@@ -405,138 +420,123 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
           sc[r] = prm.S[r] * mycol[r];
           rhs = fma(sc[r], bp, rhs);
         }
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < kVars; j++) {
           const double* cj = ws.col[grp][j];
-          double acc = 0.0;
+          double acc = (j == gl) ? wd : 0.0;
 #pragma unroll
           for (int r = 0; r < 6; r++) acc = fma(sc[r], cj[r], acc);
-          H[j] = acc + ((j == gl) ? wd : 0.0);
+          hs[j * kPitch + lane] = acc;
+          if (!have_G) ws.grow[j][lane] = acc;  // first pass (empty pattern): this is G~
         }
-        if (!have_G) {  // first pass (empty pattern): this is G~ and -g~
-#pragma unroll
-          for (int j = 0; j < kVars; j++) ws.grow[j][lane] = H[j];
-          gt = -rhs;
+        if (!have_G) {
+          gt = -rhs;                            // and -g~
           have_G = true;
         }
       }
       __syncwarp();
     }
-    if (mode == kModeIpm) {
-      // H = G~ + D~' diag(lam/s) D~ (3x3 block on the diagonal), predictor right-hand side
-      double th[5], v[5];
-#pragma unroll
-      for (int r = 0; r < 5; r++) { rs[r] = fast_rcp(s[r]); th[r] = lam[r] * rs[r]; v[r] = fma(-th[r], rp[r], lam[r]); }
-      const double t12 = th[1] + th[2], t34 = th[3] + th[4];
-      const double d12 = mu * (th[1] - th[2]), d34 = mu * (th[3] - th[4]);
-      double blk[3];
-      blk[0] = (c == 0) ? fma(mu * mu, t12 + t34, th[0]) : (c == 1 ? d12 : d34);
-      blk[1] = (c == 0) ? d12 : (c == 1 ? t12 : 0.0);
-      blk[2] = (c == 0) ? d34 : (c == 1 ? 0.0 : t34);
-#pragma unroll
-      for (int j = 0; j < kVars; j++) H[j] = ws.grow[j][lane] + ((j / 3 == leg && var_lane) ? blk[j % 3] : 0.0);
-      rhs = var_lane ? -rd - dt_apply(v, mu, c) : 0.0;
-    } else if (mode == kModeDone) {
-#pragma unroll
-      for (int j = 0; j < kVars; j++) H[j] = (j == gl) ? 1.0 : 0.0;
+    const bool any_ipm = __any_sync(kFull, mode == kModeIpm);
+    const bool ipm_round = (mode == kModeIpm);
+    if (any_ipm) {
+      // H = G~ + D~' diag(lam/s) D~ (3x3 block on the diagonal of each leg), predictor right-hand side
+      rsA = fast_rcp(sA); rsB = fast_rcp(sB);
+      const double thA = lamA * rsA, thB = lamB * rsB;
+      const double T = thA + thB, Dl = thA - thB;
+      const double T1 = gshfl(T, l0 + 1), D1 = gshfl(Dl, l0 + 1), T2 = gshfl(T, l0 + 2), D2 = gshfl(Dl, l0 + 2);
+      const double dtv = dt_lane(fma(-thA, rpA, lamA), fma(-thB, rpB, lamB), mu, c, l0);
+      if (ipm_round) {
+        double blk0, blk1, blk2;
+        if (c == 0) { blk0 = fma(mu * mu, T1 + T2, thA); blk1 = mu * D1; blk2 = mu * D2; }
+        else if (c == 1) { blk0 = mu * Dl; blk1 = T; blk2 = 0.0; }
+        else { blk0 = mu * Dl; blk1 = 0.0; blk2 = T; }
+#pragma unroll 1
+        for (int j = 0; j < kVars; j++) {
+          const int o = j - l0;
+          const double add = (var_lane && o >= 0 && o < 3) ? (o == 0 ? blk0 : (o == 1 ? blk1 : blk2)) : 0.0;
+          hs[j * kPitch + lane] = ws.grow[j][lane] + add;
+        }
+        rhs = var_lane ? -rd - dtv : 0.0;
+      }
+    }
+    if (mode == kModeDone) {
+#pragma unroll 1
+      for (int j = 0; j < kVars; j++) hs[j * kPitch + lane] = (j == gl) ? 1.0 : 0.0;
       rhs = 0.0;
     }
 
     // ---- C. factorise; the forward substitution of this round's first right-hand side is fused in
     double rdiag, zf = rhs;
-    const bool pd = group_cholesky_fwd(H, rdiag, zf, ws.xb, ws.lt[grp], grp, gl);
+    const bool pd = smem_cholesky_fwd(hs, ws.xb, rdiag, zf, grp, gl, lane);
     if (!pd && mode != kModeDone) { mode = kModeDone; status = 4; y = 0.0; }
 
     // ---- S. substitutions: phase 0 = polish solution / Mehrotra predictor, phase 1 = corrector
-    const bool any_ipm = __any_sync(kFull, mode == kModeIpm);
-    const bool ipm_round = (mode == kModeIpm);
-    double sol = 0.0, rcv[5];
-#pragma unroll
-    for (int r = 0; r < 5; r++) rcv[r] = 0.0;
+    double sol = 0.0, rcA = 0.0, rcB = 0.0;
 #pragma unroll 1
     for (int ph = 0; ph < (any_ipm ? 2 : 1); ph++) {
-      if (ph == 1) zf = group_forward(H, rdiag, rhs, gl);
-      const double x = group_backward(H, rdiag, zf, gl);
+      if (ph == 1) zf = smem_forward(hs, ws.xb, rdiag, rhs, grp, gl, lane);
+      const double x = smem_backward(hs, ws.xb, rdiag, zf, grp, gl);
       if (ph == 0) sol = x;
       if (!any_ipm) break;
-      // direction of the five rows of this leg: ds = D~ dy - rp, dl = -(rc + lam ds)/s
+      // direction of this lane's rows: ds = D~ dy - rp, dl = -(rc + lam ds)/s
       // (phase 0: rc = s lam, phase 1: rc = s lam + dsa dla - sigma mu)
-      if (var_lane) ws.vb[0][grp][gl] = x;
-      __syncwarp();
-      double de[5];
-      d_apply(ws.vb[0][grp][l0], ws.vb[0][grp][l0 + 1], ws.vb[0][grp][l0 + 2], mu, de);
-      __syncwarp();
-      double ds[5], dl[5];
-      float ratio = 0.f, pa = 0.f;
-#pragma unroll
-      for (int r = 0; r < 5; r++) {
-        ds[r] = de[r] * alive_d - rp[r];
-        const double rc = (ph == 0) ? s[r] * lam[r] : rcv[r];
-        dl[r] = -fma(lam[r], ds[r], rc) * rs[r] * alive_d;
-        const float rl = (alive && ipm_round) ? rcp_approx((float)lam[r]) : 0.f;
-        ratio = fmaxf(ratio, fmaxf(-(float)ds[r] * (float)rs[r], -(float)dl[r] * rl));
-        pa += (float)(s[r] * lam[r]);
+      double deA, deB;
+      rows_apply(gshfl(x, l0), x, mu, c, deA, deB);
+      if (!alive) deA = 0.0;
+      if (!rowB) deB = 0.0;
+      const double dsA = deA - rpA, dsB = deB - rpB;
+      const double dlA = alive ? -fma(lamA, dsA, (ph == 0) ? sA * lamA : rcA) * rsA : 0.0;
+      const double dlB = rowB ? -fma(lamB, dsB, (ph == 0) ? sB * lamB : rcB) * rsB : 0.0;
+      float ratio = 0.f;
+      if (ipm_round && alive) {
+        ratio = fmaxf(-(float)dsA * (float)rsA, -(float)dlA * rcp_approx((float)lamA));
+        if (rowB) ratio = fmaxf(ratio, fmaxf(-(float)dsB * (float)rsB, -(float)dlB * rcp_approx((float)lamB)));
+        ratio = fmaxf(ratio, 0.f);
       }
-      ratio = leg_max(ipm_round ? ratio : 0.f);
+      ratio = group_max(ratio);
       if (ph == 0) {
         // affine step length, centring parameter, corrector right-hand side
-        const float mu_c = leg_sum(ipm_round ? pa : 0.f) * (float)rm;
+        const float pa = ipm_round ? (float)(sA * lamA) + (float)(sB * lamB) : 0.f;
         const double ala = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
-        float pb = 0.f;
-#pragma unroll
-        for (int r = 0; r < 5; r++) pb += (float)(fma(ala, ds[r], s[r]) * fma(ala, dl[r], lam[r]));
-        const float mua = leg_sum(ipm_round ? pb : 0.f) * (float)rm;
+        const float pb = ipm_round ? (float)(fma(ala, dsA, sA) * fma(ala, dlA, lamA)) + (float)(fma(ala, dsB, sB) * fma(ala, dlB, lamB)) : 0.f;
+        const float mu_c = group_sum(pa) * rm;
+        const float mua = group_sum(pb) * rm;
         const float q3 = (ipm_round && mu_c > 0.f) ? mua / mu_c : 0.f;
         float sigma = q3 * q3 * q3;
         if (alpha_prev < 0.1 && sigma < 0.5f) sigma = 0.5f;  // short step last time: re-centre
         const double sigmu = (double)sigma * (double)mu_c;
-        double v[5];
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-          rcv[r] = fma(ds[r], dl[r], s[r] * lam[r]) - sigmu;
-          v[r] = (rcv[r] - lam[r] * rp[r]) * rs[r] * alive_d;
-        }
-        rhs = (var_lane && ipm_round) ? -rd - dt_apply(v, mu, c) : 0.0;
+        rcA = alive ? fma(dsA, dlA, sA * lamA) - sigmu : 0.0;
+        rcB = rowB ? fma(dsB, dlB, sB * lamB) - sigmu : 0.0;
+        const double dtv = dt_lane((rcA - lamA * rpA) * rsA, (rcB - lamB * rpB) * rsB, mu, c, l0);
+        rhs = (var_lane && ipm_round) ? -rd - dtv : 0.0;
       } else {
         double al = (ratio > 0.995f) ? 0.995 / (double)ratio : 1.0;
         // stay inside the neighbourhood min_i s_i lam_i >= gamma * mu (both groups loop together)
 #pragma unroll 1
         for (int tries = 0; tries < 20; tries++) {
-          float ps = 0.f, pm = 3e38f;
-#pragma unroll
-          for (int r = 0; r < 5; r++) {
-            const float pr = (float)(fma(al, ds[r], s[r]) * fma(al, dl[r], lam[r]));
-            ps += pr;
-            pm = fminf(pm, pr);
-          }
-          ps = leg_sum(alive ? ps : 0.f) * (float)rm;
-          pm = leg_min(alive ? pm : 3e38f);
+          const float prA = alive ? (float)(fma(al, dsA, sA) * fma(al, dlA, lamA)) : 0.f;
+          const float prB = rowB ? (float)(fma(al, dsB, sB) * fma(al, dlB, lamB)) : 0.f;
+          const float ps = group_sum(prA + prB) * rm;
+          const float pm = group_min(fminf(alive ? prA : 3e38f, rowB ? prB : 3e38f));
           const bool ok = !ipm_round || (pm >= (float)kNeighbourhood * ps && pm > 0.f);
           if (__all_sync(kFull, ok)) break;
           if (!ok) al *= 0.7;
         }
         // take the step; the residuals follow without a mat-vec:
         //   G~ dy = rhs - D~' diag(lam/s) D~ dy   =>   rd += al (rhs - D~'(theta .* de + dl)),   rp *= (1 - al)
-        double w5[5];
-        float nrp = 0.f, pn = 0.f;
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-          w5[r] = fma(lam[r] * rs[r], de[r] * alive_d, dl[r]);
-          const double sn = fma(al, ds[r], s[r]), ln = fma(al, dl[r], lam[r]);
-          pn += (float)(sn * ln);
-          if (ipm_round) { s[r] = sn; lam[r] = ln; rp[r] *= (1.0 - al); }
-          nrp = fmaxf(nrp, fabsf((float)rp[r]));
-        }
+        const double dtw = dt_lane(fma(lamA * rsA, deA, dlA), fma(lamB * rsB, deB, dlB), mu, c, l0);
         if (ipm_round) {
-          rd = fma(al, rhs - dt_apply(w5, mu, c), rd);
+          sA = fma(al, dsA, sA); lamA = fma(al, dlA, lamA); rpA *= (1.0 - al);
+          sB = fma(al, dsB, sB); lamB = fma(al, dlB, lamB); rpB *= (1.0 - al);
+          rd = fma(al, rhs - dtw, rd);
           y = fma(al, x, y);
           alpha_prev = al;
           it++;
         }
         // convergence test and decision to polish, on the new iterate
-        const float mu_n = leg_sum(ipm_round ? pn : 0.f) * (float)rm;
+        const float mu_n = group_sum(ipm_round ? (float)(sA * lamA) + (float)(sB * lamB) : 0.f) * rm;
         const float nrd = group_max((var_lane && ipm_round) ? fabsf((float)rd) : 0.f);
-        nrp = leg_max(ipm_round ? nrp : 0.f);
+        const float nrp = group_max(ipm_round ? fmaxf(fabsf((float)rpA), fabsf((float)rpB)) : 0.f);
         const float scale = fmaxf(1.f, group_max(fabsf((float)y)));
         if (ipm_round) {
           const float tolf = (float)prm.tol * scale;
@@ -552,12 +552,10 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
     //         One mat-vec site: pass 0 multiplies the polished point, pass 1 (only when a group starts
     //         its interior-point iteration) the strictly feasible start.
     if (any_pol) {
-      if (var_lane) ws.vb[0][grp][gl] = sol;
-      __syncwarp();
-      const double zn = ws.vb[0][grp][l0];
-      __syncwarp();
-      const double ynp = (a0 != 0) ? prm.fmin : zn;
-      double yp = (c == 0) ? ynp : (c == 1 ? (sg1 != 0 ? sg1 * mu * ynp : sol) : (sg2 != 0 ? sg2 * mu * ynp : sol));
+      // y of the polished point: pinned / tied components follow from the leg's normal component
+      double yp = (c == 0) ? ((pat != 0) ? prm.fmin : sol) : sol;
+      const double ynp = gshfl(yp, l0);
+      if (c != 0 && pat != 0) yp = pat * mu * ynp;
       if (!alive) yp = 0.0;
       bool start_ipm = false;
 #pragma unroll 1
@@ -566,61 +564,60 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
         if (var_lane) ws.vb[0][grp][gl] = vv;
         __syncwarp();
         double gam = gt;
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < kVars; j++) gam = fma(ws.grow[j][lane], ws.vb[0][grp][j], gam);
-        if (var_lane) ws.vb[1][grp][gl] = gam;
         const float gmaxf = group_max(var_lane ? fabsf((float)gam) : 0.f);
         __syncwarp();
         if (rep == 1) {
           // interior-point start: multipliers centred at the gradient scale, residuals of the start
           const double gmax = (double)fmaxf(1.f, gmaxf);
+          double e0A, e0B;
+          rows_apply(c0, 0.0, mu, c, e0A, e0B);
+          if (c == 0) e0A -= prm.fmin;
+          const double s0A = fmax(e0A, 1e-3 * c0), s0B = fmax(e0B, 1e-3 * c0);  // mu <= 0 would make friction rows non-positive
+          const double l0A = alive ? gmax * fast_rcp(s0A) : 0.0, l0B = rowB ? gmax * fast_rcp(s0B) : 0.0;
+          const double dtl = dt_lane(l0A, l0B, mu, c, l0);
           if (start_ipm) {
-            double e0[5];
-            d_apply(c0, 0.0, 0.0, mu, e0);
-            e0[0] -= prm.fmin;
-#pragma unroll
-            for (int r = 0; r < 5; r++) {
-              const double sr = fmax(e0[r], 1e-3 * c0);  // mu <= 0 would make the friction rows non-positive
-              s[r] = alive ? sr : 1.0;
-              lam[r] = alive ? gmax * fast_rcp(sr) : 0.0;
-              rp[r] = alive ? sr - e0[r] : 0.0;
-            }
+            sA = alive ? s0A : 1.0; lamA = l0A; rpA = alive ? s0A - e0A : 0.0;
+            sB = rowB ? s0B : 1.0;  lamB = l0B; rpB = rowB ? s0B - e0B : 0.0;
             y = vv;
-            rd = var_lane ? gam - dt_apply(lam, mu, c) : 0.0;
+            rd = var_lane ? gam - dtl : 0.0;
           }
           break;
         }
-        const double yn = ws.vb[0][grp][l0], y1 = ws.vb[0][grp][l0 + 1], y2 = ws.vb[0][grp][l0 + 2];
-        const double gn = ws.vb[1][grp][l0], g1 = ws.vb[1][grp][l0 + 1], g2 = ws.vb[1][grp][l0 + 2];
-        double e[5], u[5];
-        d_apply(yn, y1, y2, mu, e);
-        e[0] -= prm.fmin;
-        u[1] = (sg1 == -1) ? g1 : 0.0;
-        u[2] = (sg1 == 1) ? -g1 : 0.0;
-        u[3] = (sg2 == -1) ? g2 : 0.0;
-        u[4] = (sg2 == 1) ? -g2 : 0.0;
-        u[0] = (a0 != 0) ? gn - mu * ((u[1] + u[2]) + (u[3] + u[4])) : 0.0;
-        const bool act[5] = {a0 != 0, sg1 == -1, sg1 == 1, sg2 == -1, sg2 == 1};
+        // multipliers and slacks of this lane's rows
+        double eA, eB;
+        rows_apply(ynp, yp, mu, c, eA, eB);
+        if (c == 0) eA -= prm.fmin;
+        double uA = 0.0, uB = 0.0;
+        if (c != 0) { uA = (pat == -1) ? gam : 0.0; uB = (pat == 1) ? -gam : 0.0; }
+        const double su = uA + uB;
+        const double U = gshfl(su, l0 + 1) + gshfl(su, l0 + 2);
+        if (c == 0) uA = (pat != 0) ? gam - mu * U : 0.0;
+        const bool actA = (c == 0) ? (pat != 0) : (pat == -1), actB = (pat == 1);
         const float scale = fmaxf(1.f, group_max(fabsf((float)yp)));
         const float gscale = fmaxf(1.f, group_max(fabsf((float)gt)));
         const double tol_u = 1e-13 * (double)gscale, tol_s = 1e-10 * (double)scale;
-        // worst violations of this leg
-        double wd_v = -tol_u, wp_v = -tol_s;
-        int wd_r = -1, wp_r = -1;
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-          if (alive && act[r] && u[r] < wd_v) { wd_v = u[r]; wd_r = r; }
-          if (alive && !act[r] && e[r] < wp_v) { wp_v = e[r]; wp_r = r; }
+        // worst violation of this lane: a negative multiplier (drop the row) before a negative slack (add it)
+        int fix = 0;  // 0 none, 1 drop, 2 add row A, 3 add row B
+        double key = 0.0;
+        if (alive) {
+          if (actA && uA < -tol_u) { fix = 1; key = uA * 1e6; }
+          else if (actB && uB < -tol_u) { fix = 1; key = uB * 1e6; }
+          else {
+            const double vA2 = actA ? 0.0 : eA, vB2 = (rowB && !actB) ? eB : 0.0;
+            if (vA2 < -tol_s && vA2 <= vB2) { fix = 2; key = vA2; }
+            else if (vB2 < -tol_s) { fix = 3; key = vB2; }
+          }
         }
-        const bool leg_viol = (wd_r >= 0) || (wp_r >= 0);
-        const bool any_viol = ((__ballot_sync(kFull, leg_viol) >> (16 * grp)) & 0xFFFu) != 0u;
-        // globally worst leg (used after the first passes, prevents cycling); duals before primals
-        const double key = (wd_r >= 0) ? wd_v * 1e6 : ((wp_r >= 0) ? wp_v : 0.0);
-        const double best = leg_min(key);
-        const unsigned tie = (__ballot_sync(kFull, key == best && leg_viol) >> (16 * grp)) & 0xFFFu;
+        const unsigned viol = (__ballot_sync(kFull, fix != 0) >> (16 * grp)) & 0xFFFu;
+        // globally worst lane (used after the first passes, prevents cycling)
+        const float keyf = (float)key;
+        const float best = group_min(keyf);
+        const unsigned tie = (__ballot_sync(kFull, fix != 0 && keyf == best) >> (16 * grp)) & 0xFFFu;
 
         if (mode == kModePolish) {
-          if (!any_viol) {
+          if (viol == 0u) {
             y = yp;
             mode = kModeDone;
             if (status == 2) status = 0;  // iteration limit hit but the polish verified the optimum
@@ -628,22 +625,14 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
             pass++;
             const bool give_up = first ? (pass > kPdasFirst) : (pass >= kPolishPasses);
             if (!give_up) {
-              // repair: per leg, drop the most negative multiplier, else add the most violated row;
-              // after the first passes only the globally worst leg moves
-              bool mine = true;
-              if (pass > 2) mine = leg_viol && (tie != 0u) && ((__ffs(tie) - 1) / 3 == leg);
-              if (mine && alive) {
-                if (wd_r >= 0) {
-                  if (wd_r == 0) a0 = 0; else if (wd_r <= 2) sg1 = 0; else sg2 = 0;
-                } else if (wp_r >= 0) {
-                  if (wp_r == 0) a0 = 1; else if (wp_r == 1) sg1 = -1; else if (wp_r == 2) sg1 = 1; else if (wp_r == 3) sg2 = -1; else sg2 = 1;
-                }
-              }
+              // repair: every violating lane moves during the first passes, then only the worst one
+              const bool mine = (fix != 0) && (pass <= 2 || (tie != 0u && (__ffs(tie) - 1) == gl));
+              if (mine) pat = (fix == 1) ? 0 : ((c == 0) ? 1 : (fix == 2 ? -1 : 1));
             } else if (first) {
               first = false;
               mode = kModeIpm;
               start_ipm = true;
-              a0 = 0; sg1 = 0; sg2 = 0;
+              pat = 0;
             } else if (converged || status == 2) {
               // interior-point iterate is final but the polish could not certify an active set
               mode = kModeDone;
@@ -661,16 +650,14 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
       want_polish = false;
       mode = kModePolish;
       pass = 0;
-      a0 = lam[0] > s[0];
-      sg1 = (lam[1] > s[1]) ? -1 : ((lam[2] > s[2]) ? 1 : 0);
-      sg2 = (lam[3] > s[3]) ? -1 : ((lam[4] > s[4]) ? 1 : 0);
-      if (!alive) { a0 = 0; sg1 = 0; sg2 = 0; }
+      pat = 0;
+      if (alive) pat = (c == 0) ? (lamA > sA ? 1 : 0) : ((lamA > sA) ? -1 : ((lamB > sB) ? 1 : 0));
     }
   }
 
   // ---------------- outputs: forces in base frame, torques, net wrench, flags
   const bool solved = (status == 0 || status == 2 || status == 3);
-  if (!solved) { y = 0.0; a0 = 0; sg1 = 0; sg2 = 0; }
+  if (!solved) { y = 0.0; pat = 0; }
   // f_leg = y_n n + y_1 t1 + y_2 t2 : sum of the three lanes' contributions y * e
   double f[3];
 #pragma unroll
@@ -704,9 +691,9 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
   }
   {
     unsigned bits = 0u;
-    if (alive && c == 0 && solved) {
-      bits = (a0 != 0 ? 1u : 0u) | (sg1 == -1 ? 2u : 0u) | (sg1 == 1 ? 4u : 0u) | (sg2 == -1 ? 8u : 0u) | (sg2 == 1 ? 16u : 0u);
-      bits <<= (4 + 5 * leg);
+    if (alive && solved && pat != 0) {
+      const int row = (c == 0) ? 0 : (2 * c - 1 + (pat == 1 ? 1 : 0));  // reference row order: F_min, +t1, -t1, +t2, -t2
+      bits = 1u << (4 + 5 * leg + row);
     }
     // OR over the group
     bits |= __shfl_xor_sync(kFull, bits, 1, kGroup);
