@@ -12,7 +12,7 @@
 
 namespace qlb {
 
-constexpr int kBatch = 8;         // QPs staged per warp batch (64 bytes = two sectors per component row)
+constexpr int kBatch = 4;         // QPs staged per warp batch (32 bytes = one sector per component row)
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = 32 * kWarpsPerCta;
 
@@ -63,7 +63,7 @@ struct alignas(16) WarpSmem {
   double tail[7][32];        // per lane: slot direction e (3), Jacobian column (3), gravity torque
   double bw[2][6];           // per group: the wrench b
   double xb[2][2][16];       // exchange buffer of the factorisation (double buffered, one row per group)
-  double vb[2][2][16];       // vector exchange: [which][group][slot]
+  double vb[1][2][16];       // vector exchange: [which][group][slot]
   double hs[kVars * kPitch]; // the round's matrix / its Cholesky factor, one row per lane
   uint32_t flags[kBatch];
   uint8_t mask[kBatch];
@@ -72,7 +72,6 @@ struct alignas(16) WarpSmem {
 template <int ROWS>
 struct alignas(16) CtaSmem {
   WarpSmem<ROWS> w[kWarpsPerCta];
-  DeviceModel model;
   DeviceParams prm;
 };
 
@@ -709,16 +708,13 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
 
 // ---------------------------------------------------------------- kernel
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 3) qlb_solve_kernel(const SolveArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) qlb_solve_kernel(const SolveArgs a) {
   constexpr int ROWS = (MODE == 1) ? kInRowsState : kInRows;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaSmem<ROWS>& sm = *reinterpret_cast<CtaSmem<ROWS>*>(smem_raw);
   {
-    const double* src = reinterpret_cast<const double*>(a.model);
-    double* dst = reinterpret_cast<double*>(&sm.model);
-    for (int i = threadIdx.x; i < (int)(sizeof(DeviceModel) / 8); i += blockDim.x) dst[i] = src[i];
-    src = reinterpret_cast<const double*>(a.params);
-    dst = reinterpret_cast<double*>(&sm.prm);
+    const double* src = reinterpret_cast<const double*>(a.params);
+    double* dst = reinterpret_cast<double*>(&sm.prm);
     for (int i = threadIdx.x; i < (int)(sizeof(DeviceParams) / 8); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
@@ -753,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, 3) qlb_solve_kernel(const SolveArgs 
 
 #pragma unroll 1
     for (int pair = 0; 2 * pair < nvalid; pair++)
-      solve_group<MODE, ROWS>(ws, sm.model, sm.prm, 2 * pair + (lane >> 4), lane, have_mu, have_normals, want_net);
+      solve_group<MODE, ROWS>(ws, *a.model, sm.prm, 2 * pair + (lane >> 4), lane, have_mu, have_normals, want_net);
     __syncwarp();
 
     stage_out(a.grf, &ws.out[kRowGrf], 12, a.B, b0, nvalid, lane, vec);
