@@ -191,6 +191,25 @@ int qlb_solve_state_host(qlb_context* ctx, size_t B, const double* q, const doub
 int qlb_leg_kinematics(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz,
                        double* foot, double* jac, double* gravity_tau, void* stream);
 
+/* Generic small dense QP (DEVICE pointers), B problems of the same shape, in the argument convention of
+ * the reference's in-repo backend quadprogpp::solve_quadprog (qp_solver/include/qp_solver/QuadProg++.h:
+ * 8-30), which qp_solver::QuadraticProblemSolver::minimize forwards to
+ * (qp_solver/src/quadraticproblemsolver.cpp:65-97):
+ *     min 1/2 x'Gx + g0'x   s.t.   CE' x + ce0 = 0,   CI' x + ci0 >= 0
+ * G[n*n][B], g0[n][B], CE[n*p][B] (element (i,j) of the n x p matrix at slot i*p+j), ce0[p][B],
+ * CI[n*m][B], ci0[m][B]; n <= 12, m <= 24, p <= 12; CE/ce0 may be NULL when p == 0, CI/ci0 when m == 0.
+ * An all-zero equality column is treated as absent (the reference's callers pass one).
+ * Out: x[n][B]; cost[B] (NULL ok; +inf when infeasible); status[B]: 0 ok, 1 infeasible, 2 G not positive
+ * definite or non-finite input, 3 iteration limit; active[B] (NULL ok): bit i = inequality i is in the
+ * final working set.  Goldfarb-Idnani with the reference's pivoting rules: same optimum, same working set. */
+int qlb_qp_dense(qlb_context* ctx, size_t B, int n, int m, int p, const double* G, const double* g0,
+                 const double* CE, const double* ce0, const double* CI, const double* ci0, double* x,
+                 double* cost, uint32_t* status, uint32_t* active, void* stream);
+/* Same, HOST pointers; copies in, solves, copies out, synchronises. */
+int qlb_qp_dense_host(qlb_context* ctx, size_t B, int n, int m, int p, const double* G, const double* g0,
+                      const double* CE, const double* ce0, const double* CI, const double* ci0, double* x,
+                      double* cost, uint32_t* status, uint32_t* active);
+
 /* Device-side statistics over a solved batch (DEVICE pointers; stats_out is a HOST pointer,
  * the call synchronises the stream).  wrench/netwrench may be NULL (error terms then zero). */
 int qlb_batch_stats(qlb_context* ctx, size_t B, const uint32_t* flags, const double* wrench,

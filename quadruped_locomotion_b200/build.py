@@ -35,6 +35,28 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
     return LIB
 
 
+DEMO = os.path.join(PKG, "host", "tick_demo")
+QP_DEMO = os.path.join(PKG, "host", "qp_demo")
+
+
+def build_host_demo(force: bool = False, verbose: bool = False, which: str = "tick_demo") -> str:
+    """Compile a C++ adapter demo (host code only, links libqlb.so)."""
+    exe = os.path.join(PKG, "host", which)
+    src = exe + ".cpp"
+    hdrs = [os.path.join(PKG, "host", h) for h in ("qlb_adapter.hpp", "qlb_qp_adapter.hpp")]
+    build()
+    if not force and os.path.exists(exe) and os.path.getmtime(exe) > max([os.path.getmtime(f) for f in [src, LIB] + hdrs]):
+        return exe
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(PKG, "host"),
+           "-o", exe, src, "-L" + PKG, "-lqlb", "-Wl,-rpath," + PKG, "-Wl,-rpath,/usr/local/cuda/lib64"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return exe
+
+
 if __name__ == "__main__":
     extra = ["-Xptxas", "-v"] if "-v" in sys.argv else []
     print(build(force=True, verbose=True, extra=extra))
+    print(build_host_demo(force=True, verbose=True))
+    print(build_host_demo(force=True, verbose=True, which="qp_demo"))

@@ -48,7 +48,7 @@ class Stats(C.Structure):
 EXPORTS = (
     "qlb_default_params", "qlb_create", "qlb_destroy", "qlb_set_params", "qlb_get_params",
     "qlb_solve_wrench", "qlb_solve_wrench_host", "qlb_solve_state", "qlb_solve_state_host",
-    "qlb_leg_kinematics", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
+    "qlb_leg_kinematics", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
     "qlb_last_cuda_error", "qlb_abi_version",
 )
 
@@ -75,6 +75,8 @@ def load() -> C.CDLL:
     lib.qlb_solve_state.argtypes = [_vp, C.c_size_t] + [_vp] * 14
     lib.qlb_solve_state_host.argtypes = [_vp, C.c_size_t] + [_vp] * 13
     lib.qlb_leg_kinematics.argtypes = [_vp, C.c_size_t] + [_vp] * 6
+    lib.qlb_qp_dense.argtypes = [_vp, C.c_size_t, C.c_int, C.c_int, C.c_int] + [_vp] * 11
+    lib.qlb_qp_dense_host.argtypes = [_vp, C.c_size_t, C.c_int, C.c_int, C.c_int] + [_vp] * 10
     lib.qlb_batch_stats.argtypes = [_vp, C.c_size_t, _vp, _vp, _vp, C.POINTER(Stats), _vp]
     lib.qlb_measure_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
     lib.qlb_launch_count.argtypes = [_vp]
@@ -214,6 +216,23 @@ class Solver:
                                            _ptr(ttwist), _ptr(mask), _ptr(mu), _ptr(normals), _ptr(grf), _ptr(tau),
                                            _ptr(flags), _ptr(netwrench), _ptr(wrench_out))
         self._check(rc, "qlb_solve_state_host")
+
+    def qp_dense_numpy(self, G, g0, CI=None, ci0=None, CE=None, ce0=None) -> dict:
+        """Batched generic QP through the host entry point.  G[B,n,n], g0[B,n], CI[B,n,m], ci0[B,m],
+        CE[B,n,p], ce0[B,p] in QuadProg++ convention (CI' x + ci0 >= 0); returns x[B,n], cost, status, active."""
+        G = np.asarray(G, dtype=np.float64); g0 = np.asarray(g0, dtype=np.float64)
+        B, n = g0.shape
+        m = 0 if CI is None else np.asarray(CI).shape[2]
+        p = 0 if CE is None else np.asarray(CE).shape[2]
+        soa = lambda a, k: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(B, k).T)  # noqa: E731
+        Gs, gs = soa(G, n * n), soa(g0, n)
+        CIs = soa(CI, n * m) if m else None; cis = soa(ci0, m) if m else None
+        CEs = soa(CE, n * p) if p else None; ces = soa(ce0, p) if p else None
+        x = np.zeros((n, B)); cost = np.zeros(B); status = np.zeros(B, np.uint32); active = np.zeros(B, np.uint32)
+        rc = self.lib.qlb_qp_dense_host(self._ctx, B, n, m, p, _ptr(Gs), _ptr(gs), _ptr(CEs), _ptr(ces), _ptr(CIs),
+                                        _ptr(cis), _ptr(x), _ptr(cost), _ptr(status), _ptr(active))
+        self._check(rc, "qlb_qp_dense_host")
+        return dict(x=np.ascontiguousarray(x.T), cost=cost, status=status, active=active)
 
     def solve_wrench_numpy(self, states: dict, with_net=True) -> dict:
         """Convenience for tests: numpy SoA in, numpy SoA out, through the host entry point."""

@@ -9,6 +9,7 @@
 
 #include "qlb.h"
 #include "qlb_aux.cuh"
+#include "qlb_qp_dense.cuh"
 #include "qlb_solve.cuh"
 
 using namespace qlb;
@@ -437,6 +438,64 @@ int qlb_batch_stats(qlb_context* ctx, size_t B, const uint32_t* flags, const dou
   QLB_CUDA(ctx, cudaStreamSynchronize(st));
   std::memcpy(stats_out, h, sizeof h);
   return QLB_OK;
+}
+
+int qlb_qp_dense(qlb_context* ctx, size_t B, int n, int m, int p, const double* G, const double* g0, const double* CE,
+                 const double* ce0, const double* CI, const double* ci0, double* x, double* cost, uint32_t* status,
+                 uint32_t* active, void* stream) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (n < 1 || n > kQpMaxN || m < 0 || m > kQpMaxM || p < 0 || p > kQpMaxP) return QLB_ERR_INVALID_ARGUMENT;
+  if (B == 0) return QLB_OK;
+  if (!G || !g0 || !x || !status || (p > 0 && (!CE || !ce0)) || (m > 0 && (!CI || !ci0))) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  QpDenseArgs a;
+  a.B = B; a.n = n; a.m = m; a.p = p; a.G = G; a.g0 = g0; a.CE = CE; a.ce0 = ce0; a.CI = CI; a.ci0 = ci0;
+  a.x = x; a.cost = cost; a.status = status; a.active = active;
+  const unsigned threads = 64;
+  const unsigned long long blocks = (B + threads - 1) / threads;
+  if (blocks > 0x7fffffffull) return QLB_ERR_BATCH_TOO_LARGE;
+  qlb_qp_dense_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return QLB_OK;
+}
+
+int qlb_qp_dense_host(qlb_context* ctx, size_t B, int n, int m, int p, const double* G, const double* g0,
+                      const double* CE, const double* ce0, const double* CI, const double* ci0, double* x, double* cost,
+                      uint32_t* status, uint32_t* active) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (n < 1 || n > kQpMaxN || m < 0 || m > kQpMaxM || p < 0 || p > kQpMaxP) return QLB_ERR_INVALID_ARGUMENT;
+  if (B == 0) return QLB_OK;
+  if (!G || !g0 || !x || !status || (p > 0 && (!CE || !ce0)) || (m > 0 && (!CI || !ci0))) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t nin = (size_t)(n * n + n + n * p + p + n * m + m) * B, nout = (size_t)(n + 1) * B;
+  double* d_in = nullptr; double* d_out = nullptr; uint32_t* d_u = nullptr;
+  if (cudaMalloc(&d_in, nin * sizeof(double)) != cudaSuccess || cudaMalloc(&d_out, nout * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&d_u, 2 * B * sizeof(uint32_t)) != cudaSuccess) {
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_u); cudaGetLastError();
+    return QLB_ERR_ALLOC;
+  }
+  double* dG = d_in; double* dg = dG + (size_t)n * n * B; double* dCE = dg + (size_t)n * B; double* dce = dCE + (size_t)n * p * B;
+  double* dCI = dce + (size_t)p * B; double* dci = dCI + (size_t)n * m * B;
+  int rc = QLB_OK;
+  auto H2D = [&](double* d, const double* h, size_t cnt) {
+    if (cnt && rc == QLB_OK && cudaMemcpyAsync(d, h, cnt * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = QLB_ERR_CUDA;
+  };
+  H2D(dG, G, (size_t)n * n * B); H2D(dg, g0, (size_t)n * B); H2D(dCE, CE, (size_t)n * p * B); H2D(dce, ce0, (size_t)p * B);
+  H2D(dCI, CI, (size_t)n * m * B); H2D(dci, ci0, (size_t)m * B);
+  if (rc == QLB_OK) rc = qlb_qp_dense(ctx, B, n, m, p, dG, dg, p ? dCE : nullptr, p ? dce : nullptr, m ? dCI : nullptr,
+                                       m ? dci : nullptr, d_out, d_out + (size_t)n * B, d_u, d_u + B, st);
+  if (rc == QLB_OK) {
+    if (cudaMemcpyAsync(x, d_out, (size_t)n * B * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = QLB_ERR_CUDA;
+    if (cost && cudaMemcpyAsync(cost, d_out + (size_t)n * B, B * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = QLB_ERR_CUDA;
+    if (cudaMemcpyAsync(status, d_u, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = QLB_ERR_CUDA;
+    if (active && cudaMemcpyAsync(active, d_u + B, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = QLB_ERR_CUDA;
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess && rc == QLB_OK) rc = QLB_ERR_CUDA;
+  if (rc == QLB_ERR_CUDA) cuda_fail(ctx, cudaGetLastError(), "qlb_qp_dense_host");
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_u);
+  return rc;
 }
 
 int qlb_measure_fp64_peak(qlb_context* ctx, double* tflops_out) {

@@ -1,0 +1,297 @@
+// qlb_adapter.hpp - C++ host-side mirror of the reference's balance_controller math classes on top of
+// the C ABI (include/qlb.h).  A batch of 1 through these classes reproduces one controller tick.
+//
+// What it mirrors (same method names, argument meaning and bool-return error convention):
+//   balance_controller::ContactForceDistributionBase / ContactForceDistribution
+//       (balance_controller/include/balance_controller/contact_force_distribution/
+//        ContactForceDistributionBase.hpp:60-159, ContactForceDistribution.hpp:73-200)
+//   balance_controller::MotionControllerBase / VirtualModelController
+//       (.../motion_control/MotionControllerBase.hpp:58-123, VirtualModelController.cpp:89-102)
+//   the slice of free_gait::State the path reads and writes
+//       (free_gait_core/src/executor/State.cpp:59-67,93-101,227-235; quadruped_state.cpp:108-120,202-215,334-354)
+//
+// The reference's argument types are kindr/Eigen wrappers (Force, Torque, Position, RotationQuaternion,
+// JointPositions ...).  Neither library is available in this build environment, so the adapter uses the
+// plain 3-/4-/12-vectors below; in the reference tree they are replaced by `toImplementation()` views
+// of the kindr types.
+#pragma once
+
+#include <array>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+#include "qlb.h"
+#include "qlb_models.h"
+
+namespace qlb_host {
+
+using Vector3 = std::array<double, 3>;
+using Force = Vector3;
+using Torque = Vector3;
+using Position = Vector3;
+using LinearVelocity = Vector3;
+using LocalAngularVelocity = Vector3;
+using Quaternion = std::array<double, 4>;       // (w, x, y, z), base -> world, like kindr RotationQuaternion
+using JointPositions = std::array<double, 12>;  // LF, RF, RH, LH x (HAA, HFE, KFE)
+using JointEfforts = std::array<double, 12>;
+using JointEffortsLeg = Vector3;
+
+// quadruped_model::QuadrupedDescription::LimbEnum (QuadrupedModel.hpp:47-53)
+enum class LimbEnum : int { LF_LEG = 0, RF_LEG = 1, RH_LEG = 2, LH_LEG = 3 };
+
+// The part of free_gait::State / quadruped_model::QuadrupedState that the hot path touches.  Unlike the
+// reference (class-static members, quadruped_state.h:99-109) every instance owns its data.
+class State {
+ public:
+  State() {
+    support_.fill(true);
+    for (auto& n : normals_) n = {0.0, 0.0, 1.0};
+    efforts_.fill(0.0);
+    joints_.fill(0.0);
+  }
+  // State.cpp:59-67
+  bool isSupportLeg(LimbEnum limb) const { return support_[static_cast<int>(limb)]; }
+  void setSupportLeg(LimbEnum limb, bool v) { support_[static_cast<int>(limb)] = v; }
+  // State.cpp:93-101
+  const Vector3& getSurfaceNormal(LimbEnum limb) const { return normals_[static_cast<int>(limb)]; }
+  void setSurfaceNormal(LimbEnum limb, const Vector3& n) { normals_[static_cast<int>(limb)] = n; }
+  // State.cpp:227-235
+  void setJointEffortsForLimb(LimbEnum limb, const JointEffortsLeg& e) {
+    for (int j = 0; j < 3; j++) efforts_[3 * static_cast<int>(limb) + j] = e[j];
+  }
+  const JointEfforts& getAllJointEfforts() const { return efforts_; }
+  // quadruped_state.cpp:334-354 (the reference also caches FK here; ours is computed on the GPU)
+  void setCurrentLimbJoints(const JointPositions& q) { joints_ = q; }
+  const JointPositions& getJointPositionFeedback() const { return joints_; }
+  // quadruped_state.cpp:108-120
+  void setPoseBaseToWorld(const Position& p, const Quaternion& q) { position_ = p; orientation_ = q; }
+  void setBaseStateFromFeedback(const LinearVelocity& v, const LocalAngularVelocity& w) { lin_vel_ = v; ang_vel_ = w; }
+  const Position& getPositionWorldToBaseInWorldFrame() const { return position_; }
+  const Quaternion& getOrientationBaseToWorld() const { return orientation_; }
+  const LinearVelocity& getLinearVelocityBaseInWorldFrame() const { return lin_vel_; }
+  const LocalAngularVelocity& getAngularVelocityBaseInBaseFrame() const { return ang_vel_; }
+  // quadruped_state.cpp:202-215,258-267
+  void setTargetPoseBaseToWorld(const Position& p, const Quaternion& q) { t_position_ = p; t_orientation_ = q; }
+  void setTargetBaseTwist(const LinearVelocity& v, const LocalAngularVelocity& w) { t_lin_vel_ = v; t_ang_vel_ = w; }
+  const Position& getTargetPositionWorldToBaseInWorldFrame() const { return t_position_; }
+  const Quaternion& getTargetOrientationBaseToWorld() const { return t_orientation_; }
+  const LinearVelocity& getTargetLinearVelocityBaseInWorldFrame() const { return t_lin_vel_; }
+  const LocalAngularVelocity& getTargetAngularVelocityBaseInBaseFrame() const { return t_ang_vel_; }
+
+ private:
+  std::array<bool, 4> support_;
+  std::array<Vector3, 4> normals_;
+  JointEfforts efforts_;
+  JointPositions joints_;
+  Position position_{{0, 0, 0}}, t_position_{{0, 0, 0}};
+  Quaternion orientation_{{1, 0, 0, 0}}, t_orientation_{{1, 0, 0, 0}};
+  LinearVelocity lin_vel_{{0, 0, 0}}, t_lin_vel_{{0, 0, 0}};
+  LocalAngularVelocity ang_vel_{{0, 0, 0}}, t_ang_vel_{{0, 0, 0}};
+};
+
+// Shared owner of one qlb_context (one GPU).  The reference constructs ContactForceDistribution and
+// VirtualModelController around one shared free_gait::State (ros_balance_controller.cpp:73-74); here
+// they additionally share the device context.
+class Device {
+ public:
+  explicit Device(const qlb_leg_model* legs = QLB_MODEL_QUADRUPED_MODEL, int device = 0) {
+    qlb_default_params(&params_);
+    const int rc = qlb_create(&ctx_, legs, &params_, device, 1);
+    if (rc != QLB_OK) throw std::runtime_error(std::string("qlb_create: ") + qlb_strerror(rc));
+  }
+  ~Device() { qlb_destroy(ctx_); }
+  Device(const Device&) = delete;
+  Device& operator=(const Device&) = delete;
+  qlb_context* ctx() { return ctx_; }
+  qlb_params& params() { return params_; }
+  bool commit() { return qlb_set_params(ctx_, &params_) == QLB_OK; }
+
+ private:
+  qlb_context* ctx_ = nullptr;
+  qlb_params params_;
+};
+
+class ContactForceDistributionBase {
+ public:
+  virtual ~ContactForceDistributionBase() = default;
+  virtual bool loadParameters() = 0;
+  virtual bool computeForceDistribution(const Force& virtualForceInBaseFrame, const Torque& virtualTorqueInBaseFrame) = 0;
+  virtual bool getNetForceAndTorqueOnBase(Force& netForce, Torque& netTorque) = 0;
+};
+
+class ContactForceDistribution : public ContactForceDistributionBase {
+ public:
+  // ContactForceDistribution.hpp:73-89
+  struct LegInfo {
+    bool isPartOfForceDistribution_ = false;
+    bool isLoadConstraintActive_ = false;
+    int indexInStanceLegList_ = 0;
+    int startIndexInVectorX_ = 0;
+    Force desiredContactForce_{{0, 0, 0}};
+    double frictionCoefficient_ = 0.6;
+    unsigned activeRows_ = 0;  // extension: 5 active-set bits of this leg (include/qlb.h flags word)
+  };
+
+  ContactForceDistribution(std::shared_ptr<Device> device, std::shared_ptr<State> robot_state)
+      : device_(std::move(device)), robot_state_(std::move(robot_state)) {
+    for (int l = 0; l < 4; l++) legInfos_[static_cast<LimbEnum>(l)] = LegInfo();
+  }
+
+  // ContactForceDistribution::loadParameters (ContactForceDistribution.cpp:818-886): the values of
+  // controller_gains.yaml are the library defaults; setters below stand in for the ROS parameter server.
+  bool loadParameters() override {
+    for (auto& kv : legInfos_) kv.second.frictionCoefficient_ = device_->params().friction_default;
+    isParametersLoaded_ = device_->commit();
+    return isParametersLoaded_;
+  }
+  void setVirtualForceWeights(const std::array<double, 6>& w) { for (int i = 0; i < 6; i++) device_->params().wrench_weights[i] = w[i]; }
+  void setGroundForceWeight(double w) { device_->params().ground_force_weight = w; }
+  void setMinimalNormalGroundForce(double f) { device_->params().min_normal_force = f; }
+  void setFrictionCoefficient(double mu) { device_->params().friction_default = mu; }
+  double getGroundForceWeight() const { return device_->params().ground_force_weight; }
+  double getMinimalNormalGroundForce() const { return device_->params().min_normal_force; }
+  double getVirtualForceWeight(int index) const { return device_->params().wrench_weights[index]; }
+  double getFrictionCoefficient(LimbEnum leg) const { return legInfos_.at(leg).frictionCoefficient_; }
+
+  // ContactForceDistribution::computeForceDistribution (ContactForceDistribution.cpp:99-136)
+  bool computeForceDistribution(const Force& F, const Torque& T) override {
+    if (!isParametersLoaded_) return false;  // checkIfParametersLoaded
+    isForceDistributionComputed_ = false;
+    double q[12], quat[4], wrench[6], mu[4], normals[12];
+    uint8_t mask = 0;
+    const JointPositions& jq = robot_state_->getJointPositionFeedback();
+    for (int i = 0; i < 12; i++) q[i] = jq[i];
+    for (int i = 0; i < 4; i++) quat[i] = robot_state_->getOrientationBaseToWorld()[i];
+    for (int i = 0; i < 3; i++) { wrench[i] = F[i]; wrench[3 + i] = T[i]; }
+    int nstance = 0;
+    for (int l = 0; l < 4; l++) {
+      const LimbEnum limb = static_cast<LimbEnum>(l);
+      LegInfo& info = legInfos_[limb];
+      const bool stance = robot_state_->isSupportLeg(limb);  // prepareLegLoading, CFD.cpp:138-166
+      info.isPartOfForceDistribution_ = stance;
+      info.isLoadConstraintActive_ = stance;
+      info.indexInStanceLegList_ = stance ? nstance : 0;
+      info.startIndexInVectorX_ = 3 * info.indexInStanceLegList_;
+      info.desiredContactForce_ = {0, 0, 0};  // resetOptimization, CFD.cpp:580-596
+      if (stance) { mask |= (1u << l); nstance++; }
+      mu[l] = info.frictionCoefficient_;
+      for (int a = 0; a < 3; a++) normals[3 * l + a] = robot_state_->getSurfaceNormal(limb)[a];
+    }
+    double grf[12], tau[12], net[6];
+    uint32_t flags = 0;
+    const int rc = qlb_solve_wrench_host(device_->ctx(), 1, q, quat, wrench, &mask, mu, normals, grf, tau, &flags, net);
+    if (rc != QLB_OK) return false;
+    const unsigned status = (flags & QLB_FLAG_STATUS_MASK) >> QLB_FLAG_STATUS_SHIFT;
+    lastFlags_ = flags;
+    // the reference returns false (and keeps stale efforts) when the solver fails (CFD.cpp:490-494)
+    if (status != QLB_STATE_OK && status != QLB_STATE_NO_STANCE) return false;
+    for (int l = 0; l < 4; l++) {
+      const LimbEnum limb = static_cast<LimbEnum>(l);
+      LegInfo& info = legInfos_[limb];
+      info.activeRows_ = (flags >> (QLB_FLAG_ACTIVE_SHIFT + 5 * l)) & 31u;
+      if (!info.isPartOfForceDistribution_) continue;  // swing legs: efforts untouched (CFD.cpp:530)
+      info.desiredContactForce_ = {-grf[3 * l], -grf[3 * l + 1], -grf[3 * l + 2]};  // CFD.cpp:502-503
+      robot_state_->setJointEffortsForLimb(limb, {tau[3 * l], tau[3 * l + 1], tau[3 * l + 2]});
+    }
+    for (int a = 0; a < 3; a++) { netForce_[a] = net[a]; netTorque_[a] = net[3 + a]; }
+    isForceDistributionComputed_ = true;
+    return true;
+  }
+
+  // ContactForceDistribution::getNetForceAndTorqueOnBase (ContactForceDistribution.cpp:614-625)
+  bool getNetForceAndTorqueOnBase(Force& netForce, Torque& netTorque) override {
+    if (!isForceDistributionComputed_) return false;
+    netForce = netForce_;
+    netTorque = netTorque_;
+    return true;
+  }
+  const LegInfo& getLegInfo(LimbEnum leg) const { return legInfos_.at(leg); }  // ContactForceDistribution.hpp:150
+  uint32_t getLastFlags() const { return lastFlags_; }
+
+  std::map<LimbEnum, LegInfo> legInfos_;  // public in the reference too (ContactForceDistribution.hpp:200)
+
+ private:
+  std::shared_ptr<Device> device_;
+  std::shared_ptr<State> robot_state_;
+  bool isParametersLoaded_ = false, isForceDistributionComputed_ = false;
+  Force netForce_{{0, 0, 0}};
+  Torque netTorque_{{0, 0, 0}};
+  uint32_t lastFlags_ = 0;
+};
+
+class MotionControllerBase {
+ public:
+  virtual ~MotionControllerBase() = default;
+  virtual bool loadParameters() = 0;
+  virtual bool compute() = 0;  // MotionControllerBase.hpp:94
+};
+
+// VirtualModelController::compute (VirtualModelController.cpp:89-102): errors, gravity compensation,
+// virtual force / torque and the contact force distribution run as ONE fused launch (qlb_solve_state).
+class VirtualModelController : public MotionControllerBase {
+ public:
+  VirtualModelController(std::shared_ptr<Device> device, std::shared_ptr<State> robot_state,
+                         std::shared_ptr<ContactForceDistribution> cfd)
+      : device_(std::move(device)), robot_state_(std::move(robot_state)), cfd_(std::move(cfd)) {}
+
+  bool loadParameters() override { loaded_ = device_->commit(); return loaded_; }  // VMC.cpp:429-548
+  void setProportionalGainTranslation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kp_translation[i] = k[i]; }
+  void setDerivativeGainTranslation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kd_translation[i] = k[i]; }
+  void setFeedforwardGainTranslation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kff_translation[i] = k[i]; }
+  void setProportionalGainRotation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kp_rotation[i] = k[i]; }
+  void setDerivativeGainRotation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kd_rotation[i] = k[i]; }
+  void setFeedforwardGainRotation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kff_rotation[i] = k[i]; }
+  void setGravityCompensationForcePercentage(double p) { device_->params().gravity_compensation_percentage = p; }  // VMC.cpp:655
+
+  bool compute() override {
+    if (!loaded_) return false;  // isParametersLoaded
+    const State& s = *robot_state_;
+    double q[12], pose[7], twist[6], tpose[7], ttwist[6], mu[4], normals[12];
+    uint8_t mask = 0;
+    for (int i = 0; i < 12; i++) q[i] = s.getJointPositionFeedback()[i];
+    for (int a = 0; a < 3; a++) {
+      pose[a] = s.getPositionWorldToBaseInWorldFrame()[a]; tpose[a] = s.getTargetPositionWorldToBaseInWorldFrame()[a];
+      twist[a] = s.getLinearVelocityBaseInWorldFrame()[a]; twist[3 + a] = s.getAngularVelocityBaseInBaseFrame()[a];
+      ttwist[a] = s.getTargetLinearVelocityBaseInWorldFrame()[a]; ttwist[3 + a] = s.getTargetAngularVelocityBaseInBaseFrame()[a];
+    }
+    for (int i = 0; i < 4; i++) { pose[3 + i] = s.getOrientationBaseToWorld()[i]; tpose[3 + i] = s.getTargetOrientationBaseToWorld()[i]; }
+    for (int l = 0; l < 4; l++) {
+      const LimbEnum limb = static_cast<LimbEnum>(l);
+      if (s.isSupportLeg(limb)) mask |= (1u << l);
+      mu[l] = cfd_->getFrictionCoefficient(limb);
+      for (int a = 0; a < 3; a++) normals[3 * l + a] = s.getSurfaceNormal(limb)[a];
+    }
+    double grf[12], tau[12], net[6], wrench[6];
+    uint32_t flags = 0;
+    const int rc = qlb_solve_state_host(device_->ctx(), 1, q, pose, twist, tpose, ttwist, &mask, mu, normals, grf, tau,
+                                        &flags, net, wrench);
+    if (rc != QLB_OK) return false;
+    for (int a = 0; a < 3; a++) { virtualForceInBaseFrame_[a] = wrench[a]; virtualTorqueInBaseFrame_[a] = wrench[3 + a]; }
+    const unsigned status = (flags & QLB_FLAG_STATUS_MASK) >> QLB_FLAG_STATUS_SHIFT;
+    if (status != QLB_STATE_OK && status != QLB_STATE_NO_STANCE) return false;
+    for (int l = 0; l < 4; l++) {
+      const LimbEnum limb = static_cast<LimbEnum>(l);
+      auto& info = cfd_->legInfos_[limb];
+      info.isPartOfForceDistribution_ = s.isSupportLeg(limb);
+      info.desiredContactForce_ = {0, 0, 0};
+      if (!info.isPartOfForceDistribution_) continue;
+      info.desiredContactForce_ = {-grf[3 * l], -grf[3 * l + 1], -grf[3 * l + 2]};
+      robot_state_->setJointEffortsForLimb(limb, {tau[3 * l], tau[3 * l + 1], tau[3 * l + 2]});
+    }
+    return true;
+  }
+  const Force& getDesiredVirtualForceInBaseFrame() const { return virtualForceInBaseFrame_; }
+  const Torque& getDesiredVirtualTorqueInBaseFrame() const { return virtualTorqueInBaseFrame_; }
+
+ private:
+  std::shared_ptr<Device> device_;
+  std::shared_ptr<State> robot_state_;
+  std::shared_ptr<ContactForceDistribution> cfd_;
+  bool loaded_ = false;
+  Force virtualForceInBaseFrame_{{0, 0, 0}};
+  Torque virtualTorqueInBaseFrame_{{0, 0, 0}};
+};
+
+}  // namespace qlb_host

@@ -1,0 +1,111 @@
+"""Generic small dense QP entry (qlb_qp_dense) = the backend behind qp_solver::QuadraticProblemSolver::
+minimize.  Oracle: the Goldfarb-Idnani port, itself pinned to the reference's QuadProg++ (oracle/_ref)."""
+import subprocess
+
+import numpy as np
+import pytest
+
+from quadruped_locomotion_b200 import build, capi
+
+
+def _random_qps(rng, B, n, m, p):
+    A = rng.normal(size=(B, n + 2, n))
+    G = np.einsum("bki,bkj->bij", A, A) + 0.1 * np.eye(n)
+    g0 = rng.normal(size=(B, n)) * 3
+    x0 = rng.normal(size=(B, n))                      # a point that satisfies everything: feasible by construction
+    CI = rng.normal(size=(B, n, m))
+    ci0 = -np.einsum("bnm,bn->bm", CI, x0) + rng.uniform(0.0, 1.0, size=(B, m))
+    CE = rng.normal(size=(B, n, p))
+    ce0 = -np.einsum("bnp,bn->bp", CE, x0)
+    return G, g0, CI, ci0, CE, ce0
+
+
+def test_oracle_generic_qp_matches_reference_solver(oracle):
+    """CPU: the port agrees with the reference's QuadProg++ on generic QPs, equalities included."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(7)
+    for n, m, p in ((2, 3, 0), (3, 4, 1), (6, 10, 2), (12, 20, 3)):
+        G, g0, CI, ci0, CE, ce0 = _random_qps(rng, 50, n, m, p)
+        for b in range(50):
+            D, d = CI[b].T, -ci0[b]
+            a = oracle.solve_qp_gi(G[b], g0[b], D, d, CE=CE[b] if p else None, ce0=ce0[b] if p else None)
+            r = oracle.solve_qp_ref(G[b], g0[b], D, d, CE=CE[b] if p else None, ce0=ce0[b] if p else None)
+            assert np.array_equal(a["x"], r["x"]) and a["f"] == r["f"]
+            # KKT: feasibility of the answer
+            assert (CI[b].T @ a["x"] + ci0[b]).min() > -1e-9
+            if p:
+                assert np.abs(CE[b].T @ a["x"] + ce0[b]).max() < 1e-9
+
+
+@pytest.fixture(scope="module")
+def solver(qlb_built):
+    s = capi.Solver("quadruped_model")
+    yield s
+    s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m,p", [(2, 3, 0), (3, 4, 1), (6, 10, 2), (12, 20, 3), (12, 24, 0), (5, 0, 0), (4, 0, 2)])
+def test_matches_oracle(solver, oracle, n, m, p):
+    rng = np.random.default_rng(100 + n + m + p)
+    B = 257
+    G, g0, CI, ci0, CE, ce0 = _random_qps(rng, B, n, m, p)
+    out = solver.qp_dense_numpy(G, g0, CI if m else None, ci0 if m else None, CE if p else None, ce0 if p else None)
+    assert (out["status"] == 0).all()
+    for b in range(B):
+        a = oracle.solve_qp_gi(G[b], g0[b], CI[b].T if m else np.zeros((0, n)), -ci0[b] if m else np.zeros(0),
+                               CE=CE[b] if p else None, ce0=ce0[b] if p else None)
+        scale = max(1.0, np.abs(a["x"]).max())
+        assert np.abs(out["x"][b] - a["x"]).max() <= 1e-10 * scale
+        assert abs(out["cost"][b] - a["f"]) <= 1e-9 * max(1.0, abs(a["f"]))
+        bits = sum(1 << i for i in range(m) if a["active"][i])
+        assert int(out["active"][b]) == bits
+
+
+@pytest.mark.gpu
+def test_reference_known_answers(solver, kats):
+    s = kats["solver"]  # qp_solver/src/main.cc data, zero equality column dropped
+    CI = np.array(s["D"], float).T[None]
+    out = solver.qp_dense_numpy(np.array(s["G"], float)[None], np.array(s["g0"], float)[None], CI, -np.array(s["d"], float)[None])
+    np.testing.assert_allclose(out["x"][0], s["x"], atol=1e-14)
+    assert abs(out["cost"][0] - s["f"]) < 1e-13 and out["active"][0] == 0b011
+    # the same data WITH the reference's zero equality column (main.cc:64-70): treated as absent
+    out = solver.qp_dense_numpy(np.array(s["G"], float)[None], np.array(s["g0"], float)[None], CI, -np.array(s["d"], float)[None],
+                                CE=np.zeros((1, 2, 1)), ce0=np.zeros((1, 1)))
+    np.testing.assert_allclose(out["x"][0], s["x"], atol=1e-14)
+
+
+@pytest.mark.gpu
+def test_failure_statuses(solver):
+    G = np.eye(2)[None].repeat(4, 0)
+    g0 = np.zeros((4, 2))
+    CI = np.zeros((4, 2, 2)); ci0 = np.zeros((4, 2))
+    CI[:, 0, 0] = 1.0; ci0[:, 0] = -1.0        # x0 >= 1
+    CI[:, 0, 1] = -1.0; ci0[:, 1] = 2.0        # x0 <= 2
+    ci0[1, 1] = 0.5                             # problem 1: x0 >= 1 and x0 <= 0.5  -> infeasible
+    G[2, 1, 1] = -1.0                           # problem 2: indefinite Hessian
+    g0[3, 0] = np.nan                           # problem 3: NaN input
+    out = solver.qp_dense_numpy(G, g0, CI, ci0)
+    assert list(out["status"]) == [0, 1, 2, 2]
+    np.testing.assert_allclose(out["x"][0], [1.0, 0.0], atol=1e-15)
+    assert np.isinf(out["cost"][1]) and not out["x"][1].any()
+
+
+@pytest.mark.gpu
+def test_pose_optimisation_known_answer_through_the_adapter(qlb_built):
+    """qp_solver/test/PoseOptimizationQpTest.cpp:21-52 expects (0, 0, 0.3) within 1e-3."""
+    demo = build.build_host_demo(which="qp_demo")
+    r = subprocess.run([demo], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    rows = [ln.split() for ln in r.stdout.strip().splitlines()]
+    x0 = [float(v) for v in rows[0][:3]]
+    np.testing.assert_allclose(x0, [0.0, 0.0, 0.3], atol=1e-12)
+    assert rows[0][3] == "0" and rows[0][4] == "0"
+    x1 = [float(v) for v in rows[1][:3]]   # optimum pushed onto the support-polygon edge x = 1
+    np.testing.assert_allclose(x1, [1.0, 0.0, 0.3], atol=1e-12)
+    assert rows[1][3] == "0" and rows[1][4] == "1"
+
+
+def test_qp_adapter_compiles(qlb_built):
+    build.build_host_demo(which="qp_demo")
