@@ -25,6 +25,7 @@ struct qlb_context {
   unsigned long long* d_counter = nullptr;
   double* d_stats = nullptr;
   cudaStream_t stream = nullptr;  // used by the *_host entry points
+  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the *_host entry points
   // device staging for the *_host entry points
   double* d_in = nullptr;
   double* d_out = nullptr;
@@ -39,6 +40,9 @@ namespace {
 
 constexpr int kHostInRows = 12 + 7 + 6 + 7 + 6 + 4 + 12;  // state mode is the larger one (54)
 constexpr int kHostOutRows = 12 + 12 + 6 + 6;
+constexpr int kCounters = 64;            // ring of work counters: launches on different streams never share one
+constexpr int kPipe = 3;                 // host entry points: chunks in flight (H2D / kernel / D2H overlap)
+constexpr size_t kChunk = size_t(1) << 17;  // states per pipeline chunk
 
 struct DeviceGuard {
   int prev = -1;
@@ -134,6 +138,7 @@ int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
   unsigned long long want = (nbatch + kWarpsPerCta - 1) / kWarpsPerCta;
   unsigned long long cap = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm[MODE];
   const unsigned grid = (unsigned)(want < cap ? want : cap);
+  a.counter = ctx->d_counter + (ctx->launches % kCounters);
   QLB_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st));
   qlb_solve_kernel<MODE><<<grid, kThreads, smem, st>>>(a);
   QLB_CUDA(ctx, cudaGetLastError());
@@ -141,16 +146,18 @@ int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
   return QLB_OK;
 }
 
+// staging of the host entry points: kPipe slots of `cap` states each (cap <= kChunk)
 int ensure_capacity(qlb_context* ctx, size_t B) {
+  if (B > kChunk) B = kChunk;
   if (B <= ctx->cap) return QLB_OK;
   size_t cap = ctx->cap ? ctx->cap : 1024;
   while (cap < B) cap *= 2;
   cap = (cap + 15) & ~size_t(15);
   cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags);
   ctx->d_in = ctx->d_out = nullptr; ctx->d_mask = nullptr; ctx->d_flags = nullptr; ctx->cap = 0;
-  if (cudaMalloc(&ctx->d_in, cap * kHostInRows * sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&ctx->d_out, cap * kHostOutRows * sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&ctx->d_mask, cap) != cudaSuccess || cudaMalloc(&ctx->d_flags, cap * sizeof(uint32_t)) != cudaSuccess) {
+  if (cudaMalloc(&ctx->d_in, kPipe * cap * kHostInRows * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_out, kPipe * cap * kHostOutRows * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_mask, kPipe * cap) != cudaSuccess || cudaMalloc(&ctx->d_flags, kPipe * cap * sizeof(uint32_t)) != cudaSuccess) {
     cudaGetLastError();
     return QLB_ERR_ALLOC;
   }
@@ -234,10 +241,12 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
   ctx->sm_count = prop.multiProcessorCount;
   auto fail = [&](int code) { qlb_destroy(ctx); return code; };
   if (cudaMalloc(&ctx->d_model, sizeof(DeviceModel)) != cudaSuccess || cudaMalloc(&ctx->d_params, sizeof(DeviceParams)) != cudaSuccess ||
-      cudaMalloc(&ctx->d_counter, sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_counter, kCounters * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMalloc(&ctx->d_stats, QLB_STATS_NUM * sizeof(double)) != cudaSuccess)
     return fail(QLB_ERR_ALLOC);
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(QLB_ERR_CUDA);
+  for (int i = 0; i < kPipe; i++)
+    if (cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking) != cudaSuccess) return fail(QLB_ERR_CUDA);
   DeviceModel hm;
   build_device_model(legs, &hm);
   if (cudaMemcpy(ctx->d_model, &hm, sizeof hm, cudaMemcpyHostToDevice) != cudaSuccess) return fail(QLB_ERR_CUDA);
@@ -259,6 +268,8 @@ int qlb_destroy(qlb_context* ctx) {
   if (!ctx) return QLB_OK;
   DeviceGuard guard(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  for (int i = 0; i < kPipe; i++)
+    if (ctx->pipe[i]) { cudaStreamSynchronize(ctx->pipe[i]); cudaStreamDestroy(ctx->pipe[i]); }
   cudaFree(ctx->d_model); cudaFree(ctx->d_params); cudaFree(ctx->d_counter); cudaFree(ctx->d_stats);
   cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags);
   cudaGetLastError();
@@ -326,7 +337,66 @@ int qlb_solve_state(qlb_context* ctx, size_t B, const double* q, const double* b
   return launch_solve<1>(ctx, a, static_cast<cudaStream_t>(stream));
 }
 
-// ---- host-pointer entry points: copy in, solve, copy out, synchronise
+// ---- host-pointer entry points: copy in, solve, copy out, synchronise.
+// Large batches are cut into chunks of kChunk states that flow through kPipe streams, so that the H2D
+// copy of chunk i+1, the kernel of chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex).
+// The arrays are SoA with row pitch B, so a chunk is a column range: one 2-D copy per array.
+namespace {
+
+struct HostRow { const double* h; int rows; };   // input array (may be null) and its component count
+struct HostOut { double* h; int rows; };
+
+int run_host_pipeline(qlb_context* ctx, size_t B, bool state_mode, const HostRow* in, int nin, const uint8_t* mask,
+                      const HostOut* out, int nout, uint32_t* flags) {
+  int rc = ensure_capacity(ctx, B);
+  if (rc != QLB_OK) return rc;
+  const size_t cap = ctx->cap;
+  const size_t nchunks = (B + cap - 1) / cap;
+  for (size_t ci = 0; ci < nchunks; ci++) {
+    const int slot = (int)(ci % kPipe);
+    cudaStream_t st = ctx->pipe[slot];
+    const size_t b0 = ci * cap, n = (B - b0 < cap) ? (B - b0) : cap;
+    double* din = ctx->d_in + (size_t)slot * cap * kHostInRows;
+    double* dout = ctx->d_out + (size_t)slot * cap * kHostOutRows;
+    uint8_t* dmask = ctx->d_mask + (size_t)slot * cap;
+    uint32_t* dflags = ctx->d_flags + (size_t)slot * cap;
+    const double* dptr_in[8];
+    size_t off = 0;
+    for (int k = 0; k < nin; k++) {
+      dptr_in[k] = nullptr;
+      if (in[k].h) {
+        dptr_in[k] = din + off;
+        QLB_CUDA(ctx, cudaMemcpy2DAsync(din + off, n * sizeof(double), in[k].h + b0, B * sizeof(double), n * sizeof(double),
+                                        in[k].rows, cudaMemcpyHostToDevice, st));
+      }
+      off += (size_t)in[k].rows * cap;   // fixed block sizes keep every block 16-byte aligned (cap % 16 == 0)
+    }
+    QLB_CUDA(ctx, cudaMemcpyAsync(dmask, mask + b0, n, cudaMemcpyHostToDevice, st));
+    double* dptr_out[4];
+    off = 0;
+    for (int k = 0; k < nout; k++) {
+      dptr_out[k] = out[k].h ? dout + off : nullptr;
+      off += (size_t)out[k].rows * cap;
+    }
+    if (!state_mode)
+      rc = qlb_solve_wrench(ctx, n, dptr_in[0], dptr_in[1], dptr_in[2], dmask, dptr_in[3], dptr_in[4], dptr_out[0], dptr_out[1],
+                            dflags, dptr_out[2], st);
+    else
+      rc = qlb_solve_state(ctx, n, dptr_in[0], dptr_in[1], dptr_in[2], dptr_in[3], dptr_in[4], dmask, dptr_in[5], dptr_in[6],
+                           dptr_out[0], dptr_out[1], dflags, dptr_out[2], dptr_out[3], st);
+    if (rc != QLB_OK) return rc;
+    for (int k = 0; k < nout; k++)
+      if (out[k].h)
+        QLB_CUDA(ctx, cudaMemcpy2DAsync(out[k].h + b0, B * sizeof(double), dptr_out[k], n * sizeof(double), n * sizeof(double),
+                                        out[k].rows, cudaMemcpyDeviceToHost, st));
+    QLB_CUDA(ctx, cudaMemcpyAsync(flags + b0, dflags, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < kPipe; i++) QLB_CUDA(ctx, cudaStreamSynchronize(ctx->pipe[i]));
+  return QLB_OK;
+}
+
+}  // namespace
+
 int qlb_solve_wrench_host(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz, const double* wrench,
                           const uint8_t* stance_mask, const double* mu, const double* normals_world, double* grf,
                           double* tau, uint32_t* flags, double* netwrench) {
@@ -334,31 +404,9 @@ int qlb_solve_wrench_host(qlb_context* ctx, size_t B, const double* q, const dou
   if (B == 0) return QLB_OK;
   if (!q || !quat_wxyz || !wrench || !stance_mask || !grf || !tau || !flags) return QLB_ERR_INVALID_ARGUMENT;
   DeviceGuard guard(ctx->device);
-  int rc = ensure_capacity(ctx, B);
-  if (rc != QLB_OK) return rc;
-  const size_t cap = ctx->cap;  // row pitch of the staging buffers: keeps every row 16-byte aligned
-  cudaStream_t st = ctx->stream;
-  double* din = ctx->d_in;
-  double* d_q = din; double* d_quat = din + 12 * cap; double* d_wr = din + 16 * cap;
-  double* d_mu = din + 22 * cap; double* d_nr = din + 26 * cap;
-  double* dout = ctx->d_out;
-  double* d_grf = dout; double* d_tau = dout + 12 * cap; double* d_net = dout + 24 * cap;
-  // the kernel indexes rows with pitch B, so stage contiguous [C][B] blocks
-  QLB_CUDA(ctx, cudaMemcpyAsync(d_q, q, 12 * B * sizeof(double), cudaMemcpyHostToDevice, st));
-  QLB_CUDA(ctx, cudaMemcpyAsync(d_quat, quat_wxyz, 4 * B * sizeof(double), cudaMemcpyHostToDevice, st));
-  QLB_CUDA(ctx, cudaMemcpyAsync(d_wr, wrench, 6 * B * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (mu) QLB_CUDA(ctx, cudaMemcpyAsync(d_mu, mu, 4 * B * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (normals_world) QLB_CUDA(ctx, cudaMemcpyAsync(d_nr, normals_world, 12 * B * sizeof(double), cudaMemcpyHostToDevice, st));
-  QLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, stance_mask, B, cudaMemcpyHostToDevice, st));
-  rc = qlb_solve_wrench(ctx, B, d_q, d_quat, d_wr, ctx->d_mask, mu ? d_mu : nullptr, normals_world ? d_nr : nullptr,
-                        d_grf, d_tau, ctx->d_flags, netwrench ? d_net : nullptr, st);
-  if (rc != QLB_OK) return rc;
-  QLB_CUDA(ctx, cudaMemcpyAsync(grf, d_grf, 12 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  QLB_CUDA(ctx, cudaMemcpyAsync(tau, d_tau, 12 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  QLB_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  if (netwrench) QLB_CUDA(ctx, cudaMemcpyAsync(netwrench, d_net, 6 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  QLB_CUDA(ctx, cudaStreamSynchronize(st));
-  return QLB_OK;
+  const HostRow in[5] = {{q, 12}, {quat_wxyz, 4}, {wrench, 6}, {mu, 4}, {normals_world, 12}};
+  const HostOut out[3] = {{grf, 12}, {tau, 12}, {netwrench, 6}};
+  return run_host_pipeline(ctx, B, false, in, 5, stance_mask, out, 3, flags);
 }
 
 int qlb_solve_state_host(qlb_context* ctx, size_t B, const double* q, const double* base_pose, const double* base_twist,
@@ -370,34 +418,9 @@ int qlb_solve_state_host(qlb_context* ctx, size_t B, const double* q, const doub
   if (!q || !base_pose || !base_twist || !target_pose || !target_twist || !stance_mask || !grf || !tau || !flags)
     return QLB_ERR_INVALID_ARGUMENT;
   DeviceGuard guard(ctx->device);
-  int rc = ensure_capacity(ctx, B);
-  if (rc != QLB_OK) return rc;
-  const size_t cap = ctx->cap;
-  cudaStream_t st = ctx->stream;
-  double* din = ctx->d_in;
-  double* d_q = din; double* d_pose = din + 12 * cap; double* d_tw = din + 19 * cap; double* d_tp = din + 25 * cap;
-  double* d_tt = din + 32 * cap; double* d_mu = din + 38 * cap; double* d_nr = din + 42 * cap;
-  double* dout = ctx->d_out;
-  double* d_grf = dout; double* d_tau = dout + 12 * cap; double* d_net = dout + 24 * cap; double* d_wo = dout + 30 * cap;
-  QLB_CUDA(ctx, cudaMemcpyAsync(d_q, q, 12 * B * sizeof(double), cudaMemcpyHostToDevice, st));
-  QLB_CUDA(ctx, cudaMemcpyAsync(d_pose, base_pose, 7 * B * sizeof(double), cudaMemcpyHostToDevice, st));
-  QLB_CUDA(ctx, cudaMemcpyAsync(d_tw, base_twist, 6 * B * sizeof(double), cudaMemcpyHostToDevice, st));
-  QLB_CUDA(ctx, cudaMemcpyAsync(d_tp, target_pose, 7 * B * sizeof(double), cudaMemcpyHostToDevice, st));
-  QLB_CUDA(ctx, cudaMemcpyAsync(d_tt, target_twist, 6 * B * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (mu) QLB_CUDA(ctx, cudaMemcpyAsync(d_mu, mu, 4 * B * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (normals_world) QLB_CUDA(ctx, cudaMemcpyAsync(d_nr, normals_world, 12 * B * sizeof(double), cudaMemcpyHostToDevice, st));
-  QLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, stance_mask, B, cudaMemcpyHostToDevice, st));
-  rc = qlb_solve_state(ctx, B, d_q, d_pose, d_tw, d_tp, d_tt, ctx->d_mask, mu ? d_mu : nullptr,
-                       normals_world ? d_nr : nullptr, d_grf, d_tau, ctx->d_flags, netwrench ? d_net : nullptr,
-                       wrench_out ? d_wo : nullptr, st);
-  if (rc != QLB_OK) return rc;
-  QLB_CUDA(ctx, cudaMemcpyAsync(grf, d_grf, 12 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  QLB_CUDA(ctx, cudaMemcpyAsync(tau, d_tau, 12 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  QLB_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  if (netwrench) QLB_CUDA(ctx, cudaMemcpyAsync(netwrench, d_net, 6 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (wrench_out) QLB_CUDA(ctx, cudaMemcpyAsync(wrench_out, d_wo, 6 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  QLB_CUDA(ctx, cudaStreamSynchronize(st));
-  return QLB_OK;
+  const HostRow in[7] = {{q, 12}, {base_pose, 7}, {base_twist, 6}, {target_pose, 7}, {target_twist, 6}, {mu, 4}, {normals_world, 12}};
+  const HostOut out[4] = {{grf, 12}, {tau, 12}, {netwrench, 6}, {wrench_out, 6}};
+  return run_host_pipeline(ctx, B, true, in, 7, stance_mask, out, 4, flags);
 }
 
 int qlb_leg_kinematics(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz, double* foot, double* jac,
