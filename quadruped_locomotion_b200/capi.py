@@ -13,7 +13,7 @@ import numpy as np
 from . import legmodel
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libqlb.so")
+LIB_PATH = os.environ.get("QLB_LIB", os.path.join(PKG, "libqlb.so"))  # QLB_LIB: kernel-variant experiments only
 
 NUM_LEGS = 4
 STATS_NUM = 30

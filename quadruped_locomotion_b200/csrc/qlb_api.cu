@@ -124,7 +124,7 @@ void build_device_params(const qlb_params* p, DeviceParams* d) {
 bool params_ok(const qlb_params* p) {
   if (!(p->ground_force_weight > 0.0) || !(p->ipm_tolerance > 0.0) || p->ipm_max_iterations < 1) return false;
   for (int i = 0; i < 6; i++)
-    if (!(p->wrench_weights[i] >= 0.0)) return false;
+    if (!(p->wrench_weights[i] > 0.0)) return false;  // the 6x6 dual system needs S^-1
   return std::isfinite(p->min_normal_force) && std::isfinite(p->friction_default) && std::isfinite(p->gravity);
 }
 

@@ -215,15 +215,17 @@ constexpr int kPitch = 33;
 
 // Cholesky with the forward substitution of one right-hand side fused in.
 // In: acc = rhs[gl].  Out: hs = L (entry (gl, j), j <= gl), rdiag = 1/L[gl][gl], acc = z[gl] with L z = rhs.
+template <int N>
 __device__ __forceinline__ bool smem_cholesky_fwd(double* __restrict__ hs, double (*xb)[2][16], double& rdiag,
                                                   double& acc, const int grp, const int gl, const int lane) {
   bool ok = true;
   rdiag = 1.0;
 #pragma unroll 1
-  for (int k = 0; k < kVars; k++) {
+  for (int k = 0; k < N; k++) {
     double* buf = xb[k & 1][grp];
-    const double hk = hs[k * kPitch + lane];
-    if (gl >= k && gl < kVars) buf[gl] = hk;   // publish the raw column k
+    const bool row = gl < N;                   // lanes beyond the matrix carry zeros
+    const double hk = row ? hs[k * kPitch + lane] : 0.0;
+    if (gl >= k && row) buf[gl] = hk;          // publish the raw column k
     if (gl == k) buf[12] = acc;                // and the pivot row's right-hand side
     __syncwarp();
     const double dkk = buf[k];
@@ -233,43 +235,92 @@ __device__ __forceinline__ bool smem_cholesky_fwd(double* __restrict__ hs, doubl
     const double zk = rk * rinv;
     const double lik = hk * rinv;
     const double a = (gl > k) ? -lik * rinv : 0.0;  // finished rows: multiplier 0
-    if (gl >= k) hs[k * kPitch + lane] = lik;
+    if (gl >= k && row) hs[k * kPitch + lane] = lik;
     if (gl == k) { rdiag = rinv; acc = zk; }
     if (gl > k) acc = fma(-lik, zk, acc);
+    if (row) {
 #pragma unroll 4
-    for (int j = k + 1; j < kVars; j++) hs[j * kPitch + lane] = fma(a, buf[j], hs[j * kPitch + lane]);
+      for (int j = k + 1; j < N; j++) hs[j * kPitch + lane] = fma(a, buf[j], hs[j * kPitch + lane]);
+    }
   }
   return ok;
 }
 
+// 6x6 variant with the row in registers and the step loop unrolled (15 multiply-adds in all, ~170
+// instructions): the matrix is read from hs once, the factor written back for the substitutions.
+__device__ __forceinline__ bool reg_cholesky6_fwd(double* __restrict__ hs, double (*xb)[2][16], double& rdiag,
+                                                  double& acc, const int grp, const int gl, const int lane) {
+  const bool row = gl < 6;
+  double h[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) h[j] = row ? hs[j * kPitch + lane] : 0.0;
+  bool ok = true;
+  rdiag = 1.0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    double* buf = xb[k & 1][grp];
+    if (gl >= k && row) buf[gl] = h[k];  // publish the raw column k
+    if (gl == k) buf[6] = acc;           // and the pivot row's right-hand side
+    __syncwarp();
+    double bcol[8];
+#pragma unroll
+    for (int p2 = 0; p2 < 4; p2++) {
+      if (2 * p2 + 1 >= k) {             // 16-byte broadcast loads of what is still needed (pair 3 = rhs slot)
+        const double2 t = *reinterpret_cast<const double2*>(buf + 2 * p2);
+        bcol[2 * p2] = t.x;
+        bcol[2 * p2 + 1] = t.y;
+      }
+    }
+    const double dkk = bcol[k];
+    ok = ok && (dkk > 0.0);
+    const double rinv = fast_rsqrt(dkk);
+    const double zk = bcol[6] * rinv;
+    const double lik = h[k] * rinv;
+    const double a = (gl > k) ? -lik * rinv : 0.0;  // finished rows: multiplier 0
+    if (gl >= k) h[k] = lik;
+    if (gl == k) { rdiag = rinv; acc = zk; }
+    if (gl > k) acc = fma(-lik, zk, acc);
+#pragma unroll
+    for (int j = k + 1; j < 6; j++) h[j] = fma(a, bcol[j], h[j]);
+  }
+  if (row) {
+#pragma unroll
+    for (int j = 0; j < 6; j++) hs[j * kPitch + lane] = h[j];
+  }
+  __syncwarp();
+  return ok;
+}
+
 // forward substitution L z = b: lane gl passes b[gl], receives z[gl]
+template <int N>
 __device__ __forceinline__ double smem_forward(const double* __restrict__ hs, double (*xb)[2][16], const double rdiag,
                                                const double b, const int grp, const int gl, const int lane) {
   double acc = b, z = 0.0;
 #pragma unroll 1
-  for (int j = 0; j < kVars; j++) {
+  for (int j = 0; j < N; j++) {
     double* buf = xb[j & 1][grp];
     if (gl == j) buf[13] = acc * rdiag;
     __syncwarp();
     const double zj = buf[13];
     if (gl == j) z = zj;
-    if (gl > j) acc = fma(-hs[j * kPitch + lane], zj, acc);
+    if (gl > j && gl < N) acc = fma(-hs[j * kPitch + lane], zj, acc);
   }
   return z;
 }
 
 // backward substitution L^T x = z; L[j][gl] is read transposed from row j's lane
+template <int N>
 __device__ __forceinline__ double smem_backward(const double* __restrict__ hs, double (*xb)[2][16], const double rdiag,
                                                 const double z, const int grp, const int gl) {
   double acc = z, x = 0.0;
 #pragma unroll 1
-  for (int j = kVars - 1; j >= 0; j--) {
+  for (int j = N - 1; j >= 0; j--) {
     double* buf = xb[j & 1][grp];
     if (gl == j) buf[13] = acc * rdiag;
     __syncwarp();
     const double xj = buf[13];
     if (gl == j) x = xj;
-    if (gl < j) acc = fma(-hs[gl * kPitch + 16 * grp + j], xj, acc);
+    if (gl < j) acc = fma(-hs[gl * kPitch + 16 * grp + j], xj, acc);  // gl < j < N: in range
   }
   return x;
 }

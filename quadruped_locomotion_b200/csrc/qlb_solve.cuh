@@ -13,6 +13,9 @@
 namespace qlb {
 
 constexpr int kBatch = 4;         // QPs staged per warp batch (32 bytes = one sector per component row)
+#ifndef QLB_MIN_CTAS
+#define QLB_MIN_CTAS 3
+#endif
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = 32 * kWarpsPerCta;
 
@@ -56,15 +59,16 @@ template <int ROWS>
 struct alignas(16) WarpSmem {
   double in[ROWS][kBatch];
   double out[kOutRows][kBatch];
-  double atl[2][kVars][6];   // per group: wrench-map column of every slot, [e; r x e]
-  double col[2][kVars][6];   // per group: reduced columns of the current polish pass
+  double atl[2][kVars][6];   // per group: wrench-map column of every slot, a_l = [e; r x e]
+  double pc[2][kVars][6];    // per group: left factor columns P_l of the 6x6 system N = S^-1 + sum_l P_l C_l'
+  double cc[2][kVars][6];    // per group: right factor columns C_l (polish: reduced columns; IPM: a_l)
   double fix[2][4][6];       // per group, per leg: contribution of a pinned normal force
-  double grow[kVars][32];    // row of G~ of every lane (lane-minor: conflict-free)
   double tail[7][32];        // per lane: slot direction e (3), Jacobian column (3), gravity torque
   double bw[2][6];           // per group: the wrench b
+  double t6[2][8];           // per group: solution of the 6x6 system (S-weighted wrench residual)
   double xb[2][2][16];       // exchange buffer of the factorisation (double buffered, one row per group)
-  double vb[1][2][16];       // vector exchange: [which][group][slot]
-  double hs[kVars * kPitch]; // the round's matrix / its Cholesky factor, one row per lane
+  double vb[2][16];          // per group: vector exchange (right-hand sides)
+  double hs[6 * kPitch];     // the round's 6x6 matrix / its Cholesky factor, row r in lane 16*grp + r
   uint32_t flags[kBatch];
   uint8_t mask[kBatch];
 };
@@ -168,7 +172,6 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
   // ---------------- inputs
   const unsigned mask = ws.mask[qi] & 0xFu;
   const bool alive = var_lane && ((mask >> leg) & 1u);
-  const double alive_d = alive ? 1.0 : 0.0;
   const int ns = __popc(mask);
   const double qv = ws.in[kRowQ + l0 + c][qi];
   double quat[4], b[6];
@@ -254,13 +257,13 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
     t1[0] = nb[1] * ey[2] - nb[2] * ey[1];
     t1[1] = nb[2] * ey[0] - nb[0] * ey[2];
     t1[2] = nb[0] * ey[1] - nb[1] * ey[0];
-    double rn = rsqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+    double rn = fast_rsqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
 #pragma unroll
     for (int a = 0; a < 3; a++) t1[a] *= rn;
     t2[0] = nb[1] * t1[2] - nb[2] * t1[1];
     t2[1] = nb[2] * t1[0] - nb[0] * t1[2];
     t2[2] = nb[0] * t1[1] - nb[1] * t1[0];
-    rn = rsqrt(t2[0] * t2[0] + t2[1] * t2[1] + t2[2] * t2[2]);
+    rn = fast_rsqrt(t2[0] * t2[0] + t2[1] * t2[1] + t2[2] * t2[2]);
 #pragma unroll
     for (int a = 0; a < 3; a++) t2[a] *= rn;
     if (alive) {
@@ -334,24 +337,25 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
   double ev[3];
 #pragma unroll
   for (int a = 0; a < 3; a++) ev[a] = (c == 0) ? nb[a] : (c == 1 ? t1[a] : t2[a]);
-  {
-    double at[6];
-    at[0] = ev[0]; at[1] = ev[1]; at[2] = ev[2];
-    at[3] = foot[1] * ev[2] - foot[2] * ev[1];
-    at[4] = foot[2] * ev[0] - foot[0] * ev[2];
-    at[5] = foot[0] * ev[1] - foot[1] * ev[0];
-    if (var_lane) {
+  double at_raw[6];
+  at_raw[0] = ev[0]; at_raw[1] = ev[1]; at_raw[2] = ev[2];
+  at_raw[3] = foot[1] * ev[2] - foot[2] * ev[1];
+  at_raw[4] = foot[2] * ev[0] - foot[0] * ev[2];
+  at_raw[5] = foot[0] * ev[1] - foot[1] * ev[0];
+  if (var_lane) {
 #pragma unroll
-      for (int r = 0; r < 6; r++) ws.atl[grp][gl][r] = alive ? at[r] : 0.0;
-    }
+    for (int r = 0; r < 6; r++) ws.atl[grp][gl][r] = alive ? at_raw[r] : 0.0;
   }
   __syncwarp();
 
   // ---------------- solver state
+  // The 12x12 systems of this QP all have the form  K + A~' S A~  with K block diagonal (3x3 per leg) and
+  // A~ the 6 x 12 wrench map, so they are solved through the 6x6 "dual" system
+  //     (S^-1 + A~ K^-1 A~') t = A~ K^-1 r,      x = K^-1 (r - A~' t)
+  // (push-through / Woodbury): one 6x6 Cholesky per round instead of a 12x12 one.  For the polish rounds
+  // t is the S-weighted wrench residual S(b - A~ y), from which the gradient follows without a mat-vec.
   // Everything that contains a shuffle is executed by the whole warp with the full mask; a group that
-  // is not in the corresponding mode just computes values it never commits.  The loop body is kept
-  // small (one factorisation site, one substitution site, one mat-vec site): with a dozen warps per SM
-  // at different program counters the instruction cache is the first bottleneck of this kernel.
+  // is not in the corresponding mode just computes values it never commits.
   if (var_lane) {
 #pragma unroll
     for (int a = 0; a < 3; a++) { ws.tail[a][lane] = ev[a]; ws.tail[3 + a][lane] = jcol[a]; }
@@ -361,122 +365,152 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
   // strictly feasible interior-point start for this leg: push c0 along the normal
   const double c0 = fmax(fmax(2.0 * prm.fmin, (b[0] * nb[0] + b[1] * nb[1] + b[2] * nb[2]) * (ns > 0 ? 1.0 / ns : 0.0)),
                          prm.fmin + 1.0);
+  double at[6];  // own wrench-map column
+  double gt = 0.0;  // g~ of this slot = -a_l . (S b)
+#pragma unroll
+  for (int r = 0; r < 6; r++) { at[r] = alive ? at_raw[r] : 0.0; gt = fma(-at[r] * prm.S[r], b[r], gt); }
+  const float gscale = fmaxf(1.f, group_max(fabsf((float)gt)));
   __syncwarp();
 
   double* const hs = ws.hs;
-  const bool rowB = alive && c > 0;  // this lane owns a second row
-  double gt = 0.0;                   // g~ of this slot
+  const int rr = gl % 6, hh = (gl / 6) % 2;  // this lane computes entries (rr, 3hh .. 3hh+2) of the 6x6 matrix
+  const double sinv = 1.0 / prm.S[rr];
+  const bool rowB = alive && c > 0;  // this lane owns a second constraint row
   double y = 0.0;                    // interior-point iterate / final solution of this slot
   double rd = 0.0;                   // dual residual of this slot, kept up to date incrementally
   double sA = 1.0, sB = 1.0, lamA = 0.0, lamB = 0.0, rpA = 0.0, rpB = 0.0;  // slack, multiplier, primal residual
   int pat = 0;  // active pattern of this lane's rows: normal lane 1 = pinned at F_min; tangential lanes
                 // -1 = row A active (y_c = -mu y_n), +1 = row B active (y_c = +mu y_n)
   int mode = kModePolish, it = 0, pass = 0, status = 0;
-  bool first = true, converged = false, have_G = false, want_polish = false;
+  bool first = true, converged = false, want_polish = false;
   double alpha_prev = 1.0;
   if (badbits != 0u) { mode = kModeDone; status = 4; }
   else if (ns == 0) { mode = kModeDone; status = 1; }
   const float rm = ns > 0 ? 1.f / (5.f * ns) : 0.f;
 
-  // ---------------- rounds: one factorisation + one or two substitutions, shared by both groups
+  // ---------------- rounds: one 6x6 factorisation + one or two substitutions, shared by both groups
   int rounds = 0;
 #pragma unroll 1
   for (;;) {
     if (__all_sync(kFull, mode == kModeDone)) break;
     if (++rounds > 200 && mode != kModeDone) { mode = kModeDone; status = 2; }  // hard stop, never reached in practice
-    double rhs = 0.0, rsA = 1.0, rsB = 1.0;
+    const bool pol_round = (mode == kModePolish), ipm_round = (mode == kModeIpm);
+    const bool any_pol = __any_sync(kFull, pol_round), any_ipm = __any_sync(kFull, ipm_round);
+    double rhs = 0.0, rsA = 1.0, rsB = 1.0, k0 = 0.0, k1 = 0.0, k2 = 0.0, iwd = 0.0, thA = 0.0, thB = 0.0;
+    double mycol[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) mycol[r] = 0.0;
 
-    // ---- B. system of this round
-    const bool any_pol = __any_sync(kFull, mode == kModePolish);
+    // ---- B1. polish: reduced columns C_l of the pattern, P_l = C_l / wd_l, pinned contributions
     if (any_pol) {
-      // reduced system of the equality-constrained QP for the current pattern
       const int p1 = gshfl(pat, l0 + 1), p2 = gshfl(pat, l0 + 2);
-      double mycol[6];
-      const bool free_slot = alive && (pat == 0);
-      if (mode == kModePolish) {
-        const double* an = ws.atl[grp][l0];
+      if (pol_round && var_lane) {
+        const bool free_slot = alive && (pat == 0);
         const double* a1 = ws.atl[grp][l0 + 1];
         const double* a2 = ws.atl[grp][l0 + 2];
-        const double k1 = p1 * mu, k2 = p2 * mu;
+        const double q1 = p1 * mu, q2 = p2 * mu;
+        const double wd = (c == 0) ? prm.W * fma(mu * mu, (double)(p1 * p1 + p2 * p2), 1.0) : prm.W;
+        iwd = free_slot ? 1.0 / wd : 0.0;
         const double f = (c == 0 && pat != 0 && alive) ? prm.fmin : 0.0;
 #pragma unroll
         for (int r = 0; r < 6; r++) {
-          const double cn = fma(k2, a2[r], fma(k1, a1[r], an[r]));
-          const double own = (c == 0) ? cn : (c == 1 ? a1[r] : a2[r]);
-          mycol[r] = (free_slot && var_lane) ? own : 0.0;
-          if (var_lane) ws.col[grp][gl][r] = mycol[r];
-          if (var_lane && c == 0) ws.fix[grp][leg][r] = f * cn;
+          const double cn = (c == 0) ? fma(q2, a2[r], fma(q1, a1[r], at[r])) : at[r];
+          mycol[r] = free_slot ? cn : 0.0;
+          ws.cc[grp][gl][r] = mycol[r];
+          ws.pc[grp][gl][r] = mycol[r] * iwd;
+          if (c == 0) ws.fix[grp][leg][r] = f * cn;
         }
       }
-      __syncwarp();
-      if (mode == kModePolish) {
-        const double wd = free_slot ? ((c == 0) ? prm.W * fma(mu * mu, (double)(p1 * p1 + p2 * p2), 1.0) : prm.W) : 1.0;
-        double sc[6];
-        rhs = 0.0;
+    }
+    // ---- B2. interior point: K = w I + D~' diag(lam/s) D~ per leg (3x3 arrow matrix), its inverse,
+    //          P_l = A~ K^-1 e_l, C_l = a_l, predictor right-hand side
+    if (any_ipm) {
+      rsA = fast_rcp(sA); rsB = fast_rcp(sB);
+      thA = lamA * rsA; thB = lamB * rsB;
+      const double T = thA + thB, Dl = thA - thB;
+      const double T0 = gshfl(T, l0), T1 = gshfl(T, l0 + 1), D1 = gshfl(Dl, l0 + 1), T2 = gshfl(T, l0 + 2), D2 = gshfl(Dl, l0 + 2);
+      const double dtv = dt_lane(fma(-thA, rpA, lamA), fma(-thB, rpB, lamB), mu, c, l0);
+      // arrow matrix [[a, b1, b2], [b1, d1, 0], [b2, 0, d2]] and its inverse via the Schur complement of a
+      const double d1 = prm.W + T1, d2 = prm.W + T2, b1 = mu * D1, b2 = mu * D2;
+      const double a = prm.W + fma(mu * mu, T1 + T2, T0);
+      const double id1 = fast_rcp(d1), id2 = fast_rcp(d2);
+      const double e1 = b1 * id1, e2 = b2 * id2;
+      const double isg = fast_rcp(a - b1 * e1 - b2 * e2);
+      if (c == 0) { k0 = isg; k1 = -e1 * isg; k2 = -e2 * isg; }
+      else if (c == 1) { k0 = -e1 * isg; k1 = fma(e1 * e1, isg, id1); k2 = e1 * e2 * isg; }
+      else { k0 = -e2 * isg; k1 = e1 * e2 * isg; k2 = fma(e2 * e2, isg, id2); }
+      if (ipm_round && var_lane) {
+        const double* an = ws.atl[grp][l0];
+        const double* a1 = ws.atl[grp][l0 + 1];
+        const double* a2 = ws.atl[grp][l0 + 2];
 #pragma unroll
         for (int r = 0; r < 6; r++) {
-          const double bp = ws.bw[grp][r] - ((ws.fix[grp][0][r] + ws.fix[grp][1][r]) + (ws.fix[grp][2][r] + ws.fix[grp][3][r]));
-          sc[r] = prm.S[r] * mycol[r];
-          rhs = fma(sc[r], bp, rhs);
+          ws.pc[grp][gl][r] = fma(k2, a2[r], fma(k1, a1[r], k0 * an[r]));
+          ws.cc[grp][gl][r] = at[r];
         }
-#pragma unroll 1
-        for (int j = 0; j < kVars; j++) {
-          const double* cj = ws.col[grp][j];
-          double acc = (j == gl) ? wd : 0.0;
-#pragma unroll
-          for (int r = 0; r < 6; r++) acc = fma(sc[r], cj[r], acc);
-          hs[j * kPitch + lane] = acc;
-          if (!have_G) ws.grow[j][lane] = acc;  // first pass (empty pattern): this is G~
-        }
-        if (!have_G) {
-          gt = -rhs;                            // and -g~
-          have_G = true;
-        }
-      }
-      __syncwarp();
-    }
-    const bool any_ipm = __any_sync(kFull, mode == kModeIpm);
-    const bool ipm_round = (mode == kModeIpm);
-    if (any_ipm) {
-      // H = G~ + D~' diag(lam/s) D~ (3x3 block on the diagonal of each leg), predictor right-hand side
-      rsA = fast_rcp(sA); rsB = fast_rcp(sB);
-      const double thA = lamA * rsA, thB = lamB * rsB;
-      const double T = thA + thB, Dl = thA - thB;
-      const double T1 = gshfl(T, l0 + 1), D1 = gshfl(Dl, l0 + 1), T2 = gshfl(T, l0 + 2), D2 = gshfl(Dl, l0 + 2);
-      const double dtv = dt_lane(fma(-thA, rpA, lamA), fma(-thB, rpB, lamB), mu, c, l0);
-      if (ipm_round) {
-        double blk0, blk1, blk2;
-        if (c == 0) { blk0 = fma(mu * mu, T1 + T2, thA); blk1 = mu * D1; blk2 = mu * D2; }
-        else if (c == 1) { blk0 = mu * Dl; blk1 = T; blk2 = 0.0; }
-        else { blk0 = mu * Dl; blk1 = 0.0; blk2 = T; }
-#pragma unroll 1
-        for (int j = 0; j < kVars; j++) {
-          const int o = j - l0;
-          const double add = (var_lane && o >= 0 && o < 3) ? (o == 0 ? blk0 : (o == 1 ? blk1 : blk2)) : 0.0;
-          hs[j * kPitch + lane] = ws.grow[j][lane] + add;
-        }
-        rhs = var_lane ? -rd - dtv : 0.0;
+        rhs = -rd - dtv;
+        ws.vb[grp][gl] = rhs;
       }
     }
-    if (mode == kModeDone) {
-#pragma unroll 1
-      for (int j = 0; j < kVars; j++) hs[j * kPitch + lane] = (j == gl) ? 1.0 : 0.0;
-      rhs = 0.0;
-    }
+    __syncwarp();
 
-    // ---- C. factorise; the forward substitution of this round's first right-hand side is fused in
-    double rdiag, zf = rhs;
-    const bool pd = smem_cholesky_fwd(hs, ws.xb, rdiag, zf, grp, gl, lane);
+    // ---- N. the 6x6 system: N = S^-1 + sum_l P_l C_l' (three entries per lane), right-hand side
+    //         polish: b - pinned contributions;  interior point: sum_l P_l r_l
+    double rhs6 = 0.0;
+    if (var_lane && mode != kModeDone) {
+      double n0 = (rr == 3 * hh) ? sinv : 0.0, n1 = (rr == 3 * hh + 1) ? sinv : 0.0, n2 = (rr == 3 * hh + 2) ? sinv : 0.0;
+#pragma unroll 2
+      for (int l = 0; l < kVars; l++) {
+        const double pl = ws.pc[grp][l][rr];
+        const double* cl = &ws.cc[grp][l][3 * hh];
+        n0 = fma(pl, cl[0], n0);
+        n1 = fma(pl, cl[1], n1);
+        n2 = fma(pl, cl[2], n2);
+        if (ipm_round) rhs6 = fma(pl, ws.vb[grp][l], rhs6);
+      }
+      hs[(3 * hh) * kPitch + 16 * grp + rr] = n0;
+      hs[(3 * hh + 1) * kPitch + 16 * grp + rr] = n1;
+      hs[(3 * hh + 2) * kPitch + 16 * grp + rr] = n2;
+      if (pol_round)
+        rhs6 = ws.bw[grp][rr] - ((ws.fix[grp][0][rr] + ws.fix[grp][1][rr]) + (ws.fix[grp][2][rr] + ws.fix[grp][3][rr]));
+    } else if (gl < 6) {
+#pragma unroll
+      for (int j = 0; j < 6; j++) hs[j * kPitch + lane] = (j == gl) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+
+    // ---- C. factorise (forward substitution of the first right-hand side fused in), back-substitute
+    double rdiag, zf = (gl < 6) ? rhs6 : 0.0;
+    const bool pd = reg_cholesky6_fwd(hs, ws.xb, rdiag, zf, grp, gl, lane);
     if (!pd && mode != kModeDone) { mode = kModeDone; status = 4; y = 0.0; }
 
-    // ---- S. substitutions: phase 0 = polish solution / Mehrotra predictor, phase 1 = corrector
     double sol = 0.0, rcA = 0.0, rcB = 0.0;
 #pragma unroll 1
     for (int ph = 0; ph < (any_ipm ? 2 : 1); ph++) {
-      if (ph == 1) zf = smem_forward(hs, ws.xb, rdiag, rhs, grp, gl, lane);
-      const double x = smem_backward(hs, ws.xb, rdiag, zf, grp, gl);
-      if (ph == 0) sol = x;
+      if (ph == 1) {
+        // corrector: new right-hand side of the 6x6 system, full substitution
+        if (var_lane) ws.vb[grp][gl] = rhs;
+        __syncwarp();
+        double r6 = 0.0;
+        if (gl < 6) {
+#pragma unroll 2
+          for (int l = 0; l < kVars; l++) r6 = fma(ws.pc[grp][l][gl], ws.vb[grp][l], r6);
+        }
+        zf = smem_forward<6>(hs, ws.xb, rdiag, r6, grp, gl, lane);
+      }
+      const double t = smem_backward<6>(hs, ws.xb, rdiag, zf, grp, gl);
+      if (gl < 6) ws.t6[grp][gl] = t;
+      __syncwarp();
+      // a_l . t and c_l . t
+      double att = 0.0, ctt = 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; r++) { const double tr = ws.t6[grp][r]; att = fma(at[r], tr, att); ctt = fma(mycol[r], tr, ctt); }
+      if (ph == 0) sol = ctt * iwd;       // polish: z_l = c_l . t / wd_l
+      if (ph == 0 && pol_round) rhs = att;  // keep a_l . t for the gradient
       if (!any_ipm) break;
+      // interior point: x = K^-1 (r - A~' t)
+      const double wl = rhs - att;
+      const double x = fma(k2, gshfl(wl, l0 + 2), fma(k1, gshfl(wl, l0 + 1), k0 * gshfl(wl, l0)));
       // direction of this lane's rows: ds = D~ dy - rp, dl = -(rc + lam ds)/s
       // (phase 0: rc = s lam, phase 1: rc = s lam + dsa dla - sigma mu)
       double deA, deB;
@@ -507,7 +541,7 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
         rcA = alive ? fma(dsA, dlA, sA * lamA) - sigmu : 0.0;
         rcB = rowB ? fma(dsB, dlB, sB * lamB) - sigmu : 0.0;
         const double dtv = dt_lane((rcA - lamA * rpA) * rsA, (rcB - lamB * rpB) * rsB, mu, c, l0);
-        rhs = (var_lane && ipm_round) ? -rd - dtv : 0.0;
+        if (ipm_round) rhs = var_lane ? -rd - dtv : 0.0;
       } else {
         double al = (ratio > 0.995f) ? 0.995 / (double)ratio : 1.0;
         // stay inside the neighbourhood min_i s_i lam_i >= gamma * mu (both groups loop together)
@@ -523,7 +557,7 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
         }
         // take the step; the residuals follow without a mat-vec:
         //   G~ dy = rhs - D~' diag(lam/s) D~ dy   =>   rd += al (rhs - D~'(theta .* de + dl)),   rp *= (1 - al)
-        const double dtw = dt_lane(fma(lamA * rsA, deA, dlA), fma(lamB * rsB, deB, dlB), mu, c, l0);
+        const double dtw = dt_lane(fma(thA, deA, dlA), fma(thB, deB, dlB), mu, c, l0);
         if (ipm_round) {
           sA = fma(al, dsA, sA); lamA = fma(al, dlA, lamA); rpA *= (1.0 - al);
           sB = fma(al, dsB, sB); lamB = fma(al, dlB, lamB); rpB *= (1.0 - al);
@@ -545,103 +579,107 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
           if (out_of_iters && !converged) status = 2;
         }
       }
+      __syncwarp();
     }
 
-    // ---- M. polish: recover y, multipliers, slacks; verify the KKT signs; repair the pattern.
-    //         One mat-vec site: pass 0 multiplies the polished point, pass 1 (only when a group starts
-    //         its interior-point iteration) the strictly feasible start.
+    // ---- M. polish: recover y, gradient, multipliers, slacks; verify the KKT signs; repair the pattern.
     if (any_pol) {
       // y of the polished point: pinned / tied components follow from the leg's normal component
       double yp = (c == 0) ? ((pat != 0) ? prm.fmin : sol) : sol;
       const double ynp = gshfl(yp, l0);
       if (c != 0 && pat != 0) yp = pat * mu * ynp;
       if (!alive) yp = 0.0;
+      // gradient of the objective in contact coordinates: G~ y + g~ = w y - a_l . S(b - A~ y) = w y - a_l . t
+      const double gam = fma(prm.W, yp, -rhs);
+      // multipliers and slacks of this lane's rows
+      double eA, eB;
+      rows_apply(ynp, yp, mu, c, eA, eB);
+      if (c == 0) eA -= prm.fmin;
+      double uA = 0.0, uB = 0.0;
+      if (c != 0) { uA = (pat == -1) ? gam : 0.0; uB = (pat == 1) ? -gam : 0.0; }
+      const double su = uA + uB;
+      const double U = gshfl(su, l0 + 1) + gshfl(su, l0 + 2);
+      if (c == 0) uA = (pat != 0) ? gam - mu * U : 0.0;
+      const bool actA = (c == 0) ? (pat != 0) : (pat == -1), actB = (pat == 1);
+      const float scale = fmaxf(1.f, group_max(fabsf((float)yp)));
+      const double tol_u = 1e-13 * (double)gscale, tol_s = 1e-10 * (double)scale;
+      // worst violation of this lane: a negative multiplier (drop the row) before a negative slack (add it)
+      int fix = 0;  // 0 none, 1 drop, 2 add row A, 3 add row B
+      double key = 0.0;
+      if (alive && pol_round) {
+        if (actA && uA < -tol_u) { fix = 1; key = uA * 1e6; }
+        else if (actB && uB < -tol_u) { fix = 1; key = uB * 1e6; }
+        else {
+          const double vA2 = actA ? 0.0 : eA, vB2 = (rowB && !actB) ? eB : 0.0;
+          if (vA2 < -tol_s && vA2 <= vB2) { fix = 2; key = vA2; }
+          else if (vB2 < -tol_s) { fix = 3; key = vB2; }
+        }
+      }
+      const unsigned viol = (__ballot_sync(kFull, fix != 0) >> (16 * grp)) & 0xFFFu;
+      // globally worst lane (used after the first passes, prevents cycling)
+      const float keyf = (float)key;
+      const float best = group_min(keyf);
+      const unsigned tie = (__ballot_sync(kFull, fix != 0 && keyf == best) >> (16 * grp)) & 0xFFFu;
       bool start_ipm = false;
-#pragma unroll 1
-      for (int rep = 0; rep < 2; rep++) {
-        const double vv = (rep == 0) ? yp : ((alive && c == 0) ? c0 : 0.0);
-        if (var_lane) ws.vb[0][grp][gl] = vv;
-        __syncwarp();
-        double gam = gt;
-#pragma unroll 1
-        for (int j = 0; j < kVars; j++) gam = fma(ws.grow[j][lane], ws.vb[0][grp][j], gam);
-        const float gmaxf = group_max(var_lane ? fabsf((float)gam) : 0.f);
-        __syncwarp();
-        if (rep == 1) {
-          // interior-point start: multipliers centred at the gradient scale, residuals of the start
-          const double gmax = (double)fmaxf(1.f, gmaxf);
-          double e0A, e0B;
-          rows_apply(c0, 0.0, mu, c, e0A, e0B);
-          if (c == 0) e0A -= prm.fmin;
-          const double s0A = fmax(e0A, 1e-3 * c0), s0B = fmax(e0B, 1e-3 * c0);  // mu <= 0 would make friction rows non-positive
-          const double l0A = alive ? gmax * fast_rcp(s0A) : 0.0, l0B = rowB ? gmax * fast_rcp(s0B) : 0.0;
-          const double dtl = dt_lane(l0A, l0B, mu, c, l0);
-          if (start_ipm) {
-            sA = alive ? s0A : 1.0; lamA = l0A; rpA = alive ? s0A - e0A : 0.0;
-            sB = rowB ? s0B : 1.0;  lamB = l0B; rpB = rowB ? s0B - e0B : 0.0;
-            y = vv;
-            rd = var_lane ? gam - dtl : 0.0;
-          }
-          break;
-        }
-        // multipliers and slacks of this lane's rows
-        double eA, eB;
-        rows_apply(ynp, yp, mu, c, eA, eB);
-        if (c == 0) eA -= prm.fmin;
-        double uA = 0.0, uB = 0.0;
-        if (c != 0) { uA = (pat == -1) ? gam : 0.0; uB = (pat == 1) ? -gam : 0.0; }
-        const double su = uA + uB;
-        const double U = gshfl(su, l0 + 1) + gshfl(su, l0 + 2);
-        if (c == 0) uA = (pat != 0) ? gam - mu * U : 0.0;
-        const bool actA = (c == 0) ? (pat != 0) : (pat == -1), actB = (pat == 1);
-        const float scale = fmaxf(1.f, group_max(fabsf((float)yp)));
-        const float gscale = fmaxf(1.f, group_max(fabsf((float)gt)));
-        const double tol_u = 1e-13 * (double)gscale, tol_s = 1e-10 * (double)scale;
-        // worst violation of this lane: a negative multiplier (drop the row) before a negative slack (add it)
-        int fix = 0;  // 0 none, 1 drop, 2 add row A, 3 add row B
-        double key = 0.0;
-        if (alive) {
-          if (actA && uA < -tol_u) { fix = 1; key = uA * 1e6; }
-          else if (actB && uB < -tol_u) { fix = 1; key = uB * 1e6; }
-          else {
-            const double vA2 = actA ? 0.0 : eA, vB2 = (rowB && !actB) ? eB : 0.0;
-            if (vA2 < -tol_s && vA2 <= vB2) { fix = 2; key = vA2; }
-            else if (vB2 < -tol_s) { fix = 3; key = vB2; }
-          }
-        }
-        const unsigned viol = (__ballot_sync(kFull, fix != 0) >> (16 * grp)) & 0xFFFu;
-        // globally worst lane (used after the first passes, prevents cycling)
-        const float keyf = (float)key;
-        const float best = group_min(keyf);
-        const unsigned tie = (__ballot_sync(kFull, fix != 0 && keyf == best) >> (16 * grp)) & 0xFFFu;
-
-        if (mode == kModePolish) {
-          if (viol == 0u) {
-            y = yp;
+      if (pol_round && mode == kModePolish) {
+        if (viol == 0u) {
+          y = yp;
+          mode = kModeDone;
+          if (status == 2) status = 0;  // iteration limit hit but the polish verified the optimum
+        } else {
+          pass++;
+          const bool give_up = first ? (pass > kPdasFirst) : (pass >= kPolishPasses);
+          if (!give_up) {
+            // repair: every violating lane moves during the first passes, then only the worst one
+            const bool mine = (fix != 0) && (pass <= 2 || (tie != 0u && (__ffs(tie) - 1) == gl));
+            if (mine) pat = (fix == 1) ? 0 : ((c == 0) ? 1 : (fix == 2 ? -1 : 1));
+          } else if (first) {
+            first = false;
+            mode = kModeIpm;
+            start_ipm = true;
+            pat = 0;
+          } else if (converged || status == 2) {
+            // interior-point iterate is final but the polish could not certify an active set
             mode = kModeDone;
-            if (status == 2) status = 0;  // iteration limit hit but the polish verified the optimum
+            if (status == 0) status = 3;
           } else {
-            pass++;
-            const bool give_up = first ? (pass > kPdasFirst) : (pass >= kPolishPasses);
-            if (!give_up) {
-              // repair: every violating lane moves during the first passes, then only the worst one
-              const bool mine = (fix != 0) && (pass <= 2 || (tie != 0u && (__ffs(tie) - 1) == gl));
-              if (mine) pat = (fix == 1) ? 0 : ((c == 0) ? 1 : (fix == 2 ? -1 : 1));
-            } else if (first) {
-              first = false;
-              mode = kModeIpm;
-              start_ipm = true;
-              pat = 0;
-            } else if (converged || status == 2) {
-              // interior-point iterate is final but the polish could not certify an active set
-              mode = kModeDone;
-              if (status == 0) status = 3;
-            } else {
-              mode = kModeIpm;  // keep iterating, try again after the next iteration
-            }
+            mode = kModeIpm;  // keep iterating, try again after the next iteration
           }
         }
-        if (!__any_sync(kFull, start_ipm)) break;
+      }
+      // ---- a group starts its interior-point iteration: strictly feasible point y0 (every stance leg
+      //      pushes c0 along its normal), multipliers centred at the gradient scale, residuals of the start
+      if (__any_sync(kFull, start_ipm)) {
+        const double y0 = (alive && c == 0) ? c0 : 0.0;
+        if (var_lane) {
+#pragma unroll
+          for (int r = 0; r < 6; r++) ws.pc[grp][gl][r] = at[r] * y0;
+        }
+        __syncwarp();
+        if (gl < 6) {
+          double ay = 0.0;
+#pragma unroll 2
+          for (int l = 0; l < kVars; l++) ay += ws.pc[grp][l][gl];
+          ws.t6[grp][gl] = prm.S[gl] * (ws.bw[grp][gl] - ay);   // S (b - A~ y0)
+        }
+        __syncwarp();
+        double g0 = prm.W * y0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) g0 = fma(-at[r], ws.t6[grp][r], g0);
+        const double gmax = (double)fmaxf(1.f, group_max(var_lane ? fabsf((float)g0) : 0.f));
+        double e0A, e0B;
+        rows_apply(c0, 0.0, mu, c, e0A, e0B);
+        if (c == 0) e0A -= prm.fmin;
+        const double s0A = fmax(e0A, 1e-3 * c0), s0B = fmax(e0B, 1e-3 * c0);  // mu <= 0 would make friction rows non-positive
+        const double l0A = alive ? gmax * fast_rcp(s0A) : 0.0, l0B = rowB ? gmax * fast_rcp(s0B) : 0.0;
+        const double dtl = dt_lane(l0A, l0B, mu, c, l0);
+        if (start_ipm) {
+          sA = alive ? s0A : 1.0; lamA = l0A; rpA = alive ? s0A - e0A : 0.0;
+          sB = rowB ? s0B : 1.0;  lamB = l0B; rpB = rowB ? s0B - e0B : 0.0;
+          y = y0;
+          rd = var_lane ? g0 - dtl : 0.0;
+        }
+        __syncwarp();
       }
     }
     // an interior-point group that asked for a polish switches now (its iterate stays untouched)
@@ -677,13 +715,13 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
     // A x = sum over slots of column * y (CFD.cpp:614-625)
     if (var_lane) {
 #pragma unroll
-      for (int r = 0; r < 6; r++) ws.col[grp][gl][r] = solved ? ws.atl[grp][gl][r] * y : 0.0;
+      for (int r = 0; r < 6; r++) ws.pc[grp][gl][r] = solved ? ws.atl[grp][gl][r] * y : 0.0;
     }
     __syncwarp();
     if (gl < 6) {
       double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < kVars; j++) acc += ws.col[grp][j][gl];
+      for (int j = 0; j < kVars; j++) acc += ws.pc[grp][j][gl];
       ws.out[kRowNet + gl][qi] = acc;
     }
     __syncwarp();
@@ -708,7 +746,7 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
 
 // ---------------------------------------------------------------- kernel
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 4) qlb_solve_kernel(const SolveArgs a) {
+__global__ void __launch_bounds__(kThreads, QLB_MIN_CTAS) qlb_solve_kernel(const SolveArgs a) {
   constexpr int ROWS = (MODE == 1) ? kInRowsState : kInRows;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaSmem<ROWS>& sm = *reinterpret_cast<CtaSmem<ROWS>*>(smem_raw);
@@ -718,7 +756,10 @@ __global__ void __launch_bounds__(kThreads, 4) qlb_solve_kernel(const SolveArgs 
     for (int i = threadIdx.x; i < (int)(sizeof(DeviceParams) / 8); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef QLB_PIN_IDS
+  asm volatile("" : "+r"(lane), "+r"(warp));  // keep the ids in registers instead of re-deriving them from S2R
+#endif
   WarpSmem<ROWS>& ws = sm.w[warp];
   const unsigned long long nbatch = (a.B + kBatch - 1) / kBatch;
   const bool vec = a.vec_ok != 0;
