@@ -365,10 +365,10 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
   // strictly feasible interior-point start for this leg: push c0 along the normal
   const double c0 = fmax(fmax(2.0 * prm.fmin, (b[0] * nb[0] + b[1] * nb[1] + b[2] * nb[2]) * (ns > 0 ? 1.0 / ns : 0.0)),
                          prm.fmin + 1.0);
-  double at[6];  // own wrench-map column
+  const double* const at = ws.atl[grp][var_lane ? gl : 0];  // own wrench-map column (kept in shared memory)
   double gt = 0.0;  // g~ of this slot = -a_l . (S b)
 #pragma unroll
-  for (int r = 0; r < 6; r++) { at[r] = alive ? at_raw[r] : 0.0; gt = fma(-at[r] * prm.S[r], b[r], gt); }
+  for (int r = 0; r < 6; r++) gt = fma(-(alive ? at_raw[r] : 0.0) * prm.S[r], b[r], gt);
   const float gscale = fmaxf(1.f, group_max(fabsf((float)gt)));
   __syncwarp();
 
@@ -397,9 +397,6 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
     const bool pol_round = (mode == kModePolish), ipm_round = (mode == kModeIpm);
     const bool any_pol = __any_sync(kFull, pol_round), any_ipm = __any_sync(kFull, ipm_round);
     double rhs = 0.0, rsA = 1.0, rsB = 1.0, k0 = 0.0, k1 = 0.0, k2 = 0.0, iwd = 0.0, thA = 0.0, thB = 0.0;
-    double mycol[6];
-#pragma unroll
-    for (int r = 0; r < 6; r++) mycol[r] = 0.0;
 
     // ---- B1. polish: reduced columns C_l of the pattern, P_l = C_l / wd_l, pinned contributions
     if (any_pol) {
@@ -415,9 +412,9 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
 #pragma unroll
         for (int r = 0; r < 6; r++) {
           const double cn = (c == 0) ? fma(q2, a2[r], fma(q1, a1[r], at[r])) : at[r];
-          mycol[r] = free_slot ? cn : 0.0;
-          ws.cc[grp][gl][r] = mycol[r];
-          ws.pc[grp][gl][r] = mycol[r] * iwd;
+          const double cr = free_slot ? cn : 0.0;
+          ws.cc[grp][gl][r] = cr;
+          ws.pc[grp][gl][r] = cr * iwd;
           if (c == 0) ws.fix[grp][leg][r] = f * cn;
         }
       }
@@ -501,10 +498,13 @@ __device__ __forceinline__ void solve_group(WarpSmem<ROWS>& ws, const DeviceMode
       const double t = smem_backward<6>(hs, ws.xb, rdiag, zf, grp, gl);
       if (gl < 6) ws.t6[grp][gl] = t;
       __syncwarp();
-      // a_l . t and c_l . t
+      // a_l . t and c_l . t (c_l = own column of the right factor; = a_l in interior-point rounds)
       double att = 0.0, ctt = 0.0;
+      {
+        const double* const cl = ws.cc[grp][var_lane ? gl : 0];
 #pragma unroll
-      for (int r = 0; r < 6; r++) { const double tr = ws.t6[grp][r]; att = fma(at[r], tr, att); ctt = fma(mycol[r], tr, ctt); }
+        for (int r = 0; r < 6; r++) { const double tr = ws.t6[grp][r]; att = fma(at[r], tr, att); ctt = fma(cl[r], tr, ctt); }
+      }
       if (ph == 0) sol = ctt * iwd;       // polish: z_l = c_l . t / wd_l
       if (ph == 0 && pol_round) rhs = att;  // keep a_l . t for the gradient
       if (!any_ipm) break;
