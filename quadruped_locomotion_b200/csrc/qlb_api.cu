@@ -11,6 +11,8 @@
 #include "qlb_aux.cuh"
 #include "qlb_qp_dense.cuh"
 #include "qlb_solve.cuh"
+#include "qlb_solve_quad.cuh"
+#include <cstdlib>
 
 using namespace qlb;
 
@@ -18,6 +20,8 @@ struct qlb_context {
   int device = 0;
   int sm_count = 0;
   int blocks_per_sm[2] = {0, 0};
+  int blocks_per_sm_quad[2] = {0, 0};
+  bool use_quad = true;  // leg-per-lane kernel (qlb_solve_quad.cuh); QLB_KERNEL=half selects the half-warp kernel
   qlb_params params;
   qlb_leg_model legs[QLB_NUM_LEGS];
   DeviceModel* d_model = nullptr;
@@ -140,7 +144,14 @@ int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   a.counter = ctx->d_counter + (ctx->launches % kCounters);
   QLB_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st));
-  qlb_solve_kernel<MODE><<<grid, kThreads, smem, st>>>(a);
+  if (ctx->use_quad) {
+    const unsigned long long nb8 = (a.B + 7) / 8;
+    unsigned long long wantq = (nb8 + (kQuadThreads / 32) - 1) / (kQuadThreads / 32);
+    unsigned long long capq = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm_quad[MODE];
+    qlb_quad_kernel<MODE><<<(unsigned)(wantq < capq ? wantq : capq), kQuadThreads, 0, st>>>(a);
+  } else {
+    qlb_solve_kernel<MODE><<<grid, kThreads, smem, st>>>(a);
+  }
   QLB_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
   return QLB_OK;
@@ -259,6 +270,11 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], qlb_solve_kernel<1>, kThreads, sizeof(CtaSmem<kInRowsState>)) != cudaSuccess)
     return fail(QLB_ERR_CUDA);
   if (ctx->blocks_per_sm[0] < 1 || ctx->blocks_per_sm[1] < 1) return fail(QLB_ERR_CUDA);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[0], qlb_quad_kernel<0>, kQuadThreads, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[1], qlb_quad_kernel<1>, kQuadThreads, 0) != cudaSuccess)
+    return fail(QLB_ERR_CUDA);
+  if (ctx->blocks_per_sm_quad[0] < 1 || ctx->blocks_per_sm_quad[1] < 1) return fail(QLB_ERR_CUDA);
+  if (const char* k = std::getenv("QLB_KERNEL")) ctx->use_quad = (std::strcmp(k, "half") != 0);
   if (max_batch > 0 && ensure_capacity(ctx, max_batch) != QLB_OK) return fail(QLB_ERR_ALLOC);
   *out = ctx;
   return QLB_OK;
