@@ -27,6 +27,8 @@ struct qlb_context {
   DeviceModel* d_model = nullptr;
   DeviceParams* d_params = nullptr;
   unsigned long long* d_counter = nullptr;
+  unsigned* d_list[4] = {nullptr, nullptr, nullptr, nullptr};  // second-pass index lists, one per launch slot
+  size_t list_cap[4] = {0, 0, 0, 0};
   double* d_stats = nullptr;
   cudaStream_t stream = nullptr;  // used by the *_host entry points
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the *_host entry points
@@ -142,13 +144,34 @@ int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
   unsigned long long want = (nbatch + kWarpsPerCta - 1) / kWarpsPerCta;
   unsigned long long cap = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm[MODE];
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  a.counter = ctx->d_counter + (ctx->launches % kCounters);
-  QLB_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st));
+  // three counters per launch slot: work counter of pass 1, of pass 2, length of the pass-2 list
+  const int slot = (int)(ctx->launches % (kCounters / 4));
+  a.counter = ctx->d_counter + 4 * slot;
+  a.counter2 = a.counter + 1;
+  a.list_count = reinterpret_cast<unsigned*>(a.counter + 2);
+  QLB_CUDA(ctx, cudaMemsetAsync(a.counter, 0, 4 * sizeof(unsigned long long), st));
   if (ctx->use_quad) {
+    if (a.B > 0xFFFFFFF0ull) return QLB_ERR_BATCH_TOO_LARGE;
+    const int ls = slot % 4;
+    if (ctx->list_cap[ls] < a.B) {  // grow the index list of this slot (rare; synchronises)
+      QLB_CUDA(ctx, cudaDeviceSynchronize());
+      cudaFree(ctx->d_list[ls]);
+      ctx->d_list[ls] = nullptr;
+      ctx->list_cap[ls] = 0;
+      size_t cap = 1024;
+      while (cap < a.B) cap *= 2;
+      if (cudaMalloc(&ctx->d_list[ls], cap * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return QLB_ERR_ALLOC; }
+      ctx->list_cap[ls] = cap;
+    }
+    a.list = ctx->d_list[ls];
     const unsigned long long nb8 = (a.B + 7) / 8;
     unsigned long long wantq = (nb8 + (kQuadThreads / 32) - 1) / (kQuadThreads / 32);
     unsigned long long capq = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm_quad[MODE];
-    qlb_quad_kernel<MODE><<<(unsigned)(wantq < capq ? wantq : capq), kQuadThreads, 0, st>>>(a);
+    const unsigned gq = (unsigned)(wantq < capq ? wantq : capq);
+    qlb_quad_first_kernel<MODE><<<gq, kQuadThreads, 0, st>>>(a);
+    QLB_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    qlb_quad_kernel<MODE><<<gq, kQuadThreads, 0, st>>>(a);
   } else {
     qlb_solve_kernel<MODE><<<grid, kThreads, smem, st>>>(a);
   }
@@ -288,6 +311,7 @@ int qlb_destroy(qlb_context* ctx) {
     if (ctx->pipe[i]) { cudaStreamSynchronize(ctx->pipe[i]); cudaStreamDestroy(ctx->pipe[i]); }
   cudaFree(ctx->d_model); cudaFree(ctx->d_params); cudaFree(ctx->d_counter); cudaFree(ctx->d_stats);
   cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags);
+  for (int i = 0; i < 4; i++) cudaFree(ctx->d_list[i]);
   cudaGetLastError();
   delete ctx;
   return QLB_OK;

@@ -50,6 +50,9 @@ struct SolveArgs {
   double* netwrench;      // may be null
   double* wrench_out;     // may be null (state mode)
   unsigned long long* counter;  // work counter, zeroed before launch
+  unsigned long long* counter2; // work counter of the second pass (leg-per-lane kernels)
+  unsigned* list;               // indices of the states left for the second pass, or null
+  unsigned* list_count;         // their number
   const DeviceModel* model;
   const DeviceParams* params;
   int vec_ok;             // all row pointers 16-byte aligned and B even

@@ -94,44 +94,40 @@ __device__ __forceinline__ void leg_rows_t(const double (&v)[5], double mu, doub
   o[2] = v[3] - v[4];
 }
 
+// Per-leg quantities that stay fixed while the QP is solved.
+struct LegSetup {
+  double E[3][3];    // friction frame of this leg in base frame: n, t1, t2
+  double At[3][6];   // the leg's block of the wrench map in contact coordinates, At[c] = [e_c; r x e_c]
+  double J[3][3];    // translational Jacobian, J[j] = column j
+  double gtau[3];    // gravity torques
+  double b[6];       // desired wrench
+  double mu, c0;     // friction coefficient; normal force of the strictly feasible interior-point start
+  float gscale, rm;  // scale of the linear term; 1 / number of constraint rows
+  unsigned mask;
+  int ns;
+  bool alive, qbad;
+};
+
+// Load one state (lane = leg `leg` of state bx) and run everything up to the QP data.
 template <int MODE>
-__global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kernel(const SolveArgs a) {
-  __shared__ DeviceParams prm;
-  __shared__ double sinv[6];
-  __shared__ double winv;
-  {
-    const double* src = reinterpret_cast<const double*>(a.params);
-    double* dst = reinterpret_cast<double*>(&prm);
-    for (int i = threadIdx.x; i < (int)(sizeof(DeviceParams) / 8); i += blockDim.x) dst[i] = src[i];
-    if (threadIdx.x < 6) sinv[threadIdx.x] = 1.0 / a.params->S[threadIdx.x];
-    if (threadIdx.x == 6) winv = 1.0 / a.params->W;
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int leg = lane & 3, quad = lane >> 2;
+__device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParams& prm, const unsigned long long bx,
+                                           const unsigned long long bq, const bool valid, const bool write_wout,
+                                           const int leg, LegSetup& L) {
   const unsigned long long B = a.B;
-  const unsigned long long nbatch = (B + 7) / 8;
   const DeviceModel& mdl = *a.model;
   const bool have_mu = a.mu != nullptr, have_normals = a.normals != nullptr;
-
-  for (;;) {
-    unsigned long long bi = 0;
-    if (lane == 0) bi = atomicAdd(a.counter, 1ull);
-    bi = __shfl_sync(kFull, bi, 0);
-    if (bi >= nbatch) break;
-    const unsigned long long bq = bi * 8 + quad;
-    const bool valid = bq < B;
-    const unsigned long long bx = valid ? bq : (B - 1);  // clamp: idle quads read a real state, never write
-
     // ---------------- inputs (each row of 8 consecutive states is one 64-byte segment)
     const unsigned mask = valid ? (unsigned)a.mask[bx] & 0xFu : 0u;
+    L.mask = mask;
     const bool alive = (mask >> leg) & 1u;
     const int ns = __popc(mask);
+    L.alive = alive; L.ns = ns;
     double qj[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) qj[j] = __ldg(a.q + (size_t)(3 * leg + j) * B + bx);
     bool bad = !(isfinite(qj[0]) && isfinite(qj[1]) && isfinite(qj[2]));
-    double quat[4], b[6];
+    double quat[4];
+    double (&b)[6] = L.b;
     if (MODE == 1) {
       // virtual model controller prologue (VirtualModelController.cpp:104-268), redundantly on the quad
       double pose[7], tw[6], tp[7], tt[6];
@@ -176,7 +172,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
         const double dwb = R[c] * dwv[0] + R[3 + c] * dwv[1] + R[6 + c] * dwv[2];
         b[3 + c] = -prm.kp_r[c] * eR[c] + dwb + R[6 + c] * fwz + Tg[c];
       }
-      if (a.wrench_out && valid && leg == 0) {
+      if (a.wrench_out && valid && leg == 0 && write_wout) {
 #pragma unroll
         for (int r = 0; r < 6; r++) a.wrench_out[(size_t)r * B + bq] = b[r];
       }
@@ -186,7 +182,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
 #pragma unroll
       for (int r = 0; r < 6; r++) { b[r] = __ldg(a.wrench + (size_t)r * B + bx); bad |= !isfinite(b[r]); }
     }
-    const double mu = have_mu ? __ldg(a.mu + (size_t)leg * B + bx) : prm.mu_default;
+    const double mu = L.mu = have_mu ? __ldg(a.mu + (size_t)leg * B + bx) : prm.mu_default;
     double nw[3] = {0.0, 0.0, 1.0};
     if (have_normals) {
 #pragma unroll
@@ -194,7 +190,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
     }
 
     // ---------------- base rotation, friction frame (CFD.cpp:223,237,286-309), gravity in base frame (:518-519)
-    double E[3][3];  // E[0] = n, E[1] = t1, E[2] = t2 in base frame
+    double (&E)[3][3] = L.E;  // E[0] = n, E[1] = t1, E[2] = t2 in base frame
     double gb[3];
     {
       const double w = quat[0], x = quat[1], y = quat[2], z = quat[3];
@@ -226,10 +222,12 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
         for (int c = 0; c < 3; c++) bad |= !isfinite(E[0][c]) || !isfinite(E[1][c]) || !isfinite(E[2][c]);
       }
     }
-    const bool qbad = quad_or(bad ? 1u : 0u) != 0u;
+    L.qbad = quad_or(bad ? 1u : 0u) != 0u;
 
     // ---------------- leg forward kinematics, Jacobian, gravity torques (QK.cpp:143-278,485-552)
-    double foot[3], J[3][3], gtau[3];  // J[j] = column j
+    double foot[3];
+    double (&J)[3][3] = L.J;  // J[j] = column j
+    double (&gtau)[3] = L.gtau;
     {
       double R[9], p[3], zj[3][3], pj[3][3], com[4][3];
 #pragma unroll
@@ -292,7 +290,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
     }
 
     // ---------------- the leg's block of the wrench map in contact coordinates: A_k = [E'; (r x e_c)] (6 x 3)
-    double At[3][6];  // At[c] = column of slot c (0 = normal, 1, 2 = tangents)
+    double (&At)[3][6] = L.At;  // At[c] = column of slot c (0 = normal, 1, 2 = tangents)
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       At[c][0] = alive ? E[c][0] : 0.0;
@@ -310,10 +308,184 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
       for (int r = 0; r < 6; r++) g = fma(At[c][r] * prm.S[r], b[r], g);
       gsc = fmaxf(gsc, fabsf((float)g));
     }
-    const float gscale = fmaxf(1.f, quad_max(gsc));
-    const double c0 = fmax(fmax(2.0 * prm.fmin, (b[0] * E[0][0] + b[1] * E[0][1] + b[2] * E[0][2]) * (ns > 0 ? 1.0 / ns : 0.0)),
+    L.gscale = fmaxf(1.f, quad_max(gsc));
+    L.c0 = fmax(fmax(2.0 * prm.fmin, (b[0] * E[0][0] + b[1] * E[0][1] + b[2] * E[0][2]) * (ns > 0 ? 1.0 / ns : 0.0)),
                            prm.fmin + 1.0);
-    const float rm = ns > 0 ? 1.f / (5.f * ns) : 0.f;
+    L.rm = ns > 0 ? 1.f / (5.f * ns) : 0.f;
+
+}
+
+// Forces in base frame, joint torques, net wrench, flags word of one finished state.
+__device__ __forceinline__ void quad_output(const SolveArgs& a, const LegSetup& L, double (&y)[3], const int a0, const int sg1,
+                                            const int sg2, const int status, const int it, const unsigned long long bq,
+                                            const bool valid, const int leg) {
+  const unsigned long long B = a.B;
+  const bool alive = L.alive;
+  const unsigned mask = L.mask;
+  const double (&E)[3][3] = L.E;
+  const double (&At)[3][6] = L.At;
+  const double (&J)[3][3] = L.J;
+  const double (&gtau)[3] = L.gtau;
+    // ---------------- outputs: forces in base frame, torques, net wrench, flags
+    const bool solved = (status == 0 || status == 2 || status == 3);
+    const bool live = alive && solved;
+    double f[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) f[c] = live ? y[0] * E[0][c] + y[1] * E[1][c] + y[2] * E[2][c] : 0.0;
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) a.grf[(size_t)(3 * leg + c) * B + bq] = f[c];
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+        a.tau[(size_t)(3 * leg + j) * B + bq] = live ? gtau[j] - (J[j][0] * f[0] + J[j][1] * f[1] + J[j][2] * f[2]) : 0.0;
+    }
+    if (a.netwrench) {
+      // A x = sum over legs of A_k y_k (CFD.cpp:614-625)
+      double nwv[6];
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+        nwv[r] = quad_sum(live ? At[0][r] * y[0] + At[1][r] * y[1] + At[2][r] * y[2] : 0.0);
+      if (valid) {
+        // leg k writes components k and k+4 (k < 2)
+        a.netwrench[(size_t)leg * B + bq] = (leg == 0) ? nwv[0] : (leg == 1 ? nwv[1] : (leg == 2 ? nwv[2] : nwv[3]));
+        if (leg < 2) a.netwrench[(size_t)(4 + leg) * B + bq] = (leg == 0) ? nwv[4] : nwv[5];
+      }
+    }
+    {
+      unsigned bits = 0u;
+      if (live) {
+        bits = (a0 != 0 ? 1u : 0u) | (sg1 == -1 ? 2u : 0u) | (sg1 == 1 ? 4u : 0u) | (sg2 == -1 ? 8u : 0u) | (sg2 == 1 ? 16u : 0u);
+        bits <<= (4 + 5 * leg);
+      }
+      bits = quad_or(bits);
+      if (valid && leg == 0) {
+        const unsigned itc = it > 31 ? 31u : (unsigned)it;
+        a.flags[bq] = mask | bits | ((unsigned)status << 24) | (itc << 27);
+      }
+    }
+}
+
+// First pass: kinematics + QP data + the unconstrained minimiser (polish round with the empty pattern).
+// States whose unconstrained minimiser is feasible (most of them) are finished here; the others are
+// appended to a.list for the second pass.  Fixed trip count: no divergence between the eight states of a warp.
+template <int MODE>
+__global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_first_kernel(const SolveArgs a) {
+  __shared__ DeviceParams prm;
+  __shared__ double sinv[6];
+  __shared__ double winv;
+  {
+    const double* src = reinterpret_cast<const double*>(a.params);
+    double* dst = reinterpret_cast<double*>(&prm);
+    for (int i = threadIdx.x; i < (int)(sizeof(DeviceParams) / 8); i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x < 6) sinv[threadIdx.x] = 1.0 / a.params->S[threadIdx.x];
+    if (threadIdx.x == 6) winv = 1.0 / a.params->W;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int leg = lane & 3, quad = lane >> 2;
+  const unsigned long long B = a.B;
+  const unsigned long long nbatch = (B + 7) / 8;
+
+  for (;;) {
+    unsigned long long bi = 0;
+    if (lane == 0) bi = atomicAdd(a.counter, 1ull);
+    bi = __shfl_sync(kFull, bi, 0);
+    if (bi >= nbatch) break;
+    const unsigned long long slot = bi * 8 + quad;
+    const bool valid = slot < B;
+    const unsigned long long bq = valid ? slot : (B - 1);
+    LegSetup L;
+    quad_setup<MODE>(a, prm, bq, bq, valid, true, leg, L);
+    const bool alive = L.alive;
+    const double (&At)[3][6] = L.At;
+    int status = L.qbad ? 4 : (L.ns == 0 ? 1 : 0);
+    double y[3] = {0.0, 0.0, 0.0};
+    bool hard = false;
+    // unconstrained minimiser through the 6x6 system: (S^-1 + A~ A~'/w) t = b,  y = A~' t / w
+    double N[21], rdg[6], t[6];
+    const double al = alive ? winv : 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const double w0 = al * At[0][i], w1 = al * At[1][i], w2 = al * At[2][i];
+#pragma unroll
+      for (int j = 0; j <= i; j++) {
+        double acc = (i == j && leg == 0) ? sinv[i] : 0.0;
+        acc = fma(w0, At[0][j], acc);
+        acc = fma(w1, At[1][j], acc);
+        acc = fma(w2, At[2][j], acc);
+        N[QLB_TRI(i, j)] = quad_sum(acc);
+      }
+      t[i] = L.b[i];
+    }
+    const bool pd = chol6_thread(N, rdg);
+    solve6_thread(N, rdg, t);
+    if (!pd && status == 0) status = 4;
+    double e[5];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double d = 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; r++) d = fma(At[c][r], t[r], d);
+      y[c] = al * d;
+    }
+    leg_rows(y[0], y[1], y[2], L.mu, e);
+    e[0] -= prm.fmin;
+    const float scale = fmaxf(1.f, quad_max(fmaxf(fabsf((float)y[0]), fmaxf(fabsf((float)y[1]), fabsf((float)y[2])))));
+    const double tol_s = 1e-10 * (double)scale;
+    bool viol = false;
+#pragma unroll
+    for (int r = 0; r < 5; r++) viol = viol || (alive && e[r] < -tol_s);
+    hard = (status == 0) && (quad_or(viol ? 1u : 0u) != 0u);
+    // append the unfinished states to the list of the second pass (one atomic per warp)
+    const unsigned hm = __ballot_sync(kFull, hard && valid && leg == 0);
+    if (hm != 0u) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(a.list_count, __popc(hm));
+      base = __shfl_sync(kFull, base, 0);
+      if (hard && valid && leg == 0) a.list[base + __popc(hm & ((1u << lane) - 1u))] = (unsigned)bq;
+    }
+    quad_output(a, L, y, 0, 0, 0, status, 0, bq, valid && !hard, leg);  // whole warp: it contains quad shuffles
+  }
+}
+
+// Second pass / stand-alone kernel: the full algorithm (polish rounds, interior-point rounds) for the states
+// listed in a.list (or all states when a.list is null).
+template <int MODE>
+__global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kernel(const SolveArgs a) {
+  __shared__ DeviceParams prm;
+  __shared__ double sinv[6];
+  __shared__ double winv;
+  {
+    const double* src = reinterpret_cast<const double*>(a.params);
+    double* dst = reinterpret_cast<double*>(&prm);
+    for (int i = threadIdx.x; i < (int)(sizeof(DeviceParams) / 8); i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x < 6) sinv[threadIdx.x] = 1.0 / a.params->S[threadIdx.x];
+    if (threadIdx.x == 6) winv = 1.0 / a.params->W;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int leg = lane & 3, quad = lane >> 2;
+  const unsigned long long B = a.B;
+  const unsigned long long total = a.list ? (unsigned long long)(*a.list_count) : B;
+  const unsigned long long nbatch = (total + 7) / 8;
+
+  for (;;) {
+    unsigned long long bi = 0;
+    if (lane == 0) bi = atomicAdd(a.counter2, 1ull);
+    bi = __shfl_sync(kFull, bi, 0);
+    if (bi >= nbatch) break;
+    const unsigned long long slot = bi * 8 + quad;
+    const bool valid = slot < total;
+    const unsigned long long bq = valid ? (a.list ? (unsigned long long)a.list[slot] : slot) : (B - 1);
+    LegSetup L;
+    quad_setup<MODE>(a, prm, bq, bq, valid, a.list == nullptr, leg, L);
+    const bool alive = L.alive;
+    const int ns = L.ns;
+    const double mu = L.mu, c0 = L.c0;
+    const float gscale = L.gscale, rm = L.rm;
+    const bool qbad = L.qbad;
+    const double (&At)[3][6] = L.At;
+    const double (&b)[6] = L.b;
 
     // ---------------- solver state of this leg
     double y[3] = {0.0, 0.0, 0.0};   // (y_n, y_1, y_2)
@@ -669,43 +841,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
       }
     }
 
-    // ---------------- outputs: forces in base frame, torques, net wrench, flags
-    const bool solved = (status == 0 || status == 2 || status == 3);
-    const bool live = alive && solved;
-    double f[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) f[c] = live ? y[0] * E[0][c] + y[1] * E[1][c] + y[2] * E[2][c] : 0.0;
-    if (valid) {
-#pragma unroll
-      for (int c = 0; c < 3; c++) a.grf[(size_t)(3 * leg + c) * B + bq] = f[c];
-#pragma unroll
-      for (int j = 0; j < 3; j++)
-        a.tau[(size_t)(3 * leg + j) * B + bq] = live ? gtau[j] - (J[j][0] * f[0] + J[j][1] * f[1] + J[j][2] * f[2]) : 0.0;
-    }
-    if (a.netwrench) {
-      // A x = sum over legs of A_k y_k (CFD.cpp:614-625)
-      double nwv[6];
-#pragma unroll
-      for (int r = 0; r < 6; r++)
-        nwv[r] = quad_sum(live ? At[0][r] * y[0] + At[1][r] * y[1] + At[2][r] * y[2] : 0.0);
-      if (valid) {
-        // leg k writes components k and k+4 (k < 2)
-        a.netwrench[(size_t)leg * B + bq] = (leg == 0) ? nwv[0] : (leg == 1 ? nwv[1] : (leg == 2 ? nwv[2] : nwv[3]));
-        if (leg < 2) a.netwrench[(size_t)(4 + leg) * B + bq] = (leg == 0) ? nwv[4] : nwv[5];
-      }
-    }
-    {
-      unsigned bits = 0u;
-      if (live) {
-        bits = (a0 != 0 ? 1u : 0u) | (sg1 == -1 ? 2u : 0u) | (sg1 == 1 ? 4u : 0u) | (sg2 == -1 ? 8u : 0u) | (sg2 == 1 ? 16u : 0u);
-        bits <<= (4 + 5 * leg);
-      }
-      bits = quad_or(bits);
-      if (valid && leg == 0) {
-        const unsigned itc = it > 31 ? 31u : (unsigned)it;
-        a.flags[bq] = mask | bits | ((unsigned)status << 24) | (itc << 27);
-      }
-    }
+    quad_output(a, L, y, a0, sg1, sg2, status, it, bq, valid, leg);
   }
 }
 
