@@ -21,14 +21,16 @@ struct qlb_context {
   int sm_count = 0;
   int blocks_per_sm[2] = {0, 0};
   int blocks_per_sm_quad[2] = {0, 0};
+  bool single_pass = false;  // QLB_KERNEL=quad1: leg-per-lane kernel without the first pass (experiments)
   bool use_quad = true;  // leg-per-lane kernel (qlb_solve_quad.cuh); QLB_KERNEL=half selects the half-warp kernel
   qlb_params params;
   qlb_leg_model legs[QLB_NUM_LEGS];
   DeviceModel* d_model = nullptr;
   DeviceParams* d_params = nullptr;
   unsigned long long* d_counter = nullptr;
-  unsigned* d_list[4] = {nullptr, nullptr, nullptr, nullptr};  // second-pass index lists, one per launch slot
-  size_t list_cap[4] = {0, 0, 0, 0};
+  unsigned* d_list[8] = {};   // second-pass index lists, one per launch slot
+  size_t list_cap[8] = {};
+  uint64_t solve_calls = 0;   // picks the launch slot (counters + list): concurrent launches never share one
   double* d_stats = nullptr;
   cudaStream_t stream = nullptr;  // used by the *_host entry points
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the *_host entry points
@@ -145,14 +147,14 @@ int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
   unsigned long long cap = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm[MODE];
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   // three counters per launch slot: work counter of pass 1, of pass 2, length of the pass-2 list
-  const int slot = (int)(ctx->launches % (kCounters / 4));
+  const int slot = (int)(ctx->solve_calls++ % 8);
   a.counter = ctx->d_counter + 4 * slot;
   a.counter2 = a.counter + 1;
   a.list_count = reinterpret_cast<unsigned*>(a.counter + 2);
   QLB_CUDA(ctx, cudaMemsetAsync(a.counter, 0, 4 * sizeof(unsigned long long), st));
   if (ctx->use_quad) {
     if (a.B > 0xFFFFFFF0ull) return QLB_ERR_BATCH_TOO_LARGE;
-    const int ls = slot % 4;
+    const int ls = slot;
     if (ctx->list_cap[ls] < a.B) {  // grow the index list of this slot (rare; synchronises)
       QLB_CUDA(ctx, cudaDeviceSynchronize());
       cudaFree(ctx->d_list[ls]);
@@ -168,9 +170,13 @@ int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
     unsigned long long wantq = (nb8 + (kQuadThreads / 32) - 1) / (kQuadThreads / 32);
     unsigned long long capq = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm_quad[MODE];
     const unsigned gq = (unsigned)(wantq < capq ? wantq : capq);
-    qlb_quad_first_kernel<MODE><<<gq, kQuadThreads, 0, st>>>(a);
-    QLB_CUDA(ctx, cudaGetLastError());
-    ctx->launches++;
+    if (ctx->single_pass) {
+      a.list = nullptr;
+    } else {
+      qlb_quad_first_kernel<MODE><<<gq, kQuadThreads, 0, st>>>(a);
+      QLB_CUDA(ctx, cudaGetLastError());
+      ctx->launches++;
+    }
     qlb_quad_kernel<MODE><<<gq, kQuadThreads, 0, st>>>(a);
   } else {
     qlb_solve_kernel<MODE><<<grid, kThreads, smem, st>>>(a);
@@ -297,7 +303,10 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[1], qlb_quad_kernel<1>, kQuadThreads, 0) != cudaSuccess)
     return fail(QLB_ERR_CUDA);
   if (ctx->blocks_per_sm_quad[0] < 1 || ctx->blocks_per_sm_quad[1] < 1) return fail(QLB_ERR_CUDA);
-  if (const char* k = std::getenv("QLB_KERNEL")) ctx->use_quad = (std::strcmp(k, "half") != 0);
+  if (const char* k = std::getenv("QLB_KERNEL")) {
+    ctx->use_quad = (std::strcmp(k, "half") != 0);
+    ctx->single_pass = (std::strcmp(k, "quad1") == 0);
+  }
   if (max_batch > 0 && ensure_capacity(ctx, max_batch) != QLB_OK) return fail(QLB_ERR_ALLOC);
   *out = ctx;
   return QLB_OK;
@@ -311,7 +320,7 @@ int qlb_destroy(qlb_context* ctx) {
     if (ctx->pipe[i]) { cudaStreamSynchronize(ctx->pipe[i]); cudaStreamDestroy(ctx->pipe[i]); }
   cudaFree(ctx->d_model); cudaFree(ctx->d_params); cudaFree(ctx->d_counter); cudaFree(ctx->d_stats);
   cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags);
-  for (int i = 0; i < 4; i++) cudaFree(ctx->d_list[i]);
+  for (int i = 0; i < 8; i++) cudaFree(ctx->d_list[i]);
   cudaGetLastError();
   delete ctx;
   return QLB_OK;

@@ -435,7 +435,8 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_firs
     bool viol = false;
 #pragma unroll
     for (int r = 0; r < 5; r++) viol = viol || (alive && e[r] < -tol_s);
-    hard = (status == 0) && (quad_or(viol ? 1u : 0u) != 0u);
+    const bool quad_viol = quad_or(viol ? 1u : 0u) != 0u;  // not inside the && : every lane must reach the shuffle
+    hard = (status == 0) && quad_viol;
     // append the unfinished states to the list of the second pass (one atomic per warp)
     const unsigned hm = __ballot_sync(kFull, hard && valid && leg == 0);
     if (hm != 0u) {
