@@ -155,15 +155,18 @@ int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
   if (ctx->use_quad) {
     if (a.B > 0xFFFFFFF0ull) return QLB_ERR_BATCH_TOO_LARGE;
     const int ls = slot;
-    if (ctx->list_cap[ls] < a.B) {  // grow the index list of this slot (rare; synchronises)
+    if (ctx->list_cap[ls] < a.B) {  // grow the index lists of all slots at once (rare; synchronises)
       QLB_CUDA(ctx, cudaDeviceSynchronize());
-      cudaFree(ctx->d_list[ls]);
-      ctx->d_list[ls] = nullptr;
-      ctx->list_cap[ls] = 0;
       size_t cap = 1024;
       while (cap < a.B) cap *= 2;
-      if (cudaMalloc(&ctx->d_list[ls], cap * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return QLB_ERR_ALLOC; }
-      ctx->list_cap[ls] = cap;
+      for (int i = 0; i < 8; i++) {
+        if (ctx->list_cap[i] >= cap) continue;
+        cudaFree(ctx->d_list[i]);
+        ctx->d_list[i] = nullptr;
+        ctx->list_cap[i] = 0;
+        if (cudaMalloc(&ctx->d_list[i], cap * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return QLB_ERR_ALLOC; }
+        ctx->list_cap[i] = cap;
+      }
     }
     a.list = ctx->d_list[ls];
     const unsigned long long nb8 = (a.B + 7) / 8;
