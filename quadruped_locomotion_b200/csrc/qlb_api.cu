@@ -146,12 +146,14 @@ int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
   unsigned long long want = (nbatch + kWarpsPerCta - 1) / kWarpsPerCta;
   unsigned long long cap = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm[MODE];
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  // three counters per launch slot: work counter of pass 1, of pass 2, length of the pass-2 list
+  // per launch slot: work counters of the three passes, lengths of the two compacted lists
   const int slot = (int)(ctx->solve_calls++ % 8);
-  a.counter = ctx->d_counter + 4 * slot;
+  a.counter = ctx->d_counter + 8 * slot;
   a.counter2 = a.counter + 1;
-  a.list_count = reinterpret_cast<unsigned*>(a.counter + 2);
-  QLB_CUDA(ctx, cudaMemsetAsync(a.counter, 0, 4 * sizeof(unsigned long long), st));
+  a.counter3 = a.counter + 2;
+  a.list_count = reinterpret_cast<unsigned*>(a.counter + 3);
+  a.list2_count = reinterpret_cast<unsigned*>(a.counter + 4);
+  QLB_CUDA(ctx, cudaMemsetAsync(a.counter, 0, 8 * sizeof(unsigned long long), st));
   if (ctx->use_quad) {
     if (a.B > 0xFFFFFFF0ull) return QLB_ERR_BATCH_TOO_LARGE;
     const int ls = slot;
@@ -164,23 +166,29 @@ int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
         cudaFree(ctx->d_list[i]);
         ctx->d_list[i] = nullptr;
         ctx->list_cap[i] = 0;
-        if (cudaMalloc(&ctx->d_list[i], cap * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return QLB_ERR_ALLOC; }
+        if (cudaMalloc(&ctx->d_list[i], 2 * cap * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return QLB_ERR_ALLOC; }
         ctx->list_cap[i] = cap;
       }
     }
     a.list = ctx->d_list[ls];
+    a.list2 = ctx->d_list[ls] + ctx->list_cap[ls];
     const unsigned long long nb8 = (a.B + 7) / 8;
     unsigned long long wantq = (nb8 + (kQuadThreads / 32) - 1) / (kQuadThreads / 32);
     unsigned long long capq = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm_quad[MODE];
     const unsigned gq = (unsigned)(wantq < capq ? wantq : capq);
     if (ctx->single_pass) {
-      a.list = nullptr;
+      qlb_quad_kernel<MODE, 0><<<gq, kQuadThreads, 0, st>>>(a);
     } else {
+      // pass 1: everything up to the unconstrained minimiser; pass 2: active-set rounds on what is left;
+      // pass 3: interior point on what is still left.  The later grids are sized for the worst case and
+      // read the list lengths on the device (no host synchronisation between the passes).
       qlb_quad_first_kernel<MODE><<<gq, kQuadThreads, 0, st>>>(a);
       QLB_CUDA(ctx, cudaGetLastError());
-      ctx->launches++;
+      qlb_quad_kernel<MODE, 1><<<gq, kQuadThreads, 0, st>>>(a);
+      QLB_CUDA(ctx, cudaGetLastError());
+      ctx->launches += 2;
+      qlb_quad_kernel<MODE, 2><<<gq, kQuadThreads, 0, st>>>(a);
     }
-    qlb_quad_kernel<MODE><<<gq, kQuadThreads, 0, st>>>(a);
   } else {
     qlb_solve_kernel<MODE><<<grid, kThreads, smem, st>>>(a);
   }
@@ -284,7 +292,7 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
   ctx->sm_count = prop.multiProcessorCount;
   auto fail = [&](int code) { qlb_destroy(ctx); return code; };
   if (cudaMalloc(&ctx->d_model, sizeof(DeviceModel)) != cudaSuccess || cudaMalloc(&ctx->d_params, sizeof(DeviceParams)) != cudaSuccess ||
-      cudaMalloc(&ctx->d_counter, kCounters * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_counter, 64 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMalloc(&ctx->d_stats, QLB_STATS_NUM * sizeof(double)) != cudaSuccess)
     return fail(QLB_ERR_ALLOC);
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(QLB_ERR_CUDA);
@@ -302,8 +310,8 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], qlb_solve_kernel<1>, kThreads, sizeof(CtaSmem<kInRowsState>)) != cudaSuccess)
     return fail(QLB_ERR_CUDA);
   if (ctx->blocks_per_sm[0] < 1 || ctx->blocks_per_sm[1] < 1) return fail(QLB_ERR_CUDA);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[0], qlb_quad_kernel<0>, kQuadThreads, 0) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[1], qlb_quad_kernel<1>, kQuadThreads, 0) != cudaSuccess)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[0], qlb_quad_kernel<0, 2>, kQuadThreads, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[1], qlb_quad_kernel<1, 2>, kQuadThreads, 0) != cudaSuccess)
     return fail(QLB_ERR_CUDA);
   if (ctx->blocks_per_sm_quad[0] < 1 || ctx->blocks_per_sm_quad[1] < 1) return fail(QLB_ERR_CUDA);
   if (const char* k = std::getenv("QLB_KERNEL")) {

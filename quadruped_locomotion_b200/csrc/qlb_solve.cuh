@@ -53,6 +53,9 @@ struct SolveArgs {
   unsigned long long* counter2; // work counter of the second pass (leg-per-lane kernels)
   unsigned* list;               // indices of the states left for the second pass, or null
   unsigned* list_count;         // their number
+  unsigned long long* counter3; // work counter of the third pass
+  unsigned* list2;              // states left for the interior-point pass
+  unsigned* list2_count;
   const DeviceModel* model;
   const DeviceParams* params;
   int vec_ok;             // all row pointers 16-byte aligned and B even

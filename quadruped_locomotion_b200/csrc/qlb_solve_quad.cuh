@@ -449,9 +449,12 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_firs
   }
 }
 
-// Second pass / stand-alone kernel: the full algorithm (polish rounds, interior-point rounds) for the states
-// listed in a.list (or all states when a.list is null).
-template <int MODE>
+// Later passes.  STAGE 0: the full algorithm on all states (stand-alone, no lists).  STAGE 1: states of
+// a.list; active-set rounds only (unconstrained minimiser + kPdasFirst repairs); what is still not verified
+// goes to a.list2.  STAGE 2: states of a.list2; interior-point iteration from the strictly feasible start,
+// polish rounds when the complementarity gap is small.  Each pass works on a compacted list, so the eight
+// states of a warp need similar numbers of rounds.
+template <int MODE, int STAGE>
 __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kernel(const SolveArgs a) {
   __shared__ DeviceParams prm;
   __shared__ double sinv[6];
@@ -467,19 +470,21 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
   const int lane = threadIdx.x & 31;
   const int leg = lane & 3, quad = lane >> 2;
   const unsigned long long B = a.B;
-  const unsigned long long total = a.list ? (unsigned long long)(*a.list_count) : B;
+  const unsigned* const in_list = (STAGE == 0) ? nullptr : (STAGE == 1 ? a.list : a.list2);
+  const unsigned long long total = (STAGE == 0) ? B : (unsigned long long)(*(STAGE == 1 ? a.list_count : a.list2_count));
+  unsigned long long* const work = (STAGE == 0) ? a.counter : (STAGE == 1 ? a.counter2 : a.counter3);
   const unsigned long long nbatch = (total + 7) / 8;
 
   for (;;) {
     unsigned long long bi = 0;
-    if (lane == 0) bi = atomicAdd(a.counter2, 1ull);
+    if (lane == 0) bi = atomicAdd(work, 1ull);
     bi = __shfl_sync(kFull, bi, 0);
     if (bi >= nbatch) break;
     const unsigned long long slot = bi * 8 + quad;
     const bool valid = slot < total;
-    const unsigned long long bq = valid ? (a.list ? (unsigned long long)a.list[slot] : slot) : (B - 1);
+    const unsigned long long bq = valid ? ((STAGE == 0) ? slot : (unsigned long long)in_list[slot]) : (B - 1);
     LegSetup L;
-    quad_setup<MODE>(a, prm, bq, bq, valid, a.list == nullptr, leg, L);
+    quad_setup<MODE>(a, prm, bq, bq, valid, STAGE == 0, leg, L);
     const bool alive = L.alive;
     const int ns = L.ns;
     const double mu = L.mu, c0 = L.c0;
@@ -498,14 +503,52 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
     int mode = kModePolish, it = 0, pass = 0, status = 0;
     bool first = true, converged = false, want_polish = false;
     double alpha_prev = 1.0;
+    bool defer = false;  // STAGE 1: hand the state to the interior-point pass
+    bool need_start = false;  // set when this quad begins its interior-point iteration
     if (qbad) { mode = kModeDone; status = 4; }
-    else if (ns == 0) { mode = kModeDone; status = valid ? 1 : 1; }
+    else if (ns == 0) { mode = kModeDone; status = 1; }
+    else if (STAGE == 2) { mode = kModeIpm; first = false; need_start = true; }
 
     int rounds = 0;
 #pragma unroll 1
     for (;;) {
       if (__all_sync(kFull, mode == kModeDone)) break;
       if (++rounds > 200 && mode != kModeDone) { mode = kModeDone; status = 2; }
+      // ---- a quad starts its interior-point iteration: strictly feasible start, centred multipliers
+      if (STAGE != 1 && __any_sync(kFull, need_start)) {
+        const double y0 = alive ? c0 : 0.0;
+        double t0[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) t0[r] = prm.S[r] * (b[r] - quad_sum(At[0][r] * y0));  // S (b - A~ y0)
+        double g[3];
+        float gm = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          double d = (c == 0) ? prm.W * y0 : 0.0;
+#pragma unroll
+          for (int r = 0; r < 6; r++) d = fma(-At[c][r], t0[r], d);
+          g[c] = d;
+          gm = fmaxf(gm, fabsf((float)d));
+        }
+        const double gmax = (double)fmaxf(1.f, quad_max(gm));
+        if (need_start) {
+          need_start = false;
+          double e0[5], dt[3];
+          leg_rows(c0, 0.0, 0.0, mu, e0);
+          e0[0] -= prm.fmin;
+#pragma unroll
+          for (int r = 0; r < 5; r++) {
+            const double sr = fmax(e0[r], 1e-3 * c0);
+            s[r] = alive ? sr : 1.0;
+            lam[r] = alive ? gmax * fast_rcp(sr) : 0.0;
+            rp[r] = alive ? sr - e0[r] : 0.0;
+          }
+          leg_rows_t(lam, mu, dt);
+          y[0] = y0; y[1] = 0.0; y[2] = 0.0;
+#pragma unroll
+          for (int c = 0; c < 3; c++) rdl[c] = alive ? g[c] - dt[c] : 0.0;
+        }
+      }
       const bool pol_round = (mode == kModePolish), ipm_round = (mode == kModeIpm);
       const bool any_ipm = __any_sync(kFull, ipm_round);
 
@@ -581,7 +624,6 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
       if (!pd && mode != kModeDone) { mode = kModeDone; status = 4; y[0] = y[1] = y[2] = 0.0; }
 
       // ---- polish: recover y, gradient, multipliers, slacks; verify; repair the pattern
-      bool start_ipm = false;
       {
         double zt[3], att[3];
 #pragma unroll
@@ -651,9 +693,9 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
               }
             } else if (first) {
               first = false;
-              mode = kModeIpm;
-              start_ipm = true;
               a0 = 0; sg1 = 0; sg2 = 0;
+              if (STAGE == 1) { defer = true; mode = kModeDone; }  // the interior-point pass takes over
+              else { mode = kModeIpm; need_start = true; }
             } else if (converged || status == 2) {
               mode = kModeDone;
               if (status == 0) status = 3;
@@ -665,7 +707,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
       }
 
       // ---- interior point: predictor direction, centring, corrector, step
-      if (any_ipm) {
+      if (STAGE != 1 && any_ipm) {
         double ds[5], dl[5], de[5], rc[5], x[3];
         float ratio = 0.f, pa = 0.f;
         {
@@ -795,40 +837,6 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
         }
       }
 
-      // ---- a quad starts its interior-point iteration: strictly feasible start, centred multipliers
-      if (__any_sync(kFull, start_ipm)) {
-        const double y0 = alive ? c0 : 0.0;
-        double t0[6];
-#pragma unroll
-        for (int r = 0; r < 6; r++) t0[r] = prm.S[r] * (b[r] - quad_sum(At[0][r] * y0));  // S (b - A~ y0)
-        double g[3];
-        float gm = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          double d = (c == 0) ? prm.W * y0 : 0.0;
-#pragma unroll
-          for (int r = 0; r < 6; r++) d = fma(-At[c][r], t0[r], d);
-          g[c] = d;
-          gm = fmaxf(gm, fabsf((float)d));
-        }
-        const double gmax = (double)fmaxf(1.f, quad_max(gm));
-        if (start_ipm) {
-          double e0[5], dt[3];
-          leg_rows(c0, 0.0, 0.0, mu, e0);
-          e0[0] -= prm.fmin;
-#pragma unroll
-          for (int r = 0; r < 5; r++) {
-            const double sr = fmax(e0[r], 1e-3 * c0);
-            s[r] = alive ? sr : 1.0;
-            lam[r] = alive ? gmax * fast_rcp(sr) : 0.0;
-            rp[r] = alive ? sr - e0[r] : 0.0;
-          }
-          leg_rows_t(lam, mu, dt);
-          y[0] = y0; y[1] = 0.0; y[2] = 0.0;
-#pragma unroll
-          for (int c = 0; c < 3; c++) rdl[c] = alive ? g[c] - dt[c] : 0.0;
-        }
-      }
       if (mode == kModeIpm && want_polish) {
         want_polish = false;
         mode = kModePolish;
@@ -842,7 +850,16 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
       }
     }
 
-    quad_output(a, L, y, a0, sg1, sg2, status, it, bq, valid, leg);
+    if (STAGE == 1) {
+      const unsigned hm = __ballot_sync(kFull, defer && valid && leg == 0);
+      if (hm != 0u) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(a.list2_count, __popc(hm));
+        base = __shfl_sync(kFull, base, 0);
+        if (defer && valid && leg == 0) a.list2[base + __popc(hm & ((1u << lane) - 1u))] = (unsigned)bq;
+      }
+    }
+    quad_output(a, L, y, a0, sg1, sg2, status, it, bq, valid && !defer, leg);
   }
 }
 

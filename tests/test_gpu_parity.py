@@ -245,7 +245,7 @@ def test_device_pointer_api_and_stream(solver, oracle, models):
         solver.solve_wrench(d["q"], d["quat"], d["wrench"], d["mask"], d["mu"], d["normals"], grf, tau, flags, net,
                             stream=side.cuda_stream)
     side.synchronize()
-    assert solver.launches == before + 2  # first pass + second pass over the states that need iterations
+    assert solver.launches == before + 3  # three passes: first, active-set, interior-point
     out = dict(grf=grf.cpu().numpy(), tau=tau.cpu().numpy(), flags=flags.cpu().numpy().view(np.uint32),
                netwrench=net.cpu().numpy())
     ref = _oracle(oracle, models["quadruped_model"], st)
