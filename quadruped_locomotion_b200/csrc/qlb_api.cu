@@ -21,6 +21,7 @@ struct qlb_context {
   int sm_count = 0;
   int blocks_per_sm[2] = {0, 0};
   int blocks_per_sm_quad[2] = {0, 0};
+  int blocks_per_sm_first[2] = {0, 0};
   bool single_pass = false;  // QLB_KERNEL=quad1: leg-per-lane kernel without the first pass (experiments)
   bool use_quad = true;  // leg-per-lane kernel (qlb_solve_quad.cuh); QLB_KERNEL=half selects the half-warp kernel
   qlb_params params;
@@ -182,7 +183,8 @@ int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
       // pass 1: everything up to the unconstrained minimiser; pass 2: active-set rounds on what is left;
       // pass 3: interior point on what is still left.  The later grids are sized for the worst case and
       // read the list lengths on the device (no host synchronisation between the passes).
-      qlb_quad_first_kernel<MODE><<<gq, kQuadThreads, 0, st>>>(a);
+      unsigned long long capf = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm_first[MODE];
+      qlb_quad_first_kernel<MODE><<<(unsigned)(wantq < capf ? wantq : capf), kQuadThreads, 0, st>>>(a);
       QLB_CUDA(ctx, cudaGetLastError());
       qlb_quad_kernel<MODE, 1><<<gq, kQuadThreads, 0, st>>>(a);
       QLB_CUDA(ctx, cudaGetLastError());
@@ -314,6 +316,9 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[1], qlb_quad_kernel<1, 2>, kQuadThreads, 0) != cudaSuccess)
     return fail(QLB_ERR_CUDA);
   if (ctx->blocks_per_sm_quad[0] < 1 || ctx->blocks_per_sm_quad[1] < 1) return fail(QLB_ERR_CUDA);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first[0], qlb_quad_first_kernel<0>, kQuadThreads, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first[1], qlb_quad_first_kernel<1>, kQuadThreads, 0) != cudaSuccess)
+    return fail(QLB_ERR_CUDA);
   if (const char* k = std::getenv("QLB_KERNEL")) {
     ctx->use_quad = (std::strcmp(k, "half") != 0);
     ctx->single_pass = (std::strcmp(k, "quad1") == 0);

@@ -18,7 +18,10 @@
 namespace qlb {
 
 #ifndef QLB_QUAD_MIN_CTAS
-#define QLB_QUAD_MIN_CTAS 2
+#define QLB_QUAD_MIN_CTAS 3
+#endif
+#ifndef QLB_FIRST_MIN_CTAS
+#define QLB_FIRST_MIN_CTAS 3
 #endif
 constexpr int kQuadThreads = 128;
 
@@ -96,10 +99,9 @@ __device__ __forceinline__ void leg_rows_t(const double (&v)[5], double mu, doub
 
 // Per-leg quantities that stay fixed while the QP is solved.
 struct LegSetup {
-  double E[3][3];    // friction frame of this leg in base frame: n, t1, t2
   double At[3][6];   // the leg's block of the wrench map in contact coordinates, At[c] = [e_c; r x e_c]
-  double J[3][3];    // translational Jacobian, J[j] = column j
-  double gtau[3];    // gravity torques
+                     // (rows 0..2 are the friction frame n, t1, t2 itself; zero for a swing leg)
+  double nrm[3];     // the leg's contact normal in base frame (also for swing legs)
   double b[6];       // desired wrench
   double mu, c0;     // friction coefficient; normal force of the strictly feasible interior-point start
   float gscale, rm;  // scale of the linear term; 1 / number of constraint rows
@@ -112,7 +114,7 @@ struct LegSetup {
 template <int MODE>
 __device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParams& prm, const unsigned long long bx,
                                            const unsigned long long bq, const bool valid, const bool write_wout,
-                                           const int leg, LegSetup& L) {
+                                           const int leg, LegSetup& L, double (*jg)[kQuadThreads]) {
   const unsigned long long B = a.B;
   const DeviceModel& mdl = *a.model;
   const bool have_mu = a.mu != nullptr, have_normals = a.normals != nullptr;
@@ -190,7 +192,7 @@ __device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParam
     }
 
     // ---------------- base rotation, friction frame (CFD.cpp:223,237,286-309), gravity in base frame (:518-519)
-    double (&E)[3][3] = L.E;  // E[0] = n, E[1] = t1, E[2] = t2 in base frame
+    double E[3][3];  // E[0] = n, E[1] = t1, E[2] = t2 in base frame
     double gb[3];
     {
       const double w = quat[0], x = quat[1], y = quat[2], z = quat[3];
@@ -225,9 +227,7 @@ __device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParam
     L.qbad = quad_or(bad ? 1u : 0u) != 0u;
 
     // ---------------- leg forward kinematics, Jacobian, gravity torques (QK.cpp:143-278,485-552)
-    double foot[3];
-    double (&J)[3][3] = L.J;  // J[j] = column j
-    double (&gtau)[3] = L.gtau;
+    double foot[3], J[3][3], gtau[3];  // J[j] = column j
     {
       double R[9], p[3], zj[3][3], pj[3][3], com[4][3];
 #pragma unroll
@@ -300,6 +300,15 @@ __device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParam
       At[c][4] = alive ? foot[2] * E[c][0] - foot[0] * E[c][2] : 0.0;
       At[c][5] = alive ? foot[0] * E[c][1] - foot[1] * E[c][0] : 0.0;
     }
+    // Jacobian and gravity torques are only needed again for the outputs: park them in shared memory
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) jg[3 * j + c][threadIdx.x] = J[j][c];
+      jg[9 + j][threadIdx.x] = gtau[j];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) L.nrm[c] = E[0][c];
     float gsc = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -318,26 +327,24 @@ __device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParam
 // Forces in base frame, joint torques, net wrench, flags word of one finished state.
 __device__ __forceinline__ void quad_output(const SolveArgs& a, const LegSetup& L, double (&y)[3], const int a0, const int sg1,
                                             const int sg2, const int status, const int it, const unsigned long long bq,
-                                            const bool valid, const int leg) {
+                                            const bool valid, const int leg, const double (*jg)[kQuadThreads]) {
   const unsigned long long B = a.B;
   const bool alive = L.alive;
   const unsigned mask = L.mask;
-  const double (&E)[3][3] = L.E;
   const double (&At)[3][6] = L.At;
-  const double (&J)[3][3] = L.J;
-  const double (&gtau)[3] = L.gtau;
     // ---------------- outputs: forces in base frame, torques, net wrench, flags
     const bool solved = (status == 0 || status == 2 || status == 3);
     const bool live = alive && solved;
     double f[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) f[c] = live ? y[0] * E[0][c] + y[1] * E[1][c] + y[2] * E[2][c] : 0.0;
+    for (int c = 0; c < 3; c++) f[c] = live ? y[0] * At[0][c] + y[1] * At[1][c] + y[2] * At[2][c] : 0.0;
     if (valid) {
 #pragma unroll
       for (int c = 0; c < 3; c++) a.grf[(size_t)(3 * leg + c) * B + bq] = f[c];
 #pragma unroll
       for (int j = 0; j < 3; j++)
-        a.tau[(size_t)(3 * leg + j) * B + bq] = live ? gtau[j] - (J[j][0] * f[0] + J[j][1] * f[1] + J[j][2] * f[2]) : 0.0;
+        a.tau[(size_t)(3 * leg + j) * B + bq] =
+            live ? jg[9 + j][threadIdx.x] - (jg[3 * j][threadIdx.x] * f[0] + jg[3 * j + 1][threadIdx.x] * f[1] + jg[3 * j + 2][threadIdx.x] * f[2]) : 0.0;
     }
     if (a.netwrench) {
       // A x = sum over legs of A_k y_k (CFD.cpp:614-625)
@@ -369,10 +376,11 @@ __device__ __forceinline__ void quad_output(const SolveArgs& a, const LegSetup& 
 // States whose unconstrained minimiser is feasible (most of them) are finished here; the others are
 // appended to a.list for the second pass.  Fixed trip count: no divergence between the eight states of a warp.
 template <int MODE>
-__global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_first_kernel(const SolveArgs a) {
+__global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_first_kernel(const SolveArgs a) {
   __shared__ DeviceParams prm;
   __shared__ double sinv[6];
   __shared__ double winv;
+  __shared__ double jg[12][kQuadThreads];  // per thread: Jacobian (9) and gravity torques (3) of its leg
   {
     const double* src = reinterpret_cast<const double*>(a.params);
     double* dst = reinterpret_cast<double*>(&prm);
@@ -395,7 +403,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_firs
     const bool valid = slot < B;
     const unsigned long long bq = valid ? slot : (B - 1);
     LegSetup L;
-    quad_setup<MODE>(a, prm, bq, bq, valid, true, leg, L);
+    quad_setup<MODE>(a, prm, bq, bq, valid, true, leg, L, jg);
     const bool alive = L.alive;
     const double (&At)[3][6] = L.At;
     int status = L.qbad ? 4 : (L.ns == 0 ? 1 : 0);
@@ -445,7 +453,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_firs
       base = __shfl_sync(kFull, base, 0);
       if (hard && valid && leg == 0) a.list[base + __popc(hm & ((1u << lane) - 1u))] = (unsigned)bq;
     }
-    quad_output(a, L, y, 0, 0, 0, status, 0, bq, valid && !hard, leg);  // whole warp: it contains quad shuffles
+    quad_output(a, L, y, 0, 0, 0, status, 0, bq, valid && !hard, leg, jg);  // whole warp: it contains quad shuffles
   }
 }
 
@@ -459,6 +467,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
   __shared__ DeviceParams prm;
   __shared__ double sinv[6];
   __shared__ double winv;
+  __shared__ double jg[12][kQuadThreads];  // per thread: Jacobian (9) and gravity torques (3) of its leg
   {
     const double* src = reinterpret_cast<const double*>(a.params);
     double* dst = reinterpret_cast<double*>(&prm);
@@ -484,7 +493,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
     const bool valid = slot < total;
     const unsigned long long bq = valid ? ((STAGE == 0) ? slot : (unsigned long long)in_list[slot]) : (B - 1);
     LegSetup L;
-    quad_setup<MODE>(a, prm, bq, bq, valid, STAGE == 0, leg, L);
+    quad_setup<MODE>(a, prm, bq, bq, valid, STAGE == 0, leg, L, jg);
     const bool alive = L.alive;
     const int ns = L.ns;
     const double mu = L.mu, c0 = L.c0;
@@ -551,6 +560,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
       }
       const bool pol_round = (mode == kModePolish), ipm_round = (mode == kModeIpm);
       const bool any_ipm = __any_sync(kFull, ipm_round);
+      const bool any_pol = __any_sync(kFull, pol_round);
 
       // ---- build: three vectors v_c and weights al_c with  A_k K_k^-1 A_k' = sum_c al_c v_c v_c'
       double v[3][6], al[3] = {0.0, 0.0, 0.0}, r6[6];
@@ -624,7 +634,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
       if (!pd && mode != kModeDone) { mode = kModeDone; status = 4; y[0] = y[1] = y[2] = 0.0; }
 
       // ---- polish: recover y, gradient, multipliers, slacks; verify; repair the pattern
-      {
+      if (any_pol) {
         double zt[3], att[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
@@ -859,7 +869,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
         if (defer && valid && leg == 0) a.list2[base + __popc(hm & ((1u << lane) - 1u))] = (unsigned)bq;
       }
     }
-    quad_output(a, L, y, a0, sg1, sg2, status, it, bq, valid && !defer, leg);
+    quad_output(a, L, y, a0, sg1, sg2, status, it, bq, valid && !defer, leg, jg);
   }
 }
 
