@@ -256,6 +256,51 @@ def main():
     # the e2e result must be the device result
     assert torch.equal(h_grf, grf.cpu()) and torch.equal(h_flags, flags.cpu())
 
+    # ---- the FP32 twin (BASELINE config C4) on the same states: device-resident and end to end
+    d32 = {k: (v.float() if v.dtype == torch.float64 else v) for k, v in d.items()}
+    grf32 = torch.empty((12, B), dtype=torch.float32, device=dev)
+    tau32 = torch.empty_like(grf32)
+    net32 = torch.empty((6, B), dtype=torch.float32, device=dev)
+    flags32 = torch.empty(B, dtype=torch.int32, device=dev)
+
+    def step32():
+        solver.solve_wrench(d32["q"], d32["quat"], d32["wrench"], d32["mask"], d32["mu"], None, grf32, tau32, flags32,
+                            net32, stream=stream.cuda_stream)
+
+    for _ in range(warmup):
+        step32()
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step32()
+    ev1.record(stream)
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step32 = float(t.item()) / args.steps
+    h32 = {k: (v.float().pin_memory() if v.dtype == torch.float64 else v) for k, v in h.items()}
+    h_grf32 = torch.empty((12, B), dtype=torch.float32).pin_memory()
+    h_tau32 = torch.empty((12, B), dtype=torch.float32).pin_memory()
+    h_net32 = torch.empty((6, B), dtype=torch.float32).pin_memory()
+
+    def e2e_step32():
+        solver.solve_wrench_host(h32["q"], h32["quat"], h32["wrench"], h32["mask"], h32["mu"], None, h_grf32, h_tau32,
+                                 h_flags, h_net32)
+
+    for _ in range(2):
+        e2e_step32()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step32()
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s32 = float(t.item())
+    f32_err = float(((grf32.double() - grf).abs().amax(0) / grf.abs().amax(0).clamp(min=1.0)).median().item())
+
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline: FP64 pipe (not HBM-, not tensor-bound), algorithmic FLOP by stance count
@@ -289,13 +334,21 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
-                         "kernel": "qlb_solve_kernel<0>",
+                         "kernel": "one solve call = qlb_quad_first_kernel<double,double,0> + qlb_quad_kernel<..,1> "
+                                   "(active-set rounds on the listed states) + qlb_quad_kernel<..,2> (interior point)",
+                         "traffic_note": "see profiles/ (ncu dram__bytes per launch)",
                          "note": "algorithmic FP64 FLOP (30k/21k/12k per 4/3/2-stance QP, SURVEY 8d) / CUDA-event time "
                                  "of the launch, per GPU; peak = DFMA probe measured in this run (qlb_measure_fp64_peak)",
                          "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                  "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src,
                                  "bytes_per_qp": bytes_per_qp}},
             "cpu_baseline": cpu_info,
+            "f32": {"value": world * B / (ms_step32 * 1e-3), "unit": UNIT, "ms_per_step": ms_step32,
+                    "e2e": {"value": world * B * e2e_steps / e2e_s32, "unit": UNIT,
+                            "h2d_bytes_per_step": B * ((12 + 4 + 6 + 4) * 4 + 1), "d2h_bytes_per_step": B * ((12 + 12 + 6) * 4 + 4)},
+                    "median_rel_force_diff_vs_f64": f32_err,
+                    "note": "qlb_solve_wrench_f32[_host], default core: FP32 interface and kinematics, FP64 solver core; "
+                            "stated tolerance in include/qlb.h and tests/test_gpu_parity.py"},
             "stats": {"ok": sd["ok"], "max_iter": sd["max_iter"], "unverified": sd["unverified"],
                       "mean_ipm_iterations": sd["mean_iterations"], "max_ipm_iterations": sd["max_iterations"],
                       "mean_wrench_err": sd["mean_wrench_err"], "allreduce_ms": allreduce_ms,

@@ -183,6 +183,45 @@ int qlb_solve_state_host(qlb_context* ctx, size_t B, const double* q, const doub
                          const double* normals_world, double* grf, double* tau, uint32_t* flags,
                          double* netwrench, double* wrench_out);
 
+/* FP32 twins (SURVEY 8b "_f32 suffix", BASELINE config C4): the same entry points with float arrays -
+ * half the HBM / PCIe bytes.  Two solver cores, chosen per context with qlb_set_f32_core:
+ *   QLB_F32_CORE_FP64 (default): FP32 interface and kinematics, FP64 solver core.  The only error left is
+ *     the rounding of the inputs and outputs.  STATED TOLERANCE: forces within 2e-3 relative of the FP64
+ *     result (scale max(1,|f|_inf); measured 5e-4), torques within 4e-3 (measured 1.2e-3); status and
+ *     contact bits exact; active-row bits exact on states whose active set is decided by a margin above 1e-3.
+ *   QLB_F32_CORE_FP32: FP32 arithmetic throughout (the 6x6 systems with one step of iterative refinement,
+ *     active-set rounds, interior point); states the FP32 core cannot verify are solved again by the FP64
+ *     core inside the same kernel, so every status is the FP64 one.  About 1.2x the throughput.  STATED
+ *     TOLERANCE (tests/test_gpu_parity.py, measured on C2/C3): the QP Hessian has condition number ~1e5
+ *     (W = 1e-4 against S|a|^2 ~ 10), so the weakly determined internal-force directions carry errors of
+ *     order cond * eps: relative force error median 2e-7 on full-rank stances and 2e-4 on two-leg stances,
+ *     99 % of states below 2e-2, worst observed 5e-2 (more on states driven far into their friction limits);
+ *     the achieved wrench A x agrees to 1e-2, every constraint holds to 1e-4 of the force scale, the objective
+ *     is within 1e-4 relative of the optimum; contact bits exact, active-row bits equal on >= 95 % of states.
+ * Status values and layouts are unchanged. */
+int qlb_solve_wrench_f32(qlb_context* ctx, size_t B, const float* q, const float* quat_wxyz,
+                         const float* wrench, const uint8_t* stance_mask, const float* mu,
+                         const float* normals_world, float* grf, float* tau, uint32_t* flags,
+                         float* netwrench, void* stream);
+int qlb_solve_wrench_f32_host(qlb_context* ctx, size_t B, const float* q, const float* quat_wxyz,
+                              const float* wrench, const uint8_t* stance_mask, const float* mu,
+                              const float* normals_world, float* grf, float* tau, uint32_t* flags,
+                              float* netwrench);
+int qlb_solve_state_f32(qlb_context* ctx, size_t B, const float* q, const float* base_pose,
+                        const float* base_twist, const float* target_pose, const float* target_twist,
+                        const uint8_t* stance_mask, const float* mu, const float* normals_world,
+                        float* grf, float* tau, uint32_t* flags, float* netwrench, float* wrench_out,
+                        void* stream);
+int qlb_solve_state_f32_host(qlb_context* ctx, size_t B, const float* q, const float* base_pose,
+                             const float* base_twist, const float* target_pose,
+                             const float* target_twist, const uint8_t* stance_mask, const float* mu,
+                             const float* normals_world, float* grf, float* tau, uint32_t* flags,
+                             float* netwrench, float* wrench_out);
+
+#define QLB_F32_CORE_FP32 0
+#define QLB_F32_CORE_FP64 1
+int qlb_set_f32_core(qlb_context* ctx, int core);
+
 /* Kinematics only (DEVICE pointers): foot positions, translational Jacobians (row-major 3x3 per leg)
  * and gravity torques for all four legs.  Replaces QuadrupedKinematics::FowardKinematicsSolve /
  * AnalysticJacobian / getGravityCompensationForLimb (quadrupedkinematics.cpp:143-278,485-552).

@@ -48,7 +48,8 @@ class Stats(C.Structure):
 EXPORTS = (
     "qlb_default_params", "qlb_create", "qlb_destroy", "qlb_set_params", "qlb_get_params",
     "qlb_solve_wrench", "qlb_solve_wrench_host", "qlb_solve_state", "qlb_solve_state_host",
-    "qlb_leg_kinematics", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
+    "qlb_solve_wrench_f32", "qlb_solve_wrench_f32_host", "qlb_solve_state_f32", "qlb_solve_state_f32_host",
+    "qlb_set_f32_core", "qlb_leg_kinematics", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
     "qlb_last_cuda_error", "qlb_abi_version",
 )
 
@@ -74,6 +75,11 @@ def load() -> C.CDLL:
     lib.qlb_solve_wrench_host.argtypes = [_vp, C.c_size_t] + [_vp] * 10
     lib.qlb_solve_state.argtypes = [_vp, C.c_size_t] + [_vp] * 14
     lib.qlb_solve_state_host.argtypes = [_vp, C.c_size_t] + [_vp] * 13
+    lib.qlb_solve_wrench_f32.argtypes = [_vp, C.c_size_t] + [_vp] * 11
+    lib.qlb_solve_wrench_f32_host.argtypes = [_vp, C.c_size_t] + [_vp] * 10
+    lib.qlb_solve_state_f32.argtypes = [_vp, C.c_size_t] + [_vp] * 14
+    lib.qlb_solve_state_f32_host.argtypes = [_vp, C.c_size_t] + [_vp] * 13
+    lib.qlb_set_f32_core.argtypes = [_vp, C.c_int]
     lib.qlb_leg_kinematics.argtypes = [_vp, C.c_size_t] + [_vp] * 6
     lib.qlb_qp_dense.argtypes = [_vp, C.c_size_t, C.c_int, C.c_int, C.c_int] + [_vp] * 11
     lib.qlb_qp_dense_host.argtypes = [_vp, C.c_size_t, C.c_int, C.c_int, C.c_int] + [_vp] * 10
@@ -110,6 +116,11 @@ def leg_models(model: dict | str = "quadruped_model"):
                 arr[i].link_com[k][a] = leg["link_com"][k][a]
             arr[i].link_mass[k] = leg["link_mass"][k]
     return arr
+
+
+def _is_f32(t) -> bool:
+    """float32 arrays select the _f32 twins of the solve entry points."""
+    return str(t.dtype).endswith("float32")
 
 
 def _ptr(t):
@@ -165,39 +176,46 @@ class Solver:
     def set_params(self, p: Params):
         self._check(self.lib.qlb_set_params(self._ctx, C.byref(p)), "qlb_set_params")
 
+    def set_f32_core(self, fp64_core: bool):
+        """Solver core of the _f32 entry points: FP64 (default; FP32 interface only) or FP32."""
+        self._check(self.lib.qlb_set_f32_core(self._ctx, 1 if fp64_core else 0), "qlb_set_f32_core")
+
     def get_params(self) -> Params:
         p = Params()
         self._check(self.lib.qlb_get_params(self._ctx, C.byref(p)), "qlb_get_params")
         return p
 
-    # -- device-pointer entry points (torch CUDA tensors, SoA [C, B] contiguous float64)
+    # -- device-pointer entry points (torch CUDA tensors, SoA [C, B] contiguous; float64, or float32 for the
+    #    _f32 twins - every floating-point array of one call must have the same dtype)
     def solve_wrench(self, q, quat, wrench, mask, mu=None, normals=None, grf=None, tau=None, flags=None,
                      netwrench=None, stream=None):
         B = q.shape[1]
-        rc = self.lib.qlb_solve_wrench(self._ctx, B, _ptr(q), _ptr(quat), _ptr(wrench), _ptr(mask), _ptr(mu),
-                                       _ptr(normals), _ptr(grf), _ptr(tau), _ptr(flags), _ptr(netwrench),
-                                       stream if stream is not None else None)
+        fn = self.lib.qlb_solve_wrench_f32 if _is_f32(q) else self.lib.qlb_solve_wrench
+        rc = fn(self._ctx, B, _ptr(q), _ptr(quat), _ptr(wrench), _ptr(mask), _ptr(mu),
+                _ptr(normals), _ptr(grf), _ptr(tau), _ptr(flags), _ptr(netwrench),
+                stream if stream is not None else None)
         self._check(rc, "qlb_solve_wrench")
 
     def solve_state(self, q, pose, twist, tpose, ttwist, mask, mu=None, normals=None, grf=None, tau=None,
                     flags=None, netwrench=None, wrench_out=None, stream=None):
         B = q.shape[1]
-        rc = self.lib.qlb_solve_state(self._ctx, B, _ptr(q), _ptr(pose), _ptr(twist), _ptr(tpose), _ptr(ttwist),
-                                      _ptr(mask), _ptr(mu), _ptr(normals), _ptr(grf), _ptr(tau), _ptr(flags),
-                                      _ptr(netwrench), _ptr(wrench_out), stream if stream is not None else None)
+        fn = self.lib.qlb_solve_state_f32 if _is_f32(q) else self.lib.qlb_solve_state
+        rc = fn(self._ctx, B, _ptr(q), _ptr(pose), _ptr(twist), _ptr(tpose), _ptr(ttwist),
+                _ptr(mask), _ptr(mu), _ptr(normals), _ptr(grf), _ptr(tau), _ptr(flags),
+                _ptr(netwrench), _ptr(wrench_out), stream if stream is not None else None)
         self._check(rc, "qlb_solve_state")
 
     def leg_kinematics(self, q, quat=None, foot=None, jac=None, gtau=None, stream=None):
         B = q.shape[1]
         rc = self.lib.qlb_leg_kinematics(self._ctx, B, _ptr(q), _ptr(quat), _ptr(foot), _ptr(jac), _ptr(gtau),
-                                         stream if stream is not None else None)
+                stream if stream is not None else None)
         self._check(rc, "qlb_leg_kinematics")
 
     def batch_stats(self, flags, wrench=None, netwrench=None, stream=None) -> np.ndarray:
         st = Stats()
         B = flags.shape[0]
         rc = self.lib.qlb_batch_stats(self._ctx, B, _ptr(flags), _ptr(wrench), _ptr(netwrench), C.byref(st),
-                                      stream if stream is not None else None)
+                stream if stream is not None else None)
         self._check(rc, "qlb_batch_stats")
         return np.frombuffer(bytes(st), dtype=np.float64).copy()
 
@@ -205,16 +223,18 @@ class Solver:
     def solve_wrench_host(self, q, quat, wrench, mask, mu=None, normals=None, grf=None, tau=None, flags=None,
                           netwrench=None):
         B = q.shape[1]
-        rc = self.lib.qlb_solve_wrench_host(self._ctx, B, _ptr(q), _ptr(quat), _ptr(wrench), _ptr(mask), _ptr(mu),
-                                            _ptr(normals), _ptr(grf), _ptr(tau), _ptr(flags), _ptr(netwrench))
+        fn = self.lib.qlb_solve_wrench_f32_host if _is_f32(q) else self.lib.qlb_solve_wrench_host
+        rc = fn(self._ctx, B, _ptr(q), _ptr(quat), _ptr(wrench), _ptr(mask), _ptr(mu),
+                _ptr(normals), _ptr(grf), _ptr(tau), _ptr(flags), _ptr(netwrench))
         self._check(rc, "qlb_solve_wrench_host")
 
     def solve_state_host(self, q, pose, twist, tpose, ttwist, mask, mu=None, normals=None, grf=None, tau=None,
                          flags=None, netwrench=None, wrench_out=None):
         B = q.shape[1]
-        rc = self.lib.qlb_solve_state_host(self._ctx, B, _ptr(q), _ptr(pose), _ptr(twist), _ptr(tpose),
-                                           _ptr(ttwist), _ptr(mask), _ptr(mu), _ptr(normals), _ptr(grf), _ptr(tau),
-                                           _ptr(flags), _ptr(netwrench), _ptr(wrench_out))
+        fn = self.lib.qlb_solve_state_f32_host if _is_f32(q) else self.lib.qlb_solve_state_host
+        rc = fn(self._ctx, B, _ptr(q), _ptr(pose), _ptr(twist), _ptr(tpose),
+                _ptr(ttwist), _ptr(mask), _ptr(mu), _ptr(normals), _ptr(grf), _ptr(tau),
+                _ptr(flags), _ptr(netwrench), _ptr(wrench_out))
         self._check(rc, "qlb_solve_state_host")
 
     def qp_dense_numpy(self, G, g0, CI=None, ci0=None, CE=None, ce0=None) -> dict:
@@ -230,18 +250,19 @@ class Solver:
         CEs = soa(CE, n * p) if p else None; ces = soa(ce0, p) if p else None
         x = np.zeros((n, B)); cost = np.zeros(B); status = np.zeros(B, np.uint32); active = np.zeros(B, np.uint32)
         rc = self.lib.qlb_qp_dense_host(self._ctx, B, n, m, p, _ptr(Gs), _ptr(gs), _ptr(CEs), _ptr(ces), _ptr(CIs),
-                                        _ptr(cis), _ptr(x), _ptr(cost), _ptr(status), _ptr(active))
+                _ptr(cis), _ptr(x), _ptr(cost), _ptr(status), _ptr(active))
         self._check(rc, "qlb_qp_dense_host")
         return dict(x=np.ascontiguousarray(x.T), cost=cost, status=status, active=active)
 
-    def solve_wrench_numpy(self, states: dict, with_net=True) -> dict:
-        """Convenience for tests: numpy SoA in, numpy SoA out, through the host entry point."""
+    def solve_wrench_numpy(self, states: dict, with_net=True, dtype=np.float64) -> dict:
+        """Convenience for tests: numpy SoA in, numpy SoA out, through the host entry point
+        (dtype=np.float32: the _f32 twin)."""
         B = states["q"].shape[1]
-        f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=dtype)  # noqa: E731
         q, quat, wr = f64(states["q"]), f64(states["quat"]), f64(states["wrench"])
         mu, nr = f64(states.get("mu")), f64(states.get("normals"))
         mask = np.ascontiguousarray(states["mask"], dtype=np.uint8)
-        grf = np.zeros((12, B)); tau = np.zeros((12, B)); flags = np.zeros(B, dtype=np.uint32)
-        net = np.zeros((6, B)) if with_net else None
+        grf = np.zeros((12, B), dtype); tau = np.zeros((12, B), dtype); flags = np.zeros(B, dtype=np.uint32)
+        net = np.zeros((6, B), dtype) if with_net else None
         self.solve_wrench_host(q, quat, wr, mask, mu, nr, grf, tau, flags, net)
         return dict(grf=grf, tau=tau, flags=flags, netwrench=net)

@@ -28,6 +28,13 @@ struct qlb_context {
   qlb_leg_model legs[QLB_NUM_LEGS];
   DeviceModel* d_model = nullptr;
   DeviceParams* d_params = nullptr;
+  DeviceModelT<float>* d_model_f = nullptr;    // FP32 copies for the _f32 entry points
+  DeviceParamsT<float>* d_params_f = nullptr;
+  int blocks_per_sm_quad_f[2] = {0, 0};
+  int blocks_per_sm_first_f[2] = {0, 0};
+  int blocks_per_sm_quad_m[2] = {0, 0};   // FP32 interface + FP64 solver core
+  int blocks_per_sm_first_m[2] = {0, 0};
+  bool f32_pure = false;  // qlb_set_f32_core: FP32 solver core with in-kernel FP64 rescue, or FP64 core for every state
   unsigned long long* d_counter = nullptr;
   unsigned* d_list[8] = {};   // second-pass index lists, one per launch slot
   size_t list_cap[8] = {};
@@ -130,6 +137,30 @@ void build_device_params(const qlb_params* p, DeviceParams* d) {
   d->grav_pct = p->gravity_compensation_percentage;
 }
 
+// FP32 copies: same fields, rounded once on the host
+void narrow_model(const DeviceModel& m, DeviceModelT<float>* f) {
+  const double* src = reinterpret_cast<const double*>(&m);
+  float* dst = reinterpret_cast<float*>(f);
+  for (size_t i = 0; i < sizeof(DeviceModel) / sizeof(double); i++) dst[i] = (float)src[i];
+}
+void narrow_params(const DeviceParams& d, DeviceParamsT<float>* f) {
+  std::memset(f, 0, sizeof *f);
+  for (int i = 0; i < 6; i++) f->S[i] = (float)d.S[i];
+  f->W = (float)d.W; f->fmin = (float)d.fmin; f->mu_default = (float)d.mu_default; f->gravity = (float)d.gravity;
+  f->tol = (float)d.tol; f->max_iter = d.max_iter;
+  for (int i = 0; i < 3; i++) {
+    f->kp_t[i] = (float)d.kp_t[i]; f->kd_t[i] = (float)d.kd_t[i]; f->kff_t[i] = (float)d.kff_t[i];
+    f->kp_r[i] = (float)d.kp_r[i]; f->kd_r[i] = (float)d.kd_r[i]; f->kff_r[i] = (float)d.kff_r[i];
+    f->com[i] = (float)d.com[i];
+  }
+  f->torso_mass = (float)d.torso_mass;
+  for (int l = 0; l < 4; l++) {
+    f->leg_mass[l] = (float)d.leg_mass[l];
+    for (int a = 0; a < 3; a++) f->leg_pos[l][a] = (float)d.leg_pos[l][a];
+  }
+  f->grav_pct = (float)d.grav_pct;
+}
+
 bool params_ok(const qlb_params* p) {
   if (!(p->ground_force_weight > 0.0) || !(p->ipm_tolerance > 0.0) || p->ipm_max_iterations < 1) return false;
   for (int i = 0; i < 6; i++)
@@ -139,15 +170,10 @@ bool params_ok(const qlb_params* p) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <int MODE>
-int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
-  constexpr int ROWS = (MODE == 1) ? kInRowsState : kInRows;
-  const size_t smem = sizeof(CtaSmem<ROWS>);
-  const unsigned long long nbatch = (a.B + kBatch - 1) / kBatch;
-  unsigned long long want = (nbatch + kWarpsPerCta - 1) / kWarpsPerCta;
-  unsigned long long cap = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm[MODE];
-  const unsigned grid = (unsigned)(want < cap ? want : cap);
-  // per launch slot: work counters of the three passes, lengths of the two compacted lists
+// Launch slot of one solve call: work counters of the three passes, lengths and storage of the two
+// compacted index lists.  Concurrent launches (the host pipeline's streams) never share a slot.
+template <typename T>
+int prepare_slot(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st) {
   const int slot = (int)(ctx->solve_calls++ % 8);
   a.counter = ctx->d_counter + 8 * slot;
   a.counter2 = a.counter + 1;
@@ -155,48 +181,79 @@ int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
   a.list_count = reinterpret_cast<unsigned*>(a.counter + 3);
   a.list2_count = reinterpret_cast<unsigned*>(a.counter + 4);
   QLB_CUDA(ctx, cudaMemsetAsync(a.counter, 0, 8 * sizeof(unsigned long long), st));
-  if (ctx->use_quad) {
-    if (a.B > 0xFFFFFFF0ull) return QLB_ERR_BATCH_TOO_LARGE;
-    const int ls = slot;
-    if (ctx->list_cap[ls] < a.B) {  // grow the index lists of all slots at once (rare; synchronises)
-      QLB_CUDA(ctx, cudaDeviceSynchronize());
-      size_t cap = 1024;
-      while (cap < a.B) cap *= 2;
-      for (int i = 0; i < 8; i++) {
-        if (ctx->list_cap[i] >= cap) continue;
-        cudaFree(ctx->d_list[i]);
-        ctx->d_list[i] = nullptr;
-        ctx->list_cap[i] = 0;
-        if (cudaMalloc(&ctx->d_list[i], 2 * cap * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return QLB_ERR_ALLOC; }
-        ctx->list_cap[i] = cap;
-      }
+  if (!ctx->use_quad) return QLB_OK;
+  if (a.B > 0xFFFFFFF0ull) return QLB_ERR_BATCH_TOO_LARGE;
+  if (ctx->list_cap[slot] < a.B) {  // grow the index lists of all slots at once (rare; synchronises)
+    QLB_CUDA(ctx, cudaDeviceSynchronize());
+    size_t cap = 1024;
+    while (cap < a.B) cap *= 2;
+    for (int i = 0; i < 8; i++) {
+      if (ctx->list_cap[i] >= cap) continue;
+      cudaFree(ctx->d_list[i]);
+      ctx->d_list[i] = nullptr;
+      ctx->list_cap[i] = 0;
+      if (cudaMalloc(&ctx->d_list[i], 3 * cap * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return QLB_ERR_ALLOC; }
+      ctx->list_cap[i] = cap;
     }
-    a.list = ctx->d_list[ls];
-    a.list2 = ctx->d_list[ls] + ctx->list_cap[ls];
-    const unsigned long long nb8 = (a.B + 7) / 8;
-    unsigned long long wantq = (nb8 + (kQuadThreads / 32) - 1) / (kQuadThreads / 32);
-    unsigned long long capq = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm_quad[MODE];
-    const unsigned gq = (unsigned)(wantq < capq ? wantq : capq);
-    if (ctx->single_pass) {
-      qlb_quad_kernel<MODE, 0><<<gq, kQuadThreads, 0, st>>>(a);
-    } else {
-      // pass 1: everything up to the unconstrained minimiser; pass 2: active-set rounds on what is left;
-      // pass 3: interior point on what is still left.  The later grids are sized for the worst case and
-      // read the list lengths on the device (no host synchronisation between the passes).
-      unsigned long long capf = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm_first[MODE];
-      qlb_quad_first_kernel<MODE><<<(unsigned)(wantq < capf ? wantq : capf), kQuadThreads, 0, st>>>(a);
-      QLB_CUDA(ctx, cudaGetLastError());
-      qlb_quad_kernel<MODE, 1><<<gq, kQuadThreads, 0, st>>>(a);
-      QLB_CUDA(ctx, cudaGetLastError());
-      ctx->launches += 2;
-      qlb_quad_kernel<MODE, 2><<<gq, kQuadThreads, 0, st>>>(a);
-    }
+  }
+  a.list = ctx->d_list[slot];
+  a.list2 = ctx->d_list[slot] + ctx->list_cap[slot];
+  a.list_pat = ctx->d_list[slot] + 2 * ctx->list_cap[slot];
+  return QLB_OK;
+}
+
+// The three passes of the leg-per-lane kernels.  pass 1: everything up to the unconstrained minimiser;
+// pass 2: active-set rounds on what is left; pass 3: interior point on what is still left.  The later
+// grids are sized for the worst case and read the list lengths on the device (no host synchronisation
+// between the passes).
+template <typename T, typename C, int MODE>
+int launch_quad(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int bps_first, const int bps_quad) {
+  const unsigned long long nb8 = (a.B + 7) / 8;
+  const unsigned long long wantq = (nb8 + (kQuadThreads / 32) - 1) / (kQuadThreads / 32);
+  const unsigned long long capq = (unsigned long long)ctx->sm_count * bps_quad;
+  const unsigned long long capf = (unsigned long long)ctx->sm_count * bps_first;
+  const unsigned gq = (unsigned)(wantq < capq ? wantq : capq);
+  if (ctx->single_pass) {
+    qlb_quad_kernel<T, C, MODE, 0><<<gq, kQuadThreads, 0, st>>>(a);
   } else {
-    qlb_solve_kernel<MODE><<<grid, kThreads, smem, st>>>(a);
+    qlb_quad_first_kernel<T, C, MODE><<<(unsigned)(wantq < capf ? wantq : capf), kQuadThreads, 0, st>>>(a);
+    QLB_CUDA(ctx, cudaGetLastError());
+    qlb_quad_kernel<T, C, MODE, 1><<<gq, kQuadThreads, 0, st>>>(a);
+    QLB_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    qlb_quad_kernel<T, C, MODE, 2><<<gq, kQuadThreads, 0, st>>>(a);
   }
   QLB_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
   return QLB_OK;
+}
+
+template <int MODE>
+int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
+  const int rc = prepare_slot(ctx, a, st);
+  if (rc != QLB_OK) return rc;
+  if (ctx->use_quad) return launch_quad<double, double, MODE>(ctx, a, st, ctx->blocks_per_sm_first[MODE], ctx->blocks_per_sm_quad[MODE]);
+  constexpr int ROWS = (MODE == 1) ? kInRowsState : kInRows;
+  const size_t smem = sizeof(CtaSmem<ROWS>);
+  const unsigned long long nbatch = (a.B + kBatch - 1) / kBatch;
+  const unsigned long long want = (nbatch + kWarpsPerCta - 1) / kWarpsPerCta;
+  const unsigned long long cap = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm[MODE];
+  qlb_solve_kernel<MODE><<<(unsigned)(want < cap ? want : cap), kThreads, smem, st>>>(a);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return QLB_OK;
+}
+
+// FP32 twins: leg-per-lane kernels only
+template <int MODE>
+int launch_solve_f32(qlb_context* ctx, SolveArgsT<float>& a, cudaStream_t st) {
+  const bool was = ctx->use_quad;
+  ctx->use_quad = true;
+  const int rc = prepare_slot(ctx, a, st);
+  ctx->use_quad = was;
+  if (rc != QLB_OK) return rc;
+  if (ctx->f32_pure) return launch_quad<float, float, MODE>(ctx, a, st, ctx->blocks_per_sm_first_f[MODE], ctx->blocks_per_sm_quad_f[MODE]);
+  return launch_quad<float, double, MODE>(ctx, a, st, ctx->blocks_per_sm_first_m[MODE], ctx->blocks_per_sm_quad_m[MODE]);
 }
 
 // staging of the host entry points: kPipe slots of `cap` states each (cap <= kChunk)
@@ -294,6 +351,8 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
   ctx->sm_count = prop.multiProcessorCount;
   auto fail = [&](int code) { qlb_destroy(ctx); return code; };
   if (cudaMalloc(&ctx->d_model, sizeof(DeviceModel)) != cudaSuccess || cudaMalloc(&ctx->d_params, sizeof(DeviceParams)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_model_f, sizeof(DeviceModelT<float>)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_params_f, sizeof(DeviceParamsT<float>)) != cudaSuccess ||
       cudaMalloc(&ctx->d_counter, 64 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMalloc(&ctx->d_stats, QLB_STATS_NUM * sizeof(double)) != cudaSuccess)
     return fail(QLB_ERR_ALLOC);
@@ -303,6 +362,9 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
   DeviceModel hm;
   build_device_model(legs, &hm);
   if (cudaMemcpy(ctx->d_model, &hm, sizeof hm, cudaMemcpyHostToDevice) != cudaSuccess) return fail(QLB_ERR_CUDA);
+  DeviceModelT<float> hmf;
+  narrow_model(hm, &hmf);
+  if (cudaMemcpy(ctx->d_model_f, &hmf, sizeof hmf, cudaMemcpyHostToDevice) != cudaSuccess) return fail(QLB_ERR_CUDA);
   if (qlb_set_params(ctx, p) != QLB_OK) return fail(QLB_ERR_CUDA);
   // the fused kernels need more than the default 48 KB of dynamic shared memory
   if (cudaFuncSetAttribute(qlb_solve_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem<kInRows>)) != cudaSuccess ||
@@ -312,12 +374,22 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], qlb_solve_kernel<1>, kThreads, sizeof(CtaSmem<kInRowsState>)) != cudaSuccess)
     return fail(QLB_ERR_CUDA);
   if (ctx->blocks_per_sm[0] < 1 || ctx->blocks_per_sm[1] < 1) return fail(QLB_ERR_CUDA);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[0], qlb_quad_kernel<0, 2>, kQuadThreads, 0) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[1], qlb_quad_kernel<1, 2>, kQuadThreads, 0) != cudaSuccess)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[0], qlb_quad_kernel<double, double, 0, 2>, kQuadThreads, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[1], qlb_quad_kernel<double, double, 1, 2>, kQuadThreads, 0) != cudaSuccess)
     return fail(QLB_ERR_CUDA);
   if (ctx->blocks_per_sm_quad[0] < 1 || ctx->blocks_per_sm_quad[1] < 1) return fail(QLB_ERR_CUDA);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first[0], qlb_quad_first_kernel<0>, kQuadThreads, 0) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first[1], qlb_quad_first_kernel<1>, kQuadThreads, 0) != cudaSuccess)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first[0], qlb_quad_first_kernel<double, double, 0>, kQuadThreads, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first[1], qlb_quad_first_kernel<double, double, 1>, kQuadThreads, 0) != cudaSuccess)
+    return fail(QLB_ERR_CUDA);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad_f[0], qlb_quad_kernel<float, float, 0, 2>, kQuadThreads, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad_f[1], qlb_quad_kernel<float, float, 1, 2>, kQuadThreads, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first_f[0], qlb_quad_first_kernel<float, float, 0>, kQuadThreads, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first_f[1], qlb_quad_first_kernel<float, float, 1>, kQuadThreads, 0) != cudaSuccess)
+    return fail(QLB_ERR_CUDA);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad_m[0], qlb_quad_kernel<float, double, 0, 2>, kQuadThreads, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad_m[1], qlb_quad_kernel<float, double, 1, 2>, kQuadThreads, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first_m[0], qlb_quad_first_kernel<float, double, 0>, kQuadThreads, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first_m[1], qlb_quad_first_kernel<float, double, 1>, kQuadThreads, 0) != cudaSuccess)
     return fail(QLB_ERR_CUDA);
   if (const char* k = std::getenv("QLB_KERNEL")) {
     ctx->use_quad = (std::strcmp(k, "half") != 0);
@@ -335,6 +407,7 @@ int qlb_destroy(qlb_context* ctx) {
   for (int i = 0; i < kPipe; i++)
     if (ctx->pipe[i]) { cudaStreamSynchronize(ctx->pipe[i]); cudaStreamDestroy(ctx->pipe[i]); }
   cudaFree(ctx->d_model); cudaFree(ctx->d_params); cudaFree(ctx->d_counter); cudaFree(ctx->d_stats);
+  cudaFree(ctx->d_model_f); cudaFree(ctx->d_params_f);
   cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags);
   for (int i = 0; i < 8; i++) cudaFree(ctx->d_list[i]);
   cudaGetLastError();
@@ -351,6 +424,9 @@ int qlb_set_params(qlb_context* ctx, const qlb_params* params) {
   // ordered after any solve already queued on the context stream
   QLB_CUDA(ctx, cudaDeviceSynchronize());
   QLB_CUDA(ctx, cudaMemcpy(ctx->d_params, &hp, sizeof hp, cudaMemcpyHostToDevice));
+  DeviceParamsT<float> hpf;
+  narrow_params(hp, &hpf);
+  QLB_CUDA(ctx, cudaMemcpy(ctx->d_params_f, &hpf, sizeof hpf, cudaMemcpyHostToDevice));
   ctx->params = *params;
   return QLB_OK;
 }
@@ -361,58 +437,80 @@ int qlb_get_params(const qlb_context* ctx, qlb_params* params) {
   return QLB_OK;
 }
 
+int qlb_set_f32_core(qlb_context* ctx, int core) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (core != QLB_F32_CORE_FP32 && core != QLB_F32_CORE_FP64) return QLB_ERR_INVALID_ARGUMENT;
+  ctx->f32_pure = (core == QLB_F32_CORE_FP32);
+  return QLB_OK;
+}
+
 uint64_t qlb_launch_count(const qlb_context* ctx) { return ctx ? ctx->launches : 0; }
 
-int qlb_solve_wrench(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz, const double* wrench,
-                     const uint8_t* stance_mask, const double* mu, const double* normals_world, double* grf,
-                     double* tau, uint32_t* flags, double* netwrench, void* stream) {
+// ---- device-pointer entry points (T = double, and float for the _f32 twins)
+extern "C++" {
+namespace {
+
+template <typename T> struct Typed;
+template <> struct Typed<double> {
+  static const DeviceModel* model(const qlb_context* c) { return c->d_model; }
+  static const DeviceParams* params(const qlb_context* c) { return c->d_params; }
+  template <int MODE> static int launch(qlb_context* c, SolveArgs& a, cudaStream_t st) { return launch_solve<MODE>(c, a, st); }
+};
+template <> struct Typed<float> {
+  static const DeviceModelT<float>* model(const qlb_context* c) { return c->d_model_f; }
+  static const DeviceParamsT<float>* params(const qlb_context* c) { return c->d_params_f; }
+  template <int MODE> static int launch(qlb_context* c, SolveArgsT<float>& a, cudaStream_t st) { return launch_solve_f32<MODE>(c, a, st); }
+};
+
+template <typename T>
+int solve_wrench_t(qlb_context* ctx, size_t B, const T* q, const T* quat_wxyz, const T* wrench, const uint8_t* stance_mask,
+                   const T* mu, const T* normals_world, T* grf, T* tau, uint32_t* flags, T* netwrench, void* stream) {
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
   if (!q || !quat_wxyz || !wrench || !stance_mask || !grf || !tau || !flags) return QLB_ERR_INVALID_ARGUMENT;
   DeviceGuard guard(ctx->device);
-  SolveArgs a;
+  SolveArgsT<T> a;
   std::memset(&a, 0, sizeof a);
   a.B = B; a.q = q; a.quat = quat_wxyz; a.wrench = wrench; a.mask = stance_mask; a.mu = mu; a.normals = normals_world;
   a.grf = grf; a.tau = tau; a.flags = flags; a.netwrench = netwrench;
-  a.counter = ctx->d_counter; a.model = ctx->d_model; a.params = ctx->d_params;
+  a.counter = ctx->d_counter; a.model = Typed<T>::model(ctx); a.params = Typed<T>::params(ctx); a.params64 = ctx->d_params;
   a.vec_ok = (B % 2 == 0) && aligned16(q) && aligned16(quat_wxyz) && aligned16(wrench) && aligned16(grf) && aligned16(tau) &&
              (!mu || aligned16(mu)) && (!normals_world || aligned16(normals_world)) && (!netwrench || aligned16(netwrench));
-  return launch_solve<0>(ctx, a, static_cast<cudaStream_t>(stream));
+  return Typed<T>::template launch<0>(ctx, a, static_cast<cudaStream_t>(stream));
 }
 
-int qlb_solve_state(qlb_context* ctx, size_t B, const double* q, const double* base_pose, const double* base_twist,
-                    const double* target_pose, const double* target_twist, const uint8_t* stance_mask,
-                    const double* mu, const double* normals_world, double* grf, double* tau, uint32_t* flags,
-                    double* netwrench, double* wrench_out, void* stream) {
+template <typename T>
+int solve_state_t(qlb_context* ctx, size_t B, const T* q, const T* base_pose, const T* base_twist, const T* target_pose,
+                  const T* target_twist, const uint8_t* stance_mask, const T* mu, const T* normals_world, T* grf, T* tau,
+                  uint32_t* flags, T* netwrench, T* wrench_out, void* stream) {
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
   if (!q || !base_pose || !base_twist || !target_pose || !target_twist || !stance_mask || !grf || !tau || !flags)
     return QLB_ERR_INVALID_ARGUMENT;
   DeviceGuard guard(ctx->device);
-  SolveArgs a;
+  SolveArgsT<T> a;
   std::memset(&a, 0, sizeof a);
   a.B = B; a.q = q; a.pose = base_pose; a.twist = base_twist; a.tpose = target_pose; a.ttwist = target_twist;
   a.mask = stance_mask; a.mu = mu; a.normals = normals_world;
   a.grf = grf; a.tau = tau; a.flags = flags; a.netwrench = netwrench; a.wrench_out = wrench_out;
-  a.counter = ctx->d_counter; a.model = ctx->d_model; a.params = ctx->d_params;
+  a.counter = ctx->d_counter; a.model = Typed<T>::model(ctx); a.params = Typed<T>::params(ctx); a.params64 = ctx->d_params;
   a.vec_ok = (B % 2 == 0) && aligned16(q) && aligned16(base_pose) && aligned16(base_twist) && aligned16(target_pose) &&
              aligned16(target_twist) && aligned16(grf) && aligned16(tau) && (!mu || aligned16(mu)) &&
              (!normals_world || aligned16(normals_world)) && (!netwrench || aligned16(netwrench)) &&
              (!wrench_out || aligned16(wrench_out));
-  return launch_solve<1>(ctx, a, static_cast<cudaStream_t>(stream));
+  return Typed<T>::template launch<1>(ctx, a, static_cast<cudaStream_t>(stream));
 }
 
 // ---- host-pointer entry points: copy in, solve, copy out, synchronise.
 // Large batches are cut into chunks of kChunk states that flow through kPipe streams, so that the H2D
 // copy of chunk i+1, the kernel of chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex).
 // The arrays are SoA with row pitch B, so a chunk is a column range: one 2-D copy per array.
-namespace {
+template <typename T> struct HostRow { const T* h; int rows; };   // input array (may be null) and its component count
+template <typename T> struct HostOut { T* h; int rows; };
 
-struct HostRow { const double* h; int rows; };   // input array (may be null) and its component count
-struct HostOut { double* h; int rows; };
-
-int run_host_pipeline(qlb_context* ctx, size_t B, bool state_mode, const HostRow* in, int nin, const uint8_t* mask,
-                      const HostOut* out, int nout, uint32_t* flags) {
+template <typename T>
+int run_host_pipeline(qlb_context* ctx, size_t B, bool state_mode, const HostRow<T>* in, int nin, const uint8_t* mask,
+                      const HostOut<T>* out, int nout, uint32_t* flags) {
   int rc = ensure_capacity(ctx, B);
   if (rc != QLB_OK) return rc;
   const size_t cap = ctx->cap;
@@ -421,71 +519,122 @@ int run_host_pipeline(qlb_context* ctx, size_t B, bool state_mode, const HostRow
     const int slot = (int)(ci % kPipe);
     cudaStream_t st = ctx->pipe[slot];
     const size_t b0 = ci * cap, n = (B - b0 < cap) ? (B - b0) : cap;
-    double* din = ctx->d_in + (size_t)slot * cap * kHostInRows;
-    double* dout = ctx->d_out + (size_t)slot * cap * kHostOutRows;
+    // the staging buffers are sized for FP64; the FP32 twins use the first half of each slot
+    T* din = reinterpret_cast<T*>(ctx->d_in + (size_t)slot * cap * kHostInRows);
+    T* dout = reinterpret_cast<T*>(ctx->d_out + (size_t)slot * cap * kHostOutRows);
     uint8_t* dmask = ctx->d_mask + (size_t)slot * cap;
     uint32_t* dflags = ctx->d_flags + (size_t)slot * cap;
-    const double* dptr_in[8];
+    const T* dptr_in[8];
     size_t off = 0;
     for (int k = 0; k < nin; k++) {
       dptr_in[k] = nullptr;
       if (in[k].h) {
         dptr_in[k] = din + off;
-        QLB_CUDA(ctx, cudaMemcpy2DAsync(din + off, n * sizeof(double), in[k].h + b0, B * sizeof(double), n * sizeof(double),
-                                        in[k].rows, cudaMemcpyHostToDevice, st));
+        QLB_CUDA(ctx, cudaMemcpy2DAsync(din + off, n * sizeof(T), in[k].h + b0, B * sizeof(T), n * sizeof(T), in[k].rows,
+                                        cudaMemcpyHostToDevice, st));
       }
       off += (size_t)in[k].rows * cap;   // fixed block sizes keep every block 16-byte aligned (cap % 16 == 0)
     }
     QLB_CUDA(ctx, cudaMemcpyAsync(dmask, mask + b0, n, cudaMemcpyHostToDevice, st));
-    double* dptr_out[4];
+    T* dptr_out[4];
     off = 0;
     for (int k = 0; k < nout; k++) {
       dptr_out[k] = out[k].h ? dout + off : nullptr;
       off += (size_t)out[k].rows * cap;
     }
     if (!state_mode)
-      rc = qlb_solve_wrench(ctx, n, dptr_in[0], dptr_in[1], dptr_in[2], dmask, dptr_in[3], dptr_in[4], dptr_out[0], dptr_out[1],
-                            dflags, dptr_out[2], st);
+      rc = solve_wrench_t<T>(ctx, n, dptr_in[0], dptr_in[1], dptr_in[2], dmask, dptr_in[3], dptr_in[4], dptr_out[0], dptr_out[1],
+                             dflags, dptr_out[2], st);
     else
-      rc = qlb_solve_state(ctx, n, dptr_in[0], dptr_in[1], dptr_in[2], dptr_in[3], dptr_in[4], dmask, dptr_in[5], dptr_in[6],
-                           dptr_out[0], dptr_out[1], dflags, dptr_out[2], dptr_out[3], st);
+      rc = solve_state_t<T>(ctx, n, dptr_in[0], dptr_in[1], dptr_in[2], dptr_in[3], dptr_in[4], dmask, dptr_in[5], dptr_in[6],
+                            dptr_out[0], dptr_out[1], dflags, dptr_out[2], dptr_out[3], st);
     if (rc != QLB_OK) return rc;
     for (int k = 0; k < nout; k++)
       if (out[k].h)
-        QLB_CUDA(ctx, cudaMemcpy2DAsync(out[k].h + b0, B * sizeof(double), dptr_out[k], n * sizeof(double), n * sizeof(double),
-                                        out[k].rows, cudaMemcpyDeviceToHost, st));
+        QLB_CUDA(ctx, cudaMemcpy2DAsync(out[k].h + b0, B * sizeof(T), dptr_out[k], n * sizeof(T), n * sizeof(T), out[k].rows,
+                                        cudaMemcpyDeviceToHost, st));
     QLB_CUDA(ctx, cudaMemcpyAsync(flags + b0, dflags, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   }
   for (int i = 0; i < kPipe; i++) QLB_CUDA(ctx, cudaStreamSynchronize(ctx->pipe[i]));
   return QLB_OK;
 }
 
-}  // namespace
-
-int qlb_solve_wrench_host(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz, const double* wrench,
-                          const uint8_t* stance_mask, const double* mu, const double* normals_world, double* grf,
-                          double* tau, uint32_t* flags, double* netwrench) {
+template <typename T>
+int solve_wrench_host_t(qlb_context* ctx, size_t B, const T* q, const T* quat_wxyz, const T* wrench, const uint8_t* stance_mask,
+                        const T* mu, const T* normals_world, T* grf, T* tau, uint32_t* flags, T* netwrench) {
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
   if (!q || !quat_wxyz || !wrench || !stance_mask || !grf || !tau || !flags) return QLB_ERR_INVALID_ARGUMENT;
   DeviceGuard guard(ctx->device);
-  const HostRow in[5] = {{q, 12}, {quat_wxyz, 4}, {wrench, 6}, {mu, 4}, {normals_world, 12}};
-  const HostOut out[3] = {{grf, 12}, {tau, 12}, {netwrench, 6}};
-  return run_host_pipeline(ctx, B, false, in, 5, stance_mask, out, 3, flags);
+  const HostRow<T> in[5] = {{q, 12}, {quat_wxyz, 4}, {wrench, 6}, {mu, 4}, {normals_world, 12}};
+  const HostOut<T> out[3] = {{grf, 12}, {tau, 12}, {netwrench, 6}};
+  return run_host_pipeline<T>(ctx, B, false, in, 5, stance_mask, out, 3, flags);
 }
 
-int qlb_solve_state_host(qlb_context* ctx, size_t B, const double* q, const double* base_pose, const double* base_twist,
-                         const double* target_pose, const double* target_twist, const uint8_t* stance_mask,
-                         const double* mu, const double* normals_world, double* grf, double* tau, uint32_t* flags,
-                         double* netwrench, double* wrench_out) {
+template <typename T>
+int solve_state_host_t(qlb_context* ctx, size_t B, const T* q, const T* base_pose, const T* base_twist, const T* target_pose,
+                       const T* target_twist, const uint8_t* stance_mask, const T* mu, const T* normals_world, T* grf, T* tau,
+                       uint32_t* flags, T* netwrench, T* wrench_out) {
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
   if (!q || !base_pose || !base_twist || !target_pose || !target_twist || !stance_mask || !grf || !tau || !flags)
     return QLB_ERR_INVALID_ARGUMENT;
   DeviceGuard guard(ctx->device);
-  const HostRow in[7] = {{q, 12}, {base_pose, 7}, {base_twist, 6}, {target_pose, 7}, {target_twist, 6}, {mu, 4}, {normals_world, 12}};
-  const HostOut out[4] = {{grf, 12}, {tau, 12}, {netwrench, 6}, {wrench_out, 6}};
-  return run_host_pipeline(ctx, B, true, in, 7, stance_mask, out, 4, flags);
+  const HostRow<T> in[7] = {{q, 12}, {base_pose, 7}, {base_twist, 6}, {target_pose, 7}, {target_twist, 6}, {mu, 4}, {normals_world, 12}};
+  const HostOut<T> out[4] = {{grf, 12}, {tau, 12}, {netwrench, 6}, {wrench_out, 6}};
+  return run_host_pipeline<T>(ctx, B, true, in, 7, stance_mask, out, 4, flags);
+}
+
+}  // namespace
+}  // extern "C++"
+
+int qlb_solve_wrench(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz, const double* wrench,
+                     const uint8_t* stance_mask, const double* mu, const double* normals_world, double* grf,
+                     double* tau, uint32_t* flags, double* netwrench, void* stream) {
+  return solve_wrench_t<double>(ctx, B, q, quat_wxyz, wrench, stance_mask, mu, normals_world, grf, tau, flags, netwrench, stream);
+}
+int qlb_solve_wrench_f32(qlb_context* ctx, size_t B, const float* q, const float* quat_wxyz, const float* wrench,
+                         const uint8_t* stance_mask, const float* mu, const float* normals_world, float* grf, float* tau,
+                         uint32_t* flags, float* netwrench, void* stream) {
+  return solve_wrench_t<float>(ctx, B, q, quat_wxyz, wrench, stance_mask, mu, normals_world, grf, tau, flags, netwrench, stream);
+}
+int qlb_solve_state(qlb_context* ctx, size_t B, const double* q, const double* base_pose, const double* base_twist,
+                    const double* target_pose, const double* target_twist, const uint8_t* stance_mask,
+                    const double* mu, const double* normals_world, double* grf, double* tau, uint32_t* flags,
+                    double* netwrench, double* wrench_out, void* stream) {
+  return solve_state_t<double>(ctx, B, q, base_pose, base_twist, target_pose, target_twist, stance_mask, mu, normals_world, grf,
+                               tau, flags, netwrench, wrench_out, stream);
+}
+int qlb_solve_state_f32(qlb_context* ctx, size_t B, const float* q, const float* base_pose, const float* base_twist,
+                        const float* target_pose, const float* target_twist, const uint8_t* stance_mask, const float* mu,
+                        const float* normals_world, float* grf, float* tau, uint32_t* flags, float* netwrench,
+                        float* wrench_out, void* stream) {
+  return solve_state_t<float>(ctx, B, q, base_pose, base_twist, target_pose, target_twist, stance_mask, mu, normals_world, grf,
+                              tau, flags, netwrench, wrench_out, stream);
+}
+int qlb_solve_wrench_host(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz, const double* wrench,
+                          const uint8_t* stance_mask, const double* mu, const double* normals_world, double* grf,
+                          double* tau, uint32_t* flags, double* netwrench) {
+  return solve_wrench_host_t<double>(ctx, B, q, quat_wxyz, wrench, stance_mask, mu, normals_world, grf, tau, flags, netwrench);
+}
+int qlb_solve_wrench_f32_host(qlb_context* ctx, size_t B, const float* q, const float* quat_wxyz, const float* wrench,
+                              const uint8_t* stance_mask, const float* mu, const float* normals_world, float* grf, float* tau,
+                              uint32_t* flags, float* netwrench) {
+  return solve_wrench_host_t<float>(ctx, B, q, quat_wxyz, wrench, stance_mask, mu, normals_world, grf, tau, flags, netwrench);
+}
+int qlb_solve_state_host(qlb_context* ctx, size_t B, const double* q, const double* base_pose, const double* base_twist,
+                         const double* target_pose, const double* target_twist, const uint8_t* stance_mask,
+                         const double* mu, const double* normals_world, double* grf, double* tau, uint32_t* flags,
+                         double* netwrench, double* wrench_out) {
+  return solve_state_host_t<double>(ctx, B, q, base_pose, base_twist, target_pose, target_twist, stance_mask, mu, normals_world,
+                                    grf, tau, flags, netwrench, wrench_out);
+}
+int qlb_solve_state_f32_host(qlb_context* ctx, size_t B, const float* q, const float* base_pose, const float* base_twist,
+                             const float* target_pose, const float* target_twist, const uint8_t* stance_mask, const float* mu,
+                             const float* normals_world, float* grf, float* tau, uint32_t* flags, float* netwrench,
+                             float* wrench_out) {
+  return solve_state_host_t<float>(ctx, B, q, base_pose, base_twist, target_pose, target_twist, stance_mask, mu, normals_world,
+                                   grf, tau, flags, netwrench, wrench_out);
 }
 
 int qlb_leg_kinematics(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz, double* foot, double* jac,

@@ -64,6 +64,8 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return r * fma(-x, r, 2.0);
 }
 
+__device__ __forceinline__ float fast_rcp(float x) { return rcp_approx(x); }
+
 // 1/sqrt(x) to FP64 rounding: FP32 seed (one MUFU.RSQ) + two Newton steps in FP64.  x must be a
 // normal FP32-range number (pivots of the KKT matrices are 1e-4 .. 1e16); x <= 0 gives NaN.
 __device__ __forceinline__ double fast_rsqrt(double x) {
@@ -73,6 +75,13 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   const double hx = 0.5 * x;
   r = r * fma(-hx * r, r, 1.5);
   return r * fma(-hx * r, r, 1.5);
+}
+
+// FP32 twin: MUFU.RSQ + one Newton step
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * fmaf(-0.5f * x * r, r, 1.5f);
 }
 
 // sin and cos for joint angles (|x| up to ~1e4 rad; URDF limits are +-3 rad): two-constant Cody-Waite
@@ -100,6 +109,8 @@ __device__ __forceinline__ void sincos_small(double x, double* sn, double* cs) {
   *sn = (k & 2) ? -s0 : s0;
   *cs = ((k + 1) & 2) ? -c0 : c0;
 }
+
+__device__ __forceinline__ void sincos_small(float x, float* sn, float* cs) { sincosf(x, sn, cs); }
 
 // ---------------------------------------------------------------- 12x12 Cholesky through shuffles
 // In : H[j] = entry (gl, j) of a symmetric positive definite matrix (full row; lanes >= 12: zeros).
@@ -326,23 +337,28 @@ __device__ __forceinline__ double smem_backward(const double* __restrict__ hs, d
 }
 
 // ---------------------------------------------------------------- model / parameters in device memory
-struct DeviceModel {
-  double rot[4][4][9];   // [leg][joint] rotation of <origin rpy>, row-major
-  double xyz[4][4][3];   // [leg][joint] <origin xyz>
-  double mass[4][4];     // link masses
-  double com[4][4][3];   // link COM in link frame (the foot link's is pre-rotated by rot[leg][3])
-  double msuf[4][4];     // suffix sums of mass: msuf[leg][c] = sum_{l>=c} mass[leg][l]
+// T = double for the FP64 entry points, float for their _f32 twins (the context keeps both copies).
+template <typename T>
+struct DeviceModelT {
+  T rot[4][4][9];   // [leg][joint] rotation of <origin rpy>, row-major
+  T xyz[4][4][3];   // [leg][joint] <origin xyz>
+  T mass[4][4];     // link masses
+  T com[4][4][3];   // link COM in link frame (the foot link's is pre-rotated by rot[leg][3])
+  T msuf[4][4];     // suffix sums of mass: msuf[leg][c] = sum_{l>=c} mass[leg][l]
 };
+using DeviceModel = DeviceModelT<double>;
 
-struct DeviceParams {
-  double S[6];
-  double W, fmin, mu_default, gravity;
-  double tol;
+template <typename T>
+struct DeviceParamsT {
+  T S[6];
+  T W, fmin, mu_default, gravity;
+  T tol;
   int max_iter;
   int pad;
   // virtual model controller
-  double kp_t[3], kd_t[3], kff_t[3], kp_r[3], kd_r[3], kff_r[3];
-  double torso_mass, leg_mass[4], leg_pos[4][3], com[3], grav_pct;
+  T kp_t[3], kd_t[3], kff_t[3], kp_r[3], kd_r[3], kff_r[3];
+  T torso_mass, leg_mass[4], leg_pos[4][3], com[3], grav_pct;
 };
+using DeviceParams = DeviceParamsT<double>;
 
 }  // namespace qlb

@@ -31,35 +31,39 @@ constexpr int kPdasFirst = 1;      // active-set passes tried right after the un
 constexpr int kPolishPasses = 10;  // passes per polish attempt
 constexpr double kNeighbourhood = 1e-3;
 
-struct SolveArgs {
+template <typename T>
+struct SolveArgsT {
   unsigned long long B;
-  const double* q;
-  const double* quat;
-  const double* wrench;
+  const T* q;
+  const T* quat;
+  const T* wrench;
   const uint8_t* mask;
-  const double* mu;       // may be null
-  const double* normals;  // may be null
+  const T* mu;       // may be null
+  const T* normals;  // may be null
   // state mode
-  const double* pose;
-  const double* twist;
-  const double* tpose;
-  const double* ttwist;
-  double* grf;
-  double* tau;
+  const T* pose;
+  const T* twist;
+  const T* tpose;
+  const T* ttwist;
+  T* grf;
+  T* tau;
   uint32_t* flags;
-  double* netwrench;      // may be null
-  double* wrench_out;     // may be null (state mode)
+  T* netwrench;      // may be null
+  T* wrench_out;     // may be null (state mode)
   unsigned long long* counter;  // work counter, zeroed before launch
   unsigned long long* counter2; // work counter of the second pass (leg-per-lane kernels)
   unsigned* list;               // indices of the states left for the second pass, or null
+  unsigned* list_pat;           // per listed state: its first repaired pattern, 5 bits per leg
   unsigned* list_count;         // their number
   unsigned long long* counter3; // work counter of the third pass
   unsigned* list2;              // states left for the interior-point pass
   unsigned* list2_count;
-  const DeviceModel* model;
-  const DeviceParams* params;
+  const DeviceModelT<T>* model;
+  const DeviceParamsT<T>* params;
+  const DeviceParamsT<double>* params64;  // the same parameters in FP64 (solver core of the mixed FP32 variant)
   int vec_ok;             // all row pointers 16-byte aligned and B even
 };
+using SolveArgs = SolveArgsT<double>;
 
 template <int ROWS>
 struct alignas(16) WarpSmem {
@@ -149,17 +153,18 @@ __device__ __forceinline__ float group_min(float v) {
 }
 
 // kindr logarithmic map of (q_t^-1 * q): see VirtualModelController.cpp:120,124
-__device__ __forceinline__ void quat_rel_log(const double* qt, const double* q, double (&v)[3]) {
+template <typename T>
+__device__ __forceinline__ void quat_rel_log(const T* qt, const T* q, T (&v)[3]) {
   // rel = conj(qt) * q
-  const double aw = qt[0], ax = -qt[1], ay = -qt[2], az = -qt[3];
-  double w = aw * q[0] - ax * q[1] - ay * q[2] - az * q[3];
-  double x = aw * q[1] + ax * q[0] + ay * q[3] - az * q[2];
-  double y = aw * q[2] - ax * q[3] + ay * q[0] + az * q[1];
-  double z = aw * q[3] + ax * q[2] - ay * q[1] + az * q[0];
-  if (w < 0.0) { w = -w; x = -x; y = -y; z = -z; }
-  const double n = sqrt(x * x + y * y + z * z);
-  double k = 2.0;
-  if (n >= 1e-12) k = 2.0 * atan2(n, w) / n;
+  const T aw = qt[0], ax = -qt[1], ay = -qt[2], az = -qt[3];
+  T w = aw * q[0] - ax * q[1] - ay * q[2] - az * q[3];
+  T x = aw * q[1] + ax * q[0] + ay * q[3] - az * q[2];
+  T y = aw * q[2] - ax * q[3] + ay * q[0] + az * q[1];
+  T z = aw * q[3] + ax * q[2] - ay * q[1] + az * q[0];
+  if (w < T(0.0)) { w = -w; x = -x; y = -y; z = -z; }
+  const T n = sqrt(x * x + y * y + z * z);
+  T k = T(2.0);
+  if (n >= T(1e-12)) k = T(2.0) * atan2(n, w) / n;
   v[0] = k * x; v[1] = k * y; v[2] = k * z;
 }
 

@@ -17,6 +17,12 @@
 
 namespace qlb {
 
+#ifndef QLB_PDAS_ROUNDS
+#define QLB_PDAS_ROUNDS 3    // active-set repair rounds before a state is handed to the interior point
+#endif
+#ifndef QLB_IPM_MIN_CTAS
+#define QLB_IPM_MIN_CTAS 3   // interior-point pass (and the single-pass variant)
+#endif
 #ifndef QLB_QUAD_MIN_CTAS
 #define QLB_QUAD_MIN_CTAS 3
 #endif
@@ -46,64 +52,120 @@ __device__ __forceinline__ unsigned quad_or(unsigned v) {
   return v | __shfl_xor_sync(kFull, v, 2);
 }
 
+// Tolerances of the two arithmetic types (relative to the force scale / the gradient scale of the state).
+template <typename T> struct Tol;
+template <> struct Tol<double> {
+  __device__ static double feas() { return 1e-10; }   // a row counts as violated below -feas * scale
+  __device__ static double mult() { return 1e-13; }   // a multiplier counts as negative below -mult * gscale
+  __device__ static float ipm(float tol) { return tol; }
+  static constexpr bool refine = false;
+  static constexpr bool rescue = false;
+};
+template <> struct Tol<float> {
+  __device__ static float feas() { return 1e-5f; }
+  __device__ static float mult() { return 3e-6f; }
+  __device__ static float ipm(float tol) { return fmaxf(tol, 1e-4f); }  // FP32 residuals stall near 1e-5 * scale
+  static constexpr bool refine = true;  // iterative refinement of the polish solves
+  static constexpr bool rescue = true;  // states the FP32 core cannot verify go to a.list3 (FP64-core pass)
+};
+
 #define QLB_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
 // In-thread Cholesky of a packed lower-triangular 6x6 SPD matrix; A <- L (strict lower part), rdg = 1/diag(L).
-__device__ __forceinline__ bool chol6_thread(double (&A)[21], double (&rdg)[6]) {
+// All loops have constant trip counts and the triangle is cut with `if`: nvcc does not unroll loops whose
+// bounds depend on an outer induction variable, and a rolled loop would put the matrix in local memory.
+template <typename real>
+__device__ __forceinline__ bool chol6_thread(real (&A)[21], real (&rdg)[6]) {
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 6; j++) {
-    double d = A[QLB_TRI(j, j)];
+    real d = A[QLB_TRI(j, j)];
 #pragma unroll
-    for (int k = 0; k < j; k++) d = fma(-A[QLB_TRI(j, k)], A[QLB_TRI(j, k)], d);
-    ok = ok && (d > 0.0);
-    const double r = fast_rsqrt(d);
+    for (int k = 0; k < 6; k++)
+      if (k < j) d = fma(-A[QLB_TRI(j, k)], A[QLB_TRI(j, k)], d);
+    ok = ok && (d > real(0.0));
+    const real r = fast_rsqrt(d);
     rdg[j] = r;
 #pragma unroll
-    for (int i = j + 1; i < 6; i++) {
-      double s = A[QLB_TRI(i, j)];
+    for (int i = 0; i < 6; i++) {
+      if (i > j) {
+        real s = A[QLB_TRI(i, j)];
 #pragma unroll
-      for (int k = 0; k < j; k++) s = fma(-A[QLB_TRI(i, k)], A[QLB_TRI(j, k)], s);
-      A[QLB_TRI(i, j)] = s * r;
+        for (int k = 0; k < 6; k++)
+          if (k < j) s = fma(-A[QLB_TRI(i, k)], A[QLB_TRI(j, k)], s);
+        A[QLB_TRI(i, j)] = s * r;
+      }
     }
   }
   return ok;
 }
-__device__ __forceinline__ void solve6_thread(const double (&L)[21], const double (&rdg)[6], double (&x)[6]) {
+template <typename real>
+__device__ __forceinline__ void solve6_thread(const real (&L)[21], const real (&rdg)[6], real (&x)[6]) {
 #pragma unroll
   for (int i = 0; i < 6; i++) {
-    double s = x[i];
+    real s = x[i];
 #pragma unroll
-    for (int k = 0; k < i; k++) s = fma(-L[QLB_TRI(i, k)], x[k], s);
+    for (int k = 0; k < 6; k++)
+      if (k < i) s = fma(-L[QLB_TRI(i, k)], x[k], s);
     x[i] = s * rdg[i];
   }
 #pragma unroll
   for (int i = 5; i >= 0; i--) {
-    double s = x[i];
+    real s = x[i];
 #pragma unroll
-    for (int k = i + 1; k < 6; k++) s = fma(-L[QLB_TRI(k, i)], x[k], s);
+    for (int k = 0; k < 6; k++)
+      if (k > i) s = fma(-L[QLB_TRI(k, i)], x[k], s);
     x[i] = s * rdg[i];
   }
 }
 
+// One step of iterative refinement for (S^-1 + sum_legs sum_c al_c v_c v_c') t = rhs with the residual
+// evaluated through the factors v_c (not through the assembled matrix, whose large entries have already
+// rounded the S^-1 part away).  Used by the FP32 core only: it brings the solve from cond * eps ~ 5e-3
+// to the level of the input rounding.  Whole warp (quad shuffles).
+template <typename real>
+__device__ __forceinline__ void refine6(const real (&N)[21], const real (&rdg)[6], const real (&v)[3][6], const real (&al)[3],
+                                        const real* sinv, const real (&rhs)[6], real (&t)[6]) {
+  real d[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    real acc = real(0.0);
+#pragma unroll
+    for (int r = 0; r < 6; r++) acc = fma(v[c][r], t[r], acc);
+    d[c] = al[c] * acc;
+  }
+  real res[6];
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    const real kt = quad_sum(fma(d[0], v[0][r], fma(d[1], v[1][r], d[2] * v[2][r])));
+    res[r] = (rhs[r] - sinv[r] * t[r]) - kt;
+  }
+  solve6_thread(N, rdg, res);
+#pragma unroll
+  for (int r = 0; r < 6; r++) t[r] += res[r];
+}
+
 // D~ y and D~' v for one leg (rows: y_n >= F_min, mu y_n +- y_1 >= 0, mu y_n +- y_2 >= 0); slots (n, 1, 2)
-__device__ __forceinline__ void leg_rows(double yn, double y1, double y2, double mu, double (&e)[5]) {
-  const double m = mu * yn;
+template <typename real>
+__device__ __forceinline__ void leg_rows(real yn, real y1, real y2, real mu, real (&e)[5]) {
+  const real m = mu * yn;
   e[0] = yn; e[1] = m + y1; e[2] = m - y1; e[3] = m + y2; e[4] = m - y2;
 }
-__device__ __forceinline__ void leg_rows_t(const double (&v)[5], double mu, double (&o)[3]) {
+template <typename real>
+__device__ __forceinline__ void leg_rows_t(const real (&v)[5], real mu, real (&o)[3]) {
   o[0] = fma(mu, (v[1] + v[2]) + (v[3] + v[4]), v[0]);
   o[1] = v[1] - v[2];
   o[2] = v[3] - v[4];
 }
 
 // Per-leg quantities that stay fixed while the QP is solved.
+template <typename real>
 struct LegSetup {
-  double At[3][6];   // the leg's block of the wrench map in contact coordinates, At[c] = [e_c; r x e_c]
+  real At[3][6];   // the leg's block of the wrench map in contact coordinates, At[c] = [e_c; r x e_c]
                      // (rows 0..2 are the friction frame n, t1, t2 itself; zero for a swing leg)
-  double nrm[3];     // the leg's contact normal in base frame (also for swing legs)
-  double b[6];       // desired wrench
-  double mu, c0;     // friction coefficient; normal force of the strictly feasible interior-point start
+  real nrm[3];     // the leg's contact normal in base frame (also for swing legs)
+  real b[6];       // desired wrench
+  real mu, c0;     // friction coefficient; normal force of the strictly feasible interior-point start
   float gscale, rm;  // scale of the linear term; 1 / number of constraint rows
   unsigned mask;
   int ns;
@@ -111,12 +173,12 @@ struct LegSetup {
 };
 
 // Load one state (lane = leg `leg` of state bx) and run everything up to the QP data.
-template <int MODE>
-__device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParams& prm, const unsigned long long bx,
+template <typename real, int MODE>
+__device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const DeviceParamsT<real>& prm, const unsigned long long bx,
                                            const unsigned long long bq, const bool valid, const bool write_wout,
-                                           const int leg, LegSetup& L, double (*jg)[kQuadThreads]) {
+                                           const int leg, LegSetup<real>& L, real (*jg)[kQuadThreads]) {
   const unsigned long long B = a.B;
-  const DeviceModel& mdl = *a.model;
+  const DeviceModelT<real>& mdl = *a.model;
   const bool have_mu = a.mu != nullptr, have_normals = a.normals != nullptr;
     // ---------------- inputs (each row of 8 consecutive states is one 64-byte segment)
     const unsigned mask = valid ? (unsigned)a.mask[bx] & 0xFu : 0u;
@@ -124,31 +186,31 @@ __device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParam
     const bool alive = (mask >> leg) & 1u;
     const int ns = __popc(mask);
     L.alive = alive; L.ns = ns;
-    double qj[3];
+    real qj[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) qj[j] = __ldg(a.q + (size_t)(3 * leg + j) * B + bx);
     bool bad = !(isfinite(qj[0]) && isfinite(qj[1]) && isfinite(qj[2]));
-    double quat[4];
-    double (&b)[6] = L.b;
+    real quat[4];
+    real (&b)[6] = L.b;
     if (MODE == 1) {
       // virtual model controller prologue (VirtualModelController.cpp:104-268), redundantly on the quad
-      double pose[7], tw[6], tp[7], tt[6];
+      real pose[7], tw[6], tp[7], tt[6];
 #pragma unroll
       for (int r = 0; r < 7; r++) { pose[r] = __ldg(a.pose + (size_t)r * B + bx); tp[r] = __ldg(a.tpose + (size_t)r * B + bx); bad |= !isfinite(pose[r]) || !isfinite(tp[r]); }
 #pragma unroll
       for (int r = 0; r < 6; r++) { tw[r] = __ldg(a.twist + (size_t)r * B + bx); tt[r] = __ldg(a.ttwist + (size_t)r * B + bx); bad |= !isfinite(tw[r]) || !isfinite(tt[r]); }
 #pragma unroll
       for (int r = 0; r < 4; r++) quat[r] = pose[3 + r];
-      const double w = quat[0], x = quat[1], y = quat[2], z = quat[3];
-      double R[9];
-      R[0] = w * w + x * x - y * y - z * z; R[1] = 2.0 * (x * y - w * z); R[2] = 2.0 * (x * z + w * y);
-      R[3] = 2.0 * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = 2.0 * (y * z - w * x);
-      R[6] = 2.0 * (x * z - w * y); R[7] = 2.0 * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
-      double ep[3], ev[3], ew[3], eR[3];
+      const real w = quat[0], x = quat[1], y = quat[2], z = quat[3];
+      real R[9];
+      R[0] = w * w + x * x - y * y - z * z; R[1] = real(2.0) * (x * y - w * z); R[2] = real(2.0) * (x * z + w * y);
+      R[3] = real(2.0) * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = real(2.0) * (y * z - w * x);
+      R[6] = real(2.0) * (x * z - w * y); R[7] = real(2.0) * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
+      real ep[3], ev[3], ew[3], eR[3];
 #pragma unroll
       for (int c = 0; c < 3; c++) { ep[c] = tp[c] - pose[c]; ev[c] = tt[c] - tw[c]; ew[c] = tt[3 + c] - tw[3 + c]; }
       quat_rel_log(tp + 3, quat, eR);
-      double gbv[3], Fg[3], Tg[3], ft[3];
+      real gbv[3], Fg[3], Tg[3], ft[3];
 #pragma unroll
       for (int c = 0; c < 3; c++) { gbv[c] = -prm.gravity * R[6 + c]; ft[c] = -prm.grav_pct * prm.torso_mass * gbv[c]; Fg[c] = ft[c]; }
       Tg[0] = prm.com[1] * ft[2] - prm.com[2] * ft[1];
@@ -156,22 +218,22 @@ __device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParam
       Tg[2] = prm.com[0] * ft[1] - prm.com[1] * ft[0];
 #pragma unroll
       for (int l = 0; l < 4; l++) {
-        double fl[3], rr[3];
+        real fl[3], rr[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) { fl[c] = -prm.grav_pct * prm.leg_mass[l] * gbv[c]; Fg[c] += fl[c]; rr[c] = prm.leg_pos[l][c] - prm.com[c]; }
         Tg[0] += rr[1] * fl[2] - rr[2] * fl[1];
         Tg[1] += rr[2] * fl[0] - rr[0] * fl[2];
         Tg[2] += rr[0] * fl[1] - rr[1] * fl[0];
       }
-      const double gfz = prm.kp_t[2] * ep[2], gdz = prm.kd_t[2] * ev[2], fwz = prm.kff_r[2] * tt[5];
-      const double dwv[3] = {prm.kd_r[0] * ew[0], prm.kd_r[1] * ew[1], prm.kd_r[2] * ew[2]};
+      const real gfz = prm.kp_t[2] * ep[2], gdz = prm.kd_t[2] * ev[2], fwz = prm.kff_r[2] * tt[5];
+      const real dwv[3] = {prm.kd_r[0] * ew[0], prm.kd_r[1] * ew[1], prm.kd_r[2] * ew[2]};
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-        const double epb = R[c] * ep[0] + R[3 + c] * ep[1] + R[6 + c] * ep[2];
-        const double evb = R[c] * ev[0] + R[3 + c] * ev[1] + R[6 + c] * ev[2];
-        const double ffb = R[c] * tt[0] + R[3 + c] * tt[1];
+        const real epb = R[c] * ep[0] + R[3 + c] * ep[1] + R[6 + c] * ep[2];
+        const real evb = R[c] * ev[0] + R[3 + c] * ev[1] + R[6 + c] * ev[2];
+        const real ffb = R[c] * tt[0] + R[3 + c] * tt[1];
         b[c] = prm.kp_t[c] * epb + prm.kd_t[c] * evb + prm.kff_t[c] * ffb + Fg[c] + R[6 + c] * gfz + R[6 + c] * gdz;
-        const double dwb = R[c] * dwv[0] + R[3 + c] * dwv[1] + R[6 + c] * dwv[2];
+        const real dwb = R[c] * dwv[0] + R[3 + c] * dwv[1] + R[6 + c] * dwv[2];
         b[3 + c] = -prm.kp_r[c] * eR[c] + dwb + R[6 + c] * fwz + Tg[c];
       }
       if (a.wrench_out && valid && leg == 0 && write_wout) {
@@ -184,32 +246,32 @@ __device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParam
 #pragma unroll
       for (int r = 0; r < 6; r++) { b[r] = __ldg(a.wrench + (size_t)r * B + bx); bad |= !isfinite(b[r]); }
     }
-    const double mu = L.mu = have_mu ? __ldg(a.mu + (size_t)leg * B + bx) : prm.mu_default;
-    double nw[3] = {0.0, 0.0, 1.0};
+    const real mu = L.mu = have_mu ? __ldg(a.mu + (size_t)leg * B + bx) : prm.mu_default;
+    real nw[3] = {real(0.0), real(0.0), real(1.0)};
     if (have_normals) {
 #pragma unroll
       for (int c = 0; c < 3; c++) nw[c] = __ldg(a.normals + (size_t)(3 * leg + c) * B + bx);
     }
 
     // ---------------- base rotation, friction frame (CFD.cpp:223,237,286-309), gravity in base frame (:518-519)
-    double E[3][3];  // E[0] = n, E[1] = t1, E[2] = t2 in base frame
-    double gb[3];
+    real E[3][3];  // E[0] = n, E[1] = t1, E[2] = t2 in base frame
+    real gb[3];
     {
-      const double w = quat[0], x = quat[1], y = quat[2], z = quat[3];
-      double R[9];
-      R[0] = w * w + x * x - y * y - z * z; R[1] = 2.0 * (x * y - w * z); R[2] = 2.0 * (x * z + w * y);
-      R[3] = 2.0 * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = 2.0 * (y * z - w * x);
-      R[6] = 2.0 * (x * z - w * y); R[7] = 2.0 * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
+      const real w = quat[0], x = quat[1], y = quat[2], z = quat[3];
+      real R[9];
+      R[0] = w * w + x * x - y * y - z * z; R[1] = real(2.0) * (x * y - w * z); R[2] = real(2.0) * (x * z + w * y);
+      R[3] = real(2.0) * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = real(2.0) * (y * z - w * x);
+      R[6] = real(2.0) * (x * z - w * y); R[7] = real(2.0) * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         E[0][c] = R[c] * nw[0] + R[3 + c] * nw[1] + R[6 + c] * nw[2];
         gb[c] = -prm.gravity * R[6 + c];
       }
-      const double ey[3] = {R[3], R[4], R[5]};
+      const real ey[3] = {R[3], R[4], R[5]};
       E[1][0] = E[0][1] * ey[2] - E[0][2] * ey[1];
       E[1][1] = E[0][2] * ey[0] - E[0][0] * ey[2];
       E[1][2] = E[0][0] * ey[1] - E[0][1] * ey[0];
-      double rn = fast_rsqrt(E[1][0] * E[1][0] + E[1][1] * E[1][1] + E[1][2] * E[1][2]);
+      real rn = fast_rsqrt(E[1][0] * E[1][0] + E[1][1] * E[1][1] + E[1][2] * E[1][2]);
 #pragma unroll
       for (int c = 0; c < 3; c++) E[1][c] *= rn;
       E[2][0] = E[0][1] * E[1][2] - E[0][2] * E[1][1];
@@ -227,9 +289,9 @@ __device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParam
     L.qbad = quad_or(bad ? 1u : 0u) != 0u;
 
     // ---------------- leg forward kinematics, Jacobian, gravity torques (QK.cpp:143-278,485-552)
-    double foot[3], J[3][3], gtau[3];  // J[j] = column j
+    real foot[3], J[3][3], gtau[3];  // J[j] = column j
     {
-      double R[9], p[3], zj[3][3], pj[3][3], com[4][3];
+      real R[9], p[3], zj[3][3], pj[3][3], com[4][3];
 #pragma unroll
       for (int e = 0; e < 9; e++) R[e] = __ldg(&mdl.rot[leg][0][e]);
 #pragma unroll
@@ -237,11 +299,11 @@ __device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParam
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         if (j > 0) {
-          const double x0 = __ldg(&mdl.xyz[leg][j][0]), x1 = __ldg(&mdl.xyz[leg][j][1]), x2 = __ldg(&mdl.xyz[leg][j][2]);
+          const real x0 = __ldg(&mdl.xyz[leg][j][0]), x1 = __ldg(&mdl.xyz[leg][j][1]), x2 = __ldg(&mdl.xyz[leg][j][2]);
 #pragma unroll
           for (int c = 0; c < 3; c++) p[c] += R[3 * c] * x0 + R[3 * c + 1] * x1 + R[3 * c + 2] * x2;
           if (j < 3) {
-            double Rj[9], T[9];
+            real Rj[9], T[9];
 #pragma unroll
             for (int e = 0; e < 9; e++) Rj[e] = __ldg(&mdl.rot[leg][j][e]);
 #pragma unroll
@@ -255,34 +317,34 @@ __device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParam
         if (j < 3) {
 #pragma unroll
           for (int c = 0; c < 3; c++) { zj[j][c] = R[3 * c + 2]; pj[j][c] = p[c]; }
-          double sj, cj;
+          real sj, cj;
           sincos_small(qj[j], &sj, &cj);
 #pragma unroll
           for (int r = 0; r < 3; r++) {
-            const double a0 = R[3 * r], a1 = R[3 * r + 1];
+            const real a0 = R[3 * r], a1 = R[3 * r + 1];
             R[3 * r] = cj * a0 + sj * a1;
             R[3 * r + 1] = cj * a1 - sj * a0;
           }
         }
-        const double c0 = __ldg(&mdl.com[leg][j][0]), c1 = __ldg(&mdl.com[leg][j][1]), c2 = __ldg(&mdl.com[leg][j][2]);
-        const double mj = __ldg(&mdl.mass[leg][j]);
+        const real c0 = __ldg(&mdl.com[leg][j][0]), c1 = __ldg(&mdl.com[leg][j][1]), c2 = __ldg(&mdl.com[leg][j][2]);
+        const real mj = __ldg(&mdl.mass[leg][j]);
 #pragma unroll
         for (int c = 0; c < 3; c++) com[j][c] = mj * (p[c] + R[3 * c] * c0 + R[3 * c + 1] * c1 + R[3 * c + 2] * c2);
       }
 #pragma unroll
       for (int c = 0; c < 3; c++) foot[c] = p[c];
-      double mcs[3] = {0.0, 0.0, 0.0};
+      real mcs[3] = {real(0.0), real(0.0), real(0.0)};
 #pragma unroll
       for (int j = 3; j >= 0; j--) {
 #pragma unroll
         for (int c = 0; c < 3; c++) mcs[c] += com[j][c];
         if (j < 3) {
-          const double dv[3] = {foot[0] - pj[j][0], foot[1] - pj[j][1], foot[2] - pj[j][2]};
+          const real dv[3] = {foot[0] - pj[j][0], foot[1] - pj[j][1], foot[2] - pj[j][2]};
           J[j][0] = zj[j][1] * dv[2] - zj[j][2] * dv[1];
           J[j][1] = zj[j][2] * dv[0] - zj[j][0] * dv[2];
           J[j][2] = zj[j][0] * dv[1] - zj[j][1] * dv[0];
-          const double ms = __ldg(&mdl.msuf[leg][j]);
-          const double arm[3] = {mcs[0] - ms * pj[j][0], mcs[1] - ms * pj[j][1], mcs[2] - ms * pj[j][2]};
+          const real ms = __ldg(&mdl.msuf[leg][j]);
+          const real arm[3] = {mcs[0] - ms * pj[j][0], mcs[1] - ms * pj[j][1], mcs[2] - ms * pj[j][2]};
           gtau[j] = -(zj[j][0] * (arm[1] * gb[2] - arm[2] * gb[1]) + zj[j][1] * (arm[2] * gb[0] - arm[0] * gb[2]) +
                       zj[j][2] * (arm[0] * gb[1] - arm[1] * gb[0]));
         }
@@ -290,15 +352,15 @@ __device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParam
     }
 
     // ---------------- the leg's block of the wrench map in contact coordinates: A_k = [E'; (r x e_c)] (6 x 3)
-    double (&At)[3][6] = L.At;  // At[c] = column of slot c (0 = normal, 1, 2 = tangents)
+    real (&At)[3][6] = L.At;  // At[c] = column of slot c (0 = normal, 1, 2 = tangents)
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      At[c][0] = alive ? E[c][0] : 0.0;
-      At[c][1] = alive ? E[c][1] : 0.0;
-      At[c][2] = alive ? E[c][2] : 0.0;
-      At[c][3] = alive ? foot[1] * E[c][2] - foot[2] * E[c][1] : 0.0;
-      At[c][4] = alive ? foot[2] * E[c][0] - foot[0] * E[c][2] : 0.0;
-      At[c][5] = alive ? foot[0] * E[c][1] - foot[1] * E[c][0] : 0.0;
+      At[c][0] = alive ? E[c][0] : real(0.0);
+      At[c][1] = alive ? E[c][1] : real(0.0);
+      At[c][2] = alive ? E[c][2] : real(0.0);
+      At[c][3] = alive ? foot[1] * E[c][2] - foot[2] * E[c][1] : real(0.0);
+      At[c][4] = alive ? foot[2] * E[c][0] - foot[0] * E[c][2] : real(0.0);
+      At[c][5] = alive ? foot[0] * E[c][1] - foot[1] * E[c][0] : real(0.0);
     }
     // Jacobian and gravity torques are only needed again for the outputs: park them in shared memory
 #pragma unroll
@@ -312,50 +374,66 @@ __device__ __forceinline__ void quad_setup(const SolveArgs& a, const DeviceParam
     float gsc = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      double g = 0.0;
+      real g = real(0.0);
 #pragma unroll
       for (int r = 0; r < 6; r++) g = fma(At[c][r] * prm.S[r], b[r], g);
       gsc = fmaxf(gsc, fabsf((float)g));
     }
     L.gscale = fmaxf(1.f, quad_max(gsc));
-    L.c0 = fmax(fmax(2.0 * prm.fmin, (b[0] * E[0][0] + b[1] * E[0][1] + b[2] * E[0][2]) * (ns > 0 ? 1.0 / ns : 0.0)),
-                           prm.fmin + 1.0);
+    L.c0 = fmax(fmax(real(2.0) * prm.fmin, (b[0] * E[0][0] + b[1] * E[0][1] + b[2] * E[0][2]) * (ns > 0 ? real(1.0) / ns : real(0.0))),
+                           prm.fmin + real(1.0));
     L.rm = ns > 0 ? 1.f / (5.f * ns) : 0.f;
 
 }
 
+// The solver core may run in a wider type than the inputs / kinematics (FP32 interface, FP64 core).
+template <typename real, typename creal>
+__device__ __forceinline__ void widen_setup(const LegSetup<real>& s, LegSetup<creal>& d) {
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+#pragma unroll
+    for (int r = 0; r < 6; r++) d.At[c][r] = (creal)s.At[c][r];
+    d.nrm[c] = (creal)s.nrm[c];
+  }
+#pragma unroll
+  for (int r = 0; r < 6; r++) d.b[r] = (creal)s.b[r];
+  d.mu = (creal)s.mu; d.c0 = (creal)s.c0;
+  d.gscale = s.gscale; d.rm = s.rm; d.mask = s.mask; d.ns = s.ns; d.alive = s.alive; d.qbad = s.qbad;
+}
+
 // Forces in base frame, joint torques, net wrench, flags word of one finished state.
-__device__ __forceinline__ void quad_output(const SolveArgs& a, const LegSetup& L, double (&y)[3], const int a0, const int sg1,
+template <typename real, typename creal>
+__device__ __forceinline__ void quad_output(const SolveArgsT<real>& a, const LegSetup<creal>& L, creal (&y)[3], const int a0, const int sg1,
                                             const int sg2, const int status, const int it, const unsigned long long bq,
-                                            const bool valid, const int leg, const double (*jg)[kQuadThreads]) {
+                                            const bool valid, const int leg, const real (*jg)[kQuadThreads]) {
   const unsigned long long B = a.B;
   const bool alive = L.alive;
   const unsigned mask = L.mask;
-  const double (&At)[3][6] = L.At;
+  const creal (&At)[3][6] = L.At;
     // ---------------- outputs: forces in base frame, torques, net wrench, flags
     const bool solved = (status == 0 || status == 2 || status == 3);
     const bool live = alive && solved;
-    double f[3];
+    creal f[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) f[c] = live ? y[0] * At[0][c] + y[1] * At[1][c] + y[2] * At[2][c] : 0.0;
+    for (int c = 0; c < 3; c++) f[c] = live ? y[0] * At[0][c] + y[1] * At[1][c] + y[2] * At[2][c] : creal(0.0);
     if (valid) {
 #pragma unroll
-      for (int c = 0; c < 3; c++) a.grf[(size_t)(3 * leg + c) * B + bq] = f[c];
+      for (int c = 0; c < 3; c++) a.grf[(size_t)(3 * leg + c) * B + bq] = (real)f[c];
 #pragma unroll
       for (int j = 0; j < 3; j++)
-        a.tau[(size_t)(3 * leg + j) * B + bq] =
-            live ? jg[9 + j][threadIdx.x] - (jg[3 * j][threadIdx.x] * f[0] + jg[3 * j + 1][threadIdx.x] * f[1] + jg[3 * j + 2][threadIdx.x] * f[2]) : 0.0;
+        a.tau[(size_t)(3 * leg + j) * B + bq] = (real)(
+            live ? (creal)jg[9 + j][threadIdx.x] - ((creal)jg[3 * j][threadIdx.x] * f[0] + (creal)jg[3 * j + 1][threadIdx.x] * f[1] + (creal)jg[3 * j + 2][threadIdx.x] * f[2]) : creal(0.0));
     }
     if (a.netwrench) {
       // A x = sum over legs of A_k y_k (CFD.cpp:614-625)
-      double nwv[6];
+      creal nwv[6];
 #pragma unroll
       for (int r = 0; r < 6; r++)
-        nwv[r] = quad_sum(live ? At[0][r] * y[0] + At[1][r] * y[1] + At[2][r] * y[2] : 0.0);
+        nwv[r] = quad_sum(live ? At[0][r] * y[0] + At[1][r] * y[1] + At[2][r] * y[2] : creal(0.0));
       if (valid) {
         // leg k writes components k and k+4 (k < 2)
-        a.netwrench[(size_t)leg * B + bq] = (leg == 0) ? nwv[0] : (leg == 1 ? nwv[1] : (leg == 2 ? nwv[2] : nwv[3]));
-        if (leg < 2) a.netwrench[(size_t)(4 + leg) * B + bq] = (leg == 0) ? nwv[4] : nwv[5];
+        a.netwrench[(size_t)leg * B + bq] = (real)((leg == 0) ? nwv[0] : (leg == 1 ? nwv[1] : (leg == 2 ? nwv[2] : nwv[3])));
+        if (leg < 2) a.netwrench[(size_t)(4 + leg) * B + bq] = (real)((leg == 0) ? nwv[4] : nwv[5]);
       }
     }
     {
@@ -375,18 +453,19 @@ __device__ __forceinline__ void quad_output(const SolveArgs& a, const LegSetup& 
 // First pass: kinematics + QP data + the unconstrained minimiser (polish round with the empty pattern).
 // States whose unconstrained minimiser is feasible (most of them) are finished here; the others are
 // appended to a.list for the second pass.  Fixed trip count: no divergence between the eight states of a warp.
-template <int MODE>
-__global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_first_kernel(const SolveArgs a) {
-  __shared__ DeviceParams prm;
-  __shared__ double sinv[6];
-  __shared__ double winv;
-  __shared__ double jg[12][kQuadThreads];  // per thread: Jacobian (9) and gravity torques (3) of its leg
+template <typename real, typename creal, int MODE>
+__global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_first_kernel(const SolveArgsT<real> a) {
+  __shared__ DeviceParamsT<real> prm;
+  __shared__ creal sinv[6], cS[6];
+  __shared__ creal winv, cW, cfmin;
+  __shared__ real jg[12][kQuadThreads];  // per thread: Jacobian (9) and gravity torques (3) of its leg
   {
-    const double* src = reinterpret_cast<const double*>(a.params);
-    double* dst = reinterpret_cast<double*>(&prm);
-    for (int i = threadIdx.x; i < (int)(sizeof(DeviceParams) / 8); i += blockDim.x) dst[i] = src[i];
-    if (threadIdx.x < 6) sinv[threadIdx.x] = 1.0 / a.params->S[threadIdx.x];
-    if (threadIdx.x == 6) winv = 1.0 / a.params->W;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.params);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&prm);
+    for (int i = threadIdx.x; i < (int)(sizeof(DeviceParamsT<real>) / 4); i += blockDim.x) dst[i] = src[i];
+    // the solver core reads its weights from the FP64 parameter block, in its own type
+    if (threadIdx.x < 6) { cS[threadIdx.x] = (creal)a.params64->S[threadIdx.x]; sinv[threadIdx.x] = (creal)(1.0 / a.params64->S[threadIdx.x]); }
+    if (threadIdx.x == 6) { cW = (creal)a.params64->W; winv = (creal)(1.0 / a.params64->W); cfmin = (creal)a.params64->fmin; }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -402,59 +481,506 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
     const unsigned long long slot = bi * 8 + quad;
     const bool valid = slot < B;
     const unsigned long long bq = valid ? slot : (B - 1);
-    LegSetup L;
-    quad_setup<MODE>(a, prm, bq, bq, valid, true, leg, L, jg);
+    LegSetup<creal> L;
+    {
+      LegSetup<real> L0;
+      quad_setup<real, MODE>(a, prm, bq, bq, valid, true, leg, L0, jg);
+      widen_setup(L0, L);
+    }
     const bool alive = L.alive;
-    const double (&At)[3][6] = L.At;
+    const creal (&At)[3][6] = L.At;
     int status = L.qbad ? 4 : (L.ns == 0 ? 1 : 0);
-    double y[3] = {0.0, 0.0, 0.0};
+    creal y[3] = {creal(0.0), creal(0.0), creal(0.0)};
     bool hard = false;
     // unconstrained minimiser through the 6x6 system: (S^-1 + A~ A~'/w) t = b,  y = A~' t / w
-    double N[21], rdg[6], t[6];
-    const double al = alive ? winv : 0.0;
+    creal N[21], rdg[6], t[6];
+    const creal al = alive ? winv : creal(0.0);
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-      const double w0 = al * At[0][i], w1 = al * At[1][i], w2 = al * At[2][i];
+      const creal w0 = al * At[0][i], w1 = al * At[1][i], w2 = al * At[2][i];
 #pragma unroll
-      for (int j = 0; j <= i; j++) {
-        double acc = (i == j && leg == 0) ? sinv[i] : 0.0;
-        acc = fma(w0, At[0][j], acc);
-        acc = fma(w1, At[1][j], acc);
-        acc = fma(w2, At[2][j], acc);
-        N[QLB_TRI(i, j)] = quad_sum(acc);
+      for (int j = 0; j < 6; j++) {
+        if (j <= i) {
+          creal acc = (i == j && leg == 0) ? sinv[i] : creal(0.0);
+          acc = fma(w0, At[0][j], acc);
+          acc = fma(w1, At[1][j], acc);
+          acc = fma(w2, At[2][j], acc);
+          N[QLB_TRI(i, j)] = quad_sum(acc);
+        }
       }
       t[i] = L.b[i];
     }
     const bool pd = chol6_thread(N, rdg);
     solve6_thread(N, rdg, t);
-    if (!pd && status == 0) status = 4;
-    double e[5];
+    if (Tol<creal>::refine) {
+      const creal al3[3] = {al, al, al};
+      refine6(N, rdg, At, al3, sinv, L.b, t);
+    }
+    const bool pd_fail = !pd && status == 0;   // quad-uniform: every lane factors the same matrix
+    if (pd_fail && !Tol<creal>::rescue) status = 4;
+    creal e[5];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      double d = 0.0;
+      creal d = creal(0.0);
 #pragma unroll
       for (int r = 0; r < 6; r++) d = fma(At[c][r], t[r], d);
       y[c] = al * d;
     }
     leg_rows(y[0], y[1], y[2], L.mu, e);
-    e[0] -= prm.fmin;
+    e[0] -= cfmin;
     const float scale = fmaxf(1.f, quad_max(fmaxf(fabsf((float)y[0]), fmaxf(fabsf((float)y[1]), fabsf((float)y[2])))));
-    const double tol_s = 1e-10 * (double)scale;
+    const creal tol_s = Tol<creal>::feas() * (creal)scale;
     bool viol = false;
 #pragma unroll
     for (int r = 0; r < 5; r++) viol = viol || (alive && e[r] < -tol_s);
     const bool quad_viol = quad_or(viol ? 1u : 0u) != 0u;  // not inside the && : every lane must reach the shuffle
-    hard = (status == 0) && quad_viol;
+    hard = (status == 0) && (quad_viol || pd_fail);
+    // first repair of the empty pattern: every violated row becomes active (the more violated one of a +- pair)
+    unsigned pat = 0u;
+    if (alive && !pd_fail) {
+      const bool v0 = e[0] < -tol_s, v1 = e[1] < -tol_s, v2 = e[2] < -tol_s, v3 = e[3] < -tol_s, v4 = e[4] < -tol_s;
+      pat = v0 ? 1u : 0u;
+      if (v1 || v2) pat |= ((v1 && (!v2 || e[1] <= e[2])) ? 1u : 2u) << 1;
+      if (v3 || v4) pat |= ((v3 && (!v4 || e[3] <= e[4])) ? 1u : 2u) << 3;
+    }
+    pat = quad_or(pat << (5 * leg));
     // append the unfinished states to the list of the second pass (one atomic per warp)
     const unsigned hm = __ballot_sync(kFull, hard && valid && leg == 0);
     if (hm != 0u) {
       unsigned base = 0;
       if (lane == 0) base = atomicAdd(a.list_count, __popc(hm));
       base = __shfl_sync(kFull, base, 0);
-      if (hard && valid && leg == 0) a.list[base + __popc(hm & ((1u << lane) - 1u))] = (unsigned)bq;
+      if (hard && valid && leg == 0) {
+        const unsigned at = base + __popc(hm & ((1u << lane) - 1u));
+        a.list[at] = (unsigned)bq;
+        a.list_pat[at] = pat;
+      }
     }
-    quad_output(a, L, y, 0, 0, 0, status, 0, bq, valid && !hard, leg, jg);  // whole warp: it contains quad shuffles
+    quad_output<real, creal>(a, L, y, 0, 0, 0, status, 0, bq, valid && !hard, leg, jg);  // whole warp: it contains quad shuffles
   }
+}
+
+// Shared constants of the solver core, in the core's arithmetic type.
+template <typename creal>
+struct CoreConst {
+  creal sinv[6], S[6];
+  creal winv, W, fmin;
+  float tol;
+  int max_iter;
+  // filled by the first threads of the CTA from the FP64 parameter block (followed by __syncthreads)
+  __device__ void load(const DeviceParamsT<double>* p) {
+    if (threadIdx.x < 6) { S[threadIdx.x] = (creal)p->S[threadIdx.x]; sinv[threadIdx.x] = (creal)(1.0 / p->S[threadIdx.x]); }
+    if (threadIdx.x == 6) {
+      W = (creal)p->W; winv = (creal)(1.0 / p->W); fmin = (creal)p->fmin;
+      tol = (float)p->tol; max_iter = p->max_iter;
+    }
+  }
+};
+
+// The QP of one state, one leg per lane (whole warp: eight states side by side).
+//   STAGE 0: the full algorithm - active-set rounds from the unconstrained minimiser, then the interior
+//            point, each candidate pattern verified by an exact polish round;
+//   STAGE 1: active-set rounds only, starting from the pattern pat0 of this leg; `defer` is set when they do not verify (and, with DEFER_FAIL, when a
+//            factorisation fails): the state goes to the interior-point pass;
+//   STAGE 2: interior point from the strictly feasible start, then polish rounds.
+// enable = false: the quad idles (used when only some states of a warp are solved again).
+// Out: y = forces in contact coordinates, pattern (a0, sg1, sg2), status, interior-point iterations.
+template <typename creal, int STAGE, bool DEFER_FAIL>
+__device__ __forceinline__ void quad_solve(const LegSetup<creal>& L, const CoreConst<creal>& cc, const int leg, const int quad,
+                                           const bool enable, const unsigned pat0, creal (&y)[3], int& a0, int& sg1, int& sg2,
+                                           int& status, int& it, bool& defer) {
+  const bool alive = L.alive;
+  const int ns = L.ns;
+  const creal mu = L.mu, c0 = L.c0;
+  const float gscale = L.gscale, rm = L.rm;
+  const bool qbad = L.qbad;
+  const creal (&At)[3][6] = L.At;
+  const creal (&b)[6] = L.b;
+
+  // ---------------- solver state of this leg
+  y[0] = y[1] = y[2] = creal(0.0);   // (y_n, y_1, y_2)
+  creal rdl[3] = {creal(0.0), creal(0.0), creal(0.0)}; // dual residual of the three slots
+  creal s[5], lam[5], rp[5];
+#pragma unroll
+  for (int r = 0; r < 5; r++) { s[r] = creal(1.0); lam[r] = creal(0.0); rp[r] = creal(0.0); }
+  a0 = 0; sg1 = 0; sg2 = 0;    // pattern: y_n pinned at F_min; y_1 = sg1 mu y_n; y_2 = sg2 mu y_n
+  int mode = kModePolish, pass = 0;
+  it = 0; status = 0;
+  bool first = true, converged = false, want_polish = false;
+  creal alpha_prev = creal(1.0);
+  defer = false;  // STAGE 1: hand the state to the interior-point pass
+  bool need_start = false;  // set when this quad begins its interior-point iteration
+  if (!enable) { mode = kModeDone; }
+  else if (qbad) { mode = kModeDone; status = 4; }
+  else if (ns == 0) { mode = kModeDone; status = 1; }
+  else if (STAGE == 2) { mode = kModeIpm; first = false; need_start = true; }
+  else if (STAGE == 1) {
+    // the first pass already repaired the empty pattern once: start from its result (bit 0: y_n pinned;
+    // bits 1-2 / 3-4: tangent tied to -mu y_n (1) or +mu y_n (2))
+    a0 = (int)(pat0 & 1u);
+    sg1 = ((pat0 >> 1) & 3u) == 1u ? -1 : (((pat0 >> 1) & 3u) == 2u ? 1 : 0);
+    sg2 = ((pat0 >> 3) & 3u) == 1u ? -1 : (((pat0 >> 3) & 3u) == 2u ? 1 : 0);
+    pass = 1;
+  }
+
+  int rounds = 0;
+#pragma unroll 1
+  for (;;) {
+    if (__all_sync(kFull, mode == kModeDone)) break;
+    if (++rounds > 200 && mode != kModeDone) { mode = kModeDone; status = 2; }
+    // ---- a quad starts its interior-point iteration: strictly feasible start, centred multipliers
+    if (STAGE != 1 && __any_sync(kFull, need_start)) {
+      const creal y0 = alive ? c0 : creal(0.0);
+      creal t0[6];
+#pragma unroll
+      for (int r = 0; r < 6; r++) t0[r] = cc.S[r] * (b[r] - quad_sum(At[0][r] * y0));  // S (b - A~ y0)
+      creal g[3];
+      float gm = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        creal d = (c == 0) ? cc.W * y0 : creal(0.0);
+#pragma unroll
+        for (int r = 0; r < 6; r++) d = fma(-At[c][r], t0[r], d);
+        g[c] = d;
+        gm = fmaxf(gm, fabsf((float)d));
+      }
+      const creal gmax = (creal)fmaxf(1.f, quad_max(gm));
+      if (need_start) {
+        need_start = false;
+        creal e0[5], dt[3];
+        leg_rows(c0, creal(0.0), creal(0.0), mu, e0);
+        e0[0] -= cc.fmin;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          const creal sr = fmax(e0[r], creal(1e-3) * c0);
+          s[r] = alive ? sr : creal(1.0);
+          lam[r] = alive ? gmax * fast_rcp(sr) : creal(0.0);
+          rp[r] = alive ? sr - e0[r] : creal(0.0);
+        }
+        leg_rows_t(lam, mu, dt);
+        y[0] = y0; y[1] = creal(0.0); y[2] = creal(0.0);
+#pragma unroll
+        for (int c = 0; c < 3; c++) rdl[c] = alive ? g[c] - dt[c] : creal(0.0);
+      }
+    }
+    const bool pol_round = (mode == kModePolish), ipm_round = (mode == kModeIpm);
+    const bool any_ipm = __any_sync(kFull, ipm_round);
+    const bool any_pol = __any_sync(kFull, pol_round);
+
+    // ---- build: three vectors v_c and weights al_c with  A_k K_k^-1 A_k' = sum_c al_c v_c v_c'
+    creal v[3][6], al[3] = {creal(0.0), creal(0.0), creal(0.0)}, r6[6];
+    creal rs[5], th[5], e1 = creal(0.0), e2 = creal(0.0), rr[3] = {creal(0.0), creal(0.0), creal(0.0)};
+#pragma unroll
+    for (int r = 0; r < 5; r++) { rs[r] = creal(1.0); th[r] = creal(0.0); }
+#pragma unroll
+    for (int r = 0; r < 6; r++) { v[0][r] = creal(0.0); v[1][r] = creal(0.0); v[2][r] = creal(0.0); r6[r] = creal(0.0); }
+    if (pol_round) {
+      // reduced columns of the equality-constrained QP for the current pattern
+      const creal q1 = sg1 * mu, q2 = sg2 * mu;
+      const bool fn = alive && a0 == 0, f1 = alive && sg1 == 0, f2 = alive && sg2 == 0;
+      const creal wn = cc.W * fma(mu * mu, (creal)(sg1 * sg1 + sg2 * sg2), creal(1.0));
+      al[0] = fn ? fast_rcp(wn) : creal(0.0);
+      al[1] = f1 ? cc.winv : creal(0.0);
+      al[2] = f2 ? cc.winv : creal(0.0);
+      const creal pin = (alive && a0 != 0) ? cc.fmin : creal(0.0);
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        const creal cn = fma(q2, At[2][r], fma(q1, At[1][r], At[0][r]));
+        v[0][r] = fn ? cn : creal(0.0);
+        v[1][r] = f1 ? At[1][r] : creal(0.0);
+        v[2][r] = f2 ? At[2][r] : creal(0.0);
+        r6[r] = ((leg == 0) ? b[r] : creal(0.0)) - pin * cn;
+      }
+    } else if (ipm_round) {
+      // K = w I + D~' diag(lam/s) D~ is an arrow matrix; K^-1 = M' diag(al) M with M = [[1,0,0],[0,1,0],[-e1,-e2,1]]
+      // (slots ordered 1, 2, n), so v = (a_1, a_2, a_n - e1 a_1 - e2 a_2), al = (1/d1, 1/d2, 1/sigma)
+      creal vv[5];
+#pragma unroll
+      for (int r = 0; r < 5; r++) { rs[r] = fast_rcp(s[r]); th[r] = lam[r] * rs[r]; vv[r] = fma(-th[r], rp[r], lam[r]); }
+      const creal T1 = th[1] + th[2], T2 = th[3] + th[4];
+      const creal b1 = mu * (th[1] - th[2]), b2 = mu * (th[3] - th[4]);
+      const creal d1 = cc.W + T1, d2 = cc.W + T2;
+      al[1] = fast_rcp(d1); al[2] = fast_rcp(d2);
+      e1 = b1 * al[1]; e2 = b2 * al[2];
+      // Schur complement of the arrow matrix, sigma = w + th0 + mu^2 (T1 + T2) - b1 e1 - b2 e2, written without
+      // the cancellation: mu^2 T - b^2 / d = mu^2 (T w + 4 th+ th-) / d  (all terms positive)
+      const creal sc1 = fma(T1, cc.W, creal(4.0) * th[1] * th[2]) * al[1];
+      const creal sc2 = fma(T2, cc.W, creal(4.0) * th[3] * th[4]) * al[2];
+      al[0] = fast_rcp(cc.W + fma(mu * mu, sc1 + sc2, th[0]));
+      creal dt[3];
+      leg_rows_t(vv, mu, dt);
+#pragma unroll
+      for (int c = 0; c < 3; c++) rr[c] = alive ? -rdl[c] - dt[c] : creal(0.0);
+      const creal m0 = rr[0] - e1 * rr[1] - e2 * rr[2];
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        v[1][r] = At[1][r];
+        v[2][r] = At[2][r];
+        v[0][r] = At[0][r] - e1 * At[1][r] - e2 * At[2][r];
+        r6[r] = al[0] * m0 * v[0][r] + al[1] * rr[1] * v[1][r] + al[2] * rr[2] * v[2][r];
+      }
+    }
+
+    // ---- this leg's contribution to the 6x6 system, summed over the quad
+    creal N[21], rdg[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const creal w0 = al[0] * v[0][i], w1 = al[1] * v[1][i], w2 = al[2] * v[2][i];
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        if (j <= i) {
+          creal acc = (i == j && leg == 0) ? cc.sinv[i] : creal(0.0);
+          acc = fma(w0, v[0][j], acc);
+          acc = fma(w1, v[1][j], acc);
+          acc = fma(w2, v[2][j], acc);
+          N[QLB_TRI(i, j)] = quad_sum(acc);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) r6[r] = quad_sum(r6[r]);
+    const bool pd = chol6_thread(N, rdg);
+    if (Tol<creal>::refine && any_pol) {
+      creal rhs6[6];
+#pragma unroll
+      for (int r = 0; r < 6; r++) rhs6[r] = r6[r];
+      solve6_thread(N, rdg, r6);  // r6 <- t
+      refine6(N, rdg, v, al, cc.sinv, rhs6, r6);
+    } else {
+      solve6_thread(N, rdg, r6);  // r6 <- t
+    }
+    if (!pd && mode != kModeDone) {
+      mode = kModeDone; y[0] = y[1] = y[2] = creal(0.0);
+      if (DEFER_FAIL && STAGE == 1) defer = true; else status = 4;
+    }
+
+    // ---- polish: recover y, gradient, multipliers, slacks; verify; repair the pattern
+    if (any_pol) {
+      creal zt[3], att[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        creal d0 = creal(0.0), d1 = creal(0.0);
+#pragma unroll
+        for (int r = 0; r < 6; r++) { d0 = fma(v[c][r], r6[r], d0); d1 = fma(At[c][r], r6[r], d1); }
+        zt[c] = al[c] * d0;
+        att[c] = d1;
+      }
+      const creal yn = (a0 != 0) ? cc.fmin : zt[0];
+      creal yp[3];
+      yp[0] = alive ? yn : creal(0.0);
+      yp[1] = alive ? ((sg1 != 0) ? sg1 * mu * yn : zt[1]) : creal(0.0);
+      yp[2] = alive ? ((sg2 != 0) ? sg2 * mu * yn : zt[2]) : creal(0.0);
+      // gradient G~ y + g~ = w y - A_k' t,  t = S (b - A~ y)
+      const creal g0 = fma(cc.W, yp[0], -att[0]), g1 = fma(cc.W, yp[1], -att[1]), g2 = fma(cc.W, yp[2], -att[2]);
+      creal e[5], u[5];
+      leg_rows(yp[0], yp[1], yp[2], mu, e);
+      e[0] -= cc.fmin;
+      u[1] = (sg1 == -1) ? g1 : creal(0.0);
+      u[2] = (sg1 == 1) ? -g1 : creal(0.0);
+      u[3] = (sg2 == -1) ? g2 : creal(0.0);
+      u[4] = (sg2 == 1) ? -g2 : creal(0.0);
+      u[0] = (a0 != 0) ? g0 - mu * ((u[1] + u[2]) + (u[3] + u[4])) : creal(0.0);
+      const bool act[5] = {a0 != 0, sg1 == -1, sg1 == 1, sg2 == -1, sg2 == 1};
+      const float scale = fmaxf(1.f, quad_max(fmaxf(fabsf((float)yp[0]), fmaxf(fabsf((float)yp[1]), fabsf((float)yp[2])))));
+      const creal tol_u = Tol<creal>::mult() * (creal)gscale, tol_s = Tol<creal>::feas() * (creal)scale;
+      // violations of this leg: negative multipliers (drop), else negative slacks (add; one per tangent pair)
+      creal wd_v = -tol_u, wp_v = -tol_s;
+      int wd_r = -1, wp_r = -1, nviol = 0;
+      bool drop[5], add[5];
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        drop[r] = alive && pol_round && act[r] && u[r] < -tol_u;
+        add[r] = alive && pol_round && !act[r] && e[r] < -tol_s;
+        if (drop[r] && u[r] < wd_v) { wd_v = u[r]; wd_r = r; }
+        if (add[r] && e[r] < wp_v) { wp_v = e[r]; wp_r = r; }
+        nviol += (drop[r] || add[r]) ? 1 : 0;
+      }
+      const bool leg_viol = nviol > 0;
+      const bool any_viol = quad_or(leg_viol ? 1u : 0u) != 0u;
+      const float keyf = (wd_r >= 0) ? (float)(wd_v * creal(1e6)) : ((wp_r >= 0) ? (float)wp_v : 0.f);
+      const float best = quad_min(keyf);
+      const unsigned tie = (__ballot_sync(kFull, leg_viol && keyf == best) >> (4 * quad)) & 0xFu;
+      if (pol_round && mode == kModePolish) {
+        if (!any_viol) {
+          y[0] = yp[0]; y[1] = yp[1]; y[2] = yp[2];
+          mode = kModeDone;
+          if (status == 2) status = 0;
+        } else {
+          pass++;
+          const bool give_up = first ? (pass > QLB_PDAS_ROUNDS) : (pass >= kPolishPasses);
+          if (!give_up) {
+            if (pass <= 2) {
+              // every violated row of every leg moves
+              if (drop[0]) a0 = 0; else if (add[0]) a0 = 1;
+              if (drop[1] || drop[2]) sg1 = 0; else if (add[1] || add[2]) sg1 = (add[1] && (!add[2] || e[1] <= e[2])) ? -1 : 1;
+              if (drop[3] || drop[4]) sg2 = 0; else if (add[3] || add[4]) sg2 = (add[3] && (!add[4] || e[3] <= e[4])) ? -1 : 1;
+            } else if (leg_viol && tie != 0u && (__ffs(tie) - 1) == leg) {
+              // only the globally worst row moves (prevents cycling)
+              if (wd_r >= 0) {
+                if (wd_r == 0) a0 = 0; else if (wd_r <= 2) sg1 = 0; else sg2 = 0;
+              } else {
+                if (wp_r == 0) a0 = 1; else if (wp_r == 1) sg1 = -1; else if (wp_r == 2) sg1 = 1; else if (wp_r == 3) sg2 = -1; else sg2 = 1;
+              }
+            }
+          } else if (first) {
+            first = false;
+            a0 = 0; sg1 = 0; sg2 = 0;
+            if (STAGE == 1) { defer = true; mode = kModeDone; }  // the interior-point pass takes over
+            else { mode = kModeIpm; need_start = true; }
+          } else if (converged || status == 2) {
+            mode = kModeDone;
+            if (status == 0) status = 3;
+          } else {
+            mode = kModeIpm;
+          }
+        }
+      }
+    }
+
+    // ---- interior point: predictor direction, centring, corrector, step
+    if (STAGE != 1 && any_ipm) {
+      creal ds[5], dl[5], de[5], rc[5], x[3];
+      float ratio = 0.f, pa = 0.f;
+      {
+        // x = K^-1 (r - A_k' t)
+        creal g[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          creal d = rr[c];
+#pragma unroll
+          for (int r = 0; r < 6; r++) d = fma(-At[c][r], r6[r], d);
+          g[c] = d;
+        }
+        const creal hn = al[0] * (g[0] - e1 * g[1] - e2 * g[2]);
+        x[0] = hn; x[1] = fma(-e1, hn, al[1] * g[1]); x[2] = fma(-e2, hn, al[2] * g[2]);
+      }
+      leg_rows(x[0], x[1], x[2], mu, de);
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        de[r] = (alive && ipm_round) ? de[r] : creal(0.0);
+        ds[r] = de[r] - rp[r];
+        dl[r] = (alive && ipm_round) ? -fma(lam[r], ds[r], s[r] * lam[r]) * rs[r] : creal(0.0);
+        if (alive && ipm_round) ratio = fmaxf(ratio, fmaxf(-(float)ds[r] * (float)rs[r], -(float)dl[r] * rcp_approx((float)lam[r])));
+        pa += (float)(s[r] * lam[r]);
+      }
+      ratio = quad_max(ratio);
+      const float mu_c = quad_sum(ipm_round ? pa : 0.f) * rm;
+      const creal ala = (ratio > 1.f) ? creal(1.0) / (creal)ratio : creal(1.0);
+      float pb = 0.f;
+#pragma unroll
+      for (int r = 0; r < 5; r++) pb += (float)(fma(ala, ds[r], s[r]) * fma(ala, dl[r], lam[r]));
+      const float mua = quad_sum(ipm_round ? pb : 0.f) * rm;
+      const float q3 = (ipm_round && mu_c > 0.f) ? mua / mu_c : 0.f;
+      float sigma = q3 * q3 * q3;
+      if (alpha_prev < creal(0.1) && sigma < 0.5f) sigma = 0.5f;
+      const creal sigmu = (creal)sigma * (creal)mu_c;
+      creal vv[5], dt[3], r2[3];
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        rc[r] = (alive && ipm_round) ? fma(ds[r], dl[r], s[r] * lam[r]) - sigmu : creal(0.0);
+        vv[r] = (rc[r] - lam[r] * rp[r]) * rs[r];
+      }
+      leg_rows_t(vv, mu, dt);
+#pragma unroll
+      for (int c = 0; c < 3; c++) r2[c] = (alive && ipm_round) ? -rdl[c] - dt[c] : creal(0.0);
+      // corrector: same matrix, new right-hand side
+      creal t2[6];
+      {
+        const creal m0 = r2[0] - e1 * r2[1] - e2 * r2[2];
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+          t2[r] = quad_sum(al[0] * m0 * v[0][r] + al[1] * r2[1] * v[1][r] + al[2] * r2[2] * v[2][r]);
+      }
+      solve6_thread(N, rdg, t2);
+      {
+        creal g[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          creal d = r2[c];
+#pragma unroll
+          for (int r = 0; r < 6; r++) d = fma(-At[c][r], t2[r], d);
+          g[c] = d;
+        }
+        const creal hn = al[0] * (g[0] - e1 * g[1] - e2 * g[2]);
+        x[0] = hn; x[1] = fma(-e1, hn, al[1] * g[1]); x[2] = fma(-e2, hn, al[2] * g[2]);
+      }
+      leg_rows(x[0], x[1], x[2], mu, de);
+      ratio = 0.f;
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        de[r] = (alive && ipm_round) ? de[r] : creal(0.0);
+        ds[r] = de[r] - rp[r];
+        dl[r] = (alive && ipm_round) ? -fma(lam[r], ds[r], rc[r]) * rs[r] : creal(0.0);
+        if (alive && ipm_round) ratio = fmaxf(ratio, fmaxf(-(float)ds[r] * (float)rs[r], -(float)dl[r] * rcp_approx((float)lam[r])));
+      }
+      ratio = quad_max(ratio);
+      creal alp = (ratio > 0.995f) ? creal(0.995) / (creal)ratio : creal(1.0);
+#pragma unroll 1
+      for (int tries = 0; tries < 20; tries++) {
+        float ps = 0.f, pm = 3e38f;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          const float pr = (float)(fma(alp, ds[r], s[r]) * fma(alp, dl[r], lam[r]));
+          ps += pr;
+          pm = fminf(pm, pr);
+        }
+        ps = quad_sum((alive && ipm_round) ? ps : 0.f) * rm;
+        pm = quad_min((alive && ipm_round) ? pm : 3e38f);
+        const bool ok = !ipm_round || (pm >= (float)kNeighbourhood * ps && pm > 0.f);
+        if (__all_sync(kFull, ok)) break;
+        if (!ok) alp *= creal(0.7);
+      }
+      // step; residuals without a mat-vec: rd += al (r2 - D~'(theta .* de + dl)), rp *= (1 - al)
+      creal w5[5];
+#pragma unroll
+      for (int r = 0; r < 5; r++) w5[r] = fma(th[r], de[r], dl[r]);
+      leg_rows_t(w5, mu, dt);
+      float pn = 0.f, nrp = 0.f, nrd = 0.f, ymax = 0.f;
+      if (ipm_round) {
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          s[r] = fma(alp, ds[r], s[r]);
+          lam[r] = fma(alp, dl[r], lam[r]);
+          rp[r] *= (creal(1.0) - alp);
+          pn += (float)(s[r] * lam[r]);
+          nrp = fmaxf(nrp, fabsf((float)rp[r]));
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          rdl[c] = alive ? fma(alp, r2[c] - dt[c], rdl[c]) : creal(0.0);
+          y[c] = fma(alp, x[c], y[c]);
+          nrd = fmaxf(nrd, fabsf((float)rdl[c]));
+          ymax = fmaxf(ymax, fabsf((float)y[c]));
+        }
+        alpha_prev = alp;
+        it++;
+      }
+      const float mu_n = quad_sum((alive && ipm_round) ? pn : 0.f) * rm;
+      nrd = quad_max(nrd);
+      nrp = quad_max(nrp);
+      const float scale = fmaxf(1.f, quad_max(ymax));
+      if (ipm_round) {
+        const float tolf = Tol<creal>::ipm(cc.tol) * scale;
+        converged = (mu_n <= tolf) && (nrp <= tolf) && (nrd <= 100.f * tolf);
+        const bool out_of_iters = it >= cc.max_iter;
+        want_polish = converged || out_of_iters || (it >= 2 && mu_n <= 1e-3f * scale);
+        if (out_of_iters && !converged) status = 2;
+      }
+    }
+
+    if (mode == kModeIpm && want_polish) {
+      want_polish = false;
+      mode = kModePolish;
+      pass = 0;
+      a0 = 0; sg1 = 0; sg2 = 0;
+      if (alive) {
+        a0 = lam[0] > s[0];
+        sg1 = (lam[1] > s[1]) ? -1 : ((lam[2] > s[2]) ? 1 : 0);
+        sg2 = (lam[3] > s[3]) ? -1 : ((lam[4] > s[4]) ? 1 : 0);
+      }
+    }
+  }
+
 }
 
 // Later passes.  STAGE 0: the full algorithm on all states (stand-alone, no lists).  STAGE 1: states of
@@ -462,23 +988,25 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
 // goes to a.list2.  STAGE 2: states of a.list2; interior-point iteration from the strictly feasible start,
 // polish rounds when the complementarity gap is small.  Each pass works on a compacted list, so the eight
 // states of a warp need similar numbers of rounds.
-template <int MODE, int STAGE>
-__global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kernel(const SolveArgs a) {
-  __shared__ DeviceParams prm;
-  __shared__ double sinv[6];
-  __shared__ double winv;
-  __shared__ double jg[12][kQuadThreads];  // per thread: Jacobian (9) and gravity torques (3) of its leg
+template <typename real, typename creal, int MODE, int STAGE>
+__global__ void __launch_bounds__(kQuadThreads, STAGE == 1 ? QLB_QUAD_MIN_CTAS : QLB_IPM_MIN_CTAS) qlb_quad_kernel(const SolveArgsT<real> a) {
+  __shared__ DeviceParamsT<real> prm;
+  __shared__ CoreConst<creal> cc;
+  __shared__ CoreConst<double> cc64;  // in-kernel rescue of the FP32 core
+  __shared__ real jg[12][kQuadThreads];  // per thread: Jacobian (9) and gravity torques (3) of its leg
   {
-    const double* src = reinterpret_cast<const double*>(a.params);
-    double* dst = reinterpret_cast<double*>(&prm);
-    for (int i = threadIdx.x; i < (int)(sizeof(DeviceParams) / 8); i += blockDim.x) dst[i] = src[i];
-    if (threadIdx.x < 6) sinv[threadIdx.x] = 1.0 / a.params->S[threadIdx.x];
-    if (threadIdx.x == 6) winv = 1.0 / a.params->W;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.params);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&prm);
+    for (int i = threadIdx.x; i < (int)(sizeof(DeviceParamsT<real>) / 4); i += blockDim.x) dst[i] = src[i];
+    // the solver core reads its weights from the FP64 parameter block, in its own type
+    cc.load(a.params64);
+    if (Tol<creal>::rescue && STAGE == 2) cc64.load(a.params64);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int leg = lane & 3, quad = lane >> 2;
   const unsigned long long B = a.B;
+  constexpr bool kRescue = Tol<creal>::rescue && (STAGE == 1 || STAGE == 2);
   const unsigned* const in_list = (STAGE == 0) ? nullptr : (STAGE == 1 ? a.list : a.list2);
   const unsigned long long total = (STAGE == 0) ? B : (unsigned long long)(*(STAGE == 1 ? a.list_count : a.list2_count));
   unsigned long long* const work = (STAGE == 0) ? a.counter : (STAGE == 1 ? a.counter2 : a.counter3);
@@ -492,374 +1020,34 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
     const unsigned long long slot = bi * 8 + quad;
     const bool valid = slot < total;
     const unsigned long long bq = valid ? ((STAGE == 0) ? slot : (unsigned long long)in_list[slot]) : (B - 1);
-    LegSetup L;
-    quad_setup<MODE>(a, prm, bq, bq, valid, STAGE == 0, leg, L, jg);
-    const bool alive = L.alive;
-    const int ns = L.ns;
-    const double mu = L.mu, c0 = L.c0;
-    const float gscale = L.gscale, rm = L.rm;
-    const bool qbad = L.qbad;
-    const double (&At)[3][6] = L.At;
-    const double (&b)[6] = L.b;
-
-    // ---------------- solver state of this leg
-    double y[3] = {0.0, 0.0, 0.0};   // (y_n, y_1, y_2)
-    double rdl[3] = {0.0, 0.0, 0.0}; // dual residual of the three slots
-    double s[5], lam[5], rp[5];
-#pragma unroll
-    for (int r = 0; r < 5; r++) { s[r] = 1.0; lam[r] = 0.0; rp[r] = 0.0; }
-    int a0 = 0, sg1 = 0, sg2 = 0;    // pattern: y_n pinned at F_min; y_1 = sg1 mu y_n; y_2 = sg2 mu y_n
-    int mode = kModePolish, it = 0, pass = 0, status = 0;
-    bool first = true, converged = false, want_polish = false;
-    double alpha_prev = 1.0;
-    bool defer = false;  // STAGE 1: hand the state to the interior-point pass
-    bool need_start = false;  // set when this quad begins its interior-point iteration
-    if (qbad) { mode = kModeDone; status = 4; }
-    else if (ns == 0) { mode = kModeDone; status = 1; }
-    else if (STAGE == 2) { mode = kModeIpm; first = false; need_start = true; }
-
-    int rounds = 0;
-#pragma unroll 1
-    for (;;) {
-      if (__all_sync(kFull, mode == kModeDone)) break;
-      if (++rounds > 200 && mode != kModeDone) { mode = kModeDone; status = 2; }
-      // ---- a quad starts its interior-point iteration: strictly feasible start, centred multipliers
-      if (STAGE != 1 && __any_sync(kFull, need_start)) {
-        const double y0 = alive ? c0 : 0.0;
-        double t0[6];
-#pragma unroll
-        for (int r = 0; r < 6; r++) t0[r] = prm.S[r] * (b[r] - quad_sum(At[0][r] * y0));  // S (b - A~ y0)
-        double g[3];
-        float gm = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          double d = (c == 0) ? prm.W * y0 : 0.0;
-#pragma unroll
-          for (int r = 0; r < 6; r++) d = fma(-At[c][r], t0[r], d);
-          g[c] = d;
-          gm = fmaxf(gm, fabsf((float)d));
-        }
-        const double gmax = (double)fmaxf(1.f, quad_max(gm));
-        if (need_start) {
-          need_start = false;
-          double e0[5], dt[3];
-          leg_rows(c0, 0.0, 0.0, mu, e0);
-          e0[0] -= prm.fmin;
-#pragma unroll
-          for (int r = 0; r < 5; r++) {
-            const double sr = fmax(e0[r], 1e-3 * c0);
-            s[r] = alive ? sr : 1.0;
-            lam[r] = alive ? gmax * fast_rcp(sr) : 0.0;
-            rp[r] = alive ? sr - e0[r] : 0.0;
-          }
-          leg_rows_t(lam, mu, dt);
-          y[0] = y0; y[1] = 0.0; y[2] = 0.0;
-#pragma unroll
-          for (int c = 0; c < 3; c++) rdl[c] = alive ? g[c] - dt[c] : 0.0;
-        }
-      }
-      const bool pol_round = (mode == kModePolish), ipm_round = (mode == kModeIpm);
-      const bool any_ipm = __any_sync(kFull, ipm_round);
-      const bool any_pol = __any_sync(kFull, pol_round);
-
-      // ---- build: three vectors v_c and weights al_c with  A_k K_k^-1 A_k' = sum_c al_c v_c v_c'
-      double v[3][6], al[3] = {0.0, 0.0, 0.0}, r6[6];
-      double rs[5], th[5], e1 = 0.0, e2 = 0.0, rr[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int r = 0; r < 5; r++) { rs[r] = 1.0; th[r] = 0.0; }
-#pragma unroll
-      for (int r = 0; r < 6; r++) { v[0][r] = 0.0; v[1][r] = 0.0; v[2][r] = 0.0; r6[r] = 0.0; }
-      if (pol_round) {
-        // reduced columns of the equality-constrained QP for the current pattern
-        const double q1 = sg1 * mu, q2 = sg2 * mu;
-        const bool fn = alive && a0 == 0, f1 = alive && sg1 == 0, f2 = alive && sg2 == 0;
-        const double wn = prm.W * fma(mu * mu, (double)(sg1 * sg1 + sg2 * sg2), 1.0);
-        al[0] = fn ? fast_rcp(wn) : 0.0;
-        al[1] = f1 ? winv : 0.0;
-        al[2] = f2 ? winv : 0.0;
-        const double pin = (alive && a0 != 0) ? prm.fmin : 0.0;
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-          const double cn = fma(q2, At[2][r], fma(q1, At[1][r], At[0][r]));
-          v[0][r] = fn ? cn : 0.0;
-          v[1][r] = f1 ? At[1][r] : 0.0;
-          v[2][r] = f2 ? At[2][r] : 0.0;
-          r6[r] = ((leg == 0) ? b[r] : 0.0) - pin * cn;
-        }
-      } else if (ipm_round) {
-        // K = w I + D~' diag(lam/s) D~ is an arrow matrix; K^-1 = M' diag(al) M with M = [[1,0,0],[0,1,0],[-e1,-e2,1]]
-        // (slots ordered 1, 2, n), so v = (a_1, a_2, a_n - e1 a_1 - e2 a_2), al = (1/d1, 1/d2, 1/sigma)
-        double vv[5];
-#pragma unroll
-        for (int r = 0; r < 5; r++) { rs[r] = fast_rcp(s[r]); th[r] = lam[r] * rs[r]; vv[r] = fma(-th[r], rp[r], lam[r]); }
-        const double T1 = th[1] + th[2], T2 = th[3] + th[4];
-        const double b1 = mu * (th[1] - th[2]), b2 = mu * (th[3] - th[4]);
-        const double d1 = prm.W + T1, d2 = prm.W + T2;
-        const double aa = prm.W + fma(mu * mu, T1 + T2, th[0]);
-        al[1] = fast_rcp(d1); al[2] = fast_rcp(d2);
-        e1 = b1 * al[1]; e2 = b2 * al[2];
-        al[0] = fast_rcp(aa - b1 * e1 - b2 * e2);
-        double dt[3];
-        leg_rows_t(vv, mu, dt);
-#pragma unroll
-        for (int c = 0; c < 3; c++) rr[c] = alive ? -rdl[c] - dt[c] : 0.0;
-        const double m0 = rr[0] - e1 * rr[1] - e2 * rr[2];
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-          v[1][r] = At[1][r];
-          v[2][r] = At[2][r];
-          v[0][r] = At[0][r] - e1 * At[1][r] - e2 * At[2][r];
-          r6[r] = al[0] * m0 * v[0][r] + al[1] * rr[1] * v[1][r] + al[2] * rr[2] * v[2][r];
-        }
-      }
-
-      // ---- this leg's contribution to the 6x6 system, summed over the quad
-      double N[21], rdg[6];
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        const double w0 = al[0] * v[0][i], w1 = al[1] * v[1][i], w2 = al[2] * v[2][i];
-#pragma unroll
-        for (int j = 0; j <= i; j++) {
-          double acc = (i == j && leg == 0) ? sinv[i] : 0.0;
-          acc = fma(w0, v[0][j], acc);
-          acc = fma(w1, v[1][j], acc);
-          acc = fma(w2, v[2][j], acc);
-          N[QLB_TRI(i, j)] = quad_sum(acc);
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 6; r++) r6[r] = quad_sum(r6[r]);
-      const bool pd = chol6_thread(N, rdg);
-      solve6_thread(N, rdg, r6);  // r6 <- t
-      if (!pd && mode != kModeDone) { mode = kModeDone; status = 4; y[0] = y[1] = y[2] = 0.0; }
-
-      // ---- polish: recover y, gradient, multipliers, slacks; verify; repair the pattern
-      if (any_pol) {
-        double zt[3], att[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-          for (int r = 0; r < 6; r++) { d0 = fma(v[c][r], r6[r], d0); d1 = fma(At[c][r], r6[r], d1); }
-          zt[c] = al[c] * d0;
-          att[c] = d1;
-        }
-        const double yn = (a0 != 0) ? prm.fmin : zt[0];
-        double yp[3];
-        yp[0] = alive ? yn : 0.0;
-        yp[1] = alive ? ((sg1 != 0) ? sg1 * mu * yn : zt[1]) : 0.0;
-        yp[2] = alive ? ((sg2 != 0) ? sg2 * mu * yn : zt[2]) : 0.0;
-        // gradient G~ y + g~ = w y - A_k' t,  t = S (b - A~ y)
-        const double g0 = fma(prm.W, yp[0], -att[0]), g1 = fma(prm.W, yp[1], -att[1]), g2 = fma(prm.W, yp[2], -att[2]);
-        double e[5], u[5];
-        leg_rows(yp[0], yp[1], yp[2], mu, e);
-        e[0] -= prm.fmin;
-        u[1] = (sg1 == -1) ? g1 : 0.0;
-        u[2] = (sg1 == 1) ? -g1 : 0.0;
-        u[3] = (sg2 == -1) ? g2 : 0.0;
-        u[4] = (sg2 == 1) ? -g2 : 0.0;
-        u[0] = (a0 != 0) ? g0 - mu * ((u[1] + u[2]) + (u[3] + u[4])) : 0.0;
-        const bool act[5] = {a0 != 0, sg1 == -1, sg1 == 1, sg2 == -1, sg2 == 1};
-        const float scale = fmaxf(1.f, quad_max(fmaxf(fabsf((float)yp[0]), fmaxf(fabsf((float)yp[1]), fabsf((float)yp[2])))));
-        const double tol_u = 1e-13 * (double)gscale, tol_s = 1e-10 * (double)scale;
-        // violations of this leg: negative multipliers (drop), else negative slacks (add; one per tangent pair)
-        double wd_v = -tol_u, wp_v = -tol_s;
-        int wd_r = -1, wp_r = -1, nviol = 0;
-        bool drop[5], add[5];
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-          drop[r] = alive && pol_round && act[r] && u[r] < -tol_u;
-          add[r] = alive && pol_round && !act[r] && e[r] < -tol_s;
-          if (drop[r] && u[r] < wd_v) { wd_v = u[r]; wd_r = r; }
-          if (add[r] && e[r] < wp_v) { wp_v = e[r]; wp_r = r; }
-          nviol += (drop[r] || add[r]) ? 1 : 0;
-        }
-        const bool leg_viol = nviol > 0;
-        const bool any_viol = quad_or(leg_viol ? 1u : 0u) != 0u;
-        const float keyf = (wd_r >= 0) ? (float)(wd_v * 1e6) : ((wp_r >= 0) ? (float)wp_v : 0.f);
-        const float best = quad_min(keyf);
-        const unsigned tie = (__ballot_sync(kFull, leg_viol && keyf == best) >> (4 * quad)) & 0xFu;
-        if (pol_round && mode == kModePolish) {
-          if (!any_viol) {
-            y[0] = yp[0]; y[1] = yp[1]; y[2] = yp[2];
-            mode = kModeDone;
-            if (status == 2) status = 0;
-          } else {
-            pass++;
-            const bool give_up = first ? (pass > kPdasFirst) : (pass >= kPolishPasses);
-            if (!give_up) {
-              if (pass <= 2) {
-                // every violated row of every leg moves
-                if (drop[0]) a0 = 0; else if (add[0]) a0 = 1;
-                if (drop[1] || drop[2]) sg1 = 0; else if (add[1] || add[2]) sg1 = (add[1] && (!add[2] || e[1] <= e[2])) ? -1 : 1;
-                if (drop[3] || drop[4]) sg2 = 0; else if (add[3] || add[4]) sg2 = (add[3] && (!add[4] || e[3] <= e[4])) ? -1 : 1;
-              } else if (leg_viol && tie != 0u && (__ffs(tie) - 1) == leg) {
-                // only the globally worst row moves (prevents cycling)
-                if (wd_r >= 0) {
-                  if (wd_r == 0) a0 = 0; else if (wd_r <= 2) sg1 = 0; else sg2 = 0;
-                } else {
-                  if (wp_r == 0) a0 = 1; else if (wp_r == 1) sg1 = -1; else if (wp_r == 2) sg1 = 1; else if (wp_r == 3) sg2 = -1; else sg2 = 1;
-                }
-              }
-            } else if (first) {
-              first = false;
-              a0 = 0; sg1 = 0; sg2 = 0;
-              if (STAGE == 1) { defer = true; mode = kModeDone; }  // the interior-point pass takes over
-              else { mode = kModeIpm; need_start = true; }
-            } else if (converged || status == 2) {
-              mode = kModeDone;
-              if (status == 0) status = 3;
-            } else {
-              mode = kModeIpm;
-            }
-          }
-        }
-      }
-
-      // ---- interior point: predictor direction, centring, corrector, step
-      if (STAGE != 1 && any_ipm) {
-        double ds[5], dl[5], de[5], rc[5], x[3];
-        float ratio = 0.f, pa = 0.f;
-        {
-          // x = K^-1 (r - A_k' t)
-          double g[3];
-#pragma unroll
-          for (int c = 0; c < 3; c++) {
-            double d = rr[c];
-#pragma unroll
-            for (int r = 0; r < 6; r++) d = fma(-At[c][r], r6[r], d);
-            g[c] = d;
-          }
-          const double hn = al[0] * (g[0] - e1 * g[1] - e2 * g[2]);
-          x[0] = hn; x[1] = fma(-e1, hn, al[1] * g[1]); x[2] = fma(-e2, hn, al[2] * g[2]);
-        }
-        leg_rows(x[0], x[1], x[2], mu, de);
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-          de[r] = (alive && ipm_round) ? de[r] : 0.0;
-          ds[r] = de[r] - rp[r];
-          dl[r] = (alive && ipm_round) ? -fma(lam[r], ds[r], s[r] * lam[r]) * rs[r] : 0.0;
-          if (alive && ipm_round) ratio = fmaxf(ratio, fmaxf(-(float)ds[r] * (float)rs[r], -(float)dl[r] * rcp_approx((float)lam[r])));
-          pa += (float)(s[r] * lam[r]);
-        }
-        ratio = quad_max(ratio);
-        const float mu_c = quad_sum(ipm_round ? pa : 0.f) * rm;
-        const double ala = (ratio > 1.f) ? 1.0 / (double)ratio : 1.0;
-        float pb = 0.f;
-#pragma unroll
-        for (int r = 0; r < 5; r++) pb += (float)(fma(ala, ds[r], s[r]) * fma(ala, dl[r], lam[r]));
-        const float mua = quad_sum(ipm_round ? pb : 0.f) * rm;
-        const float q3 = (ipm_round && mu_c > 0.f) ? mua / mu_c : 0.f;
-        float sigma = q3 * q3 * q3;
-        if (alpha_prev < 0.1 && sigma < 0.5f) sigma = 0.5f;
-        const double sigmu = (double)sigma * (double)mu_c;
-        double vv[5], dt[3], r2[3];
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-          rc[r] = (alive && ipm_round) ? fma(ds[r], dl[r], s[r] * lam[r]) - sigmu : 0.0;
-          vv[r] = (rc[r] - lam[r] * rp[r]) * rs[r];
-        }
-        leg_rows_t(vv, mu, dt);
-#pragma unroll
-        for (int c = 0; c < 3; c++) r2[c] = (alive && ipm_round) ? -rdl[c] - dt[c] : 0.0;
-        // corrector: same matrix, new right-hand side
-        double t2[6];
-        {
-          const double m0 = r2[0] - e1 * r2[1] - e2 * r2[2];
-#pragma unroll
-          for (int r = 0; r < 6; r++)
-            t2[r] = quad_sum(al[0] * m0 * v[0][r] + al[1] * r2[1] * v[1][r] + al[2] * r2[2] * v[2][r]);
-        }
-        solve6_thread(N, rdg, t2);
-        {
-          double g[3];
-#pragma unroll
-          for (int c = 0; c < 3; c++) {
-            double d = r2[c];
-#pragma unroll
-            for (int r = 0; r < 6; r++) d = fma(-At[c][r], t2[r], d);
-            g[c] = d;
-          }
-          const double hn = al[0] * (g[0] - e1 * g[1] - e2 * g[2]);
-          x[0] = hn; x[1] = fma(-e1, hn, al[1] * g[1]); x[2] = fma(-e2, hn, al[2] * g[2]);
-        }
-        leg_rows(x[0], x[1], x[2], mu, de);
-        ratio = 0.f;
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-          de[r] = (alive && ipm_round) ? de[r] : 0.0;
-          ds[r] = de[r] - rp[r];
-          dl[r] = (alive && ipm_round) ? -fma(lam[r], ds[r], rc[r]) * rs[r] : 0.0;
-          if (alive && ipm_round) ratio = fmaxf(ratio, fmaxf(-(float)ds[r] * (float)rs[r], -(float)dl[r] * rcp_approx((float)lam[r])));
-        }
-        ratio = quad_max(ratio);
-        double alp = (ratio > 0.995f) ? 0.995 / (double)ratio : 1.0;
-#pragma unroll 1
-        for (int tries = 0; tries < 20; tries++) {
-          float ps = 0.f, pm = 3e38f;
-#pragma unroll
-          for (int r = 0; r < 5; r++) {
-            const float pr = (float)(fma(alp, ds[r], s[r]) * fma(alp, dl[r], lam[r]));
-            ps += pr;
-            pm = fminf(pm, pr);
-          }
-          ps = quad_sum((alive && ipm_round) ? ps : 0.f) * rm;
-          pm = quad_min((alive && ipm_round) ? pm : 3e38f);
-          const bool ok = !ipm_round || (pm >= (float)kNeighbourhood * ps && pm > 0.f);
-          if (__all_sync(kFull, ok)) break;
-          if (!ok) alp *= 0.7;
-        }
-        // step; residuals without a mat-vec: rd += al (r2 - D~'(theta .* de + dl)), rp *= (1 - al)
-        double w5[5];
-#pragma unroll
-        for (int r = 0; r < 5; r++) w5[r] = fma(th[r], de[r], dl[r]);
-        leg_rows_t(w5, mu, dt);
-        float pn = 0.f, nrp = 0.f, nrd = 0.f, ymax = 0.f;
-        if (ipm_round) {
-#pragma unroll
-          for (int r = 0; r < 5; r++) {
-            s[r] = fma(alp, ds[r], s[r]);
-            lam[r] = fma(alp, dl[r], lam[r]);
-            rp[r] *= (1.0 - alp);
-            pn += (float)(s[r] * lam[r]);
-            nrp = fmaxf(nrp, fabsf((float)rp[r]));
-          }
-#pragma unroll
-          for (int c = 0; c < 3; c++) {
-            rdl[c] = alive ? fma(alp, r2[c] - dt[c], rdl[c]) : 0.0;
-            y[c] = fma(alp, x[c], y[c]);
-            nrd = fmaxf(nrd, fabsf((float)rdl[c]));
-            ymax = fmaxf(ymax, fabsf((float)y[c]));
-          }
-          alpha_prev = alp;
-          it++;
-        }
-        const float mu_n = quad_sum((alive && ipm_round) ? pn : 0.f) * rm;
-        nrd = quad_max(nrd);
-        nrp = quad_max(nrp);
-        const float scale = fmaxf(1.f, quad_max(ymax));
-        if (ipm_round) {
-          const float tolf = (float)prm.tol * scale;
-          converged = (mu_n <= tolf) && (nrp <= tolf) && (nrd <= 100.f * tolf);
-          const bool out_of_iters = it >= prm.max_iter;
-          want_polish = converged || out_of_iters || (it >= 2 && mu_n <= 1e-3f * scale);
-          if (out_of_iters && !converged) status = 2;
-        }
-      }
-
-      if (mode == kModeIpm && want_polish) {
-        want_polish = false;
-        mode = kModePolish;
-        pass = 0;
-        a0 = 0; sg1 = 0; sg2 = 0;
-        if (alive) {
-          a0 = lam[0] > s[0];
-          sg1 = (lam[1] > s[1]) ? -1 : ((lam[2] > s[2]) ? 1 : 0);
-          sg2 = (lam[3] > s[3]) ? -1 : ((lam[4] > s[4]) ? 1 : 0);
+    LegSetup<creal> L;
+    {
+      LegSetup<real> L0;
+      quad_setup<real, MODE>(a, prm, bq, bq, valid, STAGE == 0, leg, L0, jg);
+      widen_setup(L0, L);
+    }
+    creal y[3];
+    int a0, sg1, sg2, status, it;
+    bool defer;
+    const unsigned pat0 = (STAGE == 1 && valid) ? (a.list_pat[slot] >> (5 * leg)) & 31u : 0u;
+    quad_solve<creal, STAGE, kRescue>(L, cc, leg, quad, true, pat0, y, a0, sg1, sg2, status, it, defer);
+    if (kRescue && STAGE == 2) {
+      // not verified by the FP32 core (iteration limit, pattern not confirmed, factorisation failed): the
+      // same warp solves these states again with the FP64 core, from scratch.  Rare (a few per 10^5).
+      const bool again = (status == 2 || status == 3 || (status == 4 && !L.qbad));
+      if (__any_sync(kFull, again)) {
+        LegSetup<double> Ld;
+        widen_setup(L, Ld);
+        double yd[3];
+        int a0d, sg1d, sg2d, statusd, itd;
+        bool deferd;
+        quad_solve<double, 0, false>(Ld, cc64, leg, quad, again, 0u, yd, a0d, sg1d, sg2d, statusd, itd, deferd);
+        if (again) {
+          y[0] = (creal)yd[0]; y[1] = (creal)yd[1]; y[2] = (creal)yd[2];
+          a0 = a0d; sg1 = sg1d; sg2 = sg2d; status = statusd; it = itd;
         }
       }
     }
-
     if (STAGE == 1) {
       const unsigned hm = __ballot_sync(kFull, defer && valid && leg == 0);
       if (hm != 0u) {
@@ -869,7 +1057,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_QUAD_MIN_CTAS) qlb_quad_kern
         if (defer && valid && leg == 0) a.list2[base + __popc(hm & ((1u << lane) - 1u))] = (unsigned)bq;
       }
     }
-    quad_output(a, L, y, a0, sg1, sg2, status, it, bq, valid && !defer, leg, jg);
+    quad_output<real, creal>(a, L, y, a0, sg1, sg2, status, it, bq, valid && !defer, leg, jg);
   }
 }
 

@@ -322,3 +322,134 @@ def test_parameters_can_be_changed(solver, oracle, models):
         _compare(solver.solve_wrench_numpy(st), ref)
     finally:
         solver.set_params(p)
+
+
+# ---------------------------------------------------------------- FP32 twins (BASELINE config C4)
+# Stated tolerance of the _f32 entry points with the FP32 core (include/qlb.h).  FP32 arithmetic on a QP whose
+# Hessian has condition number ~1e5 (W = 1e-4 against S |a|^2 ~ 10) cannot resolve the weakly determined
+# internal-force directions better than cond * eps ~ 5e-3; the error lives in those directions only, so the
+# achieved wrench, the feasibility and the objective value stay at FP32 rounding level.  Measured relative
+# force error (65 536 states each):   median    90 %     99 %     99.9 %   max
+#     C3 (60 % four-stance)           1.6e-7    3.2e-4   2.5e-3   2.3e-2   5.0e-2
+#     C2 (two-leg stances only)       1.8e-4    5.4e-4   1.1e-3   1.7e-3   4.3e-3
+#     C5 (perturbed pose / friction)  1.4e-7    3.0e-4   1.1e-2   3.6e-2   9.0e-2
+F32_MEDIAN, F32_P90, F32_P99, F32_MAX = 5e-4, 2e-3, 2e-2, 0.2
+F32_NET = 1e-2          # achieved wrench A x, relative
+F32_FEAS = 1e-4         # constraint violation / force scale
+F32_OBJ = 1e-4          # (f(x32) - f(x*)) / max(1, |f(x*)|); measured 9e-6
+F32_SAME_FLAGS = 0.95   # fraction of states with identical active-row bits
+MIXED_TOL = 2e-3        # FP32 interface + FP64 core: input / output rounding only (measured 5e-4 forces, 1.2e-3 torques)
+
+
+def _f32_checks(out, ref, oracle, M, st, nsample=256):
+    assert out["grf"].dtype == np.float32 and out["tau"].dtype == np.float32
+    assert np.isfinite(out["grf"]).all() and np.isfinite(out["tau"]).all()
+    so, sr = (out["flags"] >> 24) & 7, (ref["flags"] >> 24) & 7
+    assert np.array_equal(so, sr), "status differs from the FP64 oracle"
+    assert np.array_equal(out["flags"] & 0xF, ref["flags"] & 0xF)
+    e = rel_err(out["grf"].astype(np.float64), ref["grf"])
+    p50, p90, p99 = np.percentile(e, [50, 90, 99])
+    assert p50 <= F32_MEDIAN and p90 <= F32_P90 and p99 <= F32_P99 and e.max() <= F32_MAX, (p50, p90, p99, e.max())
+    et = rel_err(out["tau"].astype(np.float64), ref["tau"])
+    assert np.percentile(et, 99) <= 2 * F32_P99 and et.max() <= 2 * F32_MAX
+    assert rel_err(out["netwrench"].astype(np.float64), ref["netwrench"]).max() <= F32_NET
+    same = ((out["flags"] ^ ref["flags"]) & capi.FLAG_PARITY_MASK) == 0
+    assert same.mean() >= F32_SAME_FLAGS
+    # feasibility and optimality of the FP32 answer in the FP64 problem, on a sample
+    B = st["q"].shape[1]
+    worst_feas, worst_obj = 0.0, 0.0
+    for i in np.linspace(0, B - 1, nsample).astype(int):
+        if sr[i] != 0:
+            continue
+        qp = oracle.assemble(M, st["q"][:, i], st["quat"][:, i], st["wrench"][:, i], st["mask"][i],
+                             mu=None if st.get("mu") is None else st["mu"][:, i],
+                             normals=None if st.get("normals") is None else st["normals"][:, i])
+        slots = [3 * l + c for l in qp["legs"] for c in range(3)]
+        x32 = out["grf"][slots, i].astype(np.float64)
+        xs = ref["grf"][slots, i]
+        scale = max(1.0, np.abs(xs).max())
+        worst_feas = max(worst_feas, float((qp["d"] - qp["D"] @ x32).max() / scale))
+        f = lambda x: 0.5 * x @ qp["G"] @ x + qp["g0"] @ x  # noqa: E731
+        worst_obj = max(worst_obj, float((f(x32) - f(xs)) / max(1.0, abs(f(xs)))))
+    assert worst_feas <= F32_FEAS, worst_feas
+    assert worst_obj <= F32_OBJ, worst_obj
+
+
+@pytest.mark.parametrize("cfg,B", [("C3", 32768), ("C2", 16384)])
+def test_f32_twin_fp32_core_stated_tolerance(solver, oracle, models, cfg, B):
+    st = synth.make_states(cfg, B)
+    ref = _oracle(oracle, models["quadruped_model"], st)
+    solver.set_f32_core(False)
+    try:
+        out = solver.solve_wrench_numpy(st, dtype=np.float32)
+    finally:
+        solver.set_f32_core(True)
+    _f32_checks(out, ref, oracle, models["quadruped_model"], st)
+
+
+@pytest.mark.parametrize("cfg,B", [("C3", 32768), ("C2", 16384), ("C5", 16384)])
+def test_f32_twin_default_core(solver, oracle, models, cfg, B):
+    """The default _f32 path: FP32 interface and kinematics, FP64 solver core."""
+    st = synth.make_states(cfg, B, start=31)
+    ref = _oracle(oracle, models["quadruped_model"], st)
+    out = solver.solve_wrench_numpy(st, dtype=np.float32)
+    assert out["grf"].dtype == np.float32
+    assert rel_err(out["grf"].astype(np.float64), ref["grf"]).max() <= MIXED_TOL
+    assert rel_err(out["tau"].astype(np.float64), ref["tau"]).max() <= 2 * MIXED_TOL
+    assert np.array_equal((out["flags"] >> 24) & 7, (ref["flags"] >> 24) & 7)
+    mism = ((out["flags"] ^ ref["flags"]) & capi.FLAG_PARITY_MASK) != 0
+    assert not (mism & (ref["margin"] > 1e-3)).any()
+
+
+def test_f32_device_pointers_ragged_and_bad_inputs(solver, oracle, models):
+    B = 1003  # not a multiple of 8: the last warp has idle quads
+    st = synth.make_states("C3", B, start=555)
+    st["q"][3, 17] = np.nan
+    st["wrench"][2, 400] = np.inf
+    st["mask"][5] = 0
+    ref = _oracle(oracle, models["quadruped_model"], st)
+    dev = torch.device("cuda:0")
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in st.items()}
+    d = {k: (v.float() if v.dtype == torch.float64 else v) for k, v in d.items()}
+    grf = torch.full((12, B), 7.0, dtype=torch.float32, device=dev); tau = torch.full_like(grf, 7.0)
+    flags = torch.zeros(B, dtype=torch.int32, device=dev); net = torch.zeros((6, B), dtype=torch.float32, device=dev)
+    before = solver.launches
+    solver.solve_wrench(d["q"], d["quat"], d["wrench"], d["mask"], d["mu"], d["normals"], grf, tau, flags, net,
+                        stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert solver.launches == before + 3
+    fl = flags.cpu().numpy().view(np.uint32)
+    status = (fl >> 24) & 7
+    assert status[17] == 4 and status[400] == 4 and status[5] == 1
+    g = grf.cpu().numpy()
+    assert (g[:, [5, 17, 400]] == 0).all() and np.isfinite(g).all()
+    ok = (status == 0)
+    assert ok.sum() == B - 3
+    e = rel_err(g[:, ok].astype(np.float64), ref["grf"][:, ok])
+    assert e.max() <= MIXED_TOL
+
+
+def test_f32_state_mode_follows_fp64(solver):
+    """qlb_solve_state_f32 against qlb_solve_state on the same (FP32-representable) inputs."""
+    B = 8192
+    st = synth.make_states("C3", B, start=4242)
+    rng = np.random.default_rng(5)
+    pose = np.concatenate([rng.normal(0, 0.05, (3, B)) + np.array([[0], [0], [0.45]]), st["quat"]])
+    twist = rng.normal(0, 0.05, (6, B))
+    tpose = pose + np.concatenate([rng.normal(0, 0.004, (3, B)), np.zeros((4, B))])
+    ttwist = rng.normal(0, 0.05, (6, B))
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)  # noqa: E731
+    ins32 = [f32(a) for a in (st["q"], pose, twist, tpose, ttwist)]
+    ins64 = [np.ascontiguousarray(a, dtype=np.float64) for a in ins32]
+    mu32, nr32 = f32(st["mu"]), f32(st["normals"])
+    o64 = dict(grf=np.zeros((12, B)), tau=np.zeros((12, B)), flags=np.zeros(B, np.uint32), net=np.zeros((6, B)), w=np.zeros((6, B)))
+    o32 = dict(grf=np.zeros((12, B), np.float32), tau=np.zeros((12, B), np.float32), flags=np.zeros(B, np.uint32),
+               net=np.zeros((6, B), np.float32), w=np.zeros((6, B), np.float32))
+    solver.solve_state_host(*ins64, st["mask"], mu32.astype(np.float64), nr32.astype(np.float64), o64["grf"], o64["tau"],
+                            o64["flags"], o64["net"], o64["w"])
+    solver.solve_state_host(*ins32, st["mask"], mu32, nr32, o32["grf"], o32["tau"], o32["flags"], o32["net"], o32["w"])
+    assert rel_err(o32["w"].astype(np.float64), o64["w"]).max() <= 1e-4   # virtual wrench: gains up to 1e4 on FP32 errors
+    assert np.array_equal((o32["flags"] >> 24) & 7, (o64["flags"] >> 24) & 7)
+    e = rel_err(o32["grf"].astype(np.float64), o64["grf"])
+    print("f32 state mode vs f64: median %.2e p99 %.2e max %.2e" % (np.median(e), np.percentile(e, 99), e.max()))
+    assert e.max() <= 5 * MIXED_TOL

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--model", default="quadruped_model")
     ap.add_argument("--time-batch", type=int, default=1 << 20)
+    ap.add_argument("--f32", action="store_true", help="run the _f32 twins")
     args = ap.parse_args()
     st = synth.make_states(args.config, args.batch)
     M = O.model_array(legmodel.load_model(args.model))
@@ -29,7 +30,11 @@ def main():
                                solver=O.SOLVER_GI, want_margin=True)
     print("oracle GI: %.2fs" % (time.time() - t))
     sol = capi.Solver(args.model)
-    out = sol.solve_wrench_numpy(st)
+    if os.environ.get("QLB_F32_CORE") == "float":
+        sol.set_f32_core(False)
+    npdt = np.float32 if args.f32 else np.float64
+    tdt = torch.float32 if args.f32 else torch.float64
+    out = sol.solve_wrench_numpy(st, dtype=npdt)
     sc = np.maximum(1.0, np.abs(ref["grf"]).max(0))
     e = np.abs(out["grf"] - ref["grf"]).max(0) / sc
     sct = np.maximum(1.0, np.abs(ref["tau"]).max(0))
@@ -42,7 +47,12 @@ def main():
     stt = (out["flags"] >> 24) & 7
     it = out["flags"] >> 27
     print("status hist", np.bincount(stt, minlength=5), "iters hist", np.bincount(it))
-    bad = np.nonzero((e > 1e-6) | fm)[0][:10]
+    if args.f32:
+        for thr in (1e-2, 1e-3, 1e-4):
+            ok = ref["margin"] > thr
+            print("  margin > %g: %d states, flag mismatches %d, grf err max %.3e, tau err max %.3e" % (thr, int(ok.sum()), int((fm & ok).sum()), np.nanmax(e[ok]), np.nanmax(et[ok])))
+        print("  grf err percentiles 50/90/99/99.9/100:", np.percentile(e, [50, 90, 99, 99.9, 100]))
+    bad = np.nonzero((e > (1e-3 if args.f32 else 1e-6)) | (fm & (ref["margin"] > (1e-3 if args.f32 else 0))))[0][:10]
     for i in bad:
         print("  bad", i, "err %.3e" % e[i], "flags gpu %08x ref %08x" % (out["flags"][i], ref["flags"][i]), "margin %.2e" % ref["margin"][i])
     # timing on device-resident inputs
@@ -50,10 +60,12 @@ def main():
     st = synth.make_states(args.config, Bt)
     dev = torch.device("cuda:0")
     d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in st.items()}
-    grf = torch.empty((12, Bt), dtype=torch.float64, device=dev)
+    if args.f32:
+        d = {k: (v.to(torch.float32) if v.dtype == torch.float64 else v) for k, v in d.items()}
+    grf = torch.empty((12, Bt), dtype=tdt, device=dev)
     tau = torch.empty_like(grf)
     flags = torch.empty(Bt, dtype=torch.int32, device=dev)
-    net = torch.empty((6, Bt), dtype=torch.float64, device=dev)
+    net = torch.empty((6, Bt), dtype=tdt, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     for _ in range(3):
         sol.solve_wrench(d["q"], d["quat"], d["wrench"], d["mask"], d["mu"], d["normals"], grf, tau, flags, net, stream=stream)
@@ -67,7 +79,7 @@ def main():
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / reps
     print("device-resident: %.3f ms per %d QPs -> %.3e QP/s" % (ms, Bt, Bt / ms * 1e3))
-    s = sol.batch_stats(flags, d["wrench"], net, stream=stream)
+    s = sol.batch_stats(flags, d["wrench"].double(), net.double(), stream=stream)
     print("stats: count %d status %s mean it %.3f mean err %.4f max err %.4f" % (s[0], s[1:6], s[6] / s[0], s[7] / s[0], s[28]))
 
 
