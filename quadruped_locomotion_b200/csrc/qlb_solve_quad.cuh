@@ -556,7 +556,9 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
         a.list_pat[at] = pat;
       }
     }
-    quad_output<real, creal>(a, L, y, 0, 0, 0, status, 0, bq, valid && !hard, leg, jg);  // whole warp: it contains quad shuffles
+    // Every state is written, the listed ones provisionally (a later pass overwrites them): a row segment
+    // with holes would be a partial-sector write, which costs a DRAM read to fill (ncu: +250 MB per 2^20 states).
+    quad_output<real, creal>(a, L, y, 0, 0, 0, status, 0, bq, valid, leg, jg);  // whole warp: it contains quad shuffles
   }
 }
 
