@@ -172,6 +172,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the contract is ONE JSON line on stdout: keep NCCL's version / info banner out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- inputs: this rank's contiguous slice of the global synthetic batch (no inter-GPU traffic)

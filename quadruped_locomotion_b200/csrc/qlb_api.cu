@@ -58,7 +58,10 @@ constexpr int kHostInRows = 12 + 7 + 6 + 7 + 6 + 4 + 12;  // state mode is the l
 constexpr int kHostOutRows = 12 + 12 + 6 + 6;
 constexpr int kCounters = 64;            // ring of work counters: launches on different streams never share one
 constexpr int kPipe = 3;                 // host entry points: chunks in flight (H2D / kernel / D2H overlap)
-constexpr size_t kChunk = size_t(1) << 17;  // states per pipeline chunk
+#ifndef QLB_CHUNK_LOG2
+#define QLB_CHUNK_LOG2 17
+#endif
+constexpr size_t kChunk = size_t(1) << QLB_CHUNK_LOG2;  // states per pipeline chunk
 
 struct DeviceGuard {
   int prev = -1;

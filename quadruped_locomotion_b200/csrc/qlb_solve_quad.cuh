@@ -172,33 +172,118 @@ struct LegSetup {
   bool alive, qbad;
 };
 
-// Load one state (lane = leg `leg` of state bx) and run everything up to the QP data.
+#ifndef QLB_PIPELINE_LOADS
+#define QLB_PIPELINE_LOADS 1
+#endif
+#ifndef QLB_PREFETCH_LEVEL
+#define QLB_PREFETCH_LEVEL 2   // 0 off, 1 prefetch.global.L1, 2 prefetch.global.L2
+#endif
+__device__ __forceinline__ void prefetch_global(const void* p) {
+#if QLB_PREFETCH_LEVEL == 1
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif QLB_PREFETCH_LEVEL == 2
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
+// Prefetch the input rows of the state this lane will load next (the rows of its own leg; the rows shared
+// by the quad are spread over its four lanes).  The loads of the next work item then hit in cache
+// instead of stalling twelve warps per SM on DRAM latency (top stall of the first pass in ncu).
 template <typename real, int MODE>
-__device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const DeviceParamsT<real>& prm, const unsigned long long bx,
+__device__ __forceinline__ void quad_prefetch(const SolveArgsT<real>& a, const unsigned long long bx, const int leg) {
+#if QLB_PREFETCH_LEVEL > 0
+  const unsigned long long B = a.B;
+#pragma unroll
+  for (int j = 0; j < 3; j++) prefetch_global(a.q + (size_t)(3 * leg + j) * B + bx);
+  if (MODE == 1) {
+    prefetch_global(a.pose + (size_t)leg * B + bx);
+    if (leg < 3) prefetch_global(a.pose + (size_t)(4 + leg) * B + bx);
+    prefetch_global(a.tpose + (size_t)leg * B + bx);
+    if (leg < 3) prefetch_global(a.tpose + (size_t)(4 + leg) * B + bx);
+    prefetch_global(a.twist + (size_t)leg * B + bx);
+    if (leg < 2) prefetch_global(a.twist + (size_t)(4 + leg) * B + bx);
+    prefetch_global(a.ttwist + (size_t)leg * B + bx);
+    if (leg < 2) prefetch_global(a.ttwist + (size_t)(4 + leg) * B + bx);
+  } else {
+    prefetch_global(a.quat + (size_t)leg * B + bx);
+    prefetch_global(a.wrench + (size_t)leg * B + bx);
+    if (leg < 2) prefetch_global(a.wrench + (size_t)(4 + leg) * B + bx);
+  }
+  if (a.mu != nullptr) prefetch_global(a.mu + (size_t)leg * B + bx);
+  if (a.normals != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) prefetch_global(a.normals + (size_t)(3 * leg + c) * B + bx);
+  }
+#endif
+}
+
+// The raw inputs of one state as this lane needs them (its own leg's joint angles, friction coefficient and
+// normal; the base state and the wrench, which the four lanes of a quad load redundantly).
+template <typename real, int MODE>
+struct RawIn {
+  real qj[3];
+  real quat[4];              // wrench mode
+  real b[6];                 // wrench mode: the desired wrench
+  real pose[MODE == 1 ? 7 : 1], tw[MODE == 1 ? 6 : 1], tp[MODE == 1 ? 7 : 1], tt[MODE == 1 ? 6 : 1];  // state mode
+  real mu;
+  real nw[3];
+  unsigned mask;
+};
+
+// Issue the loads of state bx (each row of 8 consecutive states is one 64-byte segment).  Kept apart from
+// quad_setup so that the first pass can have the next work item's loads in flight while it writes the current one.
+template <typename real, int MODE>
+__device__ __forceinline__ void quad_load(const SolveArgsT<real>& a, const real mu_default, const unsigned long long bx,
+                                          const bool valid, const int leg, RawIn<real, MODE>& in) {
+  const unsigned long long B = a.B;
+  in.mask = valid ? (unsigned)a.mask[bx] & 0xFu : 0u;
+#pragma unroll
+  for (int j = 0; j < 3; j++) in.qj[j] = __ldg(a.q + (size_t)(3 * leg + j) * B + bx);
+  if (MODE == 1) {
+#pragma unroll
+    for (int r = 0; r < 7; r++) { in.pose[r] = __ldg(a.pose + (size_t)r * B + bx); in.tp[r] = __ldg(a.tpose + (size_t)r * B + bx); }
+#pragma unroll
+    for (int r = 0; r < 6; r++) { in.tw[r] = __ldg(a.twist + (size_t)r * B + bx); in.tt[r] = __ldg(a.ttwist + (size_t)r * B + bx); }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; r++) in.quat[r] = __ldg(a.quat + (size_t)r * B + bx);
+#pragma unroll
+    for (int r = 0; r < 6; r++) in.b[r] = __ldg(a.wrench + (size_t)r * B + bx);
+  }
+  in.mu = (a.mu != nullptr) ? __ldg(a.mu + (size_t)leg * B + bx) : mu_default;
+  in.nw[0] = real(0.0); in.nw[1] = real(0.0); in.nw[2] = real(1.0);
+  if (a.normals != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) in.nw[c] = __ldg(a.normals + (size_t)(3 * leg + c) * B + bx);
+  }
+}
+
+// Everything from the raw inputs of one state (lane = leg `leg`) up to the QP data.
+template <typename real, int MODE>
+__device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const DeviceParamsT<real>& prm, const RawIn<real, MODE>& in,
                                            const unsigned long long bq, const bool valid, const bool write_wout,
                                            const int leg, LegSetup<real>& L, real (*jg)[kQuadThreads]) {
   const unsigned long long B = a.B;
   const DeviceModelT<real>& mdl = *a.model;
-  const bool have_mu = a.mu != nullptr, have_normals = a.normals != nullptr;
-    // ---------------- inputs (each row of 8 consecutive states is one 64-byte segment)
-    const unsigned mask = valid ? (unsigned)a.mask[bx] & 0xFu : 0u;
+    const unsigned mask = in.mask;
     L.mask = mask;
     const bool alive = (mask >> leg) & 1u;
     const int ns = __popc(mask);
     L.alive = alive; L.ns = ns;
-    real qj[3];
-#pragma unroll
-    for (int j = 0; j < 3; j++) qj[j] = __ldg(a.q + (size_t)(3 * leg + j) * B + bx);
+    real qj[3] = {in.qj[0], in.qj[1], in.qj[2]};
     bool bad = !(isfinite(qj[0]) && isfinite(qj[1]) && isfinite(qj[2]));
     real quat[4];
     real (&b)[6] = L.b;
     if (MODE == 1) {
       // virtual model controller prologue (VirtualModelController.cpp:104-268), redundantly on the quad
-      real pose[7], tw[6], tp[7], tt[6];
+      const real (&pose)[MODE == 1 ? 7 : 1] = in.pose;
+      const real (&tw)[MODE == 1 ? 6 : 1] = in.tw;
+      const real (&tp)[MODE == 1 ? 7 : 1] = in.tp;
+      const real (&tt)[MODE == 1 ? 6 : 1] = in.tt;
 #pragma unroll
-      for (int r = 0; r < 7; r++) { pose[r] = __ldg(a.pose + (size_t)r * B + bx); tp[r] = __ldg(a.tpose + (size_t)r * B + bx); bad |= !isfinite(pose[r]) || !isfinite(tp[r]); }
+      for (int r = 0; r < 7; r++) bad |= !isfinite(pose[r]) || !isfinite(tp[r]);
 #pragma unroll
-      for (int r = 0; r < 6; r++) { tw[r] = __ldg(a.twist + (size_t)r * B + bx); tt[r] = __ldg(a.ttwist + (size_t)r * B + bx); bad |= !isfinite(tw[r]) || !isfinite(tt[r]); }
+      for (int r = 0; r < 6; r++) bad |= !isfinite(tw[r]) || !isfinite(tt[r]);
 #pragma unroll
       for (int r = 0; r < 4; r++) quat[r] = pose[3 + r];
       const real w = quat[0], x = quat[1], y = quat[2], z = quat[3];
@@ -242,16 +327,12 @@ __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const Devi
       }
     } else {
 #pragma unroll
-      for (int r = 0; r < 4; r++) { quat[r] = __ldg(a.quat + (size_t)r * B + bx); bad |= !isfinite(quat[r]); }
+      for (int r = 0; r < 4; r++) { quat[r] = in.quat[r]; bad |= !isfinite(quat[r]); }
 #pragma unroll
-      for (int r = 0; r < 6; r++) { b[r] = __ldg(a.wrench + (size_t)r * B + bx); bad |= !isfinite(b[r]); }
+      for (int r = 0; r < 6; r++) { b[r] = in.b[r]; bad |= !isfinite(b[r]); }
     }
-    const real mu = L.mu = have_mu ? __ldg(a.mu + (size_t)leg * B + bx) : prm.mu_default;
-    real nw[3] = {real(0.0), real(0.0), real(1.0)};
-    if (have_normals) {
-#pragma unroll
-      for (int c = 0; c < 3; c++) nw[c] = __ldg(a.normals + (size_t)(3 * leg + c) * B + bx);
-    }
+    const real mu = L.mu = in.mu;
+    const real nw[3] = {in.nw[0], in.nw[1], in.nw[2]};
 
     // ---------------- base rotation, friction frame (CFD.cpp:223,237,286-309), gravity in base frame (:518-519)
     real E[3][3];  // E[0] = n, E[1] = t1, E[2] = t2 in base frame
@@ -473,18 +554,31 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
   const unsigned long long B = a.B;
   const unsigned long long nbatch = (B + 7) / 8;
 
-  for (;;) {
-    unsigned long long bi = 0;
-    if (lane == 0) bi = atomicAdd(a.counter, 1ull);
-    bi = __shfl_sync(kFull, bi, 0);
-    if (bi >= nbatch) break;
+  // Software pipeline over the work items of this warp: the next item is claimed and its loads are issued
+  // before the outputs of the current one are written, so the input latency is hidden behind the stores
+  // (the FP64 kernel runs only twelve warps per SM).  QLB_PIPELINE_LOADS=0: prefetch instructions only.
+  unsigned long long bi = 0;
+  if (lane == 0) bi = atomicAdd(a.counter, 1ull);
+  bi = __shfl_sync(kFull, bi, 0);
+  RawIn<real, MODE> in;
+  if (bi < nbatch) {
+    const unsigned long long s0 = bi * 8 + quad;
+    quad_load<real, MODE>(a, prm.mu_default, s0 < B ? s0 : (B - 1), s0 < B, leg, in);
+  }
+  while (bi < nbatch) {
+    unsigned long long bn = 0;
+    if (lane == 0) bn = atomicAdd(a.counter, 1ull);
+    bn = __shfl_sync(kFull, bn, 0);
+    const unsigned long long sn = bn * 8 + quad;
+    const unsigned long long bqn = sn < B ? sn : (B - 1);
+    if (bn < nbatch) quad_prefetch<real, MODE>(a, bqn, leg);
     const unsigned long long slot = bi * 8 + quad;
     const bool valid = slot < B;
     const unsigned long long bq = valid ? slot : (B - 1);
     LegSetup<creal> L;
     {
       LegSetup<real> L0;
-      quad_setup<real, MODE>(a, prm, bq, bq, valid, true, leg, L0, jg);
+      quad_setup<real, MODE>(a, prm, in, bq, valid, true, leg, L0, jg);
       widen_setup(L0, L);
     }
     const bool alive = L.alive;
@@ -558,7 +652,14 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
     }
     // Every state is written, the listed ones provisionally (a later pass overwrites them): a row segment
     // with holes would be a partial-sector write, which costs a DRAM read to fill (ncu: +250 MB per 2^20 states).
+#if QLB_PIPELINE_LOADS
+    if (bn < nbatch) quad_load<real, MODE>(a, prm.mu_default, bqn, sn < B, leg, in);
+#endif
     quad_output<real, creal>(a, L, y, 0, 0, 0, status, 0, bq, valid, leg, jg);  // whole warp: it contains quad shuffles
+#if !QLB_PIPELINE_LOADS
+    if (bn < nbatch) quad_load<real, MODE>(a, prm.mu_default, bqn, sn < B, leg, in);
+#endif
+    bi = bn;
   }
 }
 
@@ -1025,7 +1126,9 @@ __global__ void __launch_bounds__(kQuadThreads, STAGE == 1 ? QLB_QUAD_MIN_CTAS :
     LegSetup<creal> L;
     {
       LegSetup<real> L0;
-      quad_setup<real, MODE>(a, prm, bq, bq, valid, STAGE == 0, leg, L0, jg);
+      RawIn<real, MODE> in;
+      quad_load<real, MODE>(a, prm.mu_default, bq, valid, leg, in);
+      quad_setup<real, MODE>(a, prm, in, bq, valid, STAGE == 0, leg, L0, jg);
       widen_setup(L0, L);
     }
     creal y[3];
