@@ -221,9 +221,10 @@ int launch_quad(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int b
   } else {
     qlb_quad_first_kernel<T, C, MODE><<<(unsigned)(wantq < capf ? wantq : capf), kQuadThreads, 0, st>>>(a);
     QLB_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
     qlb_quad_kernel<T, C, MODE, 1><<<gq, kQuadThreads, 0, st>>>(a);
     QLB_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches++;
     qlb_quad_kernel<T, C, MODE, 2><<<gq, kQuadThreads, 0, st>>>(a);
   }
   QLB_CUDA(ctx, cudaGetLastError());

@@ -1086,11 +1086,66 @@ __device__ __forceinline__ void quad_solve(const LegSetup<creal>& L, const CoreC
 
 }
 
-// Later passes.  STAGE 0: the full algorithm on all states (stand-alone, no lists).  STAGE 1: states of
-// a.list; active-set rounds only (unconstrained minimiser + kPdasFirst repairs); what is still not verified
-// goes to a.list2.  STAGE 2: states of a.list2; interior-point iteration from the strictly feasible start,
-// polish rounds when the complementarity gap is small.  Each pass works on a compacted list, so the eight
-// states of a warp need similar numbers of rounds.
+// One work item (eight consecutive entries of a list, or eight consecutive states for STAGE 0) of a later
+// pass, whole warp.  STAGE 0: the full algorithm (stand-alone, no lists).  STAGE 1: states of a.list;
+// active-set rounds from the pattern the first pass left in a.list_pat; what is still not verified after
+// QLB_PDAS_ROUNDS repairs is appended to a.list2.  STAGE 2: states of a.list2; interior-point iteration
+// from the strictly feasible start, polish rounds when the complementarity gap is small.  Compacted lists
+// give the eight states of a warp similar numbers of rounds.
+template <typename real, typename creal, int MODE, int STAGE>
+__device__ __forceinline__ void quad_batch(const SolveArgsT<real>& a, const DeviceParamsT<real>& prm, const CoreConst<creal>& cc,
+                                           const CoreConst<double>& cc64, real (*jg)[kQuadThreads], const unsigned long long slot,
+                                           const unsigned long long total, const int lane, const int leg, const int quad) {
+  constexpr bool kRescue = Tol<creal>::rescue && (STAGE == 1 || STAGE == 2);
+  const unsigned long long B = a.B;
+  const bool valid = slot < total;
+  unsigned long long bq = B - 1;
+  if (valid) bq = (STAGE == 0) ? slot : (unsigned long long)__ldcg((STAGE == 1 ? a.list : a.list2) + slot);
+  LegSetup<creal> L;
+  {
+    LegSetup<real> L0;
+    RawIn<real, MODE> in;
+    quad_load<real, MODE>(a, prm.mu_default, bq, valid, leg, in);
+    quad_setup<real, MODE>(a, prm, in, bq, valid, STAGE == 0, leg, L0, jg);
+    widen_setup(L0, L);
+  }
+  creal y[3];
+  int a0, sg1, sg2, status, it;
+  bool defer;
+  const unsigned pat0 = (STAGE == 1 && valid) ? (a.list_pat[slot] >> (5 * leg)) & 31u : 0u;
+  quad_solve<creal, STAGE, kRescue>(L, cc, leg, quad, true, pat0, y, a0, sg1, sg2, status, it, defer);
+  if (kRescue && STAGE == 2) {
+    // not verified by the FP32 core (iteration limit, pattern not confirmed, factorisation failed): the
+    // same warp solves these states again with the FP64 core, from scratch.  Rare (a few per 10^5).
+    const bool again = (status == 2 || status == 3 || (status == 4 && !L.qbad));
+    if (__any_sync(kFull, again)) {
+      LegSetup<double> Ld;
+      widen_setup(L, Ld);
+      double yd[3];
+      int a0d, sg1d, sg2d, statusd, itd;
+      bool deferd;
+      quad_solve<double, 0, false>(Ld, cc64, leg, quad, again, 0u, yd, a0d, sg1d, sg2d, statusd, itd, deferd);
+      if (again) {
+        y[0] = (creal)yd[0]; y[1] = (creal)yd[1]; y[2] = (creal)yd[2];
+        a0 = a0d; sg1 = sg1d; sg2 = sg2d; status = statusd; it = itd;
+      }
+    }
+  }
+  if (STAGE == 1) {
+    const unsigned hm = __ballot_sync(kFull, defer && valid && leg == 0);
+    if (hm != 0u) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(a.list2_count, __popc(hm));
+      base = __shfl_sync(kFull, base, 0);
+      if (defer && valid && leg == 0) a.list2[base + __popc(hm & ((1u << lane) - 1u))] = (unsigned)bq;
+    }
+  }
+  quad_output<real, creal>(a, L, y, a0, sg1, sg2, status, it, bq, valid && !defer, leg, jg);
+}
+
+// A later pass (STAGE as in quad_batch).  Passes 2 and 3 stay separate launches: fused into one persistent
+// kernel (warps taking interior-point items as soon as they are published) the code grows to 190 KB, past the
+// instruction cache, and the pair runs 3x slower (measured: 2.9 ms against 0.96 ms per 2^20 states).
 template <typename real, typename creal, int MODE, int STAGE>
 __global__ void __launch_bounds__(kQuadThreads, STAGE == 1 ? QLB_QUAD_MIN_CTAS : QLB_IPM_MIN_CTAS) qlb_quad_kernel(const SolveArgsT<real> a) {
   __shared__ DeviceParamsT<real> prm;
@@ -1108,61 +1163,15 @@ __global__ void __launch_bounds__(kQuadThreads, STAGE == 1 ? QLB_QUAD_MIN_CTAS :
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int leg = lane & 3, quad = lane >> 2;
-  const unsigned long long B = a.B;
-  constexpr bool kRescue = Tol<creal>::rescue && (STAGE == 1 || STAGE == 2);
-  const unsigned* const in_list = (STAGE == 0) ? nullptr : (STAGE == 1 ? a.list : a.list2);
-  const unsigned long long total = (STAGE == 0) ? B : (unsigned long long)(*(STAGE == 1 ? a.list_count : a.list2_count));
+  const unsigned long long total = (STAGE == 0) ? a.B : (unsigned long long)(*(STAGE == 1 ? a.list_count : a.list2_count));
   unsigned long long* const work = (STAGE == 0) ? a.counter : (STAGE == 1 ? a.counter2 : a.counter3);
   const unsigned long long nbatch = (total + 7) / 8;
-
   for (;;) {
     unsigned long long bi = 0;
     if (lane == 0) bi = atomicAdd(work, 1ull);
     bi = __shfl_sync(kFull, bi, 0);
     if (bi >= nbatch) break;
-    const unsigned long long slot = bi * 8 + quad;
-    const bool valid = slot < total;
-    const unsigned long long bq = valid ? ((STAGE == 0) ? slot : (unsigned long long)in_list[slot]) : (B - 1);
-    LegSetup<creal> L;
-    {
-      LegSetup<real> L0;
-      RawIn<real, MODE> in;
-      quad_load<real, MODE>(a, prm.mu_default, bq, valid, leg, in);
-      quad_setup<real, MODE>(a, prm, in, bq, valid, STAGE == 0, leg, L0, jg);
-      widen_setup(L0, L);
-    }
-    creal y[3];
-    int a0, sg1, sg2, status, it;
-    bool defer;
-    const unsigned pat0 = (STAGE == 1 && valid) ? (a.list_pat[slot] >> (5 * leg)) & 31u : 0u;
-    quad_solve<creal, STAGE, kRescue>(L, cc, leg, quad, true, pat0, y, a0, sg1, sg2, status, it, defer);
-    if (kRescue && STAGE == 2) {
-      // not verified by the FP32 core (iteration limit, pattern not confirmed, factorisation failed): the
-      // same warp solves these states again with the FP64 core, from scratch.  Rare (a few per 10^5).
-      const bool again = (status == 2 || status == 3 || (status == 4 && !L.qbad));
-      if (__any_sync(kFull, again)) {
-        LegSetup<double> Ld;
-        widen_setup(L, Ld);
-        double yd[3];
-        int a0d, sg1d, sg2d, statusd, itd;
-        bool deferd;
-        quad_solve<double, 0, false>(Ld, cc64, leg, quad, again, 0u, yd, a0d, sg1d, sg2d, statusd, itd, deferd);
-        if (again) {
-          y[0] = (creal)yd[0]; y[1] = (creal)yd[1]; y[2] = (creal)yd[2];
-          a0 = a0d; sg1 = sg1d; sg2 = sg2d; status = statusd; it = itd;
-        }
-      }
-    }
-    if (STAGE == 1) {
-      const unsigned hm = __ballot_sync(kFull, defer && valid && leg == 0);
-      if (hm != 0u) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(a.list2_count, __popc(hm));
-        base = __shfl_sync(kFull, base, 0);
-        if (defer && valid && leg == 0) a.list2[base + __popc(hm & ((1u << lane) - 1u))] = (unsigned)bq;
-      }
-    }
-    quad_output<real, creal>(a, L, y, a0, sg1, sg2, status, it, bq, valid && !defer, leg, jg);
+    quad_batch<real, creal, MODE, STAGE>(a, prm, cc, cc64, jg, bi * 8 + quad, total, lane, leg, quad);
   }
 }
 
