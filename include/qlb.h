@@ -230,6 +230,35 @@ int qlb_set_f32_core(qlb_context* ctx, int core);
 int qlb_leg_kinematics(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz,
                        double* foot, double* jac, double* gravity_tau, void* stream);
 
+/* One sample of the desired robot state as RosBalanceController::baseCommandCallback reads it from a
+ * free_gait_msgs/RobotState message (ros_balance_controller.cpp:761-811: base_pose.pose.pose,
+ * base_pose.twist.twist, {lf,rf,rh,lh}_leg_joints.position[0..2], {..}_leg_mode.support_leg and
+ * .surface_normal.vector).  Fixed layout, 304 bytes, 16-byte aligned; a planner fills an array of these (one per
+ * robot, or one per time sample of a planned motion, StateBatch.hpp / BatchExecutor.cpp:69-83). */
+typedef struct qlb_robot_state_record {
+  double base_position[3];          /* geometry_msgs/Point x, y, z (world) */
+  double base_orientation_xyzw[4];  /* geometry_msgs/Quaternion field order x, y, z, w */
+  double base_linear_velocity[3];   /* twist.linear, world frame */
+  double base_angular_velocity[3];  /* twist.angular, base frame */
+  double joint_position[12];        /* LF, RF, RH, LH x (HAA, HFE, KFE) */
+  double surface_normal[12];        /* per leg, world frame */
+  uint8_t support_leg[4];           /* LegMode.support_leg per leg */
+  uint8_t reserved[4];
+} qlb_robot_state_record;
+
+/* records[B] (DEVICE, array of structs) -> the solver's SoA arrays (any output may be NULL):
+ * q[12][B], base_pose[7][B] (position + quat w,x,y,z), base_twist[6][B], stance_mask[B], normals_world[12][B].
+ * Byte movement only; bit-exact.  SURVEY 8f rank 1 ("RobotState message -> SoA packer"). */
+int qlb_pack_robot_states(qlb_context* ctx, size_t B, const qlb_robot_state_record* records, double* q,
+                          double* base_pose, double* base_twist, uint8_t* stance_mask,
+                          double* normals_world, void* stream);
+
+/* Foot positions in the WORLD frame for every state of a batch, feet_world[12][B] (leg-major):
+ * position + R_bw * FK(q).  Replaces the per-state loop of StateBatchComputer::computeEndEffectorTrajectories
+ * (free_gait_core/src/executor/StateBatchComputer.cpp:64-77).  DEVICE pointers. */
+int qlb_feet_in_world(qlb_context* ctx, size_t B, const double* q, const double* base_pose,
+                      double* feet_world, void* stream);
+
 /* Generic small dense QP (DEVICE pointers), B problems of the same shape, in the argument convention of
  * the reference's in-repo backend quadprogpp::solve_quadprog (qp_solver/include/qp_solver/QuadProg++.h:
  * 8-30), which qp_solver::QuadraticProblemSolver::minimize forwards to

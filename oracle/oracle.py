@@ -215,3 +215,37 @@ def vmc_wrench(pose, twist, tpose, ttwist, params=None):
     w = np.zeros(6)
     lib().qo_vmc_wrench(C.byref(p), _as(a[0]), _as(a[1]), _as(a[2]), _as(a[3]), _as(w))
     return w
+
+
+# ---------------------------------------------------------------- SURVEY 8f rows 1 and 2 (numpy restatements)
+def pack_robot_states(records: np.ndarray) -> dict:
+    """What RosBalanceController::baseCommandCallback extracts from a free_gait_msgs/RobotState
+    (ros_balance_controller.cpp:761-811): desired base pose (position, then the quaternion as kindr's
+    RotationQuaternion(w, x, y, z)), twist, the twelve joint positions in LF, RF, RH, LH order, support flags
+    and surface normals.  records: structured array with the fields of qlb_robot_state_record."""
+    B = records.shape[0]
+    o = records["base_orientation_xyzw"]
+    pose = np.concatenate([records["base_position"].T, o[:, 3:4].T, o[:, 0:3].T])
+    twist = np.concatenate([records["base_linear_velocity"].T, records["base_angular_velocity"].T])
+    mask = np.zeros(B, dtype=np.uint8)
+    for leg in range(4):
+        mask |= ((records["support_leg"][:, leg] != 0).astype(np.uint8) << leg).astype(np.uint8)
+    return dict(q=np.ascontiguousarray(records["joint_position"].T), pose=np.ascontiguousarray(pose),
+                twist=np.ascontiguousarray(twist), mask=mask, normals=np.ascontiguousarray(records["surface_normal"].T))
+
+
+def feet_in_world(model_arr, q, pose) -> np.ndarray:
+    """position + R_bw FK(q) per leg (StateBatchComputer.cpp:64-77: getPositionWorldToFootInWorldFrame for
+    every state of the batch).  q[12,B], pose[7,B] (position, quat wxyz) -> [12,B]."""
+    q = np.asarray(q, dtype=np.float64); pose = np.asarray(pose, dtype=np.float64)
+    B = q.shape[1]
+    out = np.zeros((12, B))
+    for i in range(B):
+        w, x, y, z = pose[3:, i]
+        R = np.array([[w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                      [2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z]])
+        for leg in range(4):
+            foot, _, _ = leg_kinematics(model_arr, leg, q[3 * leg:3 * leg + 3, i])
+            out[3 * leg:3 * leg + 3, i] = pose[:3, i] + R @ foot
+    return out

@@ -49,9 +49,16 @@ EXPORTS = (
     "qlb_default_params", "qlb_create", "qlb_destroy", "qlb_set_params", "qlb_get_params",
     "qlb_solve_wrench", "qlb_solve_wrench_host", "qlb_solve_state", "qlb_solve_state_host",
     "qlb_solve_wrench_f32", "qlb_solve_wrench_f32_host", "qlb_solve_state_f32", "qlb_solve_state_f32_host",
-    "qlb_set_f32_core", "qlb_leg_kinematics", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
+    "qlb_set_f32_core", "qlb_leg_kinematics", "qlb_pack_robot_states", "qlb_feet_in_world", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
     "qlb_last_cuda_error", "qlb_abi_version",
 )
+
+# numpy mirror of qlb_robot_state_record (include/qlb.h)
+RECORD_DTYPE = np.dtype([("base_position", "<f8", 3), ("base_orientation_xyzw", "<f8", 4),
+                         ("base_linear_velocity", "<f8", 3), ("base_angular_velocity", "<f8", 3),
+                         ("joint_position", "<f8", 12), ("surface_normal", "<f8", 12),
+                         ("support_leg", "u1", 4), ("reserved", "u1", 4)])
+assert RECORD_DTYPE.itemsize == 304
 
 _lib = None
 _vp = C.c_void_p
@@ -80,6 +87,8 @@ def load() -> C.CDLL:
     lib.qlb_solve_state_f32.argtypes = [_vp, C.c_size_t] + [_vp] * 14
     lib.qlb_solve_state_f32_host.argtypes = [_vp, C.c_size_t] + [_vp] * 13
     lib.qlb_set_f32_core.argtypes = [_vp, C.c_int]
+    lib.qlb_pack_robot_states.argtypes = [_vp, C.c_size_t] + [_vp] * 7
+    lib.qlb_feet_in_world.argtypes = [_vp, C.c_size_t] + [_vp] * 4
     lib.qlb_leg_kinematics.argtypes = [_vp, C.c_size_t] + [_vp] * 6
     lib.qlb_qp_dense.argtypes = [_vp, C.c_size_t, C.c_int, C.c_int, C.c_int] + [_vp] * 11
     lib.qlb_qp_dense_host.argtypes = [_vp, C.c_size_t, C.c_int, C.c_int, C.c_int] + [_vp] * 10
@@ -210,6 +219,18 @@ class Solver:
         rc = self.lib.qlb_leg_kinematics(self._ctx, B, _ptr(q), _ptr(quat), _ptr(foot), _ptr(jac), _ptr(gtau),
                 stream if stream is not None else None)
         self._check(rc, "qlb_leg_kinematics")
+
+    def pack_robot_states(self, records, q=None, pose=None, twist=None, mask=None, normals=None, stream=None):
+        """records: CUDA uint8 tensor holding B qlb_robot_state_record structs (RECORD_DTYPE)."""
+        B = records.numel() // RECORD_DTYPE.itemsize
+        rc = self.lib.qlb_pack_robot_states(self._ctx, B, _ptr(records), _ptr(q), _ptr(pose), _ptr(twist), _ptr(mask),
+                                            _ptr(normals), stream if stream is not None else None)
+        self._check(rc, "qlb_pack_robot_states")
+
+    def feet_in_world(self, q, pose, feet_world, stream=None):
+        rc = self.lib.qlb_feet_in_world(self._ctx, q.shape[1], _ptr(q), _ptr(pose), _ptr(feet_world),
+                                        stream if stream is not None else None)
+        self._check(rc, "qlb_feet_in_world")
 
     def batch_stats(self, flags, wrench=None, netwrench=None, stream=None) -> np.ndarray:
         st = Stats()

@@ -658,6 +658,38 @@ int qlb_leg_kinematics(qlb_context* ctx, size_t B, const double* q, const double
   return QLB_OK;
 }
 
+int qlb_pack_robot_states(qlb_context* ctx, size_t B, const qlb_robot_state_record* records, double* q, double* base_pose,
+                          double* base_twist, uint8_t* stance_mask, double* normals_world, void* stream) {
+  static_assert(sizeof(qlb_robot_state_record) == 304, "record layout is part of the ABI");
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!records || !aligned16(records)) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  const unsigned long long blocks = ((unsigned long long)B + kPackTile - 1) / kPackTile;
+  if (blocks > 0x7fffffffull) return QLB_ERR_BATCH_TOO_LARGE;
+  qlb_pack_kernel<<<(unsigned)blocks, kPackTile, 0, static_cast<cudaStream_t>(stream)>>>(B, records, q, base_pose, base_twist,
+                                                                                       stance_mask, normals_world);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return QLB_OK;
+}
+
+int qlb_feet_in_world(qlb_context* ctx, size_t B, const double* q, const double* base_pose, double* feet_world, void* stream) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!q || !base_pose || !feet_world) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  const unsigned long long total = (unsigned long long)B * 4ull;
+  const unsigned threads = 128;
+  const unsigned long long blocks = (total + threads - 1) / threads;
+  if (blocks > 0x7fffffffull) return QLB_ERR_BATCH_TOO_LARGE;
+  qlb_kinematics_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      B, q, nullptr, nullptr, nullptr, nullptr, ctx->d_model, ctx->d_params, base_pose, feet_world);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return QLB_OK;
+}
+
 int qlb_batch_stats(qlb_context* ctx, size_t B, const uint32_t* flags, const double* wrench, const double* netwrench,
                     qlb_stats* stats_out, void* stream) {
   if (!ctx) return QLB_ERR_NOT_INITIALISED;

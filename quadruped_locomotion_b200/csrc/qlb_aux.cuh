@@ -14,7 +14,9 @@ __global__ void __launch_bounds__(128) qlb_kinematics_kernel(unsigned long long 
                                                              const double* __restrict__ quat, double* __restrict__ foot,
                                                              double* __restrict__ jac, double* __restrict__ gtau,
                                                              const DeviceModel* __restrict__ mdl,
-                                                             const DeviceParams* __restrict__ prm) {
+                                                             const DeviceParams* __restrict__ prm,
+                                                             const double* __restrict__ pose = nullptr,
+                                                             double* __restrict__ foot_world = nullptr) {
   const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 4ull * B) return;
   const int leg = (int)(t / B);
@@ -69,6 +71,16 @@ __global__ void __launch_bounds__(128) qlb_kinematics_kernel(unsigned long long 
 #pragma unroll
     for (int a = 0; a < 3; a++) foot[(size_t)(3 * leg + a) * B + i] = p[a];
   }
+  if (pose && foot_world) {
+    // world <- base: position + R_bw * foot (StateBatchComputer.cpp:64-77, getPositionWorldToFootInWorldFrame)
+    const double w = pose[3 * B + i], x = pose[4 * B + i], y = pose[5 * B + i], z = pose[6 * B + i];
+    const double Rw[9] = {w * w + x * x - y * y - z * z, 2.0 * (x * y - w * z), 2.0 * (x * z + w * y),
+                          2.0 * (x * y + w * z), w * w - x * x + y * y - z * z, 2.0 * (y * z - w * x),
+                          2.0 * (x * z - w * y), 2.0 * (y * z + w * x), w * w - x * x - y * y + z * z};
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+      foot_world[(size_t)(3 * leg + a) * B + i] = pose[(size_t)a * B + i] + Rw[3 * a] * p[0] + Rw[3 * a + 1] * p[1] + Rw[3 * a + 2] * p[2];
+  }
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     const double dv[3] = {p[0] - pj[k][0], p[1] - pj[k][1], p[2] - pj[k][2]};
@@ -91,6 +103,65 @@ __global__ void __launch_bounds__(128) qlb_kinematics_kernel(unsigned long long 
       }
       gtau[(size_t)(3 * leg + k) * B + i] = -(zax[k][0] * acc[0] + zax[k][1] * acc[1] + zax[k][2] * acc[2]);
     }
+  }
+}
+
+// RobotState records (array of structs, the fields RosBalanceController::baseCommandCallback reads from
+// free_gait_msgs/RobotState, ros_balance_controller.cpp:761-811,860-...) -> the SoA arrays of the solver.
+// Pure byte movement, HBM-bound: a CTA copies kPackTile records with 16-byte coalesced loads into shared
+// memory (row stride padded by 8 bytes against bank conflicts), then every thread walks one record and the
+// warp writes 256 contiguous bytes per component row.
+constexpr int kPackTile = 128;
+constexpr int kRecWords = (int)(sizeof(qlb_robot_state_record) / 8);   // 38 doubles
+__global__ void __launch_bounds__(kPackTile) qlb_pack_kernel(unsigned long long B, const qlb_robot_state_record* __restrict__ rec,
+                                                             double* __restrict__ q, double* __restrict__ pose,
+                                                             double* __restrict__ twist, uint8_t* __restrict__ mask,
+                                                             double* __restrict__ normals) {
+  __shared__ double tile[kPackTile * (kRecWords + 1)];
+  const unsigned long long base = (unsigned long long)blockIdx.x * kPackTile;
+  const unsigned long long left = B - base;
+  const int n = left < (unsigned long long)kPackTile ? (int)left : kPackTile;
+  const double2* src = reinterpret_cast<const double2*>(rec + base);   // records are 304 B = 19 x 16 B
+  const int nvec = n * (kRecWords / 2);
+  for (int v = threadIdx.x; v < nvec; v += kPackTile) {
+    const double2 d = __ldg(src + v);
+    const int r = v / (kRecWords / 2), c = 2 * (v - r * (kRecWords / 2));
+    tile[r * (kRecWords + 1) + c] = d.x;
+    tile[r * (kRecWords + 1) + c + 1] = d.y;
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t >= n) return;
+  const double* r = tile + t * (kRecWords + 1);
+  const unsigned long long i = base + t;
+  // record layout: position 0-2, orientation xyzw 3-6, linear velocity 7-9, angular velocity 10-12,
+  // joint positions 13-24, surface normals 25-36, support flags in word 37
+  if (pose) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) pose[(size_t)a * B + i] = r[a];
+    pose[(size_t)3 * B + i] = r[6];   // w first: kindr RotationQuaternion(w, x, y, z), ros_balance_controller.cpp:766-769
+    pose[(size_t)4 * B + i] = r[3];
+    pose[(size_t)5 * B + i] = r[4];
+    pose[(size_t)6 * B + i] = r[5];
+  }
+  if (twist) {
+#pragma unroll
+    for (int a = 0; a < 6; a++) twist[(size_t)a * B + i] = r[7 + a];
+  }
+  if (q) {
+#pragma unroll
+    for (int a = 0; a < 12; a++) q[(size_t)a * B + i] = r[13 + a];
+  }
+  if (normals) {
+#pragma unroll
+    for (int a = 0; a < 12; a++) normals[(size_t)a * B + i] = r[25 + a];
+  }
+  if (mask) {
+    const unsigned long long w = (unsigned long long)__double_as_longlong(r[37]);
+    unsigned m = 0;
+#pragma unroll
+    for (int l = 0; l < 4; l++) m |= (((w >> (8 * l)) & 0xFFull) != 0ull ? 1u : 0u) << l;
+    mask[i] = (uint8_t)m;
   }
 }
 
