@@ -12,18 +12,14 @@
 #include "qlb_qp_dense.cuh"
 #include "qlb_solve.cuh"
 #include "qlb_solve_quad.cuh"
-#include <cstdlib>
 
 using namespace qlb;
 
 struct qlb_context {
   int device = 0;
   int sm_count = 0;
-  int blocks_per_sm[2] = {0, 0};
   int blocks_per_sm_quad[2] = {0, 0};
   int blocks_per_sm_first[2] = {0, 0};
-  bool single_pass = false;  // QLB_KERNEL=quad1: leg-per-lane kernel without the first pass (experiments)
-  bool use_quad = true;  // leg-per-lane kernel (qlb_solve_quad.cuh); QLB_KERNEL=half selects the half-warp kernel
   qlb_params params;
   qlb_leg_model legs[QLB_NUM_LEGS];
   DeviceModel* d_model = nullptr;
@@ -56,7 +52,6 @@ namespace {
 
 constexpr int kHostInRows = 12 + 7 + 6 + 7 + 6 + 4 + 12;  // state mode is the larger one (54)
 constexpr int kHostOutRows = 12 + 12 + 6 + 6;
-constexpr int kCounters = 64;            // ring of work counters: launches on different streams never share one
 constexpr int kPipe = 3;                 // host entry points: chunks in flight (H2D / kernel / D2H overlap)
 #ifndef QLB_CHUNK_LOG2
 #define QLB_CHUNK_LOG2 17
@@ -184,7 +179,6 @@ int prepare_slot(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st) {
   a.list_count = reinterpret_cast<unsigned*>(a.counter + 3);
   a.list2_count = reinterpret_cast<unsigned*>(a.counter + 4);
   QLB_CUDA(ctx, cudaMemsetAsync(a.counter, 0, 8 * sizeof(unsigned long long), st));
-  if (!ctx->use_quad) return QLB_OK;
   if (a.B > 0xFFFFFFF0ull) return QLB_ERR_BATCH_TOO_LARGE;
   if (ctx->list_cap[slot] < a.B) {  // grow the index lists of all slots at once (rare; synchronises)
     QLB_CUDA(ctx, cudaDeviceSynchronize());
@@ -216,17 +210,13 @@ int launch_quad(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int b
   const unsigned long long capq = (unsigned long long)ctx->sm_count * bps_quad;
   const unsigned long long capf = (unsigned long long)ctx->sm_count * bps_first;
   const unsigned gq = (unsigned)(wantq < capq ? wantq : capq);
-  if (ctx->single_pass) {
-    qlb_quad_kernel<T, C, MODE, 0><<<gq, kQuadThreads, 0, st>>>(a);
-  } else {
-    qlb_quad_first_kernel<T, C, MODE><<<(unsigned)(wantq < capf ? wantq : capf), kQuadThreads, 0, st>>>(a);
-    QLB_CUDA(ctx, cudaGetLastError());
-    ctx->launches++;
-    qlb_quad_kernel<T, C, MODE, 1><<<gq, kQuadThreads, 0, st>>>(a);
-    QLB_CUDA(ctx, cudaGetLastError());
-    ctx->launches++;
-    qlb_quad_kernel<T, C, MODE, 2><<<gq, kQuadThreads, 0, st>>>(a);
-  }
+  qlb_quad_first_kernel<T, C, MODE><<<(unsigned)(wantq < capf ? wantq : capf), kQuadThreads, 0, st>>>(a);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  qlb_quad_kernel<T, C, MODE, 1><<<gq, kQuadThreads, 0, st>>>(a);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  qlb_quad_kernel<T, C, MODE, 2><<<gq, kQuadThreads, 0, st>>>(a);
   QLB_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
   return QLB_OK;
@@ -236,25 +226,13 @@ template <int MODE>
 int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
   const int rc = prepare_slot(ctx, a, st);
   if (rc != QLB_OK) return rc;
-  if (ctx->use_quad) return launch_quad<double, double, MODE>(ctx, a, st, ctx->blocks_per_sm_first[MODE], ctx->blocks_per_sm_quad[MODE]);
-  constexpr int ROWS = (MODE == 1) ? kInRowsState : kInRows;
-  const size_t smem = sizeof(CtaSmem<ROWS>);
-  const unsigned long long nbatch = (a.B + kBatch - 1) / kBatch;
-  const unsigned long long want = (nbatch + kWarpsPerCta - 1) / kWarpsPerCta;
-  const unsigned long long cap = (unsigned long long)ctx->sm_count * ctx->blocks_per_sm[MODE];
-  qlb_solve_kernel<MODE><<<(unsigned)(want < cap ? want : cap), kThreads, smem, st>>>(a);
-  QLB_CUDA(ctx, cudaGetLastError());
-  ctx->launches++;
-  return QLB_OK;
+  return launch_quad<double, double, MODE>(ctx, a, st, ctx->blocks_per_sm_first[MODE], ctx->blocks_per_sm_quad[MODE]);
 }
 
-// FP32 twins: leg-per-lane kernels only
+// FP32 twins: FP32 interface with the FP64 or the FP32 solver core (qlb_set_f32_core)
 template <int MODE>
 int launch_solve_f32(qlb_context* ctx, SolveArgsT<float>& a, cudaStream_t st) {
-  const bool was = ctx->use_quad;
-  ctx->use_quad = true;
   const int rc = prepare_slot(ctx, a, st);
-  ctx->use_quad = was;
   if (rc != QLB_OK) return rc;
   if (ctx->f32_pure) return launch_quad<float, float, MODE>(ctx, a, st, ctx->blocks_per_sm_first_f[MODE], ctx->blocks_per_sm_quad_f[MODE]);
   return launch_quad<float, double, MODE>(ctx, a, st, ctx->blocks_per_sm_first_m[MODE], ctx->blocks_per_sm_quad_m[MODE]);
@@ -370,14 +348,6 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
   narrow_model(hm, &hmf);
   if (cudaMemcpy(ctx->d_model_f, &hmf, sizeof hmf, cudaMemcpyHostToDevice) != cudaSuccess) return fail(QLB_ERR_CUDA);
   if (qlb_set_params(ctx, p) != QLB_OK) return fail(QLB_ERR_CUDA);
-  // the fused kernels need more than the default 48 KB of dynamic shared memory
-  if (cudaFuncSetAttribute(qlb_solve_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem<kInRows>)) != cudaSuccess ||
-      cudaFuncSetAttribute(qlb_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem<kInRowsState>)) != cudaSuccess)
-    return fail(QLB_ERR_CUDA);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[0], qlb_solve_kernel<0>, kThreads, sizeof(CtaSmem<kInRows>)) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm[1], qlb_solve_kernel<1>, kThreads, sizeof(CtaSmem<kInRowsState>)) != cudaSuccess)
-    return fail(QLB_ERR_CUDA);
-  if (ctx->blocks_per_sm[0] < 1 || ctx->blocks_per_sm[1] < 1) return fail(QLB_ERR_CUDA);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[0], qlb_quad_kernel<double, double, 0, 2>, kQuadThreads, 0) != cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_quad[1], qlb_quad_kernel<double, double, 1, 2>, kQuadThreads, 0) != cudaSuccess)
     return fail(QLB_ERR_CUDA);
@@ -395,10 +365,6 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first_m[0], qlb_quad_first_kernel<float, double, 0>, kQuadThreads, 0) != cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first_m[1], qlb_quad_first_kernel<float, double, 1>, kQuadThreads, 0) != cudaSuccess)
     return fail(QLB_ERR_CUDA);
-  if (const char* k = std::getenv("QLB_KERNEL")) {
-    ctx->use_quad = (std::strcmp(k, "half") != 0);
-    ctx->single_pass = (std::strcmp(k, "quad1") == 0);
-  }
   if (max_batch > 0 && ensure_capacity(ctx, max_batch) != QLB_OK) return fail(QLB_ERR_ALLOC);
   *out = ctx;
   return QLB_OK;
@@ -478,8 +444,6 @@ int solve_wrench_t(qlb_context* ctx, size_t B, const T* q, const T* quat_wxyz, c
   a.B = B; a.q = q; a.quat = quat_wxyz; a.wrench = wrench; a.mask = stance_mask; a.mu = mu; a.normals = normals_world;
   a.grf = grf; a.tau = tau; a.flags = flags; a.netwrench = netwrench;
   a.counter = ctx->d_counter; a.model = Typed<T>::model(ctx); a.params = Typed<T>::params(ctx); a.params64 = ctx->d_params;
-  a.vec_ok = (B % 2 == 0) && aligned16(q) && aligned16(quat_wxyz) && aligned16(wrench) && aligned16(grf) && aligned16(tau) &&
-             (!mu || aligned16(mu)) && (!normals_world || aligned16(normals_world)) && (!netwrench || aligned16(netwrench));
   return Typed<T>::template launch<0>(ctx, a, static_cast<cudaStream_t>(stream));
 }
 
@@ -498,10 +462,6 @@ int solve_state_t(qlb_context* ctx, size_t B, const T* q, const T* base_pose, co
   a.mask = stance_mask; a.mu = mu; a.normals = normals_world;
   a.grf = grf; a.tau = tau; a.flags = flags; a.netwrench = netwrench; a.wrench_out = wrench_out;
   a.counter = ctx->d_counter; a.model = Typed<T>::model(ctx); a.params = Typed<T>::params(ctx); a.params64 = ctx->d_params;
-  a.vec_ok = (B % 2 == 0) && aligned16(q) && aligned16(base_pose) && aligned16(base_twist) && aligned16(target_pose) &&
-             aligned16(target_twist) && aligned16(grf) && aligned16(tau) && (!mu || aligned16(mu)) &&
-             (!normals_world || aligned16(normals_world)) && (!netwrench || aligned16(netwrench)) &&
-             (!wrench_out || aligned16(wrench_out));
   return Typed<T>::template launch<1>(ctx, a, static_cast<cudaStream_t>(stream));
 }
 

@@ -6,8 +6,9 @@
 // 6x6 "dual" system  N t = rhs,  N = S^-1 + sum_legs A_k K_k^-1 A_k'  (A_k = the leg's 6x3 block of the
 // wrench map): every lane accumulates its leg's contribution (21 + 6 numbers), a two-step butterfly
 // (__shfl_xor 1, 2) sums them over the quad, and each lane then factorises the 6x6 matrix itself.
-// Compared with the half-warp-per-QP kernel (qlb_solve.cuh) there is no redundant kinematics, no
-// cross-lane exchange inside the linear algebra, and four times as many QPs per issued instruction.
+// Compared with the first design (a half-warp per QP around a 12x12 system, see git history) there is no
+// redundant kinematics, no cross-lane exchange inside the linear algebra, and four times as many QPs per
+// issued instruction.
 //
 // Reference path: see qlb_solve.cuh (ContactForceDistribution.cpp:99-136,138-336,385-578,614-625;
 // quadrupedkinematics.cpp:143-278,485-552; VirtualModelController.cpp:89-268).
