@@ -15,6 +15,11 @@
 
 using namespace qlb;
 
+#ifndef QLB_PIPE
+#define QLB_PIPE 3
+#endif
+constexpr int kPipe = QLB_PIPE;   // host entry points: chunks in flight (H2D / kernel / D2H overlap)
+
 struct qlb_context {
   int device = 0;
   int sm_count = 0;
@@ -37,7 +42,7 @@ struct qlb_context {
   uint64_t solve_calls = 0;   // picks the launch slot (counters + list): concurrent launches never share one
   double* d_stats = nullptr;
   cudaStream_t stream = nullptr;  // used by the *_host entry points
-  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the *_host entry points
+  cudaStream_t pipe[kPipe] = {};  // chunk pipeline of the *_host entry points
   // device staging for the *_host entry points
   double* d_in = nullptr;
   double* d_out = nullptr;
@@ -52,7 +57,6 @@ namespace {
 
 constexpr int kHostInRows = 12 + 7 + 6 + 7 + 6 + 4 + 12;  // state mode is the larger one (54)
 constexpr int kHostOutRows = 12 + 12 + 6 + 6;
-constexpr int kPipe = 3;                 // host entry points: chunks in flight (H2D / kernel / D2H overlap)
 #ifndef QLB_CHUNK_LOG2
 #define QLB_CHUNK_LOG2 17
 #endif
