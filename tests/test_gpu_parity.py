@@ -453,3 +453,28 @@ def test_f32_state_mode_follows_fp64(solver):
     e = rel_err(o32["grf"].astype(np.float64), o64["grf"])
     print("f32 state mode vs f64: median %.2e p99 %.2e max %.2e" % (np.median(e), np.percentile(e, 99), e.max()))
     assert e.max() <= 5 * MIXED_TOL
+
+
+def test_concurrent_streams_do_not_share_launch_slots(solver, oracle, models):
+    """Several solve calls in flight on different streams (what the *_host pipeline does internally): every call
+    owns its work counters and index lists."""
+    dev = torch.device("cuda:0")
+    streams = [torch.cuda.Stream() for _ in range(6)]
+    jobs = []
+    for k, s in enumerate(streams):
+        B = 20000 + 777 * k
+        st = synth.make_states("C3" if k % 2 == 0 else "C5", B, start=1000 * k)
+        d = {n: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for n, v in st.items()}
+        out = dict(grf=torch.zeros((12, B), dtype=torch.float64, device=dev), tau=torch.zeros((12, B), dtype=torch.float64, device=dev),
+                   flags=torch.zeros(B, dtype=torch.int32, device=dev), net=torch.zeros((6, B), dtype=torch.float64, device=dev))
+        jobs.append((st, d, out, s))
+    torch.cuda.synchronize()
+    for _ in range(3):   # three rounds of six concurrent calls: the slot ring wraps around
+        for st, d, out, s in jobs:
+            solver.solve_wrench(d["q"], d["quat"], d["wrench"], d["mask"], d["mu"], d["normals"], out["grf"], out["tau"],
+                                out["flags"], out["net"], stream=s.cuda_stream)
+    torch.cuda.synchronize()
+    for st, d, out, s in jobs:
+        ref = _oracle(oracle, models["quadruped_model"], st)
+        _compare(dict(grf=out["grf"].cpu().numpy(), tau=out["tau"].cpu().numpy(), flags=out["flags"].cpu().numpy().view(np.uint32),
+                      netwrench=out["net"].cpu().numpy()), ref)
