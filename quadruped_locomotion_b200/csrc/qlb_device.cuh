@@ -30,6 +30,12 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 __device__ __forceinline__ float fast_rcp(float x) { return rcp_approx(x); }
+// 1/x to FP64 rounding (three Newton steps): for pivots whose error would be amplified by cancellation
+__device__ __forceinline__ double full_rcp(double x) {
+  double r = fast_rcp(x);
+  return r * fma(-x, r, 2.0);
+}
+__device__ __forceinline__ float full_rcp(float x) { return rcp_approx(x); }
 
 // 1/sqrt(x) to FP64 rounding: FP32 seed (one MUFU.RSQ) + two Newton steps in FP64.  x must be a
 // normal FP32-range number (pivots of the KKT matrices are 1e-4 .. 1e16); x <= 0 gives NaN.

@@ -18,8 +18,12 @@
 
 namespace qlb {
 
+#ifndef QLB_POLISH_MU
+#define QLB_POLISH_MU 1e-5f      // interior point: complementarity gap (relative to the force scale) at which the
+#define QLB_POLISH_MIN_IT 2      // rows with lambda > s are tried as the active set, and the earliest iteration for it
+#endif
 #ifndef QLB_PDAS_ROUNDS
-#define QLB_PDAS_ROUNDS 3    // active-set repair rounds before a state is handed to the interior point
+#define QLB_PDAS_ROUNDS 4    // active-set repair rounds before a state is handed to the interior point
 #endif
 #ifndef QLB_IPM_MIN_CTAS
 #define QLB_IPM_MIN_CTAS 3   // interior-point pass (and the single-pass variant)
@@ -165,6 +169,7 @@ struct LegSetup {
   real At[3][6];   // the leg's block of the wrench map in contact coordinates, At[c] = [e_c; r x e_c]
                      // (rows 0..2 are the friction frame n, t1, t2 itself; zero for a swing leg)
   real nrm[3];     // the leg's contact normal in base frame (also for swing legs)
+  real foot[3];    // foot position in base frame
   real b[6];       // desired wrench
   real mu, c0;     // friction coefficient; normal force of the strictly feasible interior-point start
   float gscale, rm;  // scale of the linear term; 1 / number of constraint rows
@@ -452,7 +457,7 @@ __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const Devi
       jg[9 + j][threadIdx.x] = gtau[j];
     }
 #pragma unroll
-    for (int c = 0; c < 3; c++) L.nrm[c] = E[0][c];
+    for (int c = 0; c < 3; c++) { L.nrm[c] = E[0][c]; L.foot[c] = foot[c]; }
     float gsc = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -476,6 +481,7 @@ __device__ __forceinline__ void widen_setup(const LegSetup<real>& s, LegSetup<cr
 #pragma unroll
     for (int r = 0; r < 6; r++) d.At[c][r] = (creal)s.At[c][r];
     d.nrm[c] = (creal)s.nrm[c];
+    d.foot[c] = (creal)s.foot[c];
   }
 #pragma unroll
   for (int r = 0; r < 6; r++) d.b[r] = (creal)s.b[r];
@@ -487,7 +493,8 @@ __device__ __forceinline__ void widen_setup(const LegSetup<real>& s, LegSetup<cr
 template <typename real, typename creal>
 __device__ __forceinline__ void quad_output(const SolveArgsT<real>& a, const LegSetup<creal>& L, creal (&y)[3], const int a0, const int sg1,
                                             const int sg2, const int status, const int it, const unsigned long long bq,
-                                            const bool valid, const int leg, const real (*jg)[kQuadThreads]) {
+                                            const bool valid, const int leg, const real (*jg)[kQuadThreads],
+                                            const creal* net_pre = nullptr) {
   const unsigned long long B = a.B;
   const bool alive = L.alive;
   const unsigned mask = L.mask;
@@ -508,10 +515,13 @@ __device__ __forceinline__ void quad_output(const SolveArgsT<real>& a, const Leg
     }
     if (a.netwrench) {
       // A x = sum over legs of A_k y_k (CFD.cpp:614-625)
+      // (or, when the caller has the solution t of the 6x6 system: A x = b - S^-1 t, no reduction needed)
       creal nwv[6];
 #pragma unroll
-      for (int r = 0; r < 6; r++)
-        nwv[r] = quad_sum(live ? At[0][r] * y[0] + At[1][r] * y[1] + At[2][r] * y[2] : creal(0.0));
+      for (int r = 0; r < 6; r++) {
+        if (net_pre != nullptr) nwv[r] = solved ? net_pre[r] : creal(0.0);
+        else nwv[r] = quad_sum(live ? At[0][r] * y[0] + At[1][r] * y[1] + At[2][r] * y[2] : creal(0.0));
+      }
       if (valid) {
         // leg k writes components k and k+4 (k < 2)
         a.netwrench[(size_t)leg * B + bq] = (real)((leg == 0) ? nwv[0] : (leg == 1 ? nwv[1] : (leg == 2 ? nwv[2] : nwv[3])));
@@ -588,28 +598,78 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
     creal y[3] = {creal(0.0), creal(0.0), creal(0.0)};
     bool hard = false;
     // unconstrained minimiser through the 6x6 system: (S^-1 + A~ A~'/w) t = b,  y = A~' t / w
-    creal N[21], rdg[6], t[6];
+    creal t[6];
     const creal al = alive ? winv : creal(0.0);
+    bool pd;
+    if (Tol<creal>::refine || sizeof(real) != sizeof(creal)) {
+      // FP32 core: generic assembly + iterative refinement through the factors.  FP32 interface with the FP64
+      // core: generic assembly as well - the system must be built from the same rounded A~ that recovers y.
+      creal N[21], rdg[6];
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-      const creal w0 = al * At[0][i], w1 = al * At[1][i], w2 = al * At[2][i];
+      for (int i = 0; i < 6; i++) {
+        const creal w0 = al * At[0][i], w1 = al * At[1][i], w2 = al * At[2][i];
 #pragma unroll
-      for (int j = 0; j < 6; j++) {
-        if (j <= i) {
-          creal acc = (i == j && leg == 0) ? sinv[i] : creal(0.0);
-          acc = fma(w0, At[0][j], acc);
-          acc = fma(w1, At[1][j], acc);
-          acc = fma(w2, At[2][j], acc);
-          N[QLB_TRI(i, j)] = quad_sum(acc);
+        for (int j = 0; j < 6; j++) {
+          if (j <= i) {
+            creal acc = (i == j && leg == 0) ? sinv[i] : creal(0.0);
+            acc = fma(w0, At[0][j], acc);
+            acc = fma(w1, At[1][j], acc);
+            acc = fma(w2, At[2][j], acc);
+            N[QLB_TRI(i, j)] = quad_sum(acc);
+          }
         }
+        t[i] = L.b[i];
       }
-      t[i] = L.b[i];
-    }
-    const bool pd = chol6_thread(N, rdg);
-    solve6_thread(N, rdg, t);
-    if (Tol<creal>::refine) {
-      const creal al3[3] = {al, al, al};
-      refine6(N, rdg, At, al3, sinv, L.b, t);
+      pd = chol6_thread(N, rdg);
+      solve6_thread(N, rdg, t);
+      if (Tol<creal>::refine) {
+        const creal al3[3] = {al, al, al};
+        refine6(N, rdg, At, al3, sinv, L.b, t);
+      }
+    } else {
+      // With every slot free the friction frames drop out (Q Q' = I):  A~ A~' = sum_k [I; X_k][I, X_k'],
+      // X_k = [r_k]x, so the system is  [[D, B'], [B, C]]  with D = S_F^-1 + ns/w diagonal, B = [sum r]x / w and
+      // C = S_T^-1 + sum(|r|^2 I - r r') / w: nine sums over the quad instead of twenty-one, and a 3x3 Schur
+      // complement  (C - B D^-1 B') t_T = b_T - B D^-1 b_F  instead of a 6x6 factorisation.
+      const creal rx = alive ? L.foot[0] : creal(0.0), ry = alive ? L.foot[1] : creal(0.0), rz = alive ? L.foot[2] : creal(0.0);
+      const creal xs = winv * quad_sum(rx), ys = winv * quad_sum(ry), zs = winv * quad_sum(rz);
+      const creal qxx = quad_sum(rx * rx), qyy = quad_sum(ry * ry), qzz = quad_sum(rz * rz);
+      const creal qxy = quad_sum(rx * ry), qxz = quad_sum(rx * rz), qyz = quad_sum(ry * rz);
+      const creal nsw = (creal)L.ns * winv;
+      const creal d0 = full_rcp(sinv[0] + nsw), d1 = full_rcp(sinv[1] + nsw), d2 = full_rcp(sinv[2] + nsw);  // full precision: the Schur complement cancels
+      // Schur complement, packed lower 3x3
+      creal c00 = fma(winv, qyy + qzz, sinv[3]) - (zs * zs * d1 + ys * ys * d2);
+      creal c11 = fma(winv, qxx + qzz, sinv[4]) - (zs * zs * d0 + xs * xs * d2);
+      creal c22 = fma(winv, qxx + qyy, sinv[5]) - (ys * ys * d0 + xs * xs * d1);
+      creal c10 = fma(-winv, qxy, xs * ys * d2);
+      creal c20 = fma(-winv, qxz, xs * zs * d1);
+      creal c21 = fma(-winv, qyz, ys * zs * d0);
+      const creal u0 = d0 * L.b[0], u1 = d1 * L.b[1], u2 = d2 * L.b[2];
+      creal g0 = L.b[3] - (ys * u2 - zs * u1);
+      creal g1 = L.b[4] - (zs * u0 - xs * u2);
+      creal g2 = L.b[5] - (xs * u1 - ys * u0);
+      // 3x3 Cholesky and the two substitutions
+      pd = c00 > creal(0.0);
+      const creal r0 = fast_rsqrt(c00);
+      c10 *= r0; c20 *= r0;
+      c11 = fma(-c10, c10, c11);
+      pd = pd && (c11 > creal(0.0));
+      const creal r1 = fast_rsqrt(c11);
+      c21 = fma(-c20, c10, c21) * r1;
+      c22 = fma(-c21, c21, fma(-c20, c20, c22));
+      pd = pd && (c22 > creal(0.0));
+      const creal r2 = fast_rsqrt(c22);
+      g0 *= r0;
+      g1 = fma(-c10, g0, g1) * r1;
+      g2 = fma(-c21, g1, fma(-c20, g0, g2)) * r2;
+      g2 *= r2;
+      g1 = fma(-c21, g2, g1) * r1;
+      g0 = fma(-c20, g2, fma(-c10, g1, g0)) * r0;
+      t[3] = g0; t[4] = g1; t[5] = g2;
+      // t_F = D^-1 (b_F - B' t_T),  B' v = -(s x v) / w ... written out
+      t[0] = d0 * (L.b[0] - (zs * g1 - ys * g2));
+      t[1] = d1 * (L.b[1] - (xs * g2 - zs * g0));
+      t[2] = d2 * (L.b[2] - (ys * g0 - xs * g1));
     }
     const bool pd_fail = !pd && status == 0;   // quad-uniform: every lane factors the same matrix
     if (pd_fail && !Tol<creal>::rescue) status = 4;
@@ -656,7 +716,10 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
 #if QLB_PIPELINE_LOADS
     if (bn < nbatch) quad_load<real, MODE>(a, prm.mu_default, bqn, sn < B, leg, in);
 #endif
-    quad_output<real, creal>(a, L, y, 0, 0, 0, status, 0, bq, valid, leg, jg);  // whole warp: it contains quad shuffles
+    creal net[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) net[r] = fma(-sinv[r], t[r], L.b[r]);   // A x = b - S^-1 t
+    quad_output<real, creal>(a, L, y, 0, 0, 0, status, 0, bq, valid, leg, jg, net);  // whole warp: it contains quad shuffles
 #if !QLB_PIPELINE_LOADS
     if (bn < nbatch) quad_load<real, MODE>(a, prm.mu_default, bqn, sn < B, leg, in);
 #endif
@@ -711,6 +774,7 @@ __device__ __forceinline__ void quad_solve(const LegSetup<creal>& L, const CoreC
   int mode = kModePolish, pass = 0;
   it = 0; status = 0;
   bool first = true, converged = false, want_polish = false;
+  float gap_shrink = 1.f;  // a converged iterate whose pattern does not verify: iterate on to a smaller gap
   creal alpha_prev = creal(1.0);
   defer = false;  // STAGE 1: hand the state to the interior-point pass
   bool need_start = false;  // set when this quad begins its interior-point iteration
@@ -931,6 +995,12 @@ __device__ __forceinline__ void quad_solve(const LegSetup<creal>& L, const CoreC
             a0 = 0; sg1 = 0; sg2 = 0;
             if (STAGE == 1) { defer = true; mode = kModeDone; }  // the interior-point pass takes over
             else { mode = kModeIpm; need_start = true; }
+          } else if (converged && status == 0 && !Tol<creal>::rescue && gap_shrink > 1e-5f) {
+            // The rows with lambda > s were not the active set although the gap is at tolerance (a multiplier
+            // below sqrt(gap)): two more decades of the interior point separate them.  Rare (1 in 10^5).
+            gap_shrink *= 1e-2f;
+            converged = false;
+            mode = kModeIpm;
           } else if (converged || status == 2) {
             mode = kModeDone;
             if (status == 0) status = 3;
@@ -1065,9 +1135,9 @@ __device__ __forceinline__ void quad_solve(const LegSetup<creal>& L, const CoreC
       const float scale = fmaxf(1.f, quad_max(ymax));
       if (ipm_round) {
         const float tolf = Tol<creal>::ipm(cc.tol) * scale;
-        converged = (mu_n <= tolf) && (nrp <= tolf) && (nrd <= 100.f * tolf);
+        converged = (mu_n <= tolf * gap_shrink) && (nrp <= tolf) && (nrd <= 100.f * tolf);
         const bool out_of_iters = it >= cc.max_iter;
-        want_polish = converged || out_of_iters || (it >= 2 && mu_n <= 1e-3f * scale);
+        want_polish = converged || out_of_iters || (it >= QLB_POLISH_MIN_IT && mu_n <= QLB_POLISH_MU * scale);
         if (out_of_iters && !converged) status = 2;
       }
     }
