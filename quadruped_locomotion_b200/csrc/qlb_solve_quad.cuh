@@ -1217,7 +1217,8 @@ __device__ __forceinline__ void quad_batch(const SolveArgsT<real>& a, const Devi
 // A later pass (STAGE as in quad_batch).  Two experiments that did not pay at 2^20 states (each pass has a
 // latency floor of one warp's serial work, ~100 us): splitting pass 2 into "one round" + "remaining rounds"
 // for better packing (measured 1.04 ms against 0.95 ms), and the opposite, fusing passes 2 and 3.  Cutting the
-// batch into sub-batches on several streams so that tails overlap bulk work did not pay either (0.97 - 1.3 ms).
+// batch into sub-batches on several streams so that tails overlap bulk work did not pay either (0.97 - 1.3 ms),
+// nor did sorting the list into "one violated row" / "several violated rows" classes (0.86 against 0.84 ms).
 // Passes 2 and 3 stay separate launches: fused into one persistent
 // kernel (warps taking interior-point items as soon as they are published) the code grows to 190 KB, past the
 // instruction cache, and the pair runs 3x slower (measured: 2.9 ms against 0.96 ms per 2^20 states).
