@@ -259,6 +259,37 @@ int qlb_pack_robot_states(qlb_context* ctx, size_t B, const qlb_robot_state_reco
 int qlb_feet_in_world(qlb_context* ctx, size_t B, const double* q, const double* base_pose,
                       double* feet_world, void* stream);
 
+/* ---- swing-leg torques ----------------------------------------------------------
+ * Rigid-body table of one limb: three bodies on z-axis revolute joints (the link behind the fixed foot
+ * joint merged into the third), as a rigid-body-dynamics URDF reader builds it from the per-leg URDFs that
+ * MyRobotSolver::loadLimbModelFromURDF loads (single_leg_test/lib/model_test_header.cpp:224-247). */
+typedef struct qlb_limb_dynamics {
+  double joint_xyz[3][3];     /* <origin xyz> of the three revolute joints */
+  double joint_rpy[3][3];     /* <origin rpy> */
+  double body_mass[3];
+  double body_com[3][3];      /* centre of mass in the link frame */
+  double body_inertia[3][6];  /* Ixx, Ixy, Ixz, Iyy, Iyz, Izz about the centre of mass, link axes */
+} qlb_limb_dynamics;
+
+typedef struct qlb_swing_params {
+  double gravity[3];          /* in the base frame.  The reference never sets it on its limb models, so they run with
+                                 the dynamics library's default (0, -9.81, 0) (model_test_header.cpp:36 vs :193) */
+  double acceleration_scale;  /* the reference feeds 0.5 * qdd to the inverse dynamics (model_test_header.cpp:460) */
+  double kp[3], kd[3];        /* Cartesian gains on the foot position / velocity error in the base frame (:497-498) */
+} qlb_swing_params;
+
+int qlb_default_swing_params(qlb_swing_params* p);                     /* the reference's values; kp = kd = 0 */
+int qlb_set_limb_dynamics(qlb_context* ctx, const qlb_limb_dynamics legs[QLB_NUM_LEGS]);
+
+/* MyRobotSolver::update for every leg of every state (model_test_header.cpp:412-502): inverse dynamics of the limb
+ * (recursive Newton-Euler, fixed base) at (q, qd, acceleration_scale * qdd) plus the Cartesian PD term
+ * J^T (kp .* (p* - p) + kd .* (v* - J qd)).  DEVICE pointers, SoA: q, qd, qdd[12][B]; foot_target_position,
+ * foot_target_velocity[12][B] in the base frame (either may be NULL: that error term is zero); tau[12][B].
+ * The caller keeps the rows of its swing legs (the stance rows come from qlb_solve_*). */
+int qlb_swing_leg_torques(qlb_context* ctx, size_t B, const double* q, const double* qd, const double* qdd,
+                          const double* foot_target_position, const double* foot_target_velocity,
+                          const qlb_swing_params* params, double* tau, void* stream);
+
 /* Generic small dense QP (DEVICE pointers), B problems of the same shape, in the argument convention of
  * the reference's in-repo backend quadprogpp::solve_quadprog (qp_solver/include/qp_solver/QuadProg++.h:
  * 8-30), which qp_solver::QuadraticProblemSolver::minimize forwards to

@@ -249,3 +249,127 @@ def feet_in_world(model_arr, q, pose) -> np.ndarray:
             foot, _, _ = leg_kinematics(model_arr, leg, q[3 * leg:3 * leg + 3, i])
             out[3 * leg:3 * leg + 3, i] = pose[:3, i] + R @ foot
     return out
+
+
+# ---------------------------------------------------------------- swing-leg torques (numpy restatement)
+def _rpy_rot(rpy):
+    """URDF <origin rpy> -> rotation (child axes in parent coordinates), through the quaternion like urdfdom."""
+    hr, hp, hy = 0.5 * rpy[0], 0.5 * rpy[1], 0.5 * rpy[2]
+    x = np.sin(hr) * np.cos(hp) * np.cos(hy) - np.cos(hr) * np.sin(hp) * np.sin(hy)
+    y = np.cos(hr) * np.sin(hp) * np.cos(hy) + np.sin(hr) * np.cos(hp) * np.sin(hy)
+    z = np.cos(hr) * np.cos(hp) * np.sin(hy) - np.sin(hr) * np.sin(hp) * np.cos(hy)
+    w = np.cos(hr) * np.cos(hp) * np.cos(hy) + np.sin(hr) * np.sin(hp) * np.sin(hy)
+    n = np.sqrt(x * x + y * y + z * z + w * w)
+    x, y, z, w = x / n, y / n, z / n, w / n
+    return np.array([[w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z]])
+
+
+def _skew(v):
+    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+
+
+def limb_inverse_dynamics(limb: dict, q, qd, qdd, gravity=(0.0, -9.81, 0.0)) -> np.ndarray:
+    """Recursive Newton-Euler for one limb in SPATIAL-VECTOR form, body coordinates (the algorithm a rigid-body
+    dynamics library runs for InverseDynamics(model, Q, QDot, QDDot, Tau), model_test_header.cpp:460); fixed base,
+    gravity as base acceleration.  `limb` = one entry of models/<name>.json["limb_dynamics"].  Deliberately a
+    different formulation from the CUDA kernel (base-frame sums)."""
+    S = np.array([0, 0, 1, 0, 0, 0.0])
+    v = np.zeros(6); a = np.concatenate([np.zeros(3), -np.asarray(gravity, dtype=np.float64)])
+    Xup, f, Is = [], [], []
+
+    def crm(u):   # spatial motion cross product
+        return np.block([[_skew(u[:3]), np.zeros((3, 3))], [_skew(u[3:]), _skew(u[:3])]])
+
+    for i in range(3):
+        E = _rpy_rot(limb["joint_rpy"][i]).T           # parent coordinates -> frame before the joint
+        r = np.asarray(limb["joint_xyz"][i], dtype=np.float64)
+        XT = np.block([[E, np.zeros((3, 3))], [-E @ _skew(r), E]])
+        c, s = np.cos(q[i]), np.sin(q[i])
+        Ej = np.array([[c, s, 0], [-s, c, 0], [0, 0, 1.0]])
+        XJ = np.block([[Ej, np.zeros((3, 3))], [np.zeros((3, 3)), Ej]])
+        X = XJ @ XT
+        vJ = S * qd[i]
+        v = X @ v + vJ
+        a = X @ a + S * qdd[i] + crm(v) @ vJ
+        m = limb["body_mass"][i]; cm = np.asarray(limb["body_com"][i], dtype=np.float64)
+        i6 = limb["body_inertia"][i]
+        Ic = np.array([[i6[0], i6[1], i6[2]], [i6[1], i6[3], i6[4]], [i6[2], i6[4], i6[5]]])
+        C = _skew(cm)
+        I = np.block([[Ic + m * C @ C.T, m * C], [m * C.T, m * np.eye(3)]])
+        Xup.append(X); Is.append(I)
+        f.append(I @ a - crm(v).T @ (I @ v))           # v x* (I v) = -crm(v)^T (I v)
+    tau = np.zeros(3)
+    for i in (2, 1, 0):
+        tau[i] = S @ f[i]
+        if i > 0:
+            f[i - 1] = f[i - 1] + Xup[i].T @ f[i]
+    return tau
+
+
+def limb_lagrangian_torques(limb: dict, q, qd, qdd, gravity=(0.0, -9.81, 0.0), h=1e-5) -> np.ndarray:
+    """The same torques from the Lagrange equations with finite differences of the kinetic and potential
+    energy - no recursion, no spatial algebra: pins limb_inverse_dynamics."""
+    g = np.asarray(gravity, dtype=np.float64)
+
+    def frames(qv):
+        R = np.eye(3); p = np.zeros(3); out = []
+        for i in range(3):
+            p = p + R @ np.asarray(limb["joint_xyz"][i], dtype=np.float64)
+            R = R @ _rpy_rot(limb["joint_rpy"][i])
+            z = R[:, 2].copy()
+            c, s = np.cos(qv[i]), np.sin(qv[i])
+            R = R @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+            out.append((R.copy(), p.copy(), z))
+        return out
+
+    def coms(qv):
+        return [p + R @ np.asarray(limb["body_com"][i], dtype=np.float64) for i, (R, p, z) in enumerate(frames(qv))]
+
+    def energy(qv, qdv):
+        fr = frames(qv)
+        T = 0.0
+        cp = [coms(qv + h * e) for e in np.eye(3)]
+        cm = [coms(qv - h * e) for e in np.eye(3)]
+        w = np.zeros(3)
+        for i, (R, p, z) in enumerate(fr):
+            w = w + z * qdv[i]
+            vc = sum((cp[j][i] - cm[j][i]) / (2 * h) * qdv[j] for j in range(3))
+            i6 = limb["body_inertia"][i]
+            Ic = np.array([[i6[0], i6[1], i6[2]], [i6[1], i6[3], i6[4]], [i6[2], i6[4], i6[5]]])
+            T += 0.5 * limb["body_mass"][i] * vc @ vc + 0.5 * w @ (R @ Ic @ R.T) @ w
+        U = -sum(limb["body_mass"][i] * g @ c for i, c in enumerate(coms(qv)))
+        return T, U
+
+    q = np.asarray(q, dtype=np.float64); qd = np.asarray(qd, dtype=np.float64); qdd = np.asarray(qdd, dtype=np.float64)
+    hq = 1e-4
+    dT_dqd = lambda qv, qdv: np.array([(energy(qv, qdv + hq * e)[0] - energy(qv, qdv - hq * e)[0]) / (2 * hq) for e in np.eye(3)])  # noqa: E731
+    tau = np.zeros(3)
+    # d/dt (dT/dqd) = sum_k d(dT/dqd)/dq_k qd_k + d(dT/dqd)/dqd_k qdd_k
+    for k, e in enumerate(np.eye(3)):
+        tau += (dT_dqd(q + hq * e, qd) - dT_dqd(q - hq * e, qd)) / (2 * hq) * qd[k]
+        tau += (dT_dqd(q, qd + hq * e) - dT_dqd(q, qd - hq * e)) / (2 * hq) * qdd[k]
+    for j, e in enumerate(np.eye(3)):
+        Tp, Up = energy(q + hq * e, qd); Tm, Um = energy(q - hq * e, qd)
+        tau[j] += -(Tp - Tm) / (2 * hq) + (Up - Um) / (2 * hq)
+    return tau
+
+
+def swing_leg_torques(model: dict, model_arr, q, qd, qdd, ptarget=None, vtarget=None, gravity=(0.0, -9.81, 0.0),
+                      acceleration_scale=0.5, kp=(0.0, 0.0, 0.0), kd=(0.0, 0.0, 0.0)) -> np.ndarray:
+    """MyRobotSolver::update for every leg of every state (model_test_header.cpp:412-502): limb inverse dynamics
+    at (q, qd, acceleration_scale qdd) + J^T (kp .* (p* - p) + kd .* (v* - J qd)).  SoA [12,B] in and out."""
+    q = np.asarray(q, dtype=np.float64); B = q.shape[1]
+    out = np.zeros((12, B))
+    for i in range(B):
+        for leg in range(4):
+            sl = slice(3 * leg, 3 * leg + 3)
+            tau = limb_inverse_dynamics(model["limb_dynamics"][leg], q[sl, i], qd[sl, i], acceleration_scale * qdd[sl, i], gravity)
+            if ptarget is not None or vtarget is not None:
+                foot, J, _ = leg_kinematics(model_arr, leg, q[sl, i])
+                ep = ptarget[sl, i] - foot if ptarget is not None else np.zeros(3)
+                ev = vtarget[sl, i] - J @ qd[sl, i] if vtarget is not None else np.zeros(3)
+                tau = tau + J.T @ (np.asarray(kp) * ep + np.asarray(kd) * ev)
+            out[sl, i] = tau
+    return out

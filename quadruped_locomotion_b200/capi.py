@@ -49,9 +49,19 @@ EXPORTS = (
     "qlb_default_params", "qlb_create", "qlb_destroy", "qlb_set_params", "qlb_get_params",
     "qlb_solve_wrench", "qlb_solve_wrench_host", "qlb_solve_state", "qlb_solve_state_host",
     "qlb_solve_wrench_f32", "qlb_solve_wrench_f32_host", "qlb_solve_state_f32", "qlb_solve_state_f32_host",
+    "qlb_default_swing_params", "qlb_set_limb_dynamics", "qlb_swing_leg_torques",
     "qlb_set_f32_core", "qlb_leg_kinematics", "qlb_pack_robot_states", "qlb_feet_in_world", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
     "qlb_last_cuda_error", "qlb_abi_version",
 )
+
+class LimbDynamics(C.Structure):
+    _fields_ = [("joint_xyz", (C.c_double * 3) * 3), ("joint_rpy", (C.c_double * 3) * 3), ("body_mass", C.c_double * 3),
+                ("body_com", (C.c_double * 3) * 3), ("body_inertia", (C.c_double * 6) * 3)]
+
+
+class SwingParams(C.Structure):
+    _fields_ = [("gravity", C.c_double * 3), ("acceleration_scale", C.c_double), ("kp", C.c_double * 3), ("kd", C.c_double * 3)]
+
 
 # numpy mirror of qlb_robot_state_record (include/qlb.h)
 RECORD_DTYPE = np.dtype([("base_position", "<f8", 3), ("base_orientation_xyzw", "<f8", 4),
@@ -89,6 +99,9 @@ def load() -> C.CDLL:
     lib.qlb_set_f32_core.argtypes = [_vp, C.c_int]
     lib.qlb_pack_robot_states.argtypes = [_vp, C.c_size_t] + [_vp] * 7
     lib.qlb_feet_in_world.argtypes = [_vp, C.c_size_t] + [_vp] * 4
+    lib.qlb_default_swing_params.argtypes = [C.POINTER(SwingParams)]
+    lib.qlb_set_limb_dynamics.argtypes = [_vp, C.POINTER(LimbDynamics)]
+    lib.qlb_swing_leg_torques.argtypes = [_vp, C.c_size_t] + [_vp] * 5 + [C.POINTER(SwingParams), _vp, _vp]
     lib.qlb_leg_kinematics.argtypes = [_vp, C.c_size_t] + [_vp] * 6
     lib.qlb_qp_dense.argtypes = [_vp, C.c_size_t, C.c_int, C.c_int, C.c_int] + [_vp] * 11
     lib.qlb_qp_dense_host.argtypes = [_vp, C.c_size_t, C.c_int, C.c_int, C.c_int] + [_vp] * 10
@@ -231,6 +244,32 @@ class Solver:
         rc = self.lib.qlb_feet_in_world(self._ctx, q.shape[1], _ptr(q), _ptr(pose), _ptr(feet_world),
                                         stream if stream is not None else None)
         self._check(rc, "qlb_feet_in_world")
+
+    def set_limb_dynamics(self, model: dict | str = "quadruped_model"):
+        """Upload the rigid-body tables of the four limbs (models/<name>.json, key "limb_dynamics")."""
+        if isinstance(model, str):
+            model = legmodel.load_model(model)
+        arr = (LimbDynamics * NUM_LEGS)()
+        for i, leg in enumerate(model["limb_dynamics"]):
+            for k in range(3):
+                for a in range(3):
+                    arr[i].joint_xyz[k][a] = leg["joint_xyz"][k][a]
+                    arr[i].joint_rpy[k][a] = leg["joint_rpy"][k][a]
+                    arr[i].body_com[k][a] = leg["body_com"][k][a]
+                arr[i].body_mass[k] = leg["body_mass"][k]
+                for a in range(6):
+                    arr[i].body_inertia[k][a] = leg["body_inertia"][k][a]
+        self._check(self.lib.qlb_set_limb_dynamics(self._ctx, arr), "qlb_set_limb_dynamics")
+
+    def default_swing_params(self) -> SwingParams:
+        p = SwingParams()
+        self._check(self.lib.qlb_default_swing_params(C.byref(p)), "qlb_default_swing_params")
+        return p
+
+    def swing_leg_torques(self, q, qd, qdd, ptarget, vtarget, params: SwingParams, tau, stream=None):
+        rc = self.lib.qlb_swing_leg_torques(self._ctx, q.shape[1], _ptr(q), _ptr(qd), _ptr(qdd), _ptr(ptarget), _ptr(vtarget),
+                                            C.byref(params), _ptr(tau), stream if stream is not None else None)
+        self._check(rc, "qlb_swing_leg_torques")
 
     def batch_stats(self, flags, wrench=None, netwrench=None, stream=None) -> np.ndarray:
         st = Stats()

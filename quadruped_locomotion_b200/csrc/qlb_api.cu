@@ -12,6 +12,7 @@
 #include "qlb_qp_dense.cuh"
 #include "qlb_solve.cuh"
 #include "qlb_solve_quad.cuh"
+#include "qlb_swing.cuh"
 
 using namespace qlb;
 
@@ -29,6 +30,8 @@ struct qlb_context {
   qlb_leg_model legs[QLB_NUM_LEGS];
   DeviceModel* d_model = nullptr;
   DeviceParams* d_params = nullptr;
+  DeviceLimbDynamics* d_limb = nullptr;        // qlb_set_limb_dynamics
+  bool have_limb = false;
   DeviceModelT<float>* d_model_f = nullptr;    // FP32 copies for the _f32 entry points
   DeviceParamsT<float>* d_params_f = nullptr;
   int blocks_per_sm_quad_f[2] = {0, 0};
@@ -381,7 +384,7 @@ int qlb_destroy(qlb_context* ctx) {
   for (int i = 0; i < kPipe; i++)
     if (ctx->pipe[i]) { cudaStreamSynchronize(ctx->pipe[i]); cudaStreamDestroy(ctx->pipe[i]); }
   cudaFree(ctx->d_model); cudaFree(ctx->d_params); cudaFree(ctx->d_counter); cudaFree(ctx->d_stats);
-  cudaFree(ctx->d_model_f); cudaFree(ctx->d_params_f);
+  cudaFree(ctx->d_model_f); cudaFree(ctx->d_params_f); cudaFree(ctx->d_limb);
   cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags);
   for (int i = 0; i < 8; i++) cudaFree(ctx->d_list[i]);
   cudaGetLastError();
@@ -649,6 +652,57 @@ int qlb_feet_in_world(qlb_context* ctx, size_t B, const double* q, const double*
   if (blocks > 0x7fffffffull) return QLB_ERR_BATCH_TOO_LARGE;
   qlb_kinematics_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
       B, q, nullptr, nullptr, nullptr, nullptr, ctx->d_model, ctx->d_params, base_pose, feet_world);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return QLB_OK;
+}
+
+int qlb_default_swing_params(qlb_swing_params* p) {
+  if (!p) return QLB_ERR_INVALID_ARGUMENT;
+  std::memset(p, 0, sizeof *p);
+  p->gravity[1] = -9.81;            // the dynamics library's default, never overridden for the limb models
+  p->acceleration_scale = 0.5;      // model_test_header.cpp:460
+  return QLB_OK;
+}
+
+int qlb_set_limb_dynamics(qlb_context* ctx, const qlb_limb_dynamics legs[QLB_NUM_LEGS]) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (!legs) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  DeviceLimbDynamics h;
+  std::memset(&h, 0, sizeof h);
+  for (int l = 0; l < 4; l++)
+    for (int j = 0; j < 3; j++) {
+      rpy_to_rot(legs[l].joint_rpy[j], h.rot[l][j]);
+      for (int a = 0; a < 3; a++) { h.xyz[l][j][a] = legs[l].joint_xyz[j][a]; h.com[l][j][a] = legs[l].body_com[j][a]; }
+      h.mass[l][j] = legs[l].body_mass[j];
+      for (int a = 0; a < 6; a++) h.inertia[l][j][a] = legs[l].body_inertia[j][a];
+    }
+  if (!ctx->d_limb && cudaMalloc(&ctx->d_limb, sizeof h) != cudaSuccess) { cudaGetLastError(); return QLB_ERR_ALLOC; }
+  QLB_CUDA(ctx, cudaDeviceSynchronize());
+  QLB_CUDA(ctx, cudaMemcpy(ctx->d_limb, &h, sizeof h, cudaMemcpyHostToDevice));
+  ctx->have_limb = true;
+  return QLB_OK;
+}
+
+int qlb_swing_leg_torques(qlb_context* ctx, size_t B, const double* q, const double* qd, const double* qdd,
+                          const double* foot_target_position, const double* foot_target_velocity,
+                          const qlb_swing_params* params, double* tau, void* stream) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (!ctx->have_limb) return QLB_ERR_NOT_INITIALISED;   // qlb_set_limb_dynamics first
+  if (B == 0) return QLB_OK;
+  if (!q || !qd || !qdd || !params || !tau) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  SwingArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.B = B; a.q = q; a.qd = qd; a.qdd = qdd; a.ptarget = foot_target_position; a.vtarget = foot_target_velocity; a.tau = tau;
+  for (int c = 0; c < 3; c++) { a.gravity[c] = params->gravity[c]; a.kp[c] = params->kp[c]; a.kd[c] = params->kd[c]; }
+  a.acc_scale = params->acceleration_scale;
+  a.dyn = ctx->d_limb; a.model = ctx->d_model;
+  const unsigned long long total = (unsigned long long)B * 4ull;
+  const unsigned long long blocks = (total + 127) / 128;
+  if (blocks > 0x7fffffffull) return QLB_ERR_BATCH_TOO_LARGE;
+  qlb_swing_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
   QLB_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
   return QLB_OK;
