@@ -177,7 +177,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         # the contract is ONE JSON line on stdout: keep NCCL's version / info banner out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+        # (NCCL writes them to stdout; the level may also come from a system nccl.conf)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "WARN").upper() in ("VERSION", "INFO", "TRACE", "WARN"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
