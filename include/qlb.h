@@ -153,7 +153,10 @@ int qlb_get_params(const qlb_context* ctx, qlb_params* params);
  *        tau[12][B] joint torques J^T(-x) + G(q) for stance legs, zero for swing legs
  *        (the reference leaves swing slots unwritten, CFD.cpp:530);
  *        flags[B] result word (see above);
- *        netwrench[6][B] achieved A x (getNetForceAndTorqueOnBase), or NULL. */
+ *        netwrench[6][B] achieved A x (getNetForceAndTorqueOnBase), or NULL.
+ * Calls of one context may be in flight on different streams at the same time (the context keeps eight
+ * sets of work counters and index lists and orders a ninth call behind the first); the host entry points
+ * and the setters are not re-entrant. */
 int qlb_solve_wrench(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz,
                      const double* wrench, const uint8_t* stance_mask, const double* mu,
                      const double* normals_world, double* grf, double* tau, uint32_t* flags,

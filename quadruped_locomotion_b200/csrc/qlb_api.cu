@@ -43,6 +43,8 @@ struct qlb_context {
   unsigned* d_list[8] = {};   // second-pass index lists, one per launch slot
   size_t list_cap[8] = {};
   uint64_t solve_calls = 0;   // picks the launch slot (counters + list): concurrent launches never share one
+  cudaEvent_t slot_done[8] = {};  // recorded after the last pass of the call that used the slot; the next user waits on it
+  int last_slot = 0;
   double* d_stats = nullptr;
   cudaStream_t stream = nullptr;  // used by the *_host entry points
   cudaStream_t pipe[kPipe] = {};  // chunk pipeline of the *_host entry points
@@ -180,6 +182,9 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 template <typename T>
 int prepare_slot(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st) {
   const int slot = (int)(ctx->solve_calls++ % 8);
+  ctx->last_slot = slot;
+  // a ninth call in flight on yet another stream would reuse the slot of the first: order it behind that call
+  QLB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->slot_done[slot], 0));
   a.counter = ctx->d_counter + 8 * slot;
   a.counter2 = a.counter + 1;
   a.counter3 = a.counter + 2;
@@ -226,6 +231,7 @@ int launch_quad(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int b
   qlb_quad_kernel<T, C, MODE, 2><<<gq, kQuadThreads, 0, st>>>(a);
   QLB_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
+  QLB_CUDA(ctx, cudaEventRecord(ctx->slot_done[ctx->last_slot], st));
   return QLB_OK;
 }
 
@@ -348,6 +354,8 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(QLB_ERR_CUDA);
   for (int i = 0; i < kPipe; i++)
     if (cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking) != cudaSuccess) return fail(QLB_ERR_CUDA);
+  for (int i = 0; i < 8; i++)
+    if (cudaEventCreateWithFlags(&ctx->slot_done[i], cudaEventDisableTiming) != cudaSuccess) return fail(QLB_ERR_CUDA);
   DeviceModel hm;
   build_device_model(legs, &hm);
   if (cudaMemcpy(ctx->d_model, &hm, sizeof hm, cudaMemcpyHostToDevice) != cudaSuccess) return fail(QLB_ERR_CUDA);
@@ -387,6 +395,8 @@ int qlb_destroy(qlb_context* ctx) {
   cudaFree(ctx->d_model_f); cudaFree(ctx->d_params_f); cudaFree(ctx->d_limb);
   cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags);
   for (int i = 0; i < 8; i++) cudaFree(ctx->d_list[i]);
+  for (int i = 0; i < 8; i++)
+    if (ctx->slot_done[i]) cudaEventDestroy(ctx->slot_done[i]);
   cudaGetLastError();
   delete ctx;
   return QLB_OK;

@@ -459,7 +459,7 @@ def test_concurrent_streams_do_not_share_launch_slots(solver, oracle, models):
     """Several solve calls in flight on different streams (what the *_host pipeline does internally): every call
     owns its work counters and index lists."""
     dev = torch.device("cuda:0")
-    streams = [torch.cuda.Stream() for _ in range(6)]
+    streams = [torch.cuda.Stream() for _ in range(10)]
     jobs = []
     for k, s in enumerate(streams):
         B = 20000 + 777 * k
@@ -469,7 +469,7 @@ def test_concurrent_streams_do_not_share_launch_slots(solver, oracle, models):
                    flags=torch.zeros(B, dtype=torch.int32, device=dev), net=torch.zeros((6, B), dtype=torch.float64, device=dev))
         jobs.append((st, d, out, s))
     torch.cuda.synchronize()
-    for _ in range(3):   # three rounds of six concurrent calls: the slot ring wraps around
+    for _ in range(3):   # three rounds of ten concurrent calls: more in flight than launch slots
         for st, d, out, s in jobs:
             solver.solve_wrench(d["q"], d["quat"], d["wrench"], d["mask"], d["mu"], d["normals"], out["grf"], out["tau"],
                                 out["flags"], out["net"], stream=s.cuda_stream)
