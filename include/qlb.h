@@ -292,6 +292,10 @@ int qlb_set_limb_dynamics(qlb_context* ctx, const qlb_limb_dynamics legs[QLB_NUM
 int qlb_swing_leg_torques(qlb_context* ctx, size_t B, const double* q, const double* qd, const double* qdd,
                           const double* foot_target_position, const double* foot_target_velocity,
                           const qlb_swing_params* params, double* tau, void* stream);
+/* Same, HOST pointers: copies in, computes, copies out, synchronises (a batch-of-1 controller tick). */
+int qlb_swing_leg_torques_host(qlb_context* ctx, size_t B, const double* q, const double* qd, const double* qdd,
+                               const double* foot_target_position, const double* foot_target_velocity,
+                               const qlb_swing_params* params, double* tau);
 
 /* Generic small dense QP (DEVICE pointers), B problems of the same shape, in the argument convention of
  * the reference's in-repo backend quadprogpp::solve_quadprog (qp_solver/include/qp_solver/QuadProg++.h:

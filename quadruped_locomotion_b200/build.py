@@ -60,3 +60,4 @@ if __name__ == "__main__":
     print(build(force=True, verbose=True, extra=extra))
     print(build_host_demo(force=True, verbose=True))
     print(build_host_demo(force=True, verbose=True, which="qp_demo"))
+    print(build_host_demo(force=True, verbose=True, which="swing_demo"))

@@ -49,7 +49,7 @@ EXPORTS = (
     "qlb_default_params", "qlb_create", "qlb_destroy", "qlb_set_params", "qlb_get_params",
     "qlb_solve_wrench", "qlb_solve_wrench_host", "qlb_solve_state", "qlb_solve_state_host",
     "qlb_solve_wrench_f32", "qlb_solve_wrench_f32_host", "qlb_solve_state_f32", "qlb_solve_state_f32_host",
-    "qlb_default_swing_params", "qlb_set_limb_dynamics", "qlb_swing_leg_torques",
+    "qlb_default_swing_params", "qlb_set_limb_dynamics", "qlb_swing_leg_torques", "qlb_swing_leg_torques_host",
     "qlb_set_f32_core", "qlb_leg_kinematics", "qlb_pack_robot_states", "qlb_feet_in_world", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
     "qlb_last_cuda_error", "qlb_abi_version",
 )
@@ -102,6 +102,7 @@ def load() -> C.CDLL:
     lib.qlb_default_swing_params.argtypes = [C.POINTER(SwingParams)]
     lib.qlb_set_limb_dynamics.argtypes = [_vp, C.POINTER(LimbDynamics)]
     lib.qlb_swing_leg_torques.argtypes = [_vp, C.c_size_t] + [_vp] * 5 + [C.POINTER(SwingParams), _vp, _vp]
+    lib.qlb_swing_leg_torques_host.argtypes = [_vp, C.c_size_t] + [_vp] * 5 + [C.POINTER(SwingParams), _vp]
     lib.qlb_leg_kinematics.argtypes = [_vp, C.c_size_t] + [_vp] * 6
     lib.qlb_qp_dense.argtypes = [_vp, C.c_size_t, C.c_int, C.c_int, C.c_int] + [_vp] * 11
     lib.qlb_qp_dense_host.argtypes = [_vp, C.c_size_t, C.c_int, C.c_int, C.c_int] + [_vp] * 10
@@ -270,6 +271,11 @@ class Solver:
         rc = self.lib.qlb_swing_leg_torques(self._ctx, q.shape[1], _ptr(q), _ptr(qd), _ptr(qdd), _ptr(ptarget), _ptr(vtarget),
                                             C.byref(params), _ptr(tau), stream if stream is not None else None)
         self._check(rc, "qlb_swing_leg_torques")
+
+    def swing_leg_torques_host(self, q, qd, qdd, ptarget, vtarget, params: SwingParams, tau):
+        rc = self.lib.qlb_swing_leg_torques_host(self._ctx, q.shape[1], _ptr(q), _ptr(qd), _ptr(qdd), _ptr(ptarget), _ptr(vtarget),
+                                                 C.byref(params), _ptr(tau))
+        self._check(rc, "qlb_swing_leg_torques_host")
 
     def batch_stats(self, flags, wrench=None, netwrench=None, stream=None) -> np.ndarray:
         st = Stats()

@@ -718,6 +718,40 @@ int qlb_swing_leg_torques(qlb_context* ctx, size_t B, const double* q, const dou
   return QLB_OK;
 }
 
+// HOST pointers: staged through the context's pipeline buffers in chunks, on the context stream; synchronises.
+int qlb_swing_leg_torques_host(qlb_context* ctx, size_t B, const double* q, const double* qd, const double* qdd,
+                               const double* foot_target_position, const double* foot_target_velocity,
+                               const qlb_swing_params* params, double* tau) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (!ctx->have_limb) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!q || !qd || !qdd || !params || !tau) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  int rc = ensure_capacity(ctx, B);
+  if (rc != QLB_OK) return rc;
+  const size_t cap = ctx->cap;   // the input staging area holds kPipe * cap * 54 doubles >= 5 * 12 * cap
+  static_assert(kPipe * kHostInRows >= 60 && kPipe * kHostOutRows >= 12, "staging too small for the swing-leg arrays");
+  const double* src[5] = {q, qd, qdd, foot_target_position, foot_target_velocity};
+  for (size_t b0 = 0; b0 < B; b0 += cap) {
+    const size_t n = (B - b0 < cap) ? (B - b0) : cap;
+    const double* dptr[5];
+    for (int k = 0; k < 5; k++) {
+      dptr[k] = nullptr;
+      if (!src[k]) continue;
+      double* d = ctx->d_in + (size_t)k * 12 * cap;
+      dptr[k] = d;
+      QLB_CUDA(ctx, cudaMemcpy2DAsync(d, n * sizeof(double), src[k] + b0, B * sizeof(double), n * sizeof(double), 12,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = qlb_swing_leg_torques(ctx, n, dptr[0], dptr[1], dptr[2], dptr[3], dptr[4], params, ctx->d_out, ctx->stream);
+    if (rc != QLB_OK) return rc;
+    QLB_CUDA(ctx, cudaMemcpy2DAsync(tau + b0, B * sizeof(double), ctx->d_out, n * sizeof(double), n * sizeof(double), 12,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    QLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return QLB_OK;
+}
+
 int qlb_batch_stats(qlb_context* ctx, size_t B, const uint32_t* flags, const double* wrench, const double* netwrench,
                     qlb_stats* stats_out, void* stream) {
   if (!ctx) return QLB_ERR_NOT_INITIALISED;

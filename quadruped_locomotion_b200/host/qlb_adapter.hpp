@@ -294,4 +294,57 @@ class VirtualModelController : public MotionControllerBase {
   Torque virtualTorqueInBaseFrame_{{0, 0, 0}};
 };
 
+// ---------------------------------------------------------------- MyRobotSolver
+// Swing-leg torque solver (single_leg_test/lib/model_test_header.cpp): limb inverse dynamics + Cartesian PD for
+// one limb per update(), written into the shared State like RosBalanceController::update does for every leg that
+// is not in stance (ros_balance_controller.cpp:472-603).  The reference differentiates queues of measured joint
+// velocities itself (:421-457); here the caller hands in the joint velocity and acceleration it wants used.
+class MyRobotSolver {
+ public:
+  MyRobotSolver(std::shared_ptr<Device> device, std::shared_ptr<State> state,
+                const qlb_limb_dynamics* limbs = QLB_LIMB_DYNAMICS_QUADRUPED_MODEL)
+      : device_(std::move(device)), robot_state_(std::move(state)), limbs_(limbs) {
+    qlb_default_swing_params(&params_);
+  }
+
+  bool loadLimbModelFromURDF() {  // :224-247 - the tables were generated from those URDF files
+    loaded_ = qlb_set_limb_dynamics(device_->ctx(), limbs_) == QLB_OK;
+    return loaded_;
+  }
+  void setGains(const Vector3& kp, const Vector3& kd) {  // :347-351
+    for (int i = 0; i < 3; i++) { params_.kp[i] = kp[i]; params_.kd[i] = kd[i]; }
+  }
+  void setDesiredPositionAndVelocity(LimbEnum limb, const Vector3& position, const Vector3& velocity) {  // :398-403
+    const int l = static_cast<int>(limb);
+    for (int i = 0; i < 3; i++) { ptarget_[3 * l + i] = position[i]; vtarget_[3 * l + i] = velocity[i]; }
+  }
+  void setJointVelocityAndAcceleration(LimbEnum limb, const Vector3& qd, const Vector3& qdd) {
+    const int l = static_cast<int>(limb);
+    for (int i = 0; i < 3; i++) { qd_[3 * l + i] = qd[i]; qdd_[3 * l + i] = qdd[i]; }
+  }
+  qlb_swing_params& params() { return params_; }
+
+  bool update(LimbEnum limb) {  // :412-502
+    if (!loaded_) return false;
+    const JointPositions& jq = robot_state_->getJointPositionFeedback();
+    double q[12], tau[12];
+    for (int i = 0; i < 12; i++) q[i] = jq[i];
+    if (qlb_swing_leg_torques_host(device_->ctx(), 1, q, qd_, qdd_, ptarget_, vtarget_, &params_, tau) != QLB_OK) return false;
+    const int l = static_cast<int>(limb);
+    tau_ = {{tau[3 * l], tau[3 * l + 1], tau[3 * l + 2]}};
+    robot_state_->setJointEffortsForLimb(limb, tau_);
+    return true;
+  }
+  const JointEffortsLeg& getVecTauAct() const { return tau_; }
+
+ private:
+  std::shared_ptr<Device> device_;
+  std::shared_ptr<State> robot_state_;
+  const qlb_limb_dynamics* limbs_;
+  qlb_swing_params params_;
+  double qd_[12] = {0}, qdd_[12] = {0}, ptarget_[12] = {0}, vtarget_[12] = {0};
+  JointEffortsLeg tau_{{0, 0, 0}};
+  bool loaded_ = false;
+};
+
 }  // namespace qlb_host

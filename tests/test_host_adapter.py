@@ -52,3 +52,33 @@ def test_one_tick_matches_oracle(qlb_built, oracle, models, mask, ypr, mu, wrenc
     np.testing.assert_allclose(out["vmc_wrench"], w, rtol=1e-12, atol=1e-9)
     b = ref(w)
     np.testing.assert_allclose(out["vmc_efforts"], b["tau"][:, 0], rtol=1e-9, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_all_twelve_torques_of_a_tick(qlb_built, oracle, models):
+    """Stance legs from VirtualModelController::compute, swing legs from MyRobotSolver::update, merged in State."""
+    from quadruped_locomotion_b200 import legmodel
+    demo = build.build_host_demo(which="swing_demo")
+    rng = np.random.default_rng(9)
+    q = np.array([0.05, 0.7, -1.4, -0.03, -0.75, 1.45, 0.02, 0.65, -1.3, 0.0, -0.7, 1.4])
+    qd = rng.normal(0, 1.5, 12); qdd = rng.normal(0, 15.0, 12)
+    mask = 0b1010   # RF and LH in stance, LF and RH swinging
+    kp, kd = [300.0, 250.0, 400.0], [10.0, 12.0, 8.0]
+    pt = rng.normal(0, 0.3, 12); vt = rng.normal(0, 0.4, 12)
+    vals = list(q) + list(qd) + list(qdd) + [mask] + kp + kd + list(pt) + list(vt)
+    r = subprocess.run([demo], input=" ".join(repr(float(v)) for v in vals), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    m = legmodel.load_model("quadruped_model")
+    M = models["quadruped_model"]
+    # the swing rows only use their own leg's velocities: zero the others like the adapter does leg by leg
+    ref_swing = oracle.swing_leg_torques(m, M, q[:, None], qd[:, None], qdd[:, None], pt[:, None], vt[:, None], kp=kp, kd=kd)[:, 0]
+    pose = np.array([0, 0, 0.45, 1, 0, 0, 0.0]); tw = np.zeros(6)
+    w = oracle.vmc_wrench(pose, tw, pose, tw)
+    ref = oracle.solve_wrench_batch(M, q[:, None], pose[3:, None], w[:, None], np.array([mask], np.uint8))
+    want = ref["tau"][:, 0].copy()
+    assert [s[0] for s in out["swing"]] == [0, 2]
+    for leg, *tau in out["swing"]:
+        np.testing.assert_allclose(tau, ref_swing[3 * leg:3 * leg + 3], rtol=0, atol=1e-9)
+        want[3 * leg:3 * leg + 3] = ref_swing[3 * leg:3 * leg + 3]
+    np.testing.assert_allclose(out["efforts"], want, rtol=0, atol=1e-8)

@@ -71,6 +71,12 @@ def test_swing_kernel_against_the_restatement(qlb_built, oracle, name):
     torch.cuda.synchronize()
     ref = oracle.swing_leg_torques(m, M, q, qd, qdd, pt, vt, kp=list(prm.kp), kd=list(prm.kd))
     assert np.abs(tau.cpu().numpy() - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+    # host entry point, a batch of one (a controller tick) and a ragged batch
+    for n in (1, 37):
+        th = np.zeros((12, n))
+        c = lambda x: np.ascontiguousarray(x[:, :n])  # noqa: E731
+        s.swing_leg_torques_host(c(q), c(qd), c(qdd), c(pt), c(vt), prm, th)
+        assert np.abs(th - ref[:, :n]).max() <= 1e-10 * max(1.0, np.abs(ref).max())
     # inverse dynamics only
     s.swing_leg_torques(d[0], d[1], d[2], None, None, prm, tau, stream=stream)
     torch.cuda.synchronize()
