@@ -831,7 +831,7 @@ __device__ __forceinline__ void quad_solve(const LegSetup<creal>& L, const CoreC
         for (int c = 0; c < 3; c++) rdl[c] = alive ? g[c] - dt[c] : creal(0.0);
       }
     }
-    const bool pol_round = (mode == kModePolish), ipm_round = (mode == kModeIpm);
+    const bool pol_round = (mode == kModePolish), ipm_round = (STAGE != 1) && (mode == kModeIpm);  // STAGE 1 never iterates: keeps that code out of its kernel
     const bool any_ipm = __any_sync(kFull, ipm_round);
     const bool any_pol = __any_sync(kFull, pol_round);
 
