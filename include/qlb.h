@@ -1,8 +1,10 @@
 /*
  * qlb.h - C ABI of the B200-native batched contact-force-distribution solver.
  *
- * One call solves B independent robot states.  For every state the library runs,
- * fused in one sm_100a kernel, the hot path of the reference's balance_controller:
+ * One call solves B independent robot states.  For every state the library runs, fused in
+ * sm_100a kernels that keep everything between the input state and the outputs on chip
+ * (three launches per call: most states finish in the first, the rest on compacted lists),
+ * the hot path of the reference's balance_controller:
  *
  *   leg forward kinematics + foot Jacobians + gravity torques
  *        (reference: quadruped_model/src/quadrupedkinematics.cpp:143-278,485-552)

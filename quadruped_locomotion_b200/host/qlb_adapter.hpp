@@ -229,7 +229,7 @@ class MotionControllerBase {
 };
 
 // VirtualModelController::compute (VirtualModelController.cpp:89-102): errors, gravity compensation,
-// virtual force / torque and the contact force distribution run as ONE fused launch (qlb_solve_state).
+// virtual force / torque and the contact force distribution run in the same fused kernels (qlb_solve_state).
 class VirtualModelController : public MotionControllerBase {
  public:
   VirtualModelController(std::shared_ptr<Device> device, std::shared_ptr<State> robot_state,
