@@ -102,6 +102,26 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def pin_to_gpu_numa_node(index: int):
+    """Run this process on the CPU cores next to GPU `index` (NVML's ideal affinity) so that the pinned host
+    buffers of the end-to-end path are first-touched on that NUMA node; with one process per GPU and the default
+    scheduler the eight ranks of a box otherwise share one socket's memory controllers.  Returns the previous
+    affinity (restored before the CPU baseline runs) or None."""
+    try:
+        import pynvml
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        try:    # CUDA_VISIBLE_DEVICES may renumber the devices: go through the UUID of the CUDA device
+            import torch
+            handle = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(index).uuid))
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return prev
+    except Exception:
+        return None
+
+
 def cpu_reference(st, steps: int, warmup: int, sample: int):
     """The reference's CPU implementation of the path on the host cores: QP assembly per
     ContactForceDistribution.cpp + the reference's own QuadProg++ (oracle/_ref) when it was built,
@@ -173,6 +193,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    prev_affinity = pin_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -328,6 +349,8 @@ def main():
         value = world * B / (ms_step * 1e-3)
         cpu_v, cpu_info = (None, None)
         if world == 1:
+            if prev_affinity is not None:
+                os.sched_setaffinity(0, prev_affinity)   # the CPU baseline gets every host core
             cpu_v, cpu_info = cpu_reference(st, 3, 1, min(B, args.cpu_sample))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
