@@ -478,3 +478,40 @@ def test_concurrent_streams_do_not_share_launch_slots(solver, oracle, models):
         ref = _oracle(oracle, models["quadruped_model"], st)
         _compare(dict(grf=out["grf"].cpu().numpy(), tau=out["tau"].cpu().numpy(), flags=out["flags"].cpu().numpy().view(np.uint32),
                       netwrench=out["net"].cpu().numpy()), ref)
+
+
+def test_api_misuse_returns_error_codes(solver):
+    """The C ABI never throws and never dereferences a missing required array: int status codes instead
+    (SURVEY 8b error convention)."""
+    import ctypes as C
+    lib, ctx = solver.lib, solver._ctx
+    dev = torch.device("cuda:0")
+    t = torch.zeros((12, 8), dtype=torch.float64, device=dev)
+    m = torch.zeros(8, dtype=torch.uint8, device=dev)
+    f = torch.zeros(8, dtype=torch.int32, device=dev)
+    null = None
+    INVALID, NOT_INIT = -1, lib.qlb_solve_wrench(None, 8, *([null] * 11))
+    assert NOT_INIT < 0 and b"" != lib.qlb_strerror(NOT_INIT)
+    # missing required arrays
+    assert lib.qlb_solve_wrench(ctx, 8, null, t.data_ptr(), t.data_ptr(), m.data_ptr(), null, null, t.data_ptr(), t.data_ptr(),
+                                f.data_ptr(), null, null) == INVALID
+    assert lib.qlb_solve_wrench(ctx, 8, t.data_ptr(), t.data_ptr(), t.data_ptr(), m.data_ptr(), null, null, t.data_ptr(), t.data_ptr(),
+                                null, null, null) == INVALID
+    assert lib.qlb_solve_state(ctx, 8, t.data_ptr(), null, t.data_ptr(), t.data_ptr(), t.data_ptr(), m.data_ptr(), null, null,
+                               t.data_ptr(), t.data_ptr(), f.data_ptr(), null, null, null) == INVALID
+    assert lib.qlb_pack_robot_states(ctx, 8, null, null, null, null, null, null, null) == INVALID
+    assert lib.qlb_set_f32_core(ctx, 7) == INVALID
+    # an empty batch is a no-op, whatever the pointers
+    assert lib.qlb_solve_wrench(ctx, 0, *([null] * 11)) == 0
+    # invalid parameters are refused and leave the context usable
+    p = solver.get_params()
+    bad = solver.get_params()
+    bad.ground_force_weight = 0.0
+    assert lib.qlb_set_params(ctx, C.byref(bad)) == INVALID
+    bad = solver.get_params()
+    bad.wrench_weights[2] = -1.0
+    assert lib.qlb_set_params(ctx, C.byref(bad)) == INVALID
+    assert solver.get_params().ground_force_weight == p.ground_force_weight
+    st = synth.make_states("C3", 64)
+    out = solver.solve_wrench_numpy(st)
+    assert (((out["flags"] >> 24) & 7) == 0).all()
