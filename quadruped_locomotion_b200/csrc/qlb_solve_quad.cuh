@@ -1165,13 +1165,9 @@ __device__ __forceinline__ void quad_solve(const LegSetup<creal>& L, const CoreC
 // give the eight states of a warp similar numbers of rounds.
 template <typename real, typename creal, int MODE, int STAGE>
 __device__ __forceinline__ void quad_batch(const SolveArgsT<real>& a, const DeviceParamsT<real>& prm, const CoreConst<creal>& cc,
-                                           const CoreConst<double>& cc64, real (*jg)[kQuadThreads], const unsigned long long slot,
-                                           const unsigned long long total, const int lane, const int leg, const int quad) {
+                                           const CoreConst<double>& cc64, real (*jg)[kQuadThreads], const unsigned long long bq,
+                                           const unsigned pat_word, const bool valid, const int lane, const int leg, const int quad) {
   constexpr bool kRescue = Tol<creal>::rescue && (STAGE == 1 || STAGE == 2);
-  const unsigned long long B = a.B;
-  const bool valid = slot < total;
-  unsigned long long bq = B - 1;
-  if (valid) bq = (STAGE == 0) ? slot : (unsigned long long)__ldcg((STAGE == 1 ? a.list : a.list2) + slot);
   LegSetup<creal> L;
   {
     LegSetup<real> L0;
@@ -1183,7 +1179,7 @@ __device__ __forceinline__ void quad_batch(const SolveArgsT<real>& a, const Devi
   creal y[3];
   int a0, sg1, sg2, status, it;
   bool defer;
-  const unsigned pat0 = (STAGE == 1 && valid) ? (a.list_pat[slot] >> (5 * leg)) & 31u : 0u;
+  const unsigned pat0 = (STAGE == 1 && valid) ? (pat_word >> (5 * leg)) & 31u : 0u;
   quad_solve<creal, STAGE, kRescue>(L, cc, leg, quad, true, pat0, y, a0, sg1, sg2, status, it, defer);
   if (kRescue && STAGE == 2) {
     // not verified by the FP32 core (iteration limit, pattern not confirmed, factorisation failed): the
@@ -1245,12 +1241,42 @@ __global__ void __launch_bounds__(kQuadThreads, STAGE == 1 ? QLB_QUAD_MIN_CTAS :
   const unsigned long long total = (STAGE == 0) ? a.B : (unsigned long long)(*(STAGE == 1 ? a.list_count : a.list2_count));
   unsigned long long* const work = (STAGE == 0) ? a.counter : (STAGE == 1 ? a.counter2 : a.counter3);
   const unsigned long long nbatch = (total + 7) / 8;
-  for (;;) {
-    unsigned long long bi = 0;
-    if (lane == 0) bi = atomicAdd(work, 1ull);
-    bi = __shfl_sync(kFull, bi, 0);
-    if (bi >= nbatch) break;
-    quad_batch<real, creal, MODE, STAGE>(a, prm, cc, cc64, jg, bi * 8 + quad, total, lane, leg, quad);
+  const unsigned long long B = a.B;
+  const unsigned* const in_list = (STAGE == 1) ? a.list : a.list2;
+  // Software pipeline over the work items of this warp, two deep: the index (and pattern) of item i+2 is being
+  // loaded, the input rows of item i+1 are being prefetched, while item i is solved - the gathers of a listed
+  // state are scattered 32-byte sectors and would otherwise stall the warp at the start of every item.
+  // (Static first items - warp w takes w and w + #warps - were measured and are slower: 0.84 against 0.79 ms.)
+  auto claim = [&]() {
+    unsigned long long b = 0;
+    if (lane == 0) b = atomicAdd(work, 1ull);
+    return __shfl_sync(kFull, b, 0);
+  };
+  auto fetch = [&](const unsigned long long b, unsigned long long& idx, unsigned& pat, bool& ok) {
+    const unsigned long long slot = b * 8 + quad;
+    ok = (b < nbatch) && (slot < total);
+    idx = B - 1; pat = 0u;
+    if (ok) {
+      idx = (STAGE == 0) ? slot : (unsigned long long)__ldcg(in_list + slot);
+      if (STAGE == 1) pat = __ldcg(a.list_pat + slot);
+    }
+  };
+  unsigned long long b0 = claim(), b1 = claim();
+  unsigned long long idx0, idx1;
+  unsigned pat0w, pat1w;
+  bool ok0, ok1;
+  fetch(b0, idx0, pat0w, ok0);
+  fetch(b1, idx1, pat1w, ok1);
+  while (b0 < nbatch) {
+    const unsigned long long b2 = claim();
+    unsigned long long idx2;
+    unsigned pat2w;
+    bool ok2;
+    fetch(b2, idx2, pat2w, ok2);
+    if (b1 < nbatch) quad_prefetch<real, MODE>(a, idx1, leg);
+    quad_batch<real, creal, MODE, STAGE>(a, prm, cc, cc64, jg, idx0, pat0w, ok0, lane, leg, quad);
+    b0 = b1; idx0 = idx1; pat0w = pat1w; ok0 = ok1;
+    b1 = b2; idx1 = idx2; pat1w = pat2w; ok1 = ok2;
   }
 }
 
