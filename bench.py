@@ -40,7 +40,7 @@ WORKLOAD = ("C3: fused FK+Jacobian+QP+J^T.f torque pipeline, 2^20 randomised sta
 
 
 # DRAM bytes of one FP64 solve call on 2^20 C3 states (ncu, profiles/r1_final_ncu_summary.txt); scaled by B
-NCU_DRAM_BYTES_PER_CALL = (319.9 + 224.7 + 493.9 + 181.4 + 64.5 + 12.7) * 1e6
+NCU_DRAM_BYTES_PER_CALL = (319.9 + 223.0 + 517.2 + 187.0 + 65.0 + 13.9) * 1e6
 
 
 def load_peaks():
@@ -370,7 +370,7 @@ def main():
                          "kernel": "one solve call = qlb_quad_first_kernel<double,double,0> + qlb_quad_kernel<..,1> "
                                    "(active-set rounds on the listed states) + qlb_quad_kernel<..,2> (interior point)",
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the three launches of one solve call, from the "
-                                         "ncu --set full capture profiles/r1_final_ncu_summary.txt (545 + 675 + 77 MB per 2^20 "
+                                         "ncu --set full capture profiles/r1_final_ncu_summary.txt (543 + 704 + 79 MB per 2^20 "
                                          "states; algorithmic 475 MB - the excess is the index-gathered re-read of the listed states)",
                          "note": "algorithmic FP64 FLOP (30k/21k/12k per 4/3/2-stance QP, SURVEY 8d) / CUDA-event time "
                                  "of the launch, per GPU; peak = DFMA probe measured in this run (qlb_measure_fp64_peak)",
