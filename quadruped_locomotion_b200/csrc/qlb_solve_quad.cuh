@@ -178,6 +178,9 @@ struct LegSetup {
   bool alive, qbad;
 };
 
+#ifndef QLB_SMEM_MODEL
+#define QLB_SMEM_MODEL 1     // the leg-model table is read from a per-CTA shared copy instead of global memory
+#endif
 #ifndef QLB_PIPELINE_LOADS
 #define QLB_PIPELINE_LOADS 1
 #endif
@@ -264,13 +267,33 @@ __device__ __forceinline__ void quad_load(const SolveArgsT<real>& a, const real 
   }
 }
 
+// Per-CTA shared copy of the leg-model table (2.2 KB in FP64), filled by load_model_to_smem at kernel start.
+__device__ __forceinline__ double* smem_model_buffer() {
+  __shared__ double buf[sizeof(DeviceModelT<double>) / sizeof(double)];
+  return buf;
+}
+template <typename real>
+__device__ __forceinline__ void load_model_to_smem(const DeviceModelT<real>* src) {
+#if QLB_SMEM_MODEL
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(smem_model_buffer());
+  for (int i = threadIdx.x; i < (int)(sizeof(DeviceModelT<real>) / 4); i += blockDim.x) d32[i] = s32[i];
+#endif
+}
+
 // Everything from the raw inputs of one state (lane = leg `leg`) up to the QP data.
 template <typename real, int MODE>
 __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const DeviceParamsT<real>& prm, const RawIn<real, MODE>& in,
                                            const unsigned long long bq, const bool valid, const bool write_wout,
                                            const int leg, LegSetup<real>& L, real (*jg)[kQuadThreads]) {
   const unsigned long long B = a.B;
+#if QLB_SMEM_MODEL
+  const DeviceModelT<real>& mdl = *reinterpret_cast<const DeviceModelT<real>*>(smem_model_buffer());
+#define QLB_MDL(x) (x)
+#else
   const DeviceModelT<real>& mdl = *a.model;
+#define QLB_MDL(x) __ldg(&(x))
+#endif
     const unsigned mask = in.mask;
     L.mask = mask;
     const bool alive = (mask >> leg) & 1u;
@@ -380,19 +403,19 @@ __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const Devi
     {
       real R[9], p[3], zj[3][3], pj[3][3], com[4][3];
 #pragma unroll
-      for (int e = 0; e < 9; e++) R[e] = __ldg(&mdl.rot[leg][0][e]);
+      for (int e = 0; e < 9; e++) R[e] = QLB_MDL(mdl.rot[leg][0][e]);
 #pragma unroll
-      for (int c = 0; c < 3; c++) p[c] = __ldg(&mdl.xyz[leg][0][c]);
+      for (int c = 0; c < 3; c++) p[c] = QLB_MDL(mdl.xyz[leg][0][c]);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         if (j > 0) {
-          const real x0 = __ldg(&mdl.xyz[leg][j][0]), x1 = __ldg(&mdl.xyz[leg][j][1]), x2 = __ldg(&mdl.xyz[leg][j][2]);
+          const real x0 = QLB_MDL(mdl.xyz[leg][j][0]), x1 = QLB_MDL(mdl.xyz[leg][j][1]), x2 = QLB_MDL(mdl.xyz[leg][j][2]);
 #pragma unroll
           for (int c = 0; c < 3; c++) p[c] += R[3 * c] * x0 + R[3 * c + 1] * x1 + R[3 * c + 2] * x2;
           if (j < 3) {
             real Rj[9], T[9];
 #pragma unroll
-            for (int e = 0; e < 9; e++) Rj[e] = __ldg(&mdl.rot[leg][j][e]);
+            for (int e = 0; e < 9; e++) Rj[e] = QLB_MDL(mdl.rot[leg][j][e]);
 #pragma unroll
             for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -413,8 +436,8 @@ __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const Devi
             R[3 * r + 1] = cj * a1 - sj * a0;
           }
         }
-        const real c0 = __ldg(&mdl.com[leg][j][0]), c1 = __ldg(&mdl.com[leg][j][1]), c2 = __ldg(&mdl.com[leg][j][2]);
-        const real mj = __ldg(&mdl.mass[leg][j]);
+        const real c0 = QLB_MDL(mdl.com[leg][j][0]), c1 = QLB_MDL(mdl.com[leg][j][1]), c2 = QLB_MDL(mdl.com[leg][j][2]);
+        const real mj = QLB_MDL(mdl.mass[leg][j]);
 #pragma unroll
         for (int c = 0; c < 3; c++) com[j][c] = mj * (p[c] + R[3 * c] * c0 + R[3 * c + 1] * c1 + R[3 * c + 2] * c2);
       }
@@ -430,7 +453,7 @@ __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const Devi
           J[j][0] = zj[j][1] * dv[2] - zj[j][2] * dv[1];
           J[j][1] = zj[j][2] * dv[0] - zj[j][0] * dv[2];
           J[j][2] = zj[j][0] * dv[1] - zj[j][1] * dv[0];
-          const real ms = __ldg(&mdl.msuf[leg][j]);
+          const real ms = QLB_MDL(mdl.msuf[leg][j]);
           const real arm[3] = {mcs[0] - ms * pj[j][0], mcs[1] - ms * pj[j][1], mcs[2] - ms * pj[j][2]};
           gtau[j] = -(zj[j][0] * (arm[1] * gb[2] - arm[2] * gb[1]) + zj[j][1] * (arm[2] * gb[0] - arm[0] * gb[2]) +
                       zj[j][2] * (arm[0] * gb[1] - arm[1] * gb[0]));
@@ -558,6 +581,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
     // the solver core reads its weights from the FP64 parameter block, in its own type
     if (threadIdx.x < 6) { cS[threadIdx.x] = (creal)a.params64->S[threadIdx.x]; sinv[threadIdx.x] = (creal)(1.0 / a.params64->S[threadIdx.x]); }
     if (threadIdx.x == 6) { cW = (creal)a.params64->W; winv = (creal)(1.0 / a.params64->W); cfmin = (creal)a.params64->fmin; }
+    load_model_to_smem(a.model);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -699,18 +723,11 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
       if (v3 || v4) pat |= ((v3 && (!v4 || e[3] <= e[4])) ? 1u : 2u) << 3;
     }
     pat = quad_or(pat << (5 * leg));
-    // append the unfinished states to the list of the second pass (one atomic per warp)
+    // append the unfinished states to the list of the second pass (one atomic per warp).  The atomic is issued
+    // here and its result consumed after the outputs are written, so its round trip to L2 is not waited for.
     const unsigned hm = __ballot_sync(kFull, hard && valid && leg == 0);
-    if (hm != 0u) {
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(a.list_count, __popc(hm));
-      base = __shfl_sync(kFull, base, 0);
-      if (hard && valid && leg == 0) {
-        const unsigned at = base + __popc(hm & ((1u << lane) - 1u));
-        a.list[at] = (unsigned)bq;
-        a.list_pat[at] = pat;
-      }
-    }
+    unsigned base = 0;
+    if (hm != 0u && lane == 0) base = atomicAdd(a.list_count, __popc(hm));
     // Every state is written, the listed ones provisionally (a later pass overwrites them): a row segment
     // with holes would be a partial-sector write, which costs a DRAM read to fill (ncu: +250 MB per 2^20 states).
 #if QLB_PIPELINE_LOADS
@@ -723,6 +740,14 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
 #if !QLB_PIPELINE_LOADS
     if (bn < nbatch) quad_load<real, MODE>(a, prm.mu_default, bqn, sn < B, leg, in);
 #endif
+    if (hm != 0u) {
+      base = __shfl_sync(kFull, base, 0);
+      if (hard && valid && leg == 0) {
+        const unsigned at = base + __popc(hm & ((1u << lane) - 1u));
+        a.list[at] = (unsigned)bq;
+        a.list_pat[at] = pat;
+      }
+    }
     bi = bn;
   }
 }
@@ -1233,6 +1258,7 @@ __global__ void __launch_bounds__(kQuadThreads, STAGE == 1 ? QLB_QUAD_MIN_CTAS :
     for (int i = threadIdx.x; i < (int)(sizeof(DeviceParamsT<real>) / 4); i += blockDim.x) dst[i] = src[i];
     // the solver core reads its weights from the FP64 parameter block, in its own type
     cc.load(a.params64);
+    load_model_to_smem(a.model);
     if (Tol<creal>::rescue && STAGE == 2) cc64.load(a.params64);
   }
   __syncthreads();
