@@ -1,5 +1,6 @@
-import sys, time, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+"""End-to-end time of the host entry points (pinned host memory, copies included), FP64 and FP32 interface."""
+import os, sys, time, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quadruped_locomotion_b200 import capi, synth
 B = 1 << 20
 st = synth.make_states("C3", B)
