@@ -92,3 +92,15 @@ def test_swing_needs_the_limb_tables(qlb_built):
     with pytest.raises(RuntimeError):
         s.swing_leg_torques(t, t, t, None, None, s.default_swing_params(), t)
     s.close()
+
+
+def test_committed_model_header_matches_the_tables(tmp_path):
+    """include/qlb_models.h is generated from models/*.json (tools/make_models.py): keep them in step."""
+    import os
+    models = {"QLB_MODEL_" + n.upper(): legmodel.load_model(n) for n in ("quadruped_model", "simpledog")}
+    out = tmp_path / "qlb_models.h"
+    legmodel.emit_c_header(models, str(out))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert out.read_text() == open(os.path.join(root, "include", "qlb_models.h")).read()
+    flat = legmodel.limb_dynamics_to_flat(models["QLB_MODEL_QUADRUPED_MODEL"])
+    assert flat.shape == (4, 48) and flat[0, 18] == models["QLB_MODEL_QUADRUPED_MODEL"]["limb_dynamics"][0]["body_mass"][0]
