@@ -223,6 +223,17 @@ int qlb_solve_state_f32_host(qlb_context* ctx, size_t B, const float* q, const f
                              const float* normals_world, float* grf, float* tau, uint32_t* flags,
                              float* netwrench, float* wrench_out);
 
+/* Kernel organisation of the solve entry points (the results are the same optimum either way):
+ *   QLB_PIPELINE_FUSED (default): one persistent kernel - inputs staged through shared memory by the TMA unit,
+ *     kinematics + QP data + unconstrained minimiser per state, the states that need active-set rounds parked in
+ *     shared memory and solved by a dual block active-set method in the same kernel - followed by the
+ *     interior-point kernel for states the rounds could not verify (normally none).
+ *   QLB_PIPELINE_THREE_PASS: the round-1 organisation (first / active-set / interior-point kernels over
+ *     compacted index lists in HBM).  Always used by the FP32 solver core. */
+#define QLB_PIPELINE_FUSED 0
+#define QLB_PIPELINE_THREE_PASS 1
+int qlb_set_pipeline(qlb_context* ctx, int pipeline);
+
 #define QLB_F32_CORE_FP32 0
 #define QLB_F32_CORE_FP64 1
 int qlb_set_f32_core(qlb_context* ctx, int core);

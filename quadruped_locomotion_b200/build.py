@@ -1,6 +1,7 @@
 """Build libqlb.so (the C-ABI library) in-tree with nvcc for sm_100a."""
 from __future__ import annotations
 
+import glob
 import os
 import subprocess
 import sys
@@ -10,7 +11,6 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libqlb.so")
 SOURCES = ["qlb_api.cu"]
-HEADERS = ["qlb_device.cuh", "qlb_solve.cuh", "qlb_aux.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--fmad=true"]
 
@@ -19,7 +19,9 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "qlb.h")]
+    # every kernel header is included by qlb_api.cu: any edit under csrc/ or include/ makes the library stale
+    deps = glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        glob.glob(os.path.join(ROOT, "include", "*.h")) + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

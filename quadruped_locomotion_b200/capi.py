@@ -19,6 +19,7 @@ NUM_LEGS = 4
 STATS_NUM = 30
 STATS_NUM_SUM = 28
 FLAG_PARITY_MASK = 0x00FFFFFF
+PIPELINE_FUSED, PIPELINE_THREE_PASS = 0, 1
 STATUS_NAMES = ("ok", "no_stance", "max_iter", "unverified", "bad_input")
 
 
@@ -50,7 +51,7 @@ EXPORTS = (
     "qlb_solve_wrench", "qlb_solve_wrench_host", "qlb_solve_state", "qlb_solve_state_host",
     "qlb_solve_wrench_f32", "qlb_solve_wrench_f32_host", "qlb_solve_state_f32", "qlb_solve_state_f32_host",
     "qlb_default_swing_params", "qlb_set_limb_dynamics", "qlb_swing_leg_torques", "qlb_swing_leg_torques_host",
-    "qlb_set_f32_core", "qlb_leg_kinematics", "qlb_pack_robot_states", "qlb_feet_in_world", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
+    "qlb_set_f32_core", "qlb_set_pipeline", "qlb_leg_kinematics", "qlb_pack_robot_states", "qlb_feet_in_world", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
     "qlb_last_cuda_error", "qlb_abi_version",
 )
 
@@ -97,6 +98,7 @@ def load() -> C.CDLL:
     lib.qlb_solve_state_f32.argtypes = [_vp, C.c_size_t] + [_vp] * 14
     lib.qlb_solve_state_f32_host.argtypes = [_vp, C.c_size_t] + [_vp] * 13
     lib.qlb_set_f32_core.argtypes = [_vp, C.c_int]
+    lib.qlb_set_pipeline.argtypes = [_vp, C.c_int]
     lib.qlb_pack_robot_states.argtypes = [_vp, C.c_size_t] + [_vp] * 7
     lib.qlb_feet_in_world.argtypes = [_vp, C.c_size_t] + [_vp] * 4
     lib.qlb_default_swing_params.argtypes = [C.POINTER(SwingParams)]
@@ -202,6 +204,10 @@ class Solver:
     def set_f32_core(self, fp64_core: bool):
         """Solver core of the _f32 entry points: FP64 (default; FP32 interface only) or FP32."""
         self._check(self.lib.qlb_set_f32_core(self._ctx, 1 if fp64_core else 0), "qlb_set_f32_core")
+
+    def set_pipeline(self, fused: bool):
+        """Kernel organisation: the fused persistent kernel (default) or the three-pass pipeline."""
+        self._check(self.lib.qlb_set_pipeline(self._ctx, PIPELINE_FUSED if fused else PIPELINE_THREE_PASS), "qlb_set_pipeline")
 
     def get_params(self) -> Params:
         p = Params()

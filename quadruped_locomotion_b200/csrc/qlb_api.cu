@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -12,6 +13,7 @@
 #include "qlb_qp_dense.cuh"
 #include "qlb_solve.cuh"
 #include "qlb_solve_quad.cuh"
+#include "qlb_solve_fused.cuh"
 #include "qlb_swing.cuh"
 
 using namespace qlb;
@@ -38,6 +40,9 @@ struct qlb_context {
   int blocks_per_sm_first_f[2] = {0, 0};
   int blocks_per_sm_quad_m[2] = {0, 0};   // FP32 interface + FP64 solver core
   int blocks_per_sm_first_m[2] = {0, 0};
+  int pipeline = QLB_PIPELINE_FUSED;   // qlb_set_pipeline
+  int blocks_per_sm_fused[2][2][2] = {};   // [interface type: 0 double, 1 float][MODE][TMA]
+  bool use_tma = true;    // fused pipeline: stage the inputs with the TMA unit when the arrays allow it
   bool f32_pure = false;  // qlb_set_f32_core: FP32 solver core with in-kernel FP64 rescue, or FP64 core for every state
   unsigned long long* d_counter = nullptr;
   unsigned* d_list[8] = {};   // second-pass index lists, one per launch slot
@@ -235,10 +240,90 @@ int launch_quad(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int b
   return QLB_OK;
 }
 
+// ---- the fused pipeline (qlb_solve_fused.cuh): one persistent kernel + the interior-point kernel for the
+// states the rounds could not verify (normally none: it finds an empty list and returns)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// Tensor map of one SoA input array [rows][B]: boxes of {8 states, rows}, out-of-range columns read as zero.
+template <typename T>
+bool make_map(CUtensorMap* m, const T* ptr, unsigned long long B, int rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)B, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)B * sizeof(T)};
+  const cuuint32_t box[2] = {8u, (cuuint32_t)rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return fn(m, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<T*>(ptr), gdim,
+            gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename T, typename C, int MODE>
+int launch_fused(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int bps_ipm) {
+  using SG = Staging<T, MODE>;
+  using FL = FusedLayout<T, C, MODE>;
+  const T* src[7];
+  if (MODE == 1) { src[0] = a.q; src[1] = a.pose; src[2] = a.twist; src[3] = a.tpose; src[4] = a.ttwist; src[5] = a.mu; src[6] = a.normals; }
+  else { src[0] = a.q; src[1] = a.quat; src[2] = a.wrench; src[3] = a.mu; src[4] = a.normals; src[5] = nullptr; src[6] = nullptr; }
+  // TMA needs 16-byte aligned rows (base pointers and the row pitch B * sizeof(T)) and 32-bit coordinates
+  bool tma = ctx->use_tma && a.B >= 64 && a.B < 0x7fffff00ull && ((a.B * sizeof(T)) % 16 == 0);
+  for (int s = 0; s < SG::kNumSeg && tma; s++)
+    if (src[s] && !aligned16(src[s])) tma = false;
+  FusedMaps maps;
+  std::memset(&maps, 0, sizeof maps);
+  for (int s = 0; s < SG::kNumSeg && tma; s++)
+    if (src[s] && !make_map<T>(&maps.seg[s], src[s], a.B, SG::rows(s))) tma = false;
+  const unsigned long long ntiles = (a.B + 7) / 8;
+  const unsigned long long want = (ntiles + 3) / 4;
+  const int bps = ctx->blocks_per_sm_fused[sizeof(T) == 4 ? 1 : 0][MODE][tma ? 1 : 0];
+  const unsigned long long cap = (unsigned long long)ctx->sm_count * bps;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  if (tma) qlb_fused_kernel<T, C, MODE, true><<<grid, kQuadThreads, FL::kTotal, st>>>(a, maps);
+  else qlb_fused_kernel<T, C, MODE, false><<<grid, kQuadThreads, FL::kTotal, st>>>(a, maps);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  const unsigned long long capq = (unsigned long long)ctx->sm_count * bps_ipm;
+  qlb_quad_kernel<T, C, MODE, 2><<<(unsigned)(want < capq ? want : capq), kQuadThreads, 0, st>>>(a);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  QLB_CUDA(ctx, cudaEventRecord(ctx->slot_done[ctx->last_slot], st));
+  return QLB_OK;
+}
+
+template <typename T, typename C, int MODE>
+bool prepare_fused_kernels(qlb_context* ctx) {
+  using FL = FusedLayout<T, C, MODE>;
+  int* out = ctx->blocks_per_sm_fused[sizeof(T) == 4 ? 1 : 0][MODE];
+  if (cudaFuncSetAttribute(qlb_fused_kernel<T, C, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FL::kTotal) != cudaSuccess ||
+      cudaFuncSetAttribute(qlb_fused_kernel<T, C, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FL::kTotal) != cudaSuccess ||
+      cudaFuncSetAttribute(qlb_fused_kernel<T, C, MODE, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+      cudaFuncSetAttribute(qlb_fused_kernel<T, C, MODE, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+    return false;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out[0], qlb_fused_kernel<T, C, MODE, false>, kQuadThreads, FL::kTotal) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out[1], qlb_fused_kernel<T, C, MODE, true>, kQuadThreads, FL::kTotal) != cudaSuccess)
+    return false;
+  return out[0] >= 1 && out[1] >= 1;
+}
+
 template <int MODE>
 int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
   const int rc = prepare_slot(ctx, a, st);
   if (rc != QLB_OK) return rc;
+  if (ctx->pipeline == QLB_PIPELINE_FUSED) return launch_fused<double, double, MODE>(ctx, a, st, ctx->blocks_per_sm_quad[MODE]);
   return launch_quad<double, double, MODE>(ctx, a, st, ctx->blocks_per_sm_first[MODE], ctx->blocks_per_sm_quad[MODE]);
 }
 
@@ -248,6 +333,7 @@ int launch_solve_f32(qlb_context* ctx, SolveArgsT<float>& a, cudaStream_t st) {
   const int rc = prepare_slot(ctx, a, st);
   if (rc != QLB_OK) return rc;
   if (ctx->f32_pure) return launch_quad<float, float, MODE>(ctx, a, st, ctx->blocks_per_sm_first_f[MODE], ctx->blocks_per_sm_quad_f[MODE]);
+  if (ctx->pipeline == QLB_PIPELINE_FUSED) return launch_fused<float, double, MODE>(ctx, a, st, ctx->blocks_per_sm_quad_m[MODE]);
   return launch_quad<float, double, MODE>(ctx, a, st, ctx->blocks_per_sm_first_m[MODE], ctx->blocks_per_sm_quad_m[MODE]);
 }
 
@@ -380,6 +466,15 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first_m[0], qlb_quad_first_kernel<float, double, 0>, kQuadThreads, 0) != cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first_m[1], qlb_quad_first_kernel<float, double, 1>, kQuadThreads, 0) != cudaSuccess)
     return fail(QLB_ERR_CUDA);
+  if (!prepare_fused_kernels<double, double, 0>(ctx) || !prepare_fused_kernels<double, double, 1>(ctx) ||
+      !prepare_fused_kernels<float, double, 0>(ctx) || !prepare_fused_kernels<float, double, 1>(ctx)) {
+    cudaGetLastError();
+    return fail(QLB_ERR_CUDA);
+  }
+  if (const char* e = std::getenv("QLB_PIPELINE")) {   // experiments: three_pass | fused | fused_notma
+    if (!std::strcmp(e, "three_pass")) ctx->pipeline = QLB_PIPELINE_THREE_PASS;
+    if (!std::strcmp(e, "fused_notma")) ctx->use_tma = false;
+  }
   if (max_batch > 0 && ensure_capacity(ctx, max_batch) != QLB_OK) return fail(QLB_ERR_ALLOC);
   *out = ctx;
   return QLB_OK;
@@ -428,6 +523,13 @@ int qlb_set_f32_core(qlb_context* ctx, int core) {
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (core != QLB_F32_CORE_FP32 && core != QLB_F32_CORE_FP64) return QLB_ERR_INVALID_ARGUMENT;
   ctx->f32_pure = (core == QLB_F32_CORE_FP32);
+  return QLB_OK;
+}
+
+int qlb_set_pipeline(qlb_context* ctx, int pipeline) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (pipeline != QLB_PIPELINE_FUSED && pipeline != QLB_PIPELINE_THREE_PASS) return QLB_ERR_INVALID_ARGUMENT;
+  ctx->pipeline = pipeline;
   return QLB_OK;
 }
 

@@ -285,7 +285,8 @@ __device__ __forceinline__ void load_model_to_smem(const DeviceModelT<real>* src
 template <typename real, int MODE>
 __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const DeviceParamsT<real>& prm, const RawIn<real, MODE>& in,
                                            const unsigned long long bq, const bool valid, const bool write_wout,
-                                           const int leg, LegSetup<real>& L, real (*jg)[kQuadThreads]) {
+                                           const int leg, LegSetup<real>& L, real* const jgp, const int jgs) {
+  // jgp / jgs: where this lane parks its leg's Jacobian (9) and gravity torques (3): element k at jgp[k * jgs]
   const unsigned long long B = a.B;
 #if QLB_SMEM_MODEL
   const DeviceModelT<real>& mdl = *reinterpret_cast<const DeviceModelT<real>*>(smem_model_buffer());
@@ -476,8 +477,8 @@ __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const Devi
 #pragma unroll
     for (int j = 0; j < 3; j++) {
 #pragma unroll
-      for (int c = 0; c < 3; c++) jg[3 * j + c][threadIdx.x] = J[j][c];
-      jg[9 + j][threadIdx.x] = gtau[j];
+      for (int c = 0; c < 3; c++) jgp[(3 * j + c) * jgs] = J[j][c];
+      jgp[(9 + j) * jgs] = gtau[j];
     }
 #pragma unroll
     for (int c = 0; c < 3; c++) { L.nrm[c] = E[0][c]; L.foot[c] = foot[c]; }
@@ -516,7 +517,7 @@ __device__ __forceinline__ void widen_setup(const LegSetup<real>& s, LegSetup<cr
 template <typename real, typename creal>
 __device__ __forceinline__ void quad_output(const SolveArgsT<real>& a, const LegSetup<creal>& L, creal (&y)[3], const int a0, const int sg1,
                                             const int sg2, const int status, const int it, const unsigned long long bq,
-                                            const bool valid, const int leg, const real (*jg)[kQuadThreads],
+                                            const bool valid, const int leg, const real* const jgp, const int jgs,
                                             const creal* net_pre = nullptr) {
   const unsigned long long B = a.B;
   const bool alive = L.alive;
@@ -534,7 +535,7 @@ __device__ __forceinline__ void quad_output(const SolveArgsT<real>& a, const Leg
 #pragma unroll
       for (int j = 0; j < 3; j++)
         a.tau[(size_t)(3 * leg + j) * B + bq] = (real)(
-            live ? (creal)jg[9 + j][threadIdx.x] - ((creal)jg[3 * j][threadIdx.x] * f[0] + (creal)jg[3 * j + 1][threadIdx.x] * f[1] + (creal)jg[3 * j + 2][threadIdx.x] * f[2]) : creal(0.0));
+            live ? (creal)jgp[(9 + j) * jgs] - ((creal)jgp[(3 * j) * jgs] * f[0] + (creal)jgp[(3 * j + 1) * jgs] * f[1] + (creal)jgp[(3 * j + 2) * jgs] * f[2]) : creal(0.0));
     }
     if (a.netwrench) {
       // A x = sum over legs of A_k y_k (CFD.cpp:614-625)
@@ -563,6 +564,122 @@ __device__ __forceinline__ void quad_output(const SolveArgsT<real>& a, const Leg
         a.flags[bq] = mask | bits | ((unsigned)status << 24) | (itc << 27);
       }
     }
+}
+
+// The unconstrained minimiser of one state (all rows free) and its first repair: which rows does it violate?
+// Whole warp (quad shuffles).  Out: y (contact coordinates), t (solution of the 6x6 system; A x = b - S^-1 t),
+// status (0 ok / 1 no stance / 4 bad), hard (some row is violated: the state needs active-set rounds),
+// pat (first pattern: every violated row active, 5 bits per leg, OR-ed over the quad).
+template <typename real, typename creal>
+__device__ __forceinline__ void quad_first_solve(const LegSetup<creal>& L, const creal* sinv, const creal winv, const creal cfmin,
+                                                 const int leg, creal (&y)[3], creal (&t)[6], int& status, bool& hard,
+                                                 unsigned& pat_out) {
+  const bool alive = L.alive;
+  const creal (&At)[3][6] = L.At;
+  status = L.qbad ? 4 : (L.ns == 0 ? 1 : 0);
+  y[0] = y[1] = y[2] = creal(0.0);
+  hard = false;
+  // unconstrained minimiser through the 6x6 system: (S^-1 + A~ A~'/w) t = b,  y = A~' t / w
+  const creal al = alive ? winv : creal(0.0);
+  bool pd;
+  if (Tol<creal>::refine || sizeof(real) != sizeof(creal)) {
+    // FP32 core: generic assembly + iterative refinement through the factors.  FP32 interface with the FP64
+    // core: generic assembly as well - the system must be built from the same rounded A~ that recovers y.
+    creal N[21], rdg[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const creal w0 = al * At[0][i], w1 = al * At[1][i], w2 = al * At[2][i];
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        if (j <= i) {
+          creal acc = (i == j && leg == 0) ? sinv[i] : creal(0.0);
+          acc = fma(w0, At[0][j], acc);
+          acc = fma(w1, At[1][j], acc);
+          acc = fma(w2, At[2][j], acc);
+          N[QLB_TRI(i, j)] = quad_sum(acc);
+        }
+      }
+      t[i] = L.b[i];
+    }
+    pd = chol6_thread(N, rdg);
+    solve6_thread(N, rdg, t);
+    if (Tol<creal>::refine) {
+      const creal al3[3] = {al, al, al};
+      refine6(N, rdg, At, al3, sinv, L.b, t);
+    }
+  } else {
+    // With every slot free the friction frames drop out (Q Q' = I):  A~ A~' = sum_k [I; X_k][I, X_k'],
+    // X_k = [r_k]x, so the system is  [[D, B'], [B, C]]  with D = S_F^-1 + ns/w diagonal, B = [sum r]x / w and
+    // C = S_T^-1 + sum(|r|^2 I - r r') / w: nine sums over the quad instead of twenty-one, and a 3x3 Schur
+    // complement  (C - B D^-1 B') t_T = b_T - B D^-1 b_F  instead of a 6x6 factorisation.
+    const creal rx = alive ? L.foot[0] : creal(0.0), ry = alive ? L.foot[1] : creal(0.0), rz = alive ? L.foot[2] : creal(0.0);
+    const creal xs = winv * quad_sum(rx), ys = winv * quad_sum(ry), zs = winv * quad_sum(rz);
+    const creal qxx = quad_sum(rx * rx), qyy = quad_sum(ry * ry), qzz = quad_sum(rz * rz);
+    const creal qxy = quad_sum(rx * ry), qxz = quad_sum(rx * rz), qyz = quad_sum(ry * rz);
+    const creal nsw = (creal)L.ns * winv;
+    const creal d0 = full_rcp(sinv[0] + nsw), d1 = full_rcp(sinv[1] + nsw), d2 = full_rcp(sinv[2] + nsw);  // full precision: the Schur complement cancels
+    // Schur complement, packed lower 3x3
+    creal c00 = fma(winv, qyy + qzz, sinv[3]) - (zs * zs * d1 + ys * ys * d2);
+    creal c11 = fma(winv, qxx + qzz, sinv[4]) - (zs * zs * d0 + xs * xs * d2);
+    creal c22 = fma(winv, qxx + qyy, sinv[5]) - (ys * ys * d0 + xs * xs * d1);
+    creal c10 = fma(-winv, qxy, xs * ys * d2);
+    creal c20 = fma(-winv, qxz, xs * zs * d1);
+    creal c21 = fma(-winv, qyz, ys * zs * d0);
+    const creal u0 = d0 * L.b[0], u1 = d1 * L.b[1], u2 = d2 * L.b[2];
+    creal g0 = L.b[3] - (ys * u2 - zs * u1);
+    creal g1 = L.b[4] - (zs * u0 - xs * u2);
+    creal g2 = L.b[5] - (xs * u1 - ys * u0);
+    // 3x3 Cholesky and the two substitutions
+    pd = c00 > creal(0.0);
+    const creal r0 = fast_rsqrt(c00);
+    c10 *= r0; c20 *= r0;
+    c11 = fma(-c10, c10, c11);
+    pd = pd && (c11 > creal(0.0));
+    const creal r1 = fast_rsqrt(c11);
+    c21 = fma(-c20, c10, c21) * r1;
+    c22 = fma(-c21, c21, fma(-c20, c20, c22));
+    pd = pd && (c22 > creal(0.0));
+    const creal r2 = fast_rsqrt(c22);
+    g0 *= r0;
+    g1 = fma(-c10, g0, g1) * r1;
+    g2 = fma(-c21, g1, fma(-c20, g0, g2)) * r2;
+    g2 *= r2;
+    g1 = fma(-c21, g2, g1) * r1;
+    g0 = fma(-c20, g2, fma(-c10, g1, g0)) * r0;
+    t[3] = g0; t[4] = g1; t[5] = g2;
+    // t_F = D^-1 (b_F - B' t_T),  B' v = -(s x v) / w ... written out
+    t[0] = d0 * (L.b[0] - (zs * g1 - ys * g2));
+    t[1] = d1 * (L.b[1] - (xs * g2 - zs * g0));
+    t[2] = d2 * (L.b[2] - (ys * g0 - xs * g1));
+  }
+  const bool pd_fail = !pd && status == 0;   // quad-uniform: every lane factors the same matrix
+  if (pd_fail && !Tol<creal>::rescue) status = 4;
+  creal e[5];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    creal d = creal(0.0);
+#pragma unroll
+    for (int r = 0; r < 6; r++) d = fma(At[c][r], t[r], d);
+    y[c] = al * d;
+  }
+  leg_rows(y[0], y[1], y[2], L.mu, e);
+  e[0] -= cfmin;
+  const float scale = fmaxf(1.f, quad_max(fmaxf(fabsf((float)y[0]), fmaxf(fabsf((float)y[1]), fabsf((float)y[2])))));
+  const creal tol_s = Tol<creal>::feas() * (creal)scale;
+  bool viol = false;
+#pragma unroll
+  for (int r = 0; r < 5; r++) viol = viol || (alive && e[r] < -tol_s);
+  const bool quad_viol = quad_or(viol ? 1u : 0u) != 0u;  // not inside the && : every lane must reach the shuffle
+  hard = (status == 0) && (quad_viol || pd_fail);
+  // first repair of the empty pattern: every violated row becomes active (the more violated one of a +- pair)
+  unsigned pat = 0u;
+  if (alive && !pd_fail) {
+    const bool v0 = e[0] < -tol_s, v1 = e[1] < -tol_s, v2 = e[2] < -tol_s, v3 = e[3] < -tol_s, v4 = e[4] < -tol_s;
+    pat = v0 ? 1u : 0u;
+    if (v1 || v2) pat |= ((v1 && (!v2 || e[1] <= e[2])) ? 1u : 2u) << 1;
+    if (v3 || v4) pat |= ((v3 && (!v4 || e[3] <= e[4])) ? 1u : 2u) << 3;
+  }
+  pat_out = quad_or(pat << (5 * leg));
 }
 
 // First pass: kinematics + QP data + the unconstrained minimiser (polish round with the empty pattern).
@@ -613,116 +730,14 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
     LegSetup<creal> L;
     {
       LegSetup<real> L0;
-      quad_setup<real, MODE>(a, prm, in, bq, valid, true, leg, L0, jg);
+      quad_setup<real, MODE>(a, prm, in, bq, valid, true, leg, L0, &jg[0][threadIdx.x], kQuadThreads);
       widen_setup(L0, L);
     }
-    const bool alive = L.alive;
-    const creal (&At)[3][6] = L.At;
-    int status = L.qbad ? 4 : (L.ns == 0 ? 1 : 0);
-    creal y[3] = {creal(0.0), creal(0.0), creal(0.0)};
-    bool hard = false;
-    // unconstrained minimiser through the 6x6 system: (S^-1 + A~ A~'/w) t = b,  y = A~' t / w
-    creal t[6];
-    const creal al = alive ? winv : creal(0.0);
-    bool pd;
-    if (Tol<creal>::refine || sizeof(real) != sizeof(creal)) {
-      // FP32 core: generic assembly + iterative refinement through the factors.  FP32 interface with the FP64
-      // core: generic assembly as well - the system must be built from the same rounded A~ that recovers y.
-      creal N[21], rdg[6];
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        const creal w0 = al * At[0][i], w1 = al * At[1][i], w2 = al * At[2][i];
-#pragma unroll
-        for (int j = 0; j < 6; j++) {
-          if (j <= i) {
-            creal acc = (i == j && leg == 0) ? sinv[i] : creal(0.0);
-            acc = fma(w0, At[0][j], acc);
-            acc = fma(w1, At[1][j], acc);
-            acc = fma(w2, At[2][j], acc);
-            N[QLB_TRI(i, j)] = quad_sum(acc);
-          }
-        }
-        t[i] = L.b[i];
-      }
-      pd = chol6_thread(N, rdg);
-      solve6_thread(N, rdg, t);
-      if (Tol<creal>::refine) {
-        const creal al3[3] = {al, al, al};
-        refine6(N, rdg, At, al3, sinv, L.b, t);
-      }
-    } else {
-      // With every slot free the friction frames drop out (Q Q' = I):  A~ A~' = sum_k [I; X_k][I, X_k'],
-      // X_k = [r_k]x, so the system is  [[D, B'], [B, C]]  with D = S_F^-1 + ns/w diagonal, B = [sum r]x / w and
-      // C = S_T^-1 + sum(|r|^2 I - r r') / w: nine sums over the quad instead of twenty-one, and a 3x3 Schur
-      // complement  (C - B D^-1 B') t_T = b_T - B D^-1 b_F  instead of a 6x6 factorisation.
-      const creal rx = alive ? L.foot[0] : creal(0.0), ry = alive ? L.foot[1] : creal(0.0), rz = alive ? L.foot[2] : creal(0.0);
-      const creal xs = winv * quad_sum(rx), ys = winv * quad_sum(ry), zs = winv * quad_sum(rz);
-      const creal qxx = quad_sum(rx * rx), qyy = quad_sum(ry * ry), qzz = quad_sum(rz * rz);
-      const creal qxy = quad_sum(rx * ry), qxz = quad_sum(rx * rz), qyz = quad_sum(ry * rz);
-      const creal nsw = (creal)L.ns * winv;
-      const creal d0 = full_rcp(sinv[0] + nsw), d1 = full_rcp(sinv[1] + nsw), d2 = full_rcp(sinv[2] + nsw);  // full precision: the Schur complement cancels
-      // Schur complement, packed lower 3x3
-      creal c00 = fma(winv, qyy + qzz, sinv[3]) - (zs * zs * d1 + ys * ys * d2);
-      creal c11 = fma(winv, qxx + qzz, sinv[4]) - (zs * zs * d0 + xs * xs * d2);
-      creal c22 = fma(winv, qxx + qyy, sinv[5]) - (ys * ys * d0 + xs * xs * d1);
-      creal c10 = fma(-winv, qxy, xs * ys * d2);
-      creal c20 = fma(-winv, qxz, xs * zs * d1);
-      creal c21 = fma(-winv, qyz, ys * zs * d0);
-      const creal u0 = d0 * L.b[0], u1 = d1 * L.b[1], u2 = d2 * L.b[2];
-      creal g0 = L.b[3] - (ys * u2 - zs * u1);
-      creal g1 = L.b[4] - (zs * u0 - xs * u2);
-      creal g2 = L.b[5] - (xs * u1 - ys * u0);
-      // 3x3 Cholesky and the two substitutions
-      pd = c00 > creal(0.0);
-      const creal r0 = fast_rsqrt(c00);
-      c10 *= r0; c20 *= r0;
-      c11 = fma(-c10, c10, c11);
-      pd = pd && (c11 > creal(0.0));
-      const creal r1 = fast_rsqrt(c11);
-      c21 = fma(-c20, c10, c21) * r1;
-      c22 = fma(-c21, c21, fma(-c20, c20, c22));
-      pd = pd && (c22 > creal(0.0));
-      const creal r2 = fast_rsqrt(c22);
-      g0 *= r0;
-      g1 = fma(-c10, g0, g1) * r1;
-      g2 = fma(-c21, g1, fma(-c20, g0, g2)) * r2;
-      g2 *= r2;
-      g1 = fma(-c21, g2, g1) * r1;
-      g0 = fma(-c20, g2, fma(-c10, g1, g0)) * r0;
-      t[3] = g0; t[4] = g1; t[5] = g2;
-      // t_F = D^-1 (b_F - B' t_T),  B' v = -(s x v) / w ... written out
-      t[0] = d0 * (L.b[0] - (zs * g1 - ys * g2));
-      t[1] = d1 * (L.b[1] - (xs * g2 - zs * g0));
-      t[2] = d2 * (L.b[2] - (ys * g0 - xs * g1));
-    }
-    const bool pd_fail = !pd && status == 0;   // quad-uniform: every lane factors the same matrix
-    if (pd_fail && !Tol<creal>::rescue) status = 4;
-    creal e[5];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      creal d = creal(0.0);
-#pragma unroll
-      for (int r = 0; r < 6; r++) d = fma(At[c][r], t[r], d);
-      y[c] = al * d;
-    }
-    leg_rows(y[0], y[1], y[2], L.mu, e);
-    e[0] -= cfmin;
-    const float scale = fmaxf(1.f, quad_max(fmaxf(fabsf((float)y[0]), fmaxf(fabsf((float)y[1]), fabsf((float)y[2])))));
-    const creal tol_s = Tol<creal>::feas() * (creal)scale;
-    bool viol = false;
-#pragma unroll
-    for (int r = 0; r < 5; r++) viol = viol || (alive && e[r] < -tol_s);
-    const bool quad_viol = quad_or(viol ? 1u : 0u) != 0u;  // not inside the && : every lane must reach the shuffle
-    hard = (status == 0) && (quad_viol || pd_fail);
-    // first repair of the empty pattern: every violated row becomes active (the more violated one of a +- pair)
-    unsigned pat = 0u;
-    if (alive && !pd_fail) {
-      const bool v0 = e[0] < -tol_s, v1 = e[1] < -tol_s, v2 = e[2] < -tol_s, v3 = e[3] < -tol_s, v4 = e[4] < -tol_s;
-      pat = v0 ? 1u : 0u;
-      if (v1 || v2) pat |= ((v1 && (!v2 || e[1] <= e[2])) ? 1u : 2u) << 1;
-      if (v3 || v4) pat |= ((v3 && (!v4 || e[3] <= e[4])) ? 1u : 2u) << 3;
-    }
-    pat = quad_or(pat << (5 * leg));
+    int status;
+    creal y[3], t[6];
+    bool hard;
+    unsigned pat;
+    quad_first_solve<real, creal>(L, sinv, winv, cfmin, leg, y, t, status, hard, pat);
     // append the unfinished states to the list of the second pass (one atomic per warp).  The atomic is issued
     // here and its result consumed after the outputs are written, so its round trip to L2 is not waited for.
     const unsigned hm = __ballot_sync(kFull, hard && valid && leg == 0);
@@ -736,7 +751,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
     creal net[6];
 #pragma unroll
     for (int r = 0; r < 6; r++) net[r] = fma(-sinv[r], t[r], L.b[r]);   // A x = b - S^-1 t
-    quad_output<real, creal>(a, L, y, 0, 0, 0, status, 0, bq, valid, leg, jg, net);  // whole warp: it contains quad shuffles
+    quad_output<real, creal>(a, L, y, 0, 0, 0, status, 0, bq, valid, leg, &jg[0][threadIdx.x], kQuadThreads, net);  // whole warp: it contains quad shuffles
 #if !QLB_PIPELINE_LOADS
     if (bn < nbatch) quad_load<real, MODE>(a, prm.mu_default, bqn, sn < B, leg, in);
 #endif
@@ -1198,7 +1213,7 @@ __device__ __forceinline__ void quad_batch(const SolveArgsT<real>& a, const Devi
     LegSetup<real> L0;
     RawIn<real, MODE> in;
     quad_load<real, MODE>(a, prm.mu_default, bq, valid, leg, in);
-    quad_setup<real, MODE>(a, prm, in, bq, valid, STAGE == 0, leg, L0, jg);
+    quad_setup<real, MODE>(a, prm, in, bq, valid, STAGE == 0, leg, L0, &jg[0][threadIdx.x], kQuadThreads);
     widen_setup(L0, L);
   }
   creal y[3];
@@ -1232,7 +1247,7 @@ __device__ __forceinline__ void quad_batch(const SolveArgsT<real>& a, const Devi
       if (defer && valid && leg == 0) a.list2[base + __popc(hm & ((1u << lane) - 1u))] = (unsigned)bq;
     }
   }
-  quad_output<real, creal>(a, L, y, a0, sg1, sg2, status, it, bq, valid && !defer, leg, jg);
+  quad_output<real, creal>(a, L, y, a0, sg1, sg2, status, it, bq, valid && !defer, leg, &jg[0][threadIdx.x], kQuadThreads);
 }
 
 // A later pass (STAGE as in quad_batch).  Two experiments that did not pay at 2^20 states (each pass has a

@@ -19,11 +19,14 @@ TIGHT = 1e-9        # what the kernel actually delivers; a regression guard
 STATE_KEYS = ("q", "quat", "wrench", "mask", "mu", "normals")
 
 
-@pytest.fixture(scope="module")
-def solver(qlb_built):
+@pytest.fixture(scope="module", params=["fused", "three_pass"])
+def solver(qlb_built, request):
+    """Every parity test runs on both kernel organisations (qlb_set_pipeline)."""
     if not torch.cuda.is_available():
         pytest.fail("GPU test selected but no CUDA device: the product path has no CPU fallback")
     s = capi.Solver("quadruped_model")
+    s.set_pipeline(request.param == "fused")
+    s.launches_per_call = 2 if request.param == "fused" else 3
     yield s
     s.close()
 
@@ -245,7 +248,7 @@ def test_device_pointer_api_and_stream(solver, oracle, models):
         solver.solve_wrench(d["q"], d["quat"], d["wrench"], d["mask"], d["mu"], d["normals"], grf, tau, flags, net,
                             stream=side.cuda_stream)
     side.synchronize()
-    assert solver.launches == before + 3  # three passes: first, active-set, interior-point
+    assert solver.launches == before + solver.launches_per_call  # fused + interior point, or the three passes
     out = dict(grf=grf.cpu().numpy(), tau=tau.cpu().numpy(), flags=flags.cpu().numpy().view(np.uint32),
                netwrench=net.cpu().numpy())
     ref = _oracle(oracle, models["quadruped_model"], st)
@@ -417,7 +420,7 @@ def test_f32_device_pointers_ragged_and_bad_inputs(solver, oracle, models):
     solver.solve_wrench(d["q"], d["quat"], d["wrench"], d["mask"], d["mu"], d["normals"], grf, tau, flags, net,
                         stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    assert solver.launches == before + 3
+    assert solver.launches == before + solver.launches_per_call
     fl = flags.cpu().numpy().view(np.uint32)
     status = (fl >> 24) & 7
     assert status[17] == 4 and status[400] == 4 and status[5] == 1
