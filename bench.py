@@ -39,8 +39,27 @@ WORKLOAD = ("C3: fused FK+Jacobian+QP+J^T.f torque pipeline, 2^20 randomised sta
             "(60% four-stance, 25% diagonal pairs, 15% three-stance), FP64, model quadruped_model.urdf")
 
 
-# DRAM bytes of one FP64 solve call on 2^20 C3 states (ncu, profiles/r1_final_ncu_summary.txt); scaled by B
-NCU_DRAM_BYTES_PER_CALL = (319.9 + 223.0 + 517.2 + 187.0 + 65.0 + 13.9) * 1e6
+
+
+def bench_config(B: int, world: int) -> dict:
+    """The `config` object of the JSON line; identical for the GPU arm and the reference arm."""
+    bytes_per_qp = ((12 + 4 + 6 + 4) * 8 + 1) + ((12 + 12 + 6) * 8 + 4)
+    return {"workload": WORKLOAD, "states_per_gpu": B, "global_batch": world * B,
+            "parallelism": f"instance-sharded x{world}, no data-path collective",
+            "l2_policy": f"inputs+outputs {B * bytes_per_qp / 1e6:.0f} MB per step exceed the 126 MB L2"}
+
+
+NCU_RECORD = os.path.join(ROOT, "profiles", "r2_final_ncu.json")   # written by tools/ncu_summary.py from the committed capture
+
+
+def load_ncu_record():
+    """DRAM traffic and executed-pipe figures of one solve call on 2^20 C3 states, from the committed ncu capture
+    (a run under the profiler is never a bench value; the bench reports these next to its own timing)."""
+    try:
+        with open(NCU_RECORD) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 def load_peaks():
@@ -175,13 +194,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        st = synth.make_states(args.config, min(B, args.cpu_sample))
+        # the same workload as the GPU arm: every step is one pass over the full 2^20-state batch of rank 0
+        st = synth.make_states(args.config, B)
         sample = st["q"].shape[1]
         v, info = cpu_reference(st, args.steps, min(warmup, 3), sample)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": info["ms_per_pass"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": {"workload": WORKLOAD, "states_per_step": sample},
+                "data": "synthetic", "config": bench_config(B, args.gpus),
                 "cpu_baseline": info, "gpu_launches": 0,
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
@@ -197,11 +217,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # the contract is ONE JSON line on stdout: keep NCCL's version / info banner out of it
-        # (NCCL writes them to stdout; the level may also come from a system nccl.conf)
+        # the contract is ONE JSON line on stdout: NCCL's log (whatever NCCL_DEBUG level the caller chose) goes to
+        # stderr, the level itself is left alone so that the communicator lines stay visible to the caller
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        if os.environ.get("NCCL_DEBUG", "WARN").upper() in ("VERSION", "INFO", "TRACE", "WARN"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- inputs: this rank's contiguous slice of the global synthetic batch (no inter-GPU traffic)
@@ -352,31 +370,45 @@ def main():
             if prev_affinity is not None:
                 os.sched_setaffinity(0, prev_affinity)   # the CPU baseline gets every host core
             cpu_v, cpu_info = cpu_reference(st, 3, 1, min(B, args.cpu_sample))
+        rec = load_ncu_record()
+        tw = (rec or {}).get("time_weighted") or {}
+        roofline = {
+            "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
+            "traffic": tw.get("dram_bytes") * (B / float(1 << 20)) if tw.get("dram_bytes") else None,
+            "kernel": "one solve call = qlb_fused_kernel<double,double,0,true> (TMA-staged inputs, kinematics, QP data, "
+                      "unconstrained minimiser, active-set rounds from a shared-memory stash) + qlb_quad_kernel<..,2> "
+                      "(interior-point fallback, normally an empty list)",
+            "note": "frac is ALGORITHMIC: FP64 FLOP by the fixed accounting of SURVEY 8d (30k/21k/12k per 4/3/2-stance QP, an "
+                    "eight-iteration interior point) / CUDA-event time of the call, per GPU, over the DFMA peak measured in this "
+                    "run (qlb_measure_fp64_peak).  The kernels execute far fewer FLOP than that accounting assumes, so read it as "
+                    "throughput relative to an ideal interior-point implementation; `executed` is what the hardware did.",
+            "executed": {
+                "source": os.path.relpath(NCU_RECORD, ROOT) if rec else None,
+                "what": "ncu --set full capture of the same solve call on 2^20 C3 states (profiled run, not this one), "
+                        "time-weighted over the launches of the call",
+                "fp64_pipe_active_pct_of_elapsed": tw.get("fp64_pipe_elapsed_pct"),
+                "fp64_pipe_active_pct_of_active": tw.get("fp64_pipe_active_pct"),
+                "issue_active_pct": tw.get("issue_active_pct"),
+                "kernels": [{k: kk.get(k) for k in ("name", "time_s", "dram_bytes", "fp64_pipe_elapsed_pct", "issue_active_pct",
+                                                     "warps_active_pct", "registers")} for kk in (rec or {}).get("kernels", [])],
+            },
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the launches of one solve call from the same capture, "
+                            "scaled by states / 2^20; algorithmic bytes are 453 per QP",
+            "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                    "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src, "bytes_per_qp": bytes_per_qp},
+        }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "states_per_gpu": B, "global_batch": world * B,
-                       "parallelism": f"instance-sharded x{world}, no data-path collective",
-                       "l2_policy": f"inputs+outputs {B * bytes_per_qp / 1e6:.0f} MB per step exceed the 126 MB L2"},
+            "config": bench_config(B, world),
             "clocks": clocks,
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "qlb_solve_wrench_host (pinned host buffers, copies inside the timed region)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
-                         "traffic": NCU_DRAM_BYTES_PER_CALL * (B / float(1 << 20)),
-                         "kernel": "one solve call = qlb_quad_first_kernel<double,double,0> + qlb_quad_kernel<..,1> "
-                                   "(active-set rounds on the listed states) + qlb_quad_kernel<..,2> (interior point)",
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the three launches of one solve call, from the "
-                                         "ncu --set full capture profiles/r1_final_ncu_summary.txt (543 + 704 + 79 MB per 2^20 "
-                                         "states; algorithmic 475 MB - the excess is the index-gathered re-read of the listed states)",
-                         "note": "algorithmic FP64 FLOP (30k/21k/12k per 4/3/2-stance QP, SURVEY 8d) / CUDA-event time "
-                                 "of the launch, per GPU; peak = DFMA probe measured in this run (qlb_measure_fp64_peak)",
-                         "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                                 "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src,
-                                 "bytes_per_qp": bytes_per_qp}},
+            "roofline": roofline,
             "cpu_baseline": cpu_info,
             "f32": {"value": world * B / (ms_step32 * 1e-3), "unit": UNIT, "ms_per_step": ms_step32,
                     "e2e": {"value": world * B * e2e_steps / e2e_s32, "unit": UNIT,
@@ -385,7 +417,7 @@ def main():
                     "note": "qlb_solve_wrench_f32[_host], default core: FP32 interface and kinematics, FP64 solver core; "
                             "stated tolerance in include/qlb.h and tests/test_gpu_parity.py"},
             "stats": {"ok": sd["ok"], "max_iter": sd["max_iter"], "unverified": sd["unverified"],
-                      "mean_ipm_iterations": sd["mean_iterations"], "max_ipm_iterations": sd["max_iterations"],
+                      "mean_solver_rounds": sd["mean_iterations"], "max_solver_rounds": sd["max_iterations"],
                       "mean_wrench_err": sd["mean_wrench_err"], "allreduce_ms": allreduce_ms,
                       "algorithmic_flop_total": flop_total},
         }

@@ -42,7 +42,7 @@ extern "C" {
 
 #define QLB_NUM_LEGS 4
 #define QLB_NUM_JOINTS 12
-#define QLB_ABI_VERSION 1
+#define QLB_ABI_VERSION 2
 
 typedef enum qlb_status {
   QLB_OK = 0,
@@ -70,7 +70,8 @@ typedef struct qlb_leg_model {
 typedef struct qlb_params {
   double wrench_weights[6];   /* S: virtualForceWeights_ (heading, lateral, vertical, roll, pitch, yaw) */
   double ground_force_weight; /* W: groundForceWeight_ (1e-4) */
-  double min_normal_force;    /* F_min: minimalNormalGroundForce_ (10 N) */
+  double min_normal_force;    /* F_min: minimalNormalGroundForce_ (10 N).  A negative value acts as 0: with mu > 0 the
+                                 friction rows already imply n.f >= 0 */
   double friction_default;    /* mu used where the per-leg mu array is NULL (0.6) */
   double gravity;             /* |g|, 9.8 (ContactForceDistribution.cpp:518) */
   /* virtual-model controller (VirtualModelController.cpp:104-268) */
@@ -96,7 +97,8 @@ typedef struct qlb_params {
  *               4 = (mu n - t2).f >= 0 (:315-325); set when the row is tight at the optimum
  *               with a positive multiplier
  *   bits 24..26 status code (qlb_state_status)
- *   bits 27..31 interior-point iterations used (saturates at 31)
+ *   bits 27..31 iterations of the stage that finished the state (saturates at 31): active-set rounds, or
+ *               interior-point iterations for a state that needed that fallback; 0 = the unconstrained minimiser
  */
 #define QLB_FLAG_CONTACT_MASK 0x0000000Fu
 #define QLB_FLAG_ACTIVE_SHIFT 4
@@ -111,7 +113,9 @@ typedef enum qlb_state_status {
   QLB_STATE_NO_STANCE = 1,     /* no leg in stance: nothing solved, outputs zero (CFD.cpp:127-132) */
   QLB_STATE_MAX_ITER = 2,      /* iteration limit hit; forces are the last iterate */
   QLB_STATE_UNVERIFIED = 3,    /* converged, but the active-set polish failed its KKT check */
-  QLB_STATE_BAD_INPUT = 4      /* NaN/Inf input or degenerate surface normal; outputs zero */
+  QLB_STATE_BAD_INPUT = 4,     /* NaN/Inf input or degenerate surface normal; outputs zero */
+  QLB_STATE_INFEASIBLE = 5     /* a stance leg has a negative friction coefficient while F_min > 0: no force satisfies
+                                  mu n.f >= |t.f| and n.f >= F_min; outputs zero (QuadProg++ returns +inf, QuadProg++.cc:340-344) */
 } qlb_state_status;
 
 /* Batch statistics (device-side reduction; all-reduced over ranks by the caller, sum / max as noted). */
@@ -121,11 +125,12 @@ typedef struct qlb_stats {
   double sum_iterations;     /* sum */
   double sum_wrench_err;     /* sum of sqrt((Ax-b)' S (Ax-b)) */
   double active_hist[20];    /* sum: how often each (leg,row) was active */
+  double count_infeasible;   /* sum: states with QLB_STATE_INFEASIBLE */
   double max_wrench_err;     /* max */
   double max_iterations;     /* max */
 } qlb_stats;
-#define QLB_STATS_NUM_SUM 28 /* leading doubles that all-reduce with SUM; the rest with MAX */
-#define QLB_STATS_NUM 30
+#define QLB_STATS_NUM_SUM 29 /* leading doubles that all-reduce with SUM; the rest with MAX */
+#define QLB_STATS_NUM 31
 
 typedef struct qlb_context qlb_context;
 

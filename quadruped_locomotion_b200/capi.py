@@ -16,11 +16,11 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QLB_LIB", os.path.join(PKG, "libqlb.so"))  # QLB_LIB: kernel-variant experiments only
 
 NUM_LEGS = 4
-STATS_NUM = 30
-STATS_NUM_SUM = 28
+STATS_NUM = 31
+STATS_NUM_SUM = 29
 FLAG_PARITY_MASK = 0x00FFFFFF
 PIPELINE_FUSED, PIPELINE_THREE_PASS = 0, 1
-STATUS_NAMES = ("ok", "no_stance", "max_iter", "unverified", "bad_input")
+STATUS_NAMES = ("ok", "no_stance", "max_iter", "unverified", "bad_input", "infeasible")
 
 
 class LegModel(C.Structure):
@@ -43,7 +43,7 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("count", C.c_double), ("count_status", C.c_double * 5), ("sum_iterations", C.c_double),
                 ("sum_wrench_err", C.c_double), ("active_hist", C.c_double * 20),
-                ("max_wrench_err", C.c_double), ("max_iterations", C.c_double)]
+                ("count_infeasible", C.c_double), ("max_wrench_err", C.c_double), ("max_iterations", C.c_double)]
 
 
 EXPORTS = (

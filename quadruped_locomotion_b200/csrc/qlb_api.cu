@@ -131,7 +131,7 @@ void build_device_params(const qlb_params* p, DeviceParams* d) {
   std::memset(d, 0, sizeof *d);
   for (int i = 0; i < 6; i++) d->S[i] = p->wrench_weights[i];
   d->W = p->ground_force_weight;
-  d->fmin = p->min_normal_force;
+  d->fmin = p->min_normal_force > 0.0 ? p->min_normal_force : 0.0;   // with mu > 0 the friction rows imply n.f >= 0
   d->mu_default = p->friction_default;
   d->gravity = p->gravity;
   d->tol = p->ipm_tolerance;
@@ -173,11 +173,17 @@ void narrow_params(const DeviceParams& d, DeviceParamsT<float>* f) {
   f->grav_pct = (float)d.grav_pct;
 }
 
+// The kernels seed reciprocals and reciprocal square roots from FP32 (qlb_device.cuh): weights, their inverses and
+// the pivots built from them must stay inside the FP32 normal range, so the weights are bounded here.
 bool params_ok(const qlb_params* p) {
-  if (!(p->ground_force_weight > 0.0) || !(p->ipm_tolerance > 0.0) || p->ipm_max_iterations < 1) return false;
+  const double lo = 1e-12, hi = 1e12;
+  if (!(p->ground_force_weight >= lo && p->ground_force_weight <= hi) || !(p->ipm_tolerance > 0.0) || p->ipm_max_iterations < 1)
+    return false;
   for (int i = 0; i < 6; i++)
-    if (!(p->wrench_weights[i] > 0.0)) return false;  // the 6x6 dual system needs S^-1
-  return std::isfinite(p->min_normal_force) && std::isfinite(p->friction_default) && std::isfinite(p->gravity);
+    if (!(p->wrench_weights[i] >= lo && p->wrench_weights[i] <= hi)) return false;  // the 6x6 dual system needs S^-1
+  if (!(p->friction_default >= 0.0) || !std::isfinite(p->friction_default)) return false;
+  if (!(std::fabs(p->min_normal_force) <= 1e9)) return false;
+  return std::isfinite(p->gravity);
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -186,6 +192,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 // compacted index lists.  Concurrent launches (the host pipeline's streams) never share a slot.
 template <typename T>
 int prepare_slot(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st) {
+  if (a.B > 0xFFFFFFF0ull) return QLB_ERR_BATCH_TOO_LARGE;
   const int slot = (int)(ctx->solve_calls++ % 8);
   ctx->last_slot = slot;
   // a ninth call in flight on yet another stream would reuse the slot of the first: order it behind that call
@@ -196,7 +203,6 @@ int prepare_slot(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st) {
   a.list_count = reinterpret_cast<unsigned*>(a.counter + 3);
   a.list2_count = reinterpret_cast<unsigned*>(a.counter + 4);
   QLB_CUDA(ctx, cudaMemsetAsync(a.counter, 0, 8 * sizeof(unsigned long long), st));
-  if (a.B > 0xFFFFFFF0ull) return QLB_ERR_BATCH_TOO_LARGE;
   if (ctx->list_cap[slot] < a.B) {  // grow the index lists of all slots at once (rare; synchronises)
     QLB_CUDA(ctx, cudaDeviceSynchronize());
     size_t cap = 1024;
@@ -592,10 +598,9 @@ template <typename T> struct HostRow { const T* h; int rows; };   // input array
 template <typename T> struct HostOut { T* h; int rows; };
 
 template <typename T>
-int run_host_pipeline(qlb_context* ctx, size_t B, bool state_mode, const HostRow<T>* in, int nin, const uint8_t* mask,
+int host_pipeline_chunks(qlb_context* ctx, size_t B, bool state_mode, const HostRow<T>* in, int nin, const uint8_t* mask,
                       const HostOut<T>* out, int nout, uint32_t* flags) {
-  int rc = ensure_capacity(ctx, B);
-  if (rc != QLB_OK) return rc;
+  int rc = QLB_OK;
   const size_t cap = ctx->cap;
   const size_t nchunks = (B + cap - 1) / cap;
   for (size_t ci = 0; ci < nchunks; ci++) {
@@ -638,8 +643,20 @@ int run_host_pipeline(qlb_context* ctx, size_t B, bool state_mode, const HostRow
                                         cudaMemcpyDeviceToHost, st));
     QLB_CUDA(ctx, cudaMemcpyAsync(flags + b0, dflags, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   }
-  for (int i = 0; i < kPipe; i++) QLB_CUDA(ctx, cudaStreamSynchronize(ctx->pipe[i]));
   return QLB_OK;
+}
+
+
+template <typename T>
+int run_host_pipeline(qlb_context* ctx, size_t B, bool state_mode, const HostRow<T>* in, int nin, const uint8_t* mask,
+                      const HostOut<T>* out, int nout, uint32_t* flags) {
+  int rc = ensure_capacity(ctx, B);
+  if (rc != QLB_OK) return rc;
+  rc = host_pipeline_chunks<T>(ctx, B, state_mode, in, nin, mask, out, nout, flags);
+  // also on failure: no copy may still be reading or writing the caller's buffers when the call returns
+  for (int i = 0; i < kPipe; i++)
+    if (cudaStreamSynchronize(ctx->pipe[i]) != cudaSuccess && rc == QLB_OK) rc = cuda_fail(ctx, cudaGetLastError(), "cudaStreamSynchronize");
+  return rc;
 }
 
 template <typename T>
@@ -846,7 +863,7 @@ int qlb_swing_leg_torques_host(qlb_context* ctx, size_t B, const double* q, cons
                                       cudaMemcpyHostToDevice, ctx->stream));
     }
     rc = qlb_swing_leg_torques(ctx, n, dptr[0], dptr[1], dptr[2], dptr[3], dptr[4], params, ctx->d_out, ctx->stream);
-    if (rc != QLB_OK) return rc;
+    if (rc != QLB_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
     QLB_CUDA(ctx, cudaMemcpy2DAsync(tau + b0, B * sizeof(double), ctx->d_out, n * sizeof(double), n * sizeof(double), 12,
                                     cudaMemcpyDeviceToHost, ctx->stream));
     QLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(256) qlb_stats_kernel(unsigned long long B, co
   if (threadIdx.x < QLB_STATS_NUM) sh[threadIdx.x] = 0.0;
   __syncthreads();
   double loc_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // count, status[5], iters, err
+  double loc_inf = 0.0;
   double max_err = 0.0, max_it = 0.0;
   unsigned hist_local[20];
 #pragma unroll
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(256) qlb_stats_kernel(unsigned long long B, co
     const double it = (double)(f >> QLB_FLAG_ITER_SHIFT);
     loc_sum[0] += 1.0;
     if (st < 5) loc_sum[1 + st] += 1.0;
+    if (st == 5) loc_inf += 1.0;
     loc_sum[6] += it;
     max_it = fmax(max_it, it);
     const unsigned act = (f & QLB_FLAG_ACTIVE_MASK) >> QLB_FLAG_ACTIVE_SHIFT;
@@ -208,8 +210,9 @@ __global__ void __launch_bounds__(256) qlb_stats_kernel(unsigned long long B, co
 #pragma unroll
   for (int k = 0; k < 20; k++) atomicAdd(&sh[8 + k], (double)hist_local[k]);
   // max via atomicMax on the bit pattern (values are non-negative)
-  atomicMax(reinterpret_cast<unsigned long long*>(&sh[28]), (unsigned long long)__double_as_longlong(max_err));
-  atomicMax(reinterpret_cast<unsigned long long*>(&sh[29]), (unsigned long long)__double_as_longlong(max_it));
+  atomicAdd(&sh[28], loc_inf);
+  atomicMax(reinterpret_cast<unsigned long long*>(&sh[29]), (unsigned long long)__double_as_longlong(max_err));
+  atomicMax(reinterpret_cast<unsigned long long*>(&sh[30]), (unsigned long long)__double_as_longlong(max_it));
   __syncthreads();
   if (threadIdx.x < QLB_STATS_NUM_SUM) atomicAdd(&out[threadIdx.x], sh[threadIdx.x]);
   else if (threadIdx.x < QLB_STATS_NUM)

@@ -175,7 +175,7 @@ struct LegSetup {
   float gscale, rm;  // scale of the linear term; 1 / number of constraint rows
   unsigned mask;
   int ns;
-  bool alive, qbad;
+  bool alive, qbad, qinf;   // qinf: a stance leg has mu < 0 (no feasible force while F_min > 0)
 };
 
 #ifndef QLB_SMEM_MODEL
@@ -301,7 +301,8 @@ __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const Devi
     const int ns = __popc(mask);
     L.alive = alive; L.ns = ns;
     real qj[3] = {in.qj[0], in.qj[1], in.qj[2]};
-    bool bad = !(isfinite(qj[0]) && isfinite(qj[1]) && isfinite(qj[2]));
+    // joint angles beyond 1e6 rad are outside the range of the argument reduction (and NaN / Inf fail the comparison)
+    bool bad = !(fabs(qj[0]) <= real(1e6) && fabs(qj[1]) <= real(1e6) && fabs(qj[2]) <= real(1e6));
     real quat[4];
     real (&b)[6] = L.b;
     if (MODE == 1) {
@@ -398,6 +399,7 @@ __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const Devi
       }
     }
     L.qbad = quad_or(bad ? 1u : 0u) != 0u;
+    L.qinf = quad_or((alive && mu < real(0.0)) ? 1u : 0u) != 0u;
 
     // ---------------- leg forward kinematics, Jacobian, gravity torques (QK.cpp:143-278,485-552)
     real foot[3], J[3][3], gtau[3];  // J[j] = column j
@@ -510,7 +512,7 @@ __device__ __forceinline__ void widen_setup(const LegSetup<real>& s, LegSetup<cr
 #pragma unroll
   for (int r = 0; r < 6; r++) d.b[r] = (creal)s.b[r];
   d.mu = (creal)s.mu; d.c0 = (creal)s.c0;
-  d.gscale = s.gscale; d.rm = s.rm; d.mask = s.mask; d.ns = s.ns; d.alive = s.alive; d.qbad = s.qbad;
+  d.gscale = s.gscale; d.rm = s.rm; d.mask = s.mask; d.ns = s.ns; d.alive = s.alive; d.qbad = s.qbad; d.qinf = s.qinf;
 }
 
 // Forces in base frame, joint torques, net wrench, flags word of one finished state.
@@ -576,7 +578,7 @@ __device__ __forceinline__ void quad_first_solve(const LegSetup<creal>& L, const
                                                  unsigned& pat_out) {
   const bool alive = L.alive;
   const creal (&At)[3][6] = L.At;
-  status = L.qbad ? 4 : (L.ns == 0 ? 1 : 0);
+  status = L.qbad ? 4 : (L.ns == 0 ? 1 : (L.qinf ? 5 : 0));
   y[0] = y[1] = y[2] = creal(0.0);
   hard = false;
   // unconstrained minimiser through the 6x6 system: (S^-1 + A~ A~'/w) t = b,  y = A~' t / w
@@ -821,6 +823,7 @@ __device__ __forceinline__ void quad_solve(const LegSetup<creal>& L, const CoreC
   if (!enable) { mode = kModeDone; }
   else if (qbad) { mode = kModeDone; status = 4; }
   else if (ns == 0) { mode = kModeDone; status = 1; }
+  else if (L.qinf) { mode = kModeDone; status = 5; }
   else if (STAGE == 2) { mode = kModeIpm; first = false; need_start = true; }
   else if (STAGE == 1) {
     // the first pass already repaired the empty pattern once: start from its result (bit 0: y_n pinned;

@@ -37,4 +37,4 @@ def stats_dict(s) -> dict:
     n = max(s[0], 1.0)
     return dict(count=s[0], ok=s[1], no_stance=s[2], max_iter=s[3], unverified=s[4], bad_input=s[5],
                 mean_iterations=s[6] / n, mean_wrench_err=s[7] / n, active_hist=s[8:28],
-                max_wrench_err=s[28], max_iterations=s[29])
+                infeasible=s[28], max_wrench_err=s[29], max_iterations=s[30])

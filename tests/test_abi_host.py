@@ -102,7 +102,7 @@ def _gloo_worker(rank, world, port, q):
     stats[1] = float((((r["flags"] >> 24) & 7) == 0).sum())
     err = np.sqrt((np.array([1, 5, 1, 10, 10, 5.])[:, None] * (r["netwrench"] - st["wrench"]) ** 2).sum(0))
     stats[7] = float(err.sum())
-    stats[28] = float(err.max())
+    stats[29] = float(err.max())
     qdist.allreduce_stats(stats)
     if rank == 0:
         q.put(stats.numpy().copy())

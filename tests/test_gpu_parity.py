@@ -257,8 +257,8 @@ def test_device_pointer_api_and_stream(solver, oracle, models):
     s = solver.batch_stats(flags, d["wrench"], net)
     assert s[0] == B and s[1] == ((out["flags"] >> 24) & 7 == 0).sum()
     err = np.sqrt((np.array([1, 5, 1, 10, 10, 5.])[:, None] * (out["netwrench"] - st["wrench"]) ** 2).sum(0))
-    assert abs(s[7] - err.sum()) <= 1e-9 * err.sum() and abs(s[28] - err.max()) <= 1e-12 * err.max()
-    assert s[6] == (out["flags"] >> 27).sum() and s[29] == (out["flags"] >> 27).max()
+    assert abs(s[7] - err.sum()) <= 1e-9 * err.sum() and abs(s[29] - err.max()) <= 1e-12 * err.max()
+    assert s[6] == (out["flags"] >> 27).sum() and s[30] == (out["flags"] >> 27).max()
     for leg in range(4):
         for r in range(5):
             assert s[8 + 5 * leg + r] == ((out["flags"] >> (4 + 5 * leg + r)) & 1).sum()

@@ -46,7 +46,7 @@ def main():
     print("flag mismatches:", int(fm.sum()), "of", args.batch)
     stt = (out["flags"] >> 24) & 7
     it = out["flags"] >> 27
-    print("status hist", np.bincount(stt, minlength=5), "iters hist", np.bincount(it))
+    print("status hist", np.bincount(stt, minlength=6), "iters hist", np.bincount(it))
     if args.f32:
         for thr in (1e-2, 1e-3, 1e-4):
             ok = ref["margin"] > thr
@@ -80,7 +80,7 @@ def main():
     ms = ev0.elapsed_time(ev1) / reps
     print("device-resident: %.3f ms per %d QPs -> %.3e QP/s" % (ms, Bt, Bt / ms * 1e3))
     s = sol.batch_stats(flags, d["wrench"].double(), net.double(), stream=stream)
-    print("stats: count %d status %s mean it %.3f mean err %.4f max err %.4f" % (s[0], s[1:6], s[6] / s[0], s[7] / s[0], s[28]))
+    print("stats: count %d status %s mean it %.3f mean err %.4f max err %.4f" % (s[0], s[1:6], s[6] / s[0], s[7] / s[0], s[29]))
 
 
 if __name__ == "__main__":
