@@ -231,8 +231,9 @@ int qlb_solve_state_f32_host(qlb_context* ctx, size_t B, const float* q, const f
 /* Kernel organisation of the solve entry points (the results are the same optimum either way):
  *   QLB_PIPELINE_FUSED (default): one persistent kernel - inputs staged through shared memory by the TMA unit,
  *     kinematics + QP data + unconstrained minimiser per state, the states that need active-set rounds parked in
- *     shared memory and solved by a dual block active-set method in the same kernel - followed by the
- *     interior-point kernel for states the rounds could not verify (normally none).
+ *     shared memory and solved by a dual block active-set method in the same kernel (every quad of a warp refills
+ *     itself from the stash) - followed by the interior-point kernel for states the rounds could not verify
+ *     (normally none).
  *   QLB_PIPELINE_THREE_PASS: the round-1 organisation (first / active-set / interior-point kernels over
  *     compacted index lists in HBM).  Always used by the FP32 solver core. */
 #define QLB_PIPELINE_FUSED 0
@@ -334,10 +335,62 @@ int qlb_qp_dense_host(qlb_context* ctx, size_t B, int n, int m, int p, const dou
                       const double* CE, const double* ce0, const double* CI, const double* ci0, double* x,
                       double* cost, uint32_t* status, uint32_t* active);
 
+/* ---- array-of-structs face of the wrench-mode solve ------------------------------------------------------
+ * One robot state as ContactForceDistribution::computeForceDistribution consumes it (the State accessors of
+ * free_gait_core/src/executor/State.cpp:59-235 plus the Force / Torque arguments), and its result (LegInfo::
+ * desiredContactForce_ = -grf, State::getAllJointEfforts, getNetForceAndTorqueOnBase).  Fixed layouts, 8-byte
+ * aligned.  A host caller moves one contiguous block per direction over PCIe; the transposition to the solver's
+ * SoA arrays is a device kernel. */
+typedef struct qlb_wrench_record {
+  double q[12];           /* LF, RF, RH, LH x (HAA, HFE, KFE) */
+  double quat_wxyz[4];
+  double wrench[6];       /* desired net force (3) and torque (3) on the base, base frame */
+  double mu[4];           /* friction coefficient per leg */
+  uint8_t stance_mask;    /* bit k = leg k is a support leg */
+  uint8_t reserved[7];
+} qlb_wrench_record;      /* 216 bytes */
+typedef struct qlb_result_record {
+  double grf[12];
+  double tau[12];
+  double netwrench[6];
+  uint32_t flags;
+  uint32_t reserved;
+} qlb_result_record;      /* 248 bytes */
+
+/* DEVICE pointers, asynchronous on `stream`: unpack -> qlb_solve_wrench -> pack, in chunks that reuse the
+ * context's staging buffers.  Surface normals are the default (0, 0, 1). */
+int qlb_solve_records(qlb_context* ctx, size_t B, const qlb_wrench_record* records, qlb_result_record* results,
+                      void* stream);
+/* HOST pointers (pinned memory recommended): chunks flow through the context's copy / compute pipeline with one
+ * 1-D copy per chunk and direction; synchronises. */
+int qlb_solve_records_host(qlb_context* ctx, size_t B, const qlb_wrench_record* records,
+                           qlb_result_record* results);
+
+/* Synthetic robot states on the device (DEVICE pointers, asynchronous on `stream`): the counter-based generator of
+ * SURVEY.md 8d, BIT-IDENTICAL to the host generator (quadruped_locomotion_b200/synth.py: splitmix64 streams, elementary
+ * functions from IEEE-exact operations), so a sweep of perturbed states - the batch-of-states consumer shape of
+ * free_gait_core/src/executor/BatchExecutor.cpp:40-83 and BASELINE config C5 - needs no input staging from the host.
+ *   config 1..5 = BASELINE configs C1..C5 (4 = the C3 states); states start .. start + B - 1 of the stream;
+ *   seed 0 = the config's default seed (0x5EED0000 + config).  Any output may be NULL.
+ * The _f32 twin rounds each value to float on store (what the host generator's .astype(float32) gives). */
+int qlb_generate_states(qlb_context* ctx, int config, size_t B, uint64_t start, uint64_t seed, double* q,
+                        double* quat_wxyz, double* wrench, uint8_t* stance_mask, double* mu,
+                        double* normals_world, void* stream);
+int qlb_generate_states_f32(qlb_context* ctx, int config, size_t B, uint64_t start, uint64_t seed, float* q,
+                            float* quat_wxyz, float* wrench, uint8_t* stance_mask, float* mu,
+                            float* normals_world, void* stream);
+
 /* Device-side statistics over a solved batch (DEVICE pointers; stats_out is a HOST pointer,
  * the call synchronises the stream).  wrench/netwrench may be NULL (error terms then zero). */
 int qlb_batch_stats(qlb_context* ctx, size_t B, const uint32_t* flags, const double* wrench,
                     const double* netwrench, qlb_stats* stats_out, void* stream);
+
+/* The one collective of the design: all-reduce *stats over the ranks of an NCCL communicator - the
+ * leading QLB_STATS_NUM_SUM doubles with SUM, the rest with MAX - on `stream`; synchronises.  nccl_comm is an
+ * ncclComm_t created by the caller (one rank per GPU); stats is a HOST pointer, reduced in place.  NCCL is resolved
+ * at run time (dlopen of libnccl.so.2), so linking against libqlb.so does not need NCCL.  No data-path traffic
+ * crosses GPUs: instances are sharded, only these 31 numbers are exchanged. */
+int qlb_stats_allreduce(qlb_context* ctx, void* nccl_comm, qlb_stats* stats, void* stream);
 
 /* Measure the FP64 FMA throughput of the context's device (TFLOP/s, best of 4 runs of a register-only
  * DFMA kernel): the denominator of the FP64-pipe roofline this path is bound by.  Synchronous. */

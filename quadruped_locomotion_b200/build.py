@@ -12,7 +12,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libqlb.so")
 SOURCES = ["qlb_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "--fmad=true"]
+              "-Xcompiler", "-fPIC", "-shared", "--fmad=true", "-ldl"]
 
 
 def _stale() -> bool:

@@ -51,7 +51,7 @@ EXPORTS = (
     "qlb_solve_wrench", "qlb_solve_wrench_host", "qlb_solve_state", "qlb_solve_state_host",
     "qlb_solve_wrench_f32", "qlb_solve_wrench_f32_host", "qlb_solve_state_f32", "qlb_solve_state_f32_host",
     "qlb_default_swing_params", "qlb_set_limb_dynamics", "qlb_swing_leg_torques", "qlb_swing_leg_torques_host",
-    "qlb_set_f32_core", "qlb_set_pipeline", "qlb_leg_kinematics", "qlb_pack_robot_states", "qlb_feet_in_world", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
+    "qlb_set_f32_core", "qlb_set_pipeline", "qlb_generate_states", "qlb_generate_states_f32", "qlb_solve_records", "qlb_solve_records_host", "qlb_stats_allreduce", "qlb_leg_kinematics", "qlb_pack_robot_states", "qlb_feet_in_world", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
     "qlb_last_cuda_error", "qlb_abi_version",
 )
 
@@ -70,6 +70,23 @@ RECORD_DTYPE = np.dtype([("base_position", "<f8", 3), ("base_orientation_xyzw", 
                          ("joint_position", "<f8", 12), ("surface_normal", "<f8", 12),
                          ("support_leg", "u1", 4), ("reserved", "u1", 4)])
 assert RECORD_DTYPE.itemsize == 304
+
+# numpy mirrors of qlb_wrench_record / qlb_result_record (include/qlb.h)
+WRENCH_RECORD_DTYPE = np.dtype([("q", "<f8", 12), ("quat_wxyz", "<f8", 4), ("wrench", "<f8", 6), ("mu", "<f8", 4),
+                                ("stance_mask", "u1"), ("reserved", "u1", 7)])
+RESULT_RECORD_DTYPE = np.dtype([("grf", "<f8", 12), ("tau", "<f8", 12), ("netwrench", "<f8", 6), ("flags", "<u4"),
+                                ("reserved", "<u4")])
+assert WRENCH_RECORD_DTYPE.itemsize == 216 and RESULT_RECORD_DTYPE.itemsize == 248
+
+
+def wrench_records(states: dict) -> np.ndarray:
+    """SoA state dict (synth.make_states) -> array of qlb_wrench_record."""
+    B = states["q"].shape[1]
+    rec = np.zeros(B, dtype=WRENCH_RECORD_DTYPE)
+    rec["q"] = states["q"].T; rec["quat_wxyz"] = states["quat"].T; rec["wrench"] = states["wrench"].T
+    rec["mu"] = states["mu"].T; rec["stance_mask"] = states["mask"]
+    return rec
+
 
 _lib = None
 _vp = C.c_void_p
@@ -99,6 +116,11 @@ def load() -> C.CDLL:
     lib.qlb_solve_state_f32_host.argtypes = [_vp, C.c_size_t] + [_vp] * 13
     lib.qlb_set_f32_core.argtypes = [_vp, C.c_int]
     lib.qlb_set_pipeline.argtypes = [_vp, C.c_int]
+    lib.qlb_stats_allreduce.argtypes = [_vp, _vp, C.POINTER(Stats), _vp]
+    lib.qlb_solve_records.argtypes = [_vp, C.c_size_t, _vp, _vp, _vp]
+    lib.qlb_solve_records_host.argtypes = [_vp, C.c_size_t, _vp, _vp]
+    lib.qlb_generate_states.argtypes = [_vp, C.c_int, C.c_size_t, C.c_uint64, C.c_uint64] + [_vp] * 7
+    lib.qlb_generate_states_f32.argtypes = [_vp, C.c_int, C.c_size_t, C.c_uint64, C.c_uint64] + [_vp] * 7
     lib.qlb_pack_robot_states.argtypes = [_vp, C.c_size_t] + [_vp] * 7
     lib.qlb_feet_in_world.argtypes = [_vp, C.c_size_t] + [_vp] * 4
     lib.qlb_default_swing_params.argtypes = [C.POINTER(SwingParams)]
@@ -205,9 +227,21 @@ class Solver:
         """Solver core of the _f32 entry points: FP64 (default; FP32 interface only) or FP32."""
         self._check(self.lib.qlb_set_f32_core(self._ctx, 1 if fp64_core else 0), "qlb_set_f32_core")
 
-    def set_pipeline(self, fused: bool):
-        """Kernel organisation: the fused persistent kernel (default) or the three-pass pipeline."""
-        self._check(self.lib.qlb_set_pipeline(self._ctx, PIPELINE_FUSED if fused else PIPELINE_THREE_PASS), "qlb_set_pipeline")
+    def set_pipeline(self, which: str):
+        """Kernel organisation: "fused" (one persistent kernel, default) or "three_pass" (the round-1 kernels)."""
+        code = {"fused": PIPELINE_FUSED, "three_pass": PIPELINE_THREE_PASS}[which]
+        self._check(self.lib.qlb_set_pipeline(self._ctx, code), "qlb_set_pipeline")
+
+    def generate_states(self, config: str, B: int, start: int = 0, seed: int = 0, q=None, quat=None, wrench=None, mask=None,
+                        mu=None, normals=None, stream=None):
+        """Fill CUDA tensors (SoA [C, B]; float64, or float32 for the _f32 twin) with the synthetic states of a
+        BASELINE config - the device twin of synth.make_states, bit-identical to it."""
+        cid = {"C1": 1, "C2": 2, "C3": 3, "C4": 4, "C5": 5}[config.upper()]
+        ref = next(t for t in (q, quat, wrench, mu, normals) if t is not None)
+        fn = self.lib.qlb_generate_states_f32 if _is_f32(ref) else self.lib.qlb_generate_states
+        rc = fn(self._ctx, cid, B, int(start), int(seed), _ptr(q), _ptr(quat), _ptr(wrench), _ptr(mask), _ptr(mu), _ptr(normals),
+                stream if stream is not None else None)
+        self._check(rc, "qlb_generate_states")
 
     def get_params(self) -> Params:
         p = Params()
@@ -308,6 +342,18 @@ class Solver:
                 _ptr(ttwist), _ptr(mask), _ptr(mu), _ptr(normals), _ptr(grf), _ptr(tau),
                 _ptr(flags), _ptr(netwrench), _ptr(wrench_out))
         self._check(rc, "qlb_solve_state_host")
+
+    def solve_records_host(self, records, results):
+        """records: B qlb_wrench_record (numpy structured array or pinned torch uint8 tensor), results: B
+        qlb_result_record, both HOST memory."""
+        B = (records.shape[0] if isinstance(records, np.ndarray) else records.numel() // WRENCH_RECORD_DTYPE.itemsize)
+        self._check(self.lib.qlb_solve_records_host(self._ctx, B, _ptr(records), _ptr(results)), "qlb_solve_records_host")
+
+    def solve_records(self, records, results, stream=None):
+        """DEVICE uint8 tensors holding B qlb_wrench_record / B qlb_result_record."""
+        B = records.numel() // WRENCH_RECORD_DTYPE.itemsize
+        self._check(self.lib.qlb_solve_records(self._ctx, B, _ptr(records), _ptr(results), stream if stream is not None else None),
+                    "qlb_solve_records")
 
     def qp_dense_numpy(self, G, g0, CI=None, ci0=None, CE=None, ce0=None) -> dict:
         """Batched generic QP through the host entry point.  G[B,n,n], g0[B,n], CI[B,n,m], ci0[B,m],

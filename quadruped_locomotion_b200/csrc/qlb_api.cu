@@ -1,6 +1,8 @@
 // qlb_api.cu - the C ABI declared in include/qlb.h: context management and kernel launches.
 // No CPU fallback lives here: every compute entry point launches sm_100a kernels or returns an error.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <cmath>
 #include <cstdio>
@@ -10,10 +12,13 @@
 
 #include "qlb.h"
 #include "qlb_aux.cuh"
+#include "qlb_gen.cuh"
 #include "qlb_qp_dense.cuh"
+#include "qlb_records.cuh"
 #include "qlb_solve.cuh"
 #include "qlb_solve_quad.cuh"
 #include "qlb_solve_fused.cuh"
+#include "qlb_solve_single.cuh"
 #include "qlb_swing.cuh"
 
 using namespace qlb;
@@ -41,7 +46,7 @@ struct qlb_context {
   int blocks_per_sm_quad_m[2] = {0, 0};   // FP32 interface + FP64 solver core
   int blocks_per_sm_first_m[2] = {0, 0};
   int pipeline = QLB_PIPELINE_FUSED;   // qlb_set_pipeline
-  int blocks_per_sm_fused[2][2][2] = {};   // [interface type: 0 double, 1 float][MODE][TMA]
+  int blocks_per_sm_single[2][2][2] = {};   // [interface type: 0 double, 1 float][MODE][TMA]
   bool use_tma = true;    // fused pipeline: stage the inputs with the TMA unit when the arrays allow it
   bool f32_pure = false;  // qlb_set_f32_core: FP32 solver core with in-kernel FP64 rescue, or FP64 core for every state
   unsigned long long* d_counter = nullptr;
@@ -58,6 +63,8 @@ struct qlb_context {
   double* d_out = nullptr;
   uint8_t* d_mask = nullptr;
   uint32_t* d_flags = nullptr;
+  unsigned char* d_rec = nullptr;   // record staging of qlb_solve_records_host: kPipe x cap x (216 + 248) bytes
+  size_t rec_cap = 0;
   size_t cap = 0;
   uint64_t launches = 0;
   char last_error[256] = {0};
@@ -193,9 +200,15 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 template <typename T>
 int prepare_slot(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st) {
   if (a.B > 0xFFFFFFF0ull) return QLB_ERR_BATCH_TOO_LARGE;
-  const int slot = (int)(ctx->solve_calls++ % 8);
+  // the lowest slot whose previous call has finished (so that a serial caller keeps using one set of buffers); if all
+  // eight are busy, round robin: the call is ordered behind the previous user of its slot
+  int slot = -1;
+  for (int i = 0; i < 8 && slot < 0; i++)
+    if (cudaEventQuery(ctx->slot_done[i]) == cudaSuccess) slot = i;
+  cudaGetLastError();
+  if (slot < 0) slot = (int)(ctx->solve_calls % 8);
+  ctx->solve_calls++;
   ctx->last_slot = slot;
-  // a ninth call in flight on yet another stream would reuse the slot of the first: order it behind that call
   QLB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->slot_done[slot], 0));
   a.counter = ctx->d_counter + 8 * slot;
   a.counter2 = a.counter + 1;
@@ -264,28 +277,29 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// Tensor map of one SoA input array [rows][B]: boxes of {8 states, rows}, out-of-range columns read as zero.
+// Tensor map of one SoA input array [rows][B]: boxes of {8 QLB_SUPER states, rows}, out-of-range columns read as zero.
 template <typename T>
 bool make_map(CUtensorMap* m, const T* ptr, unsigned long long B, int rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   const cuuint64_t gdim[2] = {(cuuint64_t)B, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)B * sizeof(T)};
-  const cuuint32_t box[2] = {8u, (cuuint32_t)rows};
+  const cuuint32_t box[2] = {8u * QLB_SUPER, (cuuint32_t)rows};
   const cuuint32_t estr[2] = {1u, 1u};
   return fn(m, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<T*>(ptr), gdim,
             gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// the fused kernel (qlb_solve_single.cuh) + the interior-point kernel for the states its rounds could not verify
+// (normally none: it finds an empty list and returns)
 template <typename T, typename C, int MODE>
-int launch_fused(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int bps_ipm) {
-  using SG = Staging<T, MODE>;
-  using FL = FusedLayout<T, C, MODE>;
-  const T* src[7];
-  if (MODE == 1) { src[0] = a.q; src[1] = a.pose; src[2] = a.twist; src[3] = a.tpose; src[4] = a.ttwist; src[5] = a.mu; src[6] = a.normals; }
-  else { src[0] = a.q; src[1] = a.quat; src[2] = a.wrench; src[3] = a.mu; src[4] = a.normals; src[5] = nullptr; src[6] = nullptr; }
-  // TMA needs 16-byte aligned rows (base pointers and the row pitch B * sizeof(T)) and 32-bit coordinates
+int launch_single(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int bps_ipm) {
+  using SG = Staging<T, MODE, QLB_SUPER>;
+  using FL = FusedLayout<T, C, MODE, QLB_SUPER>;
+  const T* src[6];
+  if (MODE == 1) { src[0] = a.q; src[1] = a.pose; src[2] = a.twist; src[3] = a.tpose; src[4] = a.ttwist; src[5] = a.mu; }
+  else { src[0] = a.q; src[1] = a.quat; src[2] = a.wrench; src[3] = a.mu; src[4] = nullptr; src[5] = nullptr; }
   bool tma = ctx->use_tma && a.B >= 64 && a.B < 0x7fffff00ull && ((a.B * sizeof(T)) % 16 == 0);
   for (int s = 0; s < SG::kNumSeg && tma; s++)
     if (src[s] && !aligned16(src[s])) tma = false;
@@ -295,11 +309,11 @@ int launch_fused(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int 
     if (src[s] && !make_map<T>(&maps.seg[s], src[s], a.B, SG::rows(s))) tma = false;
   const unsigned long long ntiles = (a.B + 7) / 8;
   const unsigned long long want = (ntiles + 3) / 4;
-  const int bps = ctx->blocks_per_sm_fused[sizeof(T) == 4 ? 1 : 0][MODE][tma ? 1 : 0];
+  const int bps = ctx->blocks_per_sm_single[sizeof(T) == 4 ? 1 : 0][MODE][tma ? 1 : 0];
   const unsigned long long cap = (unsigned long long)ctx->sm_count * bps;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  if (tma) qlb_fused_kernel<T, C, MODE, true><<<grid, kQuadThreads, FL::kTotal, st>>>(a, maps);
-  else qlb_fused_kernel<T, C, MODE, false><<<grid, kQuadThreads, FL::kTotal, st>>>(a, maps);
+  if (tma) qlb_single_kernel<T, C, MODE, QLB_SUPER, true><<<grid, kQuadThreads, FL::kTotal, st>>>(a, maps);
+  else qlb_single_kernel<T, C, MODE, QLB_SUPER, false><<<grid, kQuadThreads, FL::kTotal, st>>>(a, maps);
   QLB_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
   const unsigned long long capq = (unsigned long long)ctx->sm_count * bps_ipm;
@@ -311,16 +325,16 @@ int launch_fused(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int 
 }
 
 template <typename T, typename C, int MODE>
-bool prepare_fused_kernels(qlb_context* ctx) {
-  using FL = FusedLayout<T, C, MODE>;
-  int* out = ctx->blocks_per_sm_fused[sizeof(T) == 4 ? 1 : 0][MODE];
-  if (cudaFuncSetAttribute(qlb_fused_kernel<T, C, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FL::kTotal) != cudaSuccess ||
-      cudaFuncSetAttribute(qlb_fused_kernel<T, C, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FL::kTotal) != cudaSuccess ||
-      cudaFuncSetAttribute(qlb_fused_kernel<T, C, MODE, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
-      cudaFuncSetAttribute(qlb_fused_kernel<T, C, MODE, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+bool prepare_single_kernels(qlb_context* ctx) {
+  using FL = FusedLayout<T, C, MODE, QLB_SUPER>;
+  int* out = ctx->blocks_per_sm_single[sizeof(T) == 4 ? 1 : 0][MODE];
+  if (cudaFuncSetAttribute(qlb_single_kernel<T, C, MODE, QLB_SUPER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FL::kTotal) != cudaSuccess ||
+      cudaFuncSetAttribute(qlb_single_kernel<T, C, MODE, QLB_SUPER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FL::kTotal) != cudaSuccess ||
+      cudaFuncSetAttribute(qlb_single_kernel<T, C, MODE, QLB_SUPER, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+      cudaFuncSetAttribute(qlb_single_kernel<T, C, MODE, QLB_SUPER, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
     return false;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out[0], qlb_fused_kernel<T, C, MODE, false>, kQuadThreads, FL::kTotal) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out[1], qlb_fused_kernel<T, C, MODE, true>, kQuadThreads, FL::kTotal) != cudaSuccess)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out[0], qlb_single_kernel<T, C, MODE, QLB_SUPER, false>, kQuadThreads, FL::kTotal) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out[1], qlb_single_kernel<T, C, MODE, QLB_SUPER, true>, kQuadThreads, FL::kTotal) != cudaSuccess)
     return false;
   return out[0] >= 1 && out[1] >= 1;
 }
@@ -329,7 +343,7 @@ template <int MODE>
 int launch_solve(qlb_context* ctx, SolveArgs& a, cudaStream_t st) {
   const int rc = prepare_slot(ctx, a, st);
   if (rc != QLB_OK) return rc;
-  if (ctx->pipeline == QLB_PIPELINE_FUSED) return launch_fused<double, double, MODE>(ctx, a, st, ctx->blocks_per_sm_quad[MODE]);
+  if (ctx->pipeline == QLB_PIPELINE_FUSED) return launch_single<double, double, MODE>(ctx, a, st, ctx->blocks_per_sm_quad[MODE]);
   return launch_quad<double, double, MODE>(ctx, a, st, ctx->blocks_per_sm_first[MODE], ctx->blocks_per_sm_quad[MODE]);
 }
 
@@ -339,7 +353,7 @@ int launch_solve_f32(qlb_context* ctx, SolveArgsT<float>& a, cudaStream_t st) {
   const int rc = prepare_slot(ctx, a, st);
   if (rc != QLB_OK) return rc;
   if (ctx->f32_pure) return launch_quad<float, float, MODE>(ctx, a, st, ctx->blocks_per_sm_first_f[MODE], ctx->blocks_per_sm_quad_f[MODE]);
-  if (ctx->pipeline == QLB_PIPELINE_FUSED) return launch_fused<float, double, MODE>(ctx, a, st, ctx->blocks_per_sm_quad_m[MODE]);
+  if (ctx->pipeline == QLB_PIPELINE_FUSED) return launch_single<float, double, MODE>(ctx, a, st, ctx->blocks_per_sm_quad_m[MODE]);
   return launch_quad<float, double, MODE>(ctx, a, st, ctx->blocks_per_sm_first_m[MODE], ctx->blocks_per_sm_quad_m[MODE]);
 }
 
@@ -472,13 +486,14 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first_m[0], qlb_quad_first_kernel<float, double, 0>, kQuadThreads, 0) != cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->blocks_per_sm_first_m[1], qlb_quad_first_kernel<float, double, 1>, kQuadThreads, 0) != cudaSuccess)
     return fail(QLB_ERR_CUDA);
-  if (!prepare_fused_kernels<double, double, 0>(ctx) || !prepare_fused_kernels<double, double, 1>(ctx) ||
-      !prepare_fused_kernels<float, double, 0>(ctx) || !prepare_fused_kernels<float, double, 1>(ctx)) {
+  if (!prepare_single_kernels<double, double, 0>(ctx) || !prepare_single_kernels<double, double, 1>(ctx) ||
+      !prepare_single_kernels<float, double, 0>(ctx) || !prepare_single_kernels<float, double, 1>(ctx)) {
     cudaGetLastError();
     return fail(QLB_ERR_CUDA);
   }
   if (const char* e = std::getenv("QLB_PIPELINE")) {   // experiments: three_pass | fused | fused_notma
     if (!std::strcmp(e, "three_pass")) ctx->pipeline = QLB_PIPELINE_THREE_PASS;
+
     if (!std::strcmp(e, "fused_notma")) ctx->use_tma = false;
   }
   if (max_batch > 0 && ensure_capacity(ctx, max_batch) != QLB_OK) return fail(QLB_ERR_ALLOC);
@@ -494,7 +509,7 @@ int qlb_destroy(qlb_context* ctx) {
     if (ctx->pipe[i]) { cudaStreamSynchronize(ctx->pipe[i]); cudaStreamDestroy(ctx->pipe[i]); }
   cudaFree(ctx->d_model); cudaFree(ctx->d_params); cudaFree(ctx->d_counter); cudaFree(ctx->d_stats);
   cudaFree(ctx->d_model_f); cudaFree(ctx->d_params_f); cudaFree(ctx->d_limb);
-  cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags);
+  cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags); cudaFree(ctx->d_rec);
   for (int i = 0; i < 8; i++) cudaFree(ctx->d_list[i]);
   for (int i = 0; i < 8; i++)
     if (ctx->slot_done[i]) cudaEventDestroy(ctx->slot_done[i]);
@@ -871,6 +886,123 @@ int qlb_swing_leg_torques_host(qlb_context* ctx, size_t B, const double* q, cons
   return QLB_OK;
 }
 
+namespace {
+// one chunk of records on one stream: unpack, solve, pack (device pointers; `slot` selects the SoA staging area)
+int records_chunk(qlb_context* ctx, size_t n, const qlb_wrench_record* d_in, qlb_result_record* d_out, int slot, cudaStream_t st) {
+  const size_t cap = ctx->cap;
+  double* din = ctx->d_in + (size_t)slot * cap * kHostInRows;
+  double* dout = ctx->d_out + (size_t)slot * cap * kHostOutRows;
+  uint8_t* dmask = ctx->d_mask + (size_t)slot * cap;
+  uint32_t* dflags = ctx->d_flags + (size_t)slot * cap;
+  double* q = din; double* quat = din + 12 * cap; double* wrench = din + 16 * cap; double* mu = din + 22 * cap;
+  double* grf = dout; double* tau = dout + 12 * cap; double* net = dout + 24 * cap;
+  const unsigned blocks = (unsigned)((n + kRecTile - 1) / kRecTile);
+  // the SoA staging rows have pitch n inside this chunk
+  qlb_unpack_records_kernel<<<blocks, kRecTile, 0, st>>>(n, d_in, q, quat, wrench, mu, dmask);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  const int rc = solve_wrench_t<double>(ctx, n, q, quat, wrench, dmask, mu, nullptr, grf, tau, dflags, net, st);
+  if (rc != QLB_OK) return rc;
+  qlb_pack_results_kernel<<<blocks, kRecTile, 0, st>>>(n, grf, tau, net, dflags, d_out);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return QLB_OK;
+}
+
+int records_host_chunks(qlb_context* ctx, size_t B, const qlb_wrench_record* in, qlb_result_record* out) {
+  const size_t cap = ctx->cap;
+  const size_t nchunks = (B + cap - 1) / cap;
+  for (size_t ci = 0; ci < nchunks; ci++) {
+    const int slot = (int)(ci % kPipe);
+    cudaStream_t st = ctx->pipe[slot];
+    const size_t b0 = ci * cap, n = (B - b0 < cap) ? (B - b0) : cap;
+    unsigned char* base = ctx->d_rec + (size_t)slot * cap * (sizeof(qlb_wrench_record) + sizeof(qlb_result_record));
+    qlb_wrench_record* d_in = reinterpret_cast<qlb_wrench_record*>(base);
+    qlb_result_record* d_out = reinterpret_cast<qlb_result_record*>(base + cap * sizeof(qlb_wrench_record));
+    QLB_CUDA(ctx, cudaMemcpyAsync(d_in, in + b0, n * sizeof(qlb_wrench_record), cudaMemcpyHostToDevice, st));
+    const int rc = records_chunk(ctx, n, d_in, d_out, slot, st);
+    if (rc != QLB_OK) return rc;
+    QLB_CUDA(ctx, cudaMemcpyAsync(out + b0, d_out, n * sizeof(qlb_result_record), cudaMemcpyDeviceToHost, st));
+  }
+  return QLB_OK;
+}
+}  // namespace
+
+int qlb_solve_records(qlb_context* ctx, size_t B, const qlb_wrench_record* records, qlb_result_record* results, void* stream) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!records || !results) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  int rc = ensure_capacity(ctx, B);
+  if (rc != QLB_OK) return rc;
+  const size_t cap = ctx->cap;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // one staging area, chunks in stream order (the caller's arrays are already on the device: nothing to overlap)
+  for (size_t b0 = 0; b0 < B; b0 += cap) {
+    const size_t n = (B - b0 < cap) ? (B - b0) : cap;
+    rc = records_chunk(ctx, n, records + b0, results + b0, 0, st);
+    if (rc != QLB_OK) return rc;
+  }
+  return QLB_OK;
+}
+
+int qlb_solve_records_host(qlb_context* ctx, size_t B, const qlb_wrench_record* records, qlb_result_record* results) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!records || !results) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  int rc = ensure_capacity(ctx, B);
+  if (rc != QLB_OK) return rc;
+  if (ctx->rec_cap < ctx->cap) {
+    QLB_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(ctx->d_rec);
+    ctx->d_rec = nullptr; ctx->rec_cap = 0;
+    if (cudaMalloc(&ctx->d_rec, (size_t)kPipe * ctx->cap * (sizeof(qlb_wrench_record) + sizeof(qlb_result_record))) != cudaSuccess) {
+      cudaGetLastError();
+      return QLB_ERR_ALLOC;
+    }
+    ctx->rec_cap = ctx->cap;
+  }
+  rc = records_host_chunks(ctx, B, records, results);
+  for (int i = 0; i < kPipe; i++)
+    if (cudaStreamSynchronize(ctx->pipe[i]) != cudaSuccess && rc == QLB_OK) rc = cuda_fail(ctx, cudaGetLastError(), "cudaStreamSynchronize");
+  return rc;
+}
+
+namespace {
+int generate_common(qlb_context* ctx, int config, size_t B, uint64_t start, uint64_t seed, GenArgs& g, void* stream) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (config == 4) config = 3;   // C4 = the C3 states through the FP32 interface
+  if (config != 1 && config != 2 && config != 3 && config != 5) return QLB_ERR_INVALID_ARGUMENT;
+  if (B == 0) return QLB_OK;
+  DeviceGuard guard(ctx->device);
+  g.B = B; g.start = start; g.config = config;
+  g.seed = seed ? seed : (0x5EED0000ull + (unsigned long long)config);
+  const unsigned long long blocks = ((unsigned long long)B + 255) / 256;
+  if (blocks > 0x7fffffffull) return QLB_ERR_BATCH_TOO_LARGE;
+  qlb_generate_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(g);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return QLB_OK;
+}
+}  // namespace
+
+int qlb_generate_states(qlb_context* ctx, int config, size_t B, uint64_t start, uint64_t seed, double* q, double* quat_wxyz,
+                        double* wrench, uint8_t* stance_mask, double* mu, double* normals_world, void* stream) {
+  GenArgs g;
+  std::memset(&g, 0, sizeof g);
+  g.q = q; g.quat = quat_wxyz; g.wrench = wrench; g.mask = stance_mask; g.mu = mu; g.normals = normals_world;
+  return generate_common(ctx, config, B, start, seed, g, stream);
+}
+
+int qlb_generate_states_f32(qlb_context* ctx, int config, size_t B, uint64_t start, uint64_t seed, float* q, float* quat_wxyz,
+                            float* wrench, uint8_t* stance_mask, float* mu, float* normals_world, void* stream) {
+  GenArgs g;
+  std::memset(&g, 0, sizeof g);
+  g.q32 = q; g.quat32 = quat_wxyz; g.wrench32 = wrench; g.mask = stance_mask; g.mu32 = mu; g.normals32 = normals_world;
+  return generate_common(ctx, config, B, start, seed, g, stream);
+}
+
 int qlb_batch_stats(qlb_context* ctx, size_t B, const uint32_t* flags, const double* wrench, const double* netwrench,
                     qlb_stats* stats_out, void* stream) {
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
@@ -891,6 +1023,59 @@ int qlb_batch_stats(qlb_context* ctx, size_t B, const uint32_t* flags, const dou
   QLB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost, st));
   QLB_CUDA(ctx, cudaStreamSynchronize(st));
   std::memcpy(stats_out, h, sizeof h);
+  return QLB_OK;
+}
+
+// The one collective of the design: all-reduce of the statistics vector over the ranks of an NCCL
+// communicator.  NCCL is resolved at run time (dlopen of libnccl.so.2: the copy already loaded by the process - the
+// caller created `comm` with it - or the system library), so libqlb.so itself has no link-time dependency on it.
+namespace {
+struct NcclApi {
+  ncclResult_t (*all_reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*group_start)() = nullptr;
+  ncclResult_t (*group_end)() = nullptr;
+  bool ok = false;
+};
+const NcclApi& nccl_api() {
+  static NcclApi api = []() {
+    NcclApi a;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return a;
+    a.all_reduce = reinterpret_cast<decltype(a.all_reduce)>(dlsym(h, "ncclAllReduce"));
+    a.group_start = reinterpret_cast<decltype(a.group_start)>(dlsym(h, "ncclGroupStart"));
+    a.group_end = reinterpret_cast<decltype(a.group_end)>(dlsym(h, "ncclGroupEnd"));
+    a.ok = a.all_reduce && a.group_start && a.group_end;
+    return a;
+  }();
+  return api;
+}
+}  // namespace
+
+int qlb_stats_allreduce(qlb_context* ctx, void* nccl_comm, qlb_stats* stats, void* stream) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (!nccl_comm || !stats) return QLB_ERR_INVALID_ARGUMENT;
+  const NcclApi& nccl = nccl_api();
+  if (!nccl.ok) {
+    std::snprintf(ctx->last_error, sizeof ctx->last_error, "libnccl.so.2 not found");
+    return QLB_ERR_CUDA;
+  }
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ncclComm_t comm = static_cast<ncclComm_t>(nccl_comm);
+  static_assert(sizeof(qlb_stats) == QLB_STATS_NUM * sizeof(double), "qlb_stats is a vector of doubles");
+  QLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stats, stats, sizeof(qlb_stats), cudaMemcpyHostToDevice, st));
+  bool ok = nccl.group_start() == ncclSuccess;
+  ok = ok && nccl.all_reduce(ctx->d_stats, ctx->d_stats, QLB_STATS_NUM_SUM, ncclDouble, ncclSum, comm, st) == ncclSuccess;
+  ok = ok && nccl.all_reduce(ctx->d_stats + QLB_STATS_NUM_SUM, ctx->d_stats + QLB_STATS_NUM_SUM, QLB_STATS_NUM - QLB_STATS_NUM_SUM,
+                             ncclDouble, ncclMax, comm, st) == ncclSuccess;
+  ok = (nccl.group_end() == ncclSuccess) && ok;
+  if (!ok) {
+    std::snprintf(ctx->last_error, sizeof ctx->last_error, "ncclAllReduce failed");
+    return QLB_ERR_CUDA;
+  }
+  QLB_CUDA(ctx, cudaMemcpyAsync(stats, ctx->d_stats, sizeof(qlb_stats), cudaMemcpyDeviceToHost, st));
+  QLB_CUDA(ctx, cudaStreamSynchronize(st));
   return QLB_OK;
 }
 

@@ -1,21 +1,6 @@
-// qlb_solve_fused.cuh - ONE persistent kernel for the whole contact-force pipeline of a batch.
-//
-// Every warp is autonomous (no CTA-wide synchronisation after the prologue) and alternates between two
-// phases:
-//
-//   tile phase   eight consecutive states (one leg per lane, as in qlb_solve_quad.cuh): the raw SoA input
-//                rows of the tile have been staged in shared memory by the TMA unit (one
-//                cp.async.bulk.tensor box {8 states x rows} per input array, completion on a per-warp mbarrier)
-//                while the previous tile was computed.  Kinematics, friction frames, wrench map, the
-//                unconstrained minimiser.  States whose minimiser is feasible are finished.  The others
-//                ("hard" states, 28 % of config C3) are parked in the warp's shared-memory STASH together with
-//                everything the rounds need (friction frame, foot position, Jacobian, gravity torques, ...):
-//                nothing is recomputed and nothing goes through HBM.
-//   round phase  entered when the stash holds a warp's worth of hard states: each quad takes one state
-//                and runs equality-constrained rounds on the 6x6 dual system.  A quad that finishes writes its
-//                outputs and takes the next state from the stash, so the eight quads of the warp stay busy;
-//                when the stash runs low the unfinished states are written back (iterate, multipliers,
-//                pattern) and the warp returns to the tile phase.
+// qlb_solve_fused.cuh - building blocks of the fused solve kernel (qlb_solve_single.cuh): staging of the raw input rows
+// in shared memory (TMA tensor boxes or cp.async), mbarrier / TMA primitives, and one round of the dual block
+// active-set method on the 6x6 dual system.
 //
 // The rounds are a DUAL BLOCK ACTIVE-SET method (the Goldfarb-Idnani idea with block additions; the dual of
 // the QP is a bound-constrained QP in the multipliers and this is the primal active-set method on it):
@@ -25,7 +10,7 @@
 //          t < 1: move by t, drop the blocking rows from F;
 //          t = 1: move; every violated row joins F (multiplier 0); no violated row -> optimal.
 // Each non-zero step increases the dual objective, so no working set repeats: finite, no cycling, and in
-// the common cases it takes the same steps as the "repair every violated row" heuristic it replaces (which
+// the common cases it takes the same steps as the "repair every violated row" heuristic of round 1 (which
 // needed an interior-point pass as a safety net for 1 % of the states).  Measured on 60 000 C3 / C5 states
 // (tools/proto/rounds_proto.py): 1.69 / 1.45 rounds per hard state, at most 14, no failure, active set equal to
 // the reference solver's on every state.  States that exhaust the round limit (none seen) go to a.list2 for
@@ -41,83 +26,41 @@
 
 namespace qlb {
 
-#ifndef QLB_FUSED_MIN_CTAS
-#define QLB_FUSED_MIN_CTAS 3
+#ifndef QLB_SUPER
+#define QLB_SUPER 2      // tiles (of eight states) per staged box: TMA boxes are 8 QLB_SUPER states wide
 #endif
 #ifndef QLB_DBAS_MAX_ROUNDS
 #define QLB_DBAS_MAX_ROUNDS 40
 #endif
-constexpr int kFusedSmemBudget = 75 * 1024;   // per CTA: three CTAs per SM (228 KB, 1 KB reserved per CTA)
 
 // ---------------------------------------------------------------------------------------------------------
 // Staging of the raw input rows: one segment per input array, each a dense [rows][8 states] box.
-template <typename real, int MODE>
+template <typename real, int MODE, int SUPER>
 struct Staging {
-  static constexpr int kRow = 8 * (int)sizeof(real);                           // bytes of one row of a box
-  __host__ __device__ static constexpr int align(int x) { return (x + 127) & ~127; }              // TMA destinations: 128-byte aligned
-  // wrench mode: q, quat, wrench, mu, normals;  state mode: q, pose, twist, tpose, ttwist, mu, normals
-  static constexpr int kNumSeg = (MODE == 1) ? 7 : 5;
+  static constexpr int kCols = 8 * SUPER;                                       // states per box
+  static constexpr int kRow = kCols * (int)sizeof(real);                        // bytes of one row of a box
+  __host__ __device__ static constexpr int align(int x) { return (x + 127) & ~127; }   // TMA destinations: 128-byte aligned
+  // wrench mode: q, quat, wrench, mu;  state mode: q, pose, twist, tpose, ttwist, mu.  (Per-leg surface normals, when
+  // the caller passes them, are read straight from global memory: the rare case does not take staging space.)
+  static constexpr int kNumSeg = (MODE == 1) ? 6 : 4;
   __host__ __device__ static constexpr int rows(int s) {
-    return (MODE == 1) ? (s == 0 ? 12 : s == 1 ? 7 : s == 2 ? 6 : s == 3 ? 7 : s == 4 ? 6 : s == 5 ? 4 : 12)
-                       : (s == 0 ? 12 : s == 1 ? 4 : s == 2 ? 6 : s == 3 ? 4 : 12);
+    return (MODE == 1) ? (s == 0 ? 12 : s == 1 ? 7 : s == 2 ? 6 : s == 3 ? 7 : s == 4 ? 6 : 4)
+                       : (s == 0 ? 12 : s == 1 ? 4 : s == 2 ? 6 : 4);
   }
-  __host__ __device__ static constexpr int offset(int s) { return s == 0 ? 0 : offset(s - 1) + align(rows(s - 1) * kRow); }
-  static constexpr int kBytes = offset(kNumSeg - 1) + align(rows(kNumSeg - 1) * kRow);
+  // (closed form, no recursion: a recursive constexpr function called with a run-time-looking argument is compiled
+  // as a real recursive device function - found in the SASS as CALL/RET, 29 % of all executed instructions)
+  static constexpr int kO1 = align(rows(0) * kRow), kO2 = kO1 + align(rows(1) * kRow), kO3 = kO2 + align(rows(2) * kRow),
+                       kO4 = kO3 + align(rows(3) * kRow), kO5 = kO4 + align(rows(4) * kRow), kO6 = kO5 + align(rows(5) * kRow);
+  __host__ __device__ static constexpr int offset(int s) {
+    return s == 0 ? 0 : s == 1 ? kO1 : s == 2 ? kO2 : s == 3 ? kO3 : s == 4 ? kO4 : s == 5 ? kO5 : kO6;
+  }
+  static constexpr int kBytes = (MODE == 1) ? kO6 : kO4;
   static constexpr int kSegMu = (MODE == 1) ? 5 : 3;
-  static constexpr int kSegNormals = (MODE == 1) ? 6 : 4;
 };
 
 // Tensor maps of the input arrays of one call (built on the host, qlb_api.cu), in Staging segment order.
 struct alignas(64) FusedMaps {
-  CUtensorMap seg[7];
-};
-
-// ---------------------------------------------------------------------------------------------------------
-// The stash of one warp: CAP entries.  Per-lane planes (element k of the entry in slot s, leg l at
-// plane[k * 4 CAP + 4 s + l]) and a per-entry header.
-constexpr int kStashLane = 19;   // friction frame / force rows of the wrench map (9), foot (3), mu, y (3), u (3)
-template <typename real, typename creal, int CAP>
-struct StashLayout {
-  static constexpr int kQ = 4 * CAP;
-  static constexpr int kLaneBytes = kStashLane * kQ * (int)sizeof(creal);
-  static constexpr int kJBytes = 12 * kQ * (int)sizeof(real);
-  static constexpr int kBBytes = 6 * CAP * (int)sizeof(creal);
-  static constexpr int kHBytes = 4 * CAP * 4;
-  static constexpr int kBytes = ((kLaneBytes + kJBytes + kBBytes + kHBytes) + 15) & ~15;
-};
-
-template <typename real, typename creal, int MODE>
-struct FusedLayout {
-  // fixed part: parameter block, solver constants, one mbarrier per warp (the leg-model table is a static array)
-  static constexpr int kFixed = ((((int)sizeof(DeviceParamsT<real>) + 15) & ~15) + (((int)sizeof(CoreConst<creal>) + 15) & ~15) + 64 + 127) & ~127;
-  static constexpr int kStatic = (int)sizeof(DeviceModelT<double>) + 128;
-  static constexpr int kStage = Staging<real, MODE>::kBytes;
-  static constexpr int stash_bytes(int c) {
-    return ((kStashLane * 4 * c * (int)sizeof(creal) + 12 * 4 * c * (int)sizeof(real) + 6 * c * (int)sizeof(creal) + 16 * c) + 15) & ~15;
-  }
-  static constexpr int warp_bytes(int c) { return (kStage + stash_bytes(c) + 127) & ~127; }
-  static constexpr int cap_for(int c) { return (kStatic + kFixed + 4 * warp_bytes(c) <= kFusedSmemBudget || c <= 8) ? c : cap_for(c - 1); }
-  static constexpr int kCap = cap_for(15);
-  static_assert(kCap >= 10, "stash too small");
-  static_assert(stash_bytes(kCap) == StashLayout<real, creal, kCap>::kBytes, "layout mismatch");
-  static constexpr int kWarpBytes = warp_bytes(kCap);
-  static constexpr int kTotal = kFixed + 4 * kWarpBytes;   // dynamic shared memory of the kernel
-  static_assert(kStatic + kTotal <= kFusedSmemBudget, "shared memory budget");
-};
-
-template <typename real, typename creal, int CAP>
-struct WarpStash {
-  creal* sl;      // [kStashLane][4 CAP]
-  real* sj;       // [12][4 CAP]   Jacobian (9) and gravity torques (3); also the scratch of the tile phase
-  creal* sb;      // [6][CAP]      desired wrench
-  uint32_t* sh;   // [4][CAP]      state index; mask | pattern << 4 | rounds << 24; gradient scale (float bits); spare
-  __device__ WarpStash(unsigned char* base) {
-    using SL = StashLayout<real, creal, CAP>;
-    sl = reinterpret_cast<creal*>(base);
-    sj = reinterpret_cast<real*>(base + SL::kLaneBytes);
-    sb = reinterpret_cast<creal*>(base + SL::kLaneBytes + SL::kJBytes);
-    sh = reinterpret_cast<uint32_t*>(base + SL::kLaneBytes + SL::kJBytes + SL::kBBytes);
-  }
+  CUtensorMap seg[6];
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -167,17 +110,17 @@ __device__ __forceinline__ int nth_set_bit(unsigned m, const int j) {
   return m ? (__ffs(m) - 1) : -1;
 }
 
-// Issue the loads of tile `tile` (eight states) into this warp's staging buffer.
-// TMA: lane 0 arms the mbarrier with the byte count and issues one box per input array (out-of-range
-// columns of the last tile are zero-filled by the unit).  Otherwise (batch size or pointers not 16-byte
+// Issue the loads of box `box` (8 SUPER consecutive states) into this warp's staging buffer.
+// TMA: lane 0 arms the mbarrier with the byte count and issues one tensor box per input array (out-of-range
+// columns of the last box are zero-filled by the unit).  Otherwise (batch size or pointers not 16-byte
 // aligned): every lane copies its share with 8-/4-byte cp.async, column index clamped to B - 1.
-template <typename real, int MODE, bool TMA>
-__device__ __forceinline__ void stage_issue(const SolveArgsT<real>& a, const FusedMaps& maps, const unsigned long long tile,
+template <typename real, int MODE, int SUPER, bool TMA>
+__device__ __forceinline__ void stage_issue(const SolveArgsT<real>& a, const FusedMaps& maps, const unsigned long long box,
                                             unsigned char* stage, const uint32_t bar, const int lane) {
-  using SG = Staging<real, MODE>;
-  const real* src[7];
-  if (MODE == 1) { src[0] = a.q; src[1] = a.pose; src[2] = a.twist; src[3] = a.tpose; src[4] = a.ttwist; src[5] = a.mu; src[6] = a.normals; }
-  else { src[0] = a.q; src[1] = a.quat; src[2] = a.wrench; src[3] = a.mu; src[4] = a.normals; src[5] = nullptr; src[6] = nullptr; }
+  using SG = Staging<real, MODE, SUPER>;
+  const real* src[6];
+  if (MODE == 1) { src[0] = a.q; src[1] = a.pose; src[2] = a.twist; src[3] = a.tpose; src[4] = a.ttwist; src[5] = a.mu; }
+  else { src[0] = a.q; src[1] = a.quat; src[2] = a.wrench; src[3] = a.mu; src[4] = nullptr; src[5] = nullptr; }
   if (TMA) {
     if (lane == 0) {
       uint32_t bytes = 0;
@@ -188,33 +131,34 @@ __device__ __forceinline__ void stage_issue(const SolveArgsT<real>& a, const Fus
       const uint32_t dst = smem_u32(stage);
 #pragma unroll
       for (int s = 0; s < SG::kNumSeg; s++)
-        if (src[s] != nullptr) tma_load_2d(dst + SG::offset(s), &maps.seg[s], (int)(tile * 8ull), 0, bar);
+        if (src[s] != nullptr) tma_load_2d(dst + SG::offset(s), &maps.seg[s], (int)(box * (unsigned long long)SG::kCols), 0, bar);
     }
   } else {
     const unsigned long long B = a.B;
-    const int col = lane & 7;
-    unsigned long long bx = tile * 8ull + col;
+    constexpr int kRowsPerPass = 32 / SG::kCols;
+    const int col = lane % SG::kCols;
+    unsigned long long bx = box * (unsigned long long)SG::kCols + col;
     if (bx >= B) bx = B - 1;
 #pragma unroll
     for (int s = 0; s < SG::kNumSeg; s++) {
       if (src[s] == nullptr) continue;
       const uint32_t dst = smem_u32(stage) + SG::offset(s);
 #pragma unroll
-      for (int r0 = 0; r0 < SG::rows(s); r0 += 4) {
-        const int r = r0 + (lane >> 3);
-        if (r < SG::rows(s)) cp_async_elem(dst + (r * 8 + col) * (int)sizeof(real), src[s] + (size_t)r * B + bx);
+      for (int r0 = 0; r0 < SG::rows(s); r0 += kRowsPerPass) {
+        const int r = r0 + lane / SG::kCols;
+        if (r < SG::rows(s)) cp_async_elem(dst + (r * SG::kCols + col) * (int)sizeof(real), src[s] + (size_t)r * B + bx);
       }
     }
     cp_async_commit();
   }
 }
 
-// The raw inputs of this lane's state from the staging buffer (the layout RawIn of qlb_solve_quad.cuh expects).
-template <typename real, int MODE>
+// The raw inputs of this lane's state (column `col` of the staged box) in the layout RawIn of qlb_solve_quad.cuh.
+template <typename real, int MODE, int SUPER>
 __device__ __forceinline__ void stage_read(const SolveArgsT<real>& a, const unsigned char* stage, const real mu_default,
-                                           const int leg, const int quad, RawIn<real, MODE>& in) {
-  using SG = Staging<real, MODE>;
-  auto at = [&](const int seg, const int row) { return reinterpret_cast<const real*>(stage + SG::offset(seg))[row * 8 + quad]; };
+                                           const int leg, const int col, const unsigned long long bq, RawIn<real, MODE>& in) {
+  using SG = Staging<real, MODE, SUPER>;
+  auto at = [&](const int seg, const int row) { return reinterpret_cast<const real*>(stage + SG::offset(seg))[row * SG::kCols + col]; };
 #pragma unroll
   for (int j = 0; j < 3; j++) in.qj[j] = at(0, 3 * leg + j);
   if (MODE == 1) {
@@ -232,7 +176,7 @@ __device__ __forceinline__ void stage_read(const SolveArgsT<real>& a, const unsi
   in.nw[0] = real(0.0); in.nw[1] = real(0.0); in.nw[2] = real(1.0);
   if (a.normals != nullptr) {
 #pragma unroll
-    for (int c = 0; c < 3; c++) in.nw[c] = at(SG::kSegNormals, 3 * leg + c);
+    for (int c = 0; c < 3; c++) in.nw[c] = __ldg(a.normals + (size_t)(3 * leg + c) * a.B + bq);
   }
 }
 
@@ -393,256 +337,6 @@ __device__ __forceinline__ void dbas_round(RoundState<creal>& q, const creal* b,
         if (q.rounds >= QLB_DBAS_MAX_ROUNDS) fail = true;
       }
     }
-  }
-}
-
-template <typename real, typename creal, int CAP>
-__device__ __forceinline__ void stash_load(const WarpStash<real, creal, CAP>& ws, const int slot, const int leg, RoundState<creal>& q) {
-  constexpr int Q = 4 * CAP;
-  const int e = 4 * slot + leg;
-  const uint32_t w1 = ws.sh[CAP + slot];
-  q.idx = ws.sh[slot];
-  q.gscale = __uint_as_float(ws.sh[2 * CAP + slot]);
-  q.mask = w1 & 0xFu;
-  q.alive = (w1 >> leg) & 1u;
-  q.rounds = (int)(w1 >> 24);
-  const unsigned pat = (w1 >> (4 + 5 * leg)) & 31u;
-  q.a0 = (int)(pat & 1u);
-  q.sg1 = ((pat >> 1) & 3u) == 1u ? -1 : (((pat >> 1) & 3u) == 2u ? 1 : 0);
-  q.sg2 = ((pat >> 3) & 3u) == 1u ? -1 : (((pat >> 3) & 3u) == 2u ? 1 : 0);
-  creal foot[3];
-#pragma unroll
-  for (int c = 0; c < 3; c++) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) q.At[c][k] = ws.sl[(3 * c + k) * Q + e];
-    foot[c] = ws.sl[(9 + c) * Q + e];
-  }
-  q.mu = ws.sl[12 * Q + e];
-#pragma unroll
-  for (int c = 0; c < 3; c++) { q.y[c] = ws.sl[(13 + c) * Q + e]; q.u[c] = ws.sl[(16 + c) * Q + e]; }
-  // torque rows of the wrench map: r x e_c (zero for a swing leg: its force rows are stored as zero)
-#pragma unroll
-  for (int c = 0; c < 3; c++) {
-    q.At[c][3] = foot[1] * q.At[c][2] - foot[2] * q.At[c][1];
-    q.At[c][4] = foot[2] * q.At[c][0] - foot[0] * q.At[c][2];
-    q.At[c][5] = foot[0] * q.At[c][1] - foot[1] * q.At[c][0];
-  }
-}
-
-__device__ __forceinline__ unsigned pattern_bits(const int a0, const int sg1, const int sg2) {
-  return (a0 != 0 ? 1u : 0u) | (sg1 == -1 ? 2u : (sg1 == 1 ? 4u : 0u)) | (sg2 == -1 ? 8u : (sg2 == 1 ? 16u : 0u));
-}
-
-// Write the iterate of an unfinished state back to its slot (the fixed part of the entry is still there).
-template <typename real, typename creal, int CAP>
-__device__ __forceinline__ void stash_save(const WarpStash<real, creal, CAP>& ws, const int slot, const int leg, const RoundState<creal>& q,
-                                           const bool doit) {
-  constexpr int Q = 4 * CAP;
-  const unsigned pat = quad_or(pattern_bits(q.a0, q.sg1, q.sg2) << (5 * leg));   // whole warp
-  if (doit) {
-    const int e = 4 * slot + leg;
-#pragma unroll
-    for (int c = 0; c < 3; c++) { ws.sl[(13 + c) * Q + e] = q.y[c]; ws.sl[(16 + c) * Q + e] = q.u[c]; }
-    if (leg == 0) ws.sh[CAP + slot] = q.mask | (pat << 4) | ((unsigned)q.rounds << 24);
-  }
-}
-
-// The round phase of one warp (see the header).  occ: bit s = slot s holds a pending state.
-template <typename real, typename creal, int CAP>
-__device__ __forceinline__ void round_phase(const SolveArgsT<real>& a, const CoreConst<creal>& cc, const WarpStash<real, creal, CAP>& ws,
-                                            unsigned& occ, const bool final, const int run_min, const int lane, const int leg,
-                                            const int quad) {
-  constexpr int Q = 4 * CAP;
-  unsigned unassigned = occ;
-  RoundState<creal> q;
-#pragma unroll
-  for (int c = 0; c < 3; c++) {
-#pragma unroll
-    for (int r = 0; r < 6; r++) q.At[c][r] = creal(0.0);
-    q.y[c] = creal(0.0); q.u[c] = creal(0.0);
-  }
-  q.mu = creal(0.0); q.a0 = 0; q.sg1 = 0; q.sg2 = 0; q.gscale = 1.f; q.mask = 0u; q.alive = false; q.rounds = 0; q.idx = 0u;
-  int slot = nth_set_bit(unassigned, quad);
-  bool active = slot >= 0;
-  {
-    const int ntake = min(8, __popc(unassigned));
-#pragma unroll 1
-    for (int i = 0; i < ntake; i++) unassigned &= unassigned - 1u;   // the eight lowest pending slots are taken
-  }
-  if (active) stash_load(ws, slot, leg, q);
-#pragma unroll 1
-  for (;;) {
-    bool done, fail;
-    const int bslot = active ? slot : 0;
-    dbas_round<creal>(q, ws.sb + bslot, CAP, cc, leg, active, done, fail);
-    const bool leave = active && (done || fail);
-    // ---- finished states: forces, torques, net wrench, flags (whole warp: quad shuffles inside)
-    if (__any_sync(kFull, leave)) {
-      LegSetup<creal> L;
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-#pragma unroll
-        for (int r = 0; r < 6; r++) L.At[c][r] = q.At[c][r];
-      }
-      L.alive = q.alive; L.mask = q.mask;
-      const int oslot = active ? slot : 0;
-      quad_output<real, creal>(a, L, q.y, q.a0, q.sg1, q.sg2, 0, q.rounds, (unsigned long long)q.idx, active && done, leg,
-                               ws.sj + 4 * oslot + leg, Q);
-      // not verified within the round limit (or a factorisation failed): the interior-point kernel takes the state
-      const unsigned fm = __ballot_sync(kFull, active && fail && leg == 0);
-      if (fm != 0u) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(a.list2_count, __popc(fm));
-        base = __shfl_sync(kFull, base, 0);
-        if (active && fail && leg == 0) a.list2[base + __popc(fm & ((1u << lane) - 1u))] = q.idx;
-      }
-      // release the slots, hand the next pending states to the quads that became free
-      const unsigned freed = __reduce_or_sync(kFull, leave ? (1u << slot) : 0u);
-      occ &= ~freed;
-      const unsigned wm = __ballot_sync(kFull, leave && leg == 0);
-      const int rank = __popc(wm & ((1u << (lane & ~3)) - 1u));
-      __syncwarp();
-      if (leave) {
-        slot = nth_set_bit(unassigned, rank);
-        active = slot >= 0;
-        if (active) stash_load(ws, slot, leg, q);
-      }
-      {
-        const int ntake = min(__popc(wm), __popc(unassigned));
-#pragma unroll 1
-        for (int i = 0; i < ntake; i++) unassigned &= unassigned - 1u;
-      }
-    }
-    const int nact = __popc(__ballot_sync(kFull, active && leg == 0));
-    if (nact == 0) break;
-    if (!final && nact + __popc(unassigned) < run_min) {
-      // too few states left to keep the warp busy: park the unfinished ones and fetch more tiles
-      stash_save(ws, active ? slot : 0, leg, q, active);
-      break;
-    }
-  }
-  __syncwarp();
-}
-
-// ---------------------------------------------------------------------------------------------------------
-template <typename real, typename creal, int MODE, bool TMA>
-__global__ void __launch_bounds__(kQuadThreads, QLB_FUSED_MIN_CTAS)
-qlb_fused_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps maps) {
-  using FL = FusedLayout<real, creal, MODE>;
-  constexpr int CAP = FL::kCap;
-  constexpr int Q = 4 * CAP;
-  constexpr int kRunMin = CAP - 7;            // a tile needs eight free slots: the round phase runs down to CAP - 8 pending
-  extern __shared__ __align__(128) unsigned char smem[];
-  DeviceParamsT<real>& prm = *reinterpret_cast<DeviceParamsT<real>*>(smem);
-  CoreConst<creal>& cc = *reinterpret_cast<CoreConst<creal>*>(smem + ((sizeof(DeviceParamsT<real>) + 15) & ~15));
-  static_assert(((sizeof(DeviceParamsT<real>) + 15) & ~15) + sizeof(CoreConst<creal>) + 64 <= FL::kFixed, "fixed part");
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + FL::kFixed - 64);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int leg = lane & 3, quad = lane >> 2;
-  unsigned char* wbase = smem + FL::kFixed + warp * FL::kWarpBytes;
-  unsigned char* stage = wbase;
-  const WarpStash<real, creal, CAP> ws(wbase + FL::kStage);
-  const uint32_t bar = smem_u32(&bars[warp]);
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.params);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&prm);
-    for (int i = threadIdx.x; i < (int)(sizeof(DeviceParamsT<real>) / 4); i += blockDim.x) dst[i] = src[i];
-    cc.load(a.params64);
-    load_model_to_smem(a.model);
-    if (TMA && lane == 0) {
-      mbar_init(bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-  }
-  __syncthreads();
-  const unsigned long long B = a.B;
-  const unsigned long long ntiles = (B + 7) / 8;
-  const creal winv = cc.winv, cfmin = cc.fmin;
-  unsigned occ = 0u;           // pending slots of the stash (warp-uniform)
-  uint32_t parity = 0;
-
-  auto claim = [&]() {
-    unsigned long long b = 0;
-    if (lane == 0) b = atomicAdd(a.counter, 1ull);
-    return __shfl_sync(kFull, b, 0);
-  };
-  auto mask_of = [&](const unsigned long long tile) -> unsigned {
-    const unsigned long long s = tile * 8ull + quad;
-    return (tile < ntiles && s < B) ? (unsigned)a.mask[s] & 0xFu : 0u;
-  };
-  // two tiles are claimed ahead: the loads of `cur` are in flight, `nxt` is known, the claim after it is being fetched
-  unsigned long long cur = claim();
-  if (cur < ntiles) stage_issue<real, MODE, TMA>(a, maps, cur, stage, bar, lane);
-  unsigned mask_cur = mask_of(cur);
-  unsigned long long nxt = claim();
-#pragma unroll 1
-  for (;;) {
-    const bool have = cur < ntiles;   // warp-uniform
-    if (have) {
-    const unsigned mask_nxt = mask_of(nxt);
-    // ---- the staged rows of this tile
-    if (TMA) { mbar_wait(bar, parity); parity ^= 1u; }
-    else { cp_async_wait_all(); __syncwarp(); }
-    RawIn<real, MODE> in;
-    stage_read<real, MODE>(a, stage, prm.mu_default, leg, quad, in);
-    const unsigned long long s0 = cur * 8ull + quad;
-    const bool valid = s0 < B;
-    const unsigned long long bq = valid ? s0 : (B - 1);
-    in.mask = valid ? mask_cur : 0u;
-    __syncwarp();     // every lane has read the buffer: the next tile may land in it
-    if (nxt < ntiles) stage_issue<real, MODE, TMA>(a, maps, nxt, stage, bar, lane);
-    const unsigned long long nn = claim();
-    // ---- kinematics and QP data; the Jacobian goes straight into the slot this quad would keep
-    const int slot = nth_set_bit(~occ & ((1u << CAP) - 1u), quad);
-    LegSetup<creal> L;
-    {
-      LegSetup<real> L0;
-      quad_setup<real, MODE>(a, prm, in, bq, valid, true, leg, L0, ws.sj + 4 * slot + leg, Q);
-      widen_setup(L0, L);
-    }
-    int status;
-    creal y[3], t[6];
-    bool hard;
-    unsigned pat;
-    quad_first_solve<real, creal>(L, cc.sinv, winv, cfmin, leg, y, t, status, hard, pat);
-    hard = hard && valid;
-    creal net[6];
-#pragma unroll
-    for (int r = 0; r < 6; r++) net[r] = fma(-cc.sinv[r], t[r], L.b[r]);   // A x = b - S^-1 t
-    // every state is written, the hard ones provisionally (full sectors; the round phase overwrites them while the
-    // lines are still in L2)
-    quad_output<real, creal>(a, L, y, 0, 0, 0, status, 0, bq, valid, leg, ws.sj + 4 * slot + leg, Q, net);
-    // ---- park the hard states
-    if (hard) {
-      const int e = 4 * slot + leg;
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) ws.sl[(3 * c + k) * Q + e] = L.At[c][k];
-        ws.sl[(9 + c) * Q + e] = L.foot[c];
-        ws.sl[(13 + c) * Q + e] = y[c];
-        ws.sl[(16 + c) * Q + e] = creal(0.0);
-      }
-      ws.sl[12 * Q + e] = L.mu;
-      // lane `leg` stores components leg and leg + 4 (no dynamic register indexing)
-      ws.sb[leg * CAP + slot] = (leg == 0) ? L.b[0] : (leg == 1 ? L.b[1] : (leg == 2 ? L.b[2] : L.b[3]));
-      if (leg < 2) ws.sb[(4 + leg) * CAP + slot] = (leg == 0) ? L.b[4] : L.b[5];
-      if (leg == 0) {
-        ws.sh[slot] = (unsigned)bq;
-        ws.sh[CAP + slot] = L.mask | (pat << 4);
-        ws.sh[2 * CAP + slot] = __float_as_uint(L.gscale);
-      }
-    }
-    occ |= __reduce_or_sync(kFull, hard ? (1u << slot) : 0u);
-    __syncwarp();
-    cur = nxt; nxt = nn; mask_cur = mask_nxt;
-    }
-    // one call site (the code of the round phase exists once): after a tile when the stash is full enough, and
-    // once more when the tiles are exhausted, until the stash is empty
-    const int pending = __popc(occ);
-    if (have ? (pending >= kRunMin) : (pending > 0)) round_phase<real, creal, CAP>(a, cc, ws, occ, !have, kRunMin, lane, leg, quad);
-    if (!have) break;
   }
 }
 

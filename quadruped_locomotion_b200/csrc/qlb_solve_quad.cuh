@@ -516,10 +516,10 @@ __device__ __forceinline__ void widen_setup(const LegSetup<real>& s, LegSetup<cr
 }
 
 // Forces in base frame, joint torques, net wrench, flags word of one finished state.
-template <typename real, typename creal>
+template <typename real, typename creal, typename jreal>
 __device__ __forceinline__ void quad_output(const SolveArgsT<real>& a, const LegSetup<creal>& L, creal (&y)[3], const int a0, const int sg1,
                                             const int sg2, const int status, const int it, const unsigned long long bq,
-                                            const bool valid, const int leg, const real* const jgp, const int jgs,
+                                            const bool valid, const int leg, const jreal* const jgp, const int jgs,
                                             const creal* net_pre = nullptr) {
   const unsigned long long B = a.B;
   const bool alive = L.alive;
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
     creal net[6];
 #pragma unroll
     for (int r = 0; r < 6; r++) net[r] = fma(-sinv[r], t[r], L.b[r]);   // A x = b - S^-1 t
-    quad_output<real, creal>(a, L, y, 0, 0, 0, status, 0, bq, valid, leg, &jg[0][threadIdx.x], kQuadThreads, net);  // whole warp: it contains quad shuffles
+    quad_output<real, creal, real>(a, L, y, 0, 0, 0, status, 0, bq, valid, leg, &jg[0][threadIdx.x], kQuadThreads, net);  // whole warp: it contains quad shuffles
 #if !QLB_PIPELINE_LOADS
     if (bn < nbatch) quad_load<real, MODE>(a, prm.mu_default, bqn, sn < B, leg, in);
 #endif
@@ -1250,7 +1250,7 @@ __device__ __forceinline__ void quad_batch(const SolveArgsT<real>& a, const Devi
       if (defer && valid && leg == 0) a.list2[base + __popc(hm & ((1u << lane) - 1u))] = (unsigned)bq;
     }
   }
-  quad_output<real, creal>(a, L, y, a0, sg1, sg2, status, it, bq, valid && !defer, leg, &jg[0][threadIdx.x], kQuadThreads);
+  quad_output<real, creal, real>(a, L, y, a0, sg1, sg2, status, it, bq, valid && !defer, leg, &jg[0][threadIdx.x], kQuadThreads);
 }
 
 // A later pass (STAGE as in quad_batch).  Two experiments that did not pay at 2^20 states (each pass has a

@@ -1,0 +1,342 @@
+// qlb_solve_single.cuh - the fused solve kernel: tile phase and round phase in ONE persistent kernel, every warp
+// autonomous, the states that need active-set rounds parked in a per-warp shared-memory stash (nothing goes back to
+// HBM between the two phases; the outputs of those states are overwritten while their lines are still in L2).
+//
+//   tile phase   eight consecutive states per step (one leg per lane, as in qlb_solve_quad.cuh).  The raw SoA input
+//                rows of 8 QLB_SUPER states are staged in shared memory by the TMA unit (one cp.async.bulk.tensor box
+//                per input array, completion on a per-warp mbarrier) while the previous box is computed.
+//                Kinematics, friction frames, wrench map, the unconstrained minimiser.  States whose minimiser is
+//                feasible (72 % of config C3) are finished.  The record of a "hard" state - friction frame, foot
+//                position, Jacobian, gravity torques, the minimiser - goes into one of the warp's CAP stash slots
+//                (the Jacobian of every state of the tile is written straight into the slot its quad would keep).
+//   round phase  entered when the stash holds a warp's worth of hard states: each quad takes one and runs rounds of
+//                the dual block active-set method (qlb_solve_fused.cuh); a quad that finishes writes its outputs and
+//                takes the next pending slot, so the eight quads stay busy whatever the number of rounds their states
+//                need (measured: 93 % of the quad-rounds executed are useful); when fewer than CAP - 7 states are left
+//                the unfinished ones are written back (iterate, multipliers, working set) and the warp fetches tiles
+//                again.
+#pragma once
+
+#include "qlb_solve_fused.cuh"
+
+namespace qlb {
+
+#ifndef QLB_FUSED_MIN_CTAS
+#define QLB_FUSED_MIN_CTAS 3
+#endif
+constexpr int kSingleSmemBudget = 75 * 1024;   // per CTA: three CTAs per SM (228 KB, 1 KB reserved per CTA)
+
+// ---------------------------------------------------------------------------------------------------------
+// The stash of one warp: CAP entries.  Per-lane planes (element k of the entry in slot s, leg l at
+// plane[k * 4 CAP + 4 s + l]) and a per-entry header.
+constexpr int kStashLane = 19;   // friction frame / force rows of the wrench map (9), foot (3), mu, y (3), u (3)
+template <typename real, typename creal, int CAP>
+struct StashLayout {
+  static constexpr int kQ = 4 * CAP;
+  static constexpr int kLaneBytes = kStashLane * kQ * (int)sizeof(creal);
+  static constexpr int kJBytes = 12 * kQ * (int)sizeof(real);
+  static constexpr int kBBytes = 6 * CAP * (int)sizeof(creal);
+  static constexpr int kHBytes = 4 * CAP * 4;
+  static constexpr int kBytes = ((kLaneBytes + kJBytes + kBBytes + kHBytes) + 15) & ~15;
+};
+
+template <typename real, typename creal, int MODE, int SUPER>
+struct FusedLayout {
+  // fixed part: parameter block, solver constants, one mbarrier per warp (the leg-model table is a static array)
+  static constexpr int kFixed = ((((int)sizeof(DeviceParamsT<real>) + 15) & ~15) + (((int)sizeof(CoreConst<creal>) + 15) & ~15) + 64 + 127) & ~127;
+  static constexpr int kStatic = (int)sizeof(DeviceModelT<double>) + 128;
+  static constexpr int kStage = Staging<real, MODE, SUPER>::kBytes;
+  static constexpr int stash_bytes(int c) {
+    return ((kStashLane * 4 * c * (int)sizeof(creal) + 12 * 4 * c * (int)sizeof(real) + 6 * c * (int)sizeof(creal) + 16 * c) + 15) & ~15;
+  }
+  static constexpr int warp_bytes(int c) { return (kStage + stash_bytes(c) + 127) & ~127; }
+  static constexpr int cap_for(int c) { return (kStatic + kFixed + 4 * warp_bytes(c) <= kSingleSmemBudget || c <= 8) ? c : cap_for(c - 1); }
+  static constexpr int kCap = cap_for(15);
+  static_assert(kCap >= 10, "stash too small");
+  static_assert(stash_bytes(kCap) == StashLayout<real, creal, kCap>::kBytes, "layout mismatch");
+  static constexpr int kWarpBytes = warp_bytes(kCap);
+  static constexpr int kTotal = kFixed + 4 * kWarpBytes;   // dynamic shared memory of the kernel
+  static_assert(kStatic + kTotal <= kSingleSmemBudget, "shared memory budget");
+};
+
+template <typename real, typename creal, int CAP>
+struct WarpStash {
+  creal* sl;      // [kStashLane][4 CAP]
+  real* sj;       // [12][4 CAP]   Jacobian (9) and gravity torques (3); also the scratch of the tile phase
+  creal* sb;      // [6][CAP]      desired wrench
+  uint32_t* sh;   // [4][CAP]      state index; mask | pattern << 4 | rounds << 24; gradient scale (float bits); spare
+  __device__ WarpStash(unsigned char* base) {
+    using SL = StashLayout<real, creal, CAP>;
+    sl = reinterpret_cast<creal*>(base);
+    sj = reinterpret_cast<real*>(base + SL::kLaneBytes);
+    sb = reinterpret_cast<creal*>(base + SL::kLaneBytes + SL::kJBytes);
+    sh = reinterpret_cast<uint32_t*>(base + SL::kLaneBytes + SL::kJBytes + SL::kBBytes);
+  }
+};
+
+
+template <typename real, typename creal, int CAP>
+__device__ __forceinline__ void stash_load(const WarpStash<real, creal, CAP>& ws, const int slot, const int leg, RoundState<creal>& q) {
+  constexpr int Q = 4 * CAP;
+  const int e = 4 * slot + leg;
+  const uint32_t w1 = ws.sh[CAP + slot];
+  q.idx = ws.sh[slot];
+  q.gscale = __uint_as_float(ws.sh[2 * CAP + slot]);
+  q.mask = w1 & 0xFu;
+  q.alive = (w1 >> leg) & 1u;
+  q.rounds = (int)(w1 >> 24);
+  const unsigned pat = (w1 >> (4 + 5 * leg)) & 31u;
+  q.a0 = (int)(pat & 1u);
+  q.sg1 = ((pat >> 1) & 3u) == 1u ? -1 : (((pat >> 1) & 3u) == 2u ? 1 : 0);
+  q.sg2 = ((pat >> 3) & 3u) == 1u ? -1 : (((pat >> 3) & 3u) == 2u ? 1 : 0);
+  creal foot[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) q.At[c][k] = ws.sl[(3 * c + k) * Q + e];
+    foot[c] = ws.sl[(9 + c) * Q + e];
+  }
+  q.mu = ws.sl[12 * Q + e];
+#pragma unroll
+  for (int c = 0; c < 3; c++) { q.y[c] = ws.sl[(13 + c) * Q + e]; q.u[c] = ws.sl[(16 + c) * Q + e]; }
+  // torque rows of the wrench map: r x e_c (zero for a swing leg: its force rows are stored as zero)
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    q.At[c][3] = foot[1] * q.At[c][2] - foot[2] * q.At[c][1];
+    q.At[c][4] = foot[2] * q.At[c][0] - foot[0] * q.At[c][2];
+    q.At[c][5] = foot[0] * q.At[c][1] - foot[1] * q.At[c][0];
+  }
+}
+
+__device__ __forceinline__ unsigned pattern_bits(const int a0, const int sg1, const int sg2) {
+  return (a0 != 0 ? 1u : 0u) | (sg1 == -1 ? 2u : (sg1 == 1 ? 4u : 0u)) | (sg2 == -1 ? 8u : (sg2 == 1 ? 16u : 0u));
+}
+
+// Write the iterate of an unfinished state back to its slot (the fixed part of the entry is still there).
+template <typename real, typename creal, int CAP>
+__device__ __forceinline__ void stash_save(const WarpStash<real, creal, CAP>& ws, const int slot, const int leg, const RoundState<creal>& q,
+                                           const bool doit) {
+  constexpr int Q = 4 * CAP;
+  const unsigned pat = quad_or(pattern_bits(q.a0, q.sg1, q.sg2) << (5 * leg));   // whole warp
+  if (doit) {
+    const int e = 4 * slot + leg;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { ws.sl[(13 + c) * Q + e] = q.y[c]; ws.sl[(16 + c) * Q + e] = q.u[c]; }
+    if (leg == 0) ws.sh[CAP + slot] = q.mask | (pat << 4) | ((unsigned)q.rounds << 24);
+  }
+}
+
+// The round phase of one warp (see the header).  occ: bit s = slot s holds a pending state.
+template <typename real, typename creal, int CAP>
+__device__ __forceinline__ void round_phase(const SolveArgsT<real>& a, const CoreConst<creal>& cc, const WarpStash<real, creal, CAP>& ws,
+                                            unsigned& occ, const bool final, const int run_min, const int lane, const int leg,
+                                            const int quad) {
+  constexpr int Q = 4 * CAP;
+  unsigned unassigned = occ;
+  RoundState<creal> q;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+#pragma unroll
+    for (int r = 0; r < 6; r++) q.At[c][r] = creal(0.0);
+    q.y[c] = creal(0.0); q.u[c] = creal(0.0);
+  }
+  q.mu = creal(0.0); q.a0 = 0; q.sg1 = 0; q.sg2 = 0; q.gscale = 1.f; q.mask = 0u; q.alive = false; q.rounds = 0; q.idx = 0u;
+  int slot = nth_set_bit(unassigned, quad);
+  bool active = slot >= 0;
+  {
+    const int ntake = min(8, __popc(unassigned));
+#pragma unroll 1
+    for (int i = 0; i < ntake; i++) unassigned &= unassigned - 1u;   // the eight lowest pending slots are taken
+  }
+  if (active) stash_load(ws, slot, leg, q);
+#pragma unroll 1
+  for (;;) {
+    bool done, fail;
+    const int bslot = active ? slot : 0;
+    dbas_round<creal>(q, ws.sb + bslot, CAP, cc, leg, active, done, fail);
+    const bool leave = active && (done || fail);
+    // ---- finished states: forces, torques, net wrench, flags (whole warp: quad shuffles inside)
+    if (__any_sync(kFull, leave)) {
+      LegSetup<creal> L;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+#pragma unroll
+        for (int r = 0; r < 6; r++) L.At[c][r] = q.At[c][r];
+      }
+      L.alive = q.alive; L.mask = q.mask;
+      const int oslot = active ? slot : 0;
+      quad_output<real, creal, real>(a, L, q.y, q.a0, q.sg1, q.sg2, 0, q.rounds, (unsigned long long)q.idx, active && done, leg,
+                               ws.sj + 4 * oslot + leg, Q);
+      // not verified within the round limit (or a factorisation failed): the interior-point kernel takes the state
+      const unsigned fm = __ballot_sync(kFull, active && fail && leg == 0);
+      if (fm != 0u) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(a.list2_count, __popc(fm));
+        base = __shfl_sync(kFull, base, 0);
+        if (active && fail && leg == 0) a.list2[base + __popc(fm & ((1u << lane) - 1u))] = q.idx;
+      }
+      // release the slots, hand the next pending states to the quads that became free
+      const unsigned freed = __reduce_or_sync(kFull, leave ? (1u << slot) : 0u);
+      occ &= ~freed;
+      const unsigned wm = __ballot_sync(kFull, leave && leg == 0);
+      const int rank = __popc(wm & ((1u << (lane & ~3)) - 1u));
+      __syncwarp();
+      if (leave) {
+        slot = nth_set_bit(unassigned, rank);
+        active = slot >= 0;
+        if (active) stash_load(ws, slot, leg, q);
+      }
+      {
+        const int ntake = min(__popc(wm), __popc(unassigned));
+#pragma unroll 1
+        for (int i = 0; i < ntake; i++) unassigned &= unassigned - 1u;
+      }
+    }
+    const int nact = __popc(__ballot_sync(kFull, active && leg == 0));
+    if (nact == 0) break;
+    if (!final && nact + __popc(unassigned) < run_min) {
+      // too few states left to keep the warp busy: park the unfinished ones and fetch more tiles
+      stash_save(ws, active ? slot : 0, leg, q, active);
+      break;
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename real, typename creal, int MODE, int SUPER, bool TMA>
+__global__ void __launch_bounds__(kQuadThreads, QLB_FUSED_MIN_CTAS)
+qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps maps) {
+  using FL = FusedLayout<real, creal, MODE, SUPER>;
+  constexpr int CAP = FL::kCap;
+  constexpr int Q = 4 * CAP;
+  constexpr int kRunMin = CAP - 7;            // a tile needs eight free slots: the round phase runs down to CAP - 8 pending
+  constexpr int kCols = 8 * SUPER;
+  extern __shared__ __align__(128) unsigned char smem[];
+  DeviceParamsT<real>& prm = *reinterpret_cast<DeviceParamsT<real>*>(smem);
+  CoreConst<creal>& cc = *reinterpret_cast<CoreConst<creal>*>(smem + ((sizeof(DeviceParamsT<real>) + 15) & ~15));
+  static_assert(((sizeof(DeviceParamsT<real>) + 15) & ~15) + sizeof(CoreConst<creal>) + 64 <= FL::kFixed, "fixed part");
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + FL::kFixed - 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int leg = lane & 3, quad = lane >> 2;
+  unsigned char* wbase = smem + FL::kFixed + warp * FL::kWarpBytes;
+  unsigned char* stage = wbase;
+  const WarpStash<real, creal, CAP> ws(wbase + FL::kStage);
+  const uint32_t bar = smem_u32(&bars[warp]);
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.params);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&prm);
+    for (int i = threadIdx.x; i < (int)(sizeof(DeviceParamsT<real>) / 4); i += blockDim.x) dst[i] = src[i];
+    cc.load(a.params64);
+    load_model_to_smem(a.model);
+    if (TMA && lane == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  const unsigned long long B = a.B;
+  const unsigned long long nbox = (B + kCols - 1) / kCols;
+  const creal winv = cc.winv, cfmin = cc.fmin;
+  unsigned occ = 0u;           // pending slots of the stash (warp-uniform)
+  uint32_t parity = 0;
+  asm volatile("" : "+r"(parity));   // opaque: keeps the compiler from peeling the tile loop by mbarrier phase
+
+  // Work distribution: boxes are claimed with one atomic each, TWO ahead.  The result of a claim stays in lane 0 and
+  // is broadcast only when the box number is needed - a whole tile later - so the round trip of the atomic is never
+  // waited for.  The stance masks of a box (one byte per state) are fetched by one coalesced load a box ahead.
+  auto claim_raw = [&]() {
+    unsigned long long b = 0;
+    if (lane == 0) b = atomicAdd(a.counter, 1ull);
+    return b;
+  };
+  auto mask_bytes = [&](const unsigned long long box) -> unsigned {
+    const unsigned long long s = box * (unsigned long long)kCols + lane;
+    return (lane < kCols && box < nbox && s < B) ? (unsigned)a.mask[s] : 0u;
+  };
+  unsigned long long cur = __shfl_sync(kFull, claim_raw(), 0);
+  if (cur < nbox) stage_issue<real, MODE, SUPER, TMA>(a, maps, cur, stage, bar, lane);
+  unsigned mask_cur = mask_bytes(cur), mask_nxt = 0u;
+  unsigned long long nxt = 0;
+  unsigned long long pending_claim = claim_raw();
+  int sub = 0;                 // tile of the current box
+#pragma unroll 1
+  for (;;) {
+    const bool have = cur < nbox;   // warp-uniform
+    // opaque to the optimiser: otherwise it clones the whole tile body per mbarrier phase / tile-of-the-box value
+    asm volatile("" : "+r"(parity), "+r"(sub));
+    if (have) {
+      // ---- the staged rows of this box
+      if (sub == 0) {
+        if (TMA) { mbar_wait(bar, parity); parity ^= 1u; }
+        else { cp_async_wait_all(); __syncwarp(); }
+      }
+      const int col = sub * 8 + quad;
+      const unsigned long long s0 = cur * (unsigned long long)kCols + col;
+      const bool valid = s0 < B;
+      const unsigned long long bq = valid ? s0 : (B - 1);
+      RawIn<real, MODE> in;
+      stage_read<real, MODE, SUPER>(a, stage, prm.mu_default, leg, col, bq, in);
+      in.mask = valid ? (__shfl_sync(kFull, mask_cur, col) & 0xFu) : 0u;
+      if (sub == SUPER - 1) {
+        __syncwarp();     // every lane has read the last tile of the box: the next box may land in the buffer
+        nxt = __shfl_sync(kFull, pending_claim, 0);
+        if (nxt < nbox) stage_issue<real, MODE, SUPER, TMA>(a, maps, nxt, stage, bar, lane);
+        mask_nxt = mask_bytes(nxt);
+        pending_claim = claim_raw();
+      }
+      // ---- kinematics and QP data; the Jacobian goes straight into the slot this quad would keep
+      const int slot = nth_set_bit(~occ & ((1u << CAP) - 1u), quad);
+      LegSetup<creal> L;
+      {
+        LegSetup<real> L0;
+        quad_setup<real, MODE>(a, prm, in, bq, valid, true, leg, L0, ws.sj + 4 * slot + leg, Q);
+        widen_setup(L0, L);
+      }
+      int status;
+      creal y[3], t[6];
+      bool hard;
+      unsigned pat;
+      quad_first_solve<real, creal>(L, cc.sinv, winv, cfmin, leg, y, t, status, hard, pat);
+      hard = hard && valid;
+      creal net[6];
+#pragma unroll
+      for (int r = 0; r < 6; r++) net[r] = fma(-cc.sinv[r], t[r], L.b[r]);   // A x = b - S^-1 t
+      // every state is written, the hard ones provisionally (full sectors; the round phase overwrites them while the
+      // lines are still in L2)
+      quad_output<real, creal, real>(a, L, y, 0, 0, 0, status, 0, bq, valid, leg, ws.sj + 4 * slot + leg, Q, net);
+      // ---- park the hard states
+      if (hard) {
+        const int e = 4 * slot + leg;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) ws.sl[(3 * c + k) * Q + e] = L.At[c][k];
+          ws.sl[(9 + c) * Q + e] = L.foot[c];
+          ws.sl[(13 + c) * Q + e] = y[c];
+          ws.sl[(16 + c) * Q + e] = creal(0.0);
+        }
+        ws.sl[12 * Q + e] = L.mu;
+        // lane `leg` stores components leg and leg + 4 (no dynamic register indexing)
+        ws.sb[leg * CAP + slot] = (leg == 0) ? L.b[0] : (leg == 1 ? L.b[1] : (leg == 2 ? L.b[2] : L.b[3]));
+        if (leg < 2) ws.sb[(4 + leg) * CAP + slot] = (leg == 0) ? L.b[4] : L.b[5];
+        if (leg == 0) {
+          ws.sh[slot] = (unsigned)bq;
+          ws.sh[CAP + slot] = L.mask | (pat << 4);
+          ws.sh[2 * CAP + slot] = __float_as_uint(L.gscale);
+        }
+      }
+      occ |= __reduce_or_sync(kFull, hard ? (1u << slot) : 0u);
+      __syncwarp();
+      if (++sub == SUPER) { sub = 0; cur = nxt; mask_cur = mask_nxt; }
+    }
+    // one call site (the code of the round phase exists once): after a tile when the stash is full enough, and
+    // once more when the boxes are exhausted, until the stash is empty
+    const int pending = __popc(occ);
+    if (have ? (pending >= kRunMin) : (pending > 0)) round_phase<real, creal, CAP>(a, cc, ws, occ, !have, kRunMin, lane, leg, quad);
+    if (!have) break;
+  }
+}
+
+}  // namespace qlb

@@ -44,17 +44,73 @@ def uniform(seed: int, stream: int, idx: np.ndarray, lo=0.0, hi=1.0) -> np.ndarr
     return lo + (hi - lo) * u
 
 
+# ---- elementary functions from IEEE-exact operations only (+, -, *, /, sqrt, rint, frexp; one rounding per
+# operation, no fused multiply-add): the device generator (csrc/qlb_gen.cuh) repeats the same operation sequence with
+# the __d*_rn intrinsics, so host and device produce BIT-IDENTICAL states (tests/test_generator.py).  Accuracy ~1e-16.
+_PIO2_HI = 1.57079632673412561417e+00
+_PIO2_LO = 6.07710050650619224932e-11
+_TWO_OVER_PI = 6.36619772367581382433e-01
+_SIN_C = (1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+          -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01)
+_COS_C = (-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+          2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02)
+_LN2_HI = 6.93147180369123816490e-01
+_LN2_LO = 1.90821492927058770002e-10
+_SQRT_HALF = 0.70710678118654752440
+
+
+def sincos_exact(x):
+    """(sin x, cos x) for |x| up to ~1e4: Cody-Waite reduction by pi/2 and the fdlibm kernel polynomials, every
+    multiply and add rounded separately."""
+    x = np.asarray(x, dtype=np.float64)
+    kd = np.rint(x * _TWO_OVER_PI)
+    k = kd.astype(np.int64)
+    r = (x - kd * _PIO2_HI) - kd * _PIO2_LO
+    z = r * r
+    ps = np.full_like(z, _SIN_C[0])
+    for c in _SIN_C[1:]:
+        ps = ps * z + c
+    sr = r + (z * r) * ps
+    pc = np.full_like(z, _COS_C[0])
+    for c in _COS_C[1:]:
+        pc = pc * z + c
+    cr = (1.0 - 0.5 * z) + (z * z) * pc
+    odd = (k & 1) != 0
+    s0 = np.where(odd, cr, sr)
+    c0 = np.where(odd, sr, cr)
+    sn = np.where((k & 2) != 0, -s0, s0)
+    cs = np.where(((k + 1) & 2) != 0, -c0, c0)
+    return sn, cs
+
+
+def log_exact(x):
+    """log x for 0 < x <= 1 (what Box-Muller needs): frexp, then 2 atanh((m-1)/(m+1)) as an odd series in
+    s = (m-1)/(m+1), |s| <= 0.172, through s^21."""
+    x = np.asarray(x, dtype=np.float64)
+    m, e = np.frexp(x)
+    small = m < _SQRT_HALF
+    m = np.where(small, m * 2.0, m)
+    ed = (e - small.astype(e.dtype)).astype(np.float64)
+    s = (m - 1.0) / (m + 1.0)
+    z = s * s
+    p = np.full_like(z, 1.0 / 21.0)
+    for n in (19, 17, 15, 13, 11, 9, 7, 5, 3, 1):
+        p = p * z + 1.0 / n
+    return ed * _LN2_HI + (ed * _LN2_LO + (2.0 * s) * p)
+
+
 def normal(seed: int, stream: int, idx: np.ndarray, sigma=1.0) -> np.ndarray:
     u1 = uniform(seed, 2 * stream + 1000, idx)
     u2 = uniform(seed, 2 * stream + 1001, idx)
-    return sigma * np.sqrt(-2.0 * np.log(1.0 - u1)) * np.cos(2.0 * np.pi * u2)
+    _, c = sincos_exact((2.0 * np.pi) * u2)
+    return (sigma * np.sqrt(-2.0 * log_exact(1.0 - u1))) * c
 
 
 def quat_from_ypr(yaw, pitch, roll):
     """(w,x,y,z) of R = Rz(yaw) Ry(pitch) Rx(roll), base->world."""
-    cy, sy = np.cos(0.5 * yaw), np.sin(0.5 * yaw)
-    cp, sp = np.cos(0.5 * pitch), np.sin(0.5 * pitch)
-    cr, sr = np.cos(0.5 * roll), np.sin(0.5 * roll)
+    sy, cy = sincos_exact(0.5 * np.asarray(yaw, dtype=np.float64))
+    sp, cp = sincos_exact(0.5 * np.asarray(pitch, dtype=np.float64))
+    sr, cr = sincos_exact(0.5 * np.asarray(roll, dtype=np.float64))
     w = cr * cp * cy + sr * sp * sy
     x = sr * cp * cy - cr * sp * sy
     y = cr * sp * cy + sr * cp * sy

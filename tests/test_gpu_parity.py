@@ -25,8 +25,8 @@ def solver(qlb_built, request):
     if not torch.cuda.is_available():
         pytest.fail("GPU test selected but no CUDA device: the product path has no CPU fallback")
     s = capi.Solver("quadruped_model")
-    s.set_pipeline(request.param == "fused")
-    s.launches_per_call = 2 if request.param == "fused" else 3
+    s.set_pipeline(request.param)
+    s.launches_per_call = 2 if request.param == "fused" else 3   # fused kernel + interior-point fallback, or the three passes
     yield s
     s.close()
 
@@ -248,7 +248,7 @@ def test_device_pointer_api_and_stream(solver, oracle, models):
         solver.solve_wrench(d["q"], d["quat"], d["wrench"], d["mask"], d["mu"], d["normals"], grf, tau, flags, net,
                             stream=side.cuda_stream)
     side.synchronize()
-    assert solver.launches == before + solver.launches_per_call  # fused + interior point, or the three passes
+    assert solver.launches == before + solver.launches_per_call
     out = dict(grf=grf.cpu().numpy(), tau=tau.cpu().numpy(), flags=flags.cpu().numpy().view(np.uint32),
                netwrench=net.cpu().numpy())
     ref = _oracle(oracle, models["quadruped_model"], st)
