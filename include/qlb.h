@@ -132,6 +132,21 @@ typedef struct qlb_stats {
 #define QLB_STATS_NUM_SUM 29 /* leading doubles that all-reduce with SUM; the rest with MAX */
 #define QLB_STATS_NUM 31
 
+/* Parameters under the reference's own names.  `key` is the ROS parameter path that
+ * ContactForceDistribution::loadParameters (ContactForceDistribution.cpp:818-886) and
+ * VirtualModelController::loadParameters (VirtualModelController.cpp:429-548) read, e.g.
+ * "/balance_controller/contact_force_distribution/weights/force/heading".  Returns the index of the key (>= 0) or
+ * QLB_ERR_INVALID_ARGUMENT for a path that is none of the qlb_params_num_keys() known ones. */
+int qlb_params_set_key(qlb_params* p, const char* key, double value);
+int qlb_params_get_key(const qlb_params* p, const char* key, double* value);
+int qlb_params_num_keys(void);
+const char* qlb_params_key(int index);
+/* Fill *p from the text of a parameter file in the layout of balance_controller/config/controller_gains.yaml:2-41
+ * (nested mappings, `key: number` leaves; other entries are ignored).  Returns how many of the known keys were
+ * found; *first_missing (NULL ok) = the first key the file lacks, or NULL when all are there - the reference's
+ * loadParameters() refuses to run with a key missing. */
+int qlb_params_from_yaml(qlb_params* p, const char* yaml_text, const char** first_missing);
+
 typedef struct qlb_context qlb_context;
 
 /* Fill *p with the reference's gains, weights and solver defaults. */
@@ -316,6 +331,49 @@ int qlb_swing_leg_torques_host(qlb_context* ctx, size_t B, const double* q, cons
                                const double* foot_target_position, const double* foot_target_velocity,
                                const qlb_swing_params* params, double* tau);
 
+/* The same with the joint acceleration estimated the way the reference does it (model_test_header.cpp:421-429):
+ * the caller keeps a queue of joint-velocity samples per leg; qd_back is its newest entry (also the velocity fed to
+ * the dynamics), qd_front its oldest, and qdd = (qd_back - qd_front) / (10 * period).  DEVICE pointers. */
+int qlb_swing_leg_torques_from_queue(qlb_context* ctx, size_t B, const double* q, const double* qd_back,
+                                     const double* qd_front, double period, const double* foot_target_position,
+                                     const double* foot_target_velocity, const qlb_swing_params* params,
+                                     double* tau, void* stream);
+
+/* ---- per-leg contact state machine ----------------------------------------------------
+ * Limb states in the order of StateSwitcher::States (balance_controller/include/state_switcher/StateSwitcher.hpp:62-72). */
+typedef enum qlb_limb_state {
+  QLB_LIMB_INIT = 0,
+  QLB_LIMB_STANCE_NORMAL = 1,
+  QLB_LIMB_STANCE_SLIPPING = 2,
+  QLB_LIMB_STANCE_LOST_CONTACT = 3,
+  QLB_LIMB_SWING_NORMAL = 4,
+  QLB_LIMB_SWING_LATE_LIFTOFF = 5,
+  QLB_LIMB_SWING_EARLY_TOUCHDOWN = 6,
+  QLB_LIMB_SWING_BUMPED_INTO_OBSTACLE = 7,
+  QLB_LIMB_SWING_LATELY_TOUCHDOWN = 8
+} qlb_limb_state;
+
+/* RosBalanceController::footContactsCallback (ros_balance_controller.cpp:1086-1140) for B robots at once, plus the
+ * support-leg decision update() takes from the limb state (:242-366: StanceNormal, SwingEarlyTouchDown and Init are
+ * support legs).  DEVICE pointers.
+ *   desired_stance_mask[B]  bit k = the plan has leg k in stance (limbs_desired_state_, :968-1080)
+ *   footstep_mask[B]        bit k = is_footstep_ (contact supervision on); NULL = all legs
+ *   contact_mask[B]         bit k = measured contact (sim_assiants/FootContacts.is_contact)
+ *   phase[4][B]             phase in [0,1] of the leg's current stance or swing (st_phase / sw_phase)
+ *   limb_state[4][B]        in: previous qlb_limb_state per leg, out: new one
+ *   stance_mask[B]          out (NULL ok): the stance mask to hand to qlb_solve_* */
+int qlb_contact_fsm(qlb_context* ctx, size_t B, const uint8_t* desired_stance_mask, const uint8_t* footstep_mask,
+                    const uint8_t* contact_mask, const double* phase, uint8_t* limb_state, uint8_t* stance_mask,
+                    void* stream);
+
+/* Friction margins of a solved batch (DEVICE pointers): margin[i] = min over stance legs and the four friction rows of
+ * slack / (mu n.f) - 1 = unloaded tangentially, 0 = a friction row is active; min_normal[i] (NULL ok) = min over
+ * stance legs of n.f - F_min.  What a preview of a planned motion reports next to forces and torques
+ * (StateBatchComputer / BatchExecutor consumers).  mu / normals_world as in qlb_solve_wrench. */
+int qlb_friction_margins(qlb_context* ctx, size_t B, const double* grf, const double* quat_wxyz,
+                         const uint8_t* stance_mask, const double* mu, const double* normals_world, double* margin,
+                         double* min_normal, void* stream);
+
 /* Generic small dense QP (DEVICE pointers), B problems of the same shape, in the argument convention of
  * the reference's in-repo backend quadprogpp::solve_quadprog (qp_solver/include/qp_solver/QuadProg++.h:
  * 8-30), which qp_solver::QuadraticProblemSolver::minimize forwards to
@@ -326,7 +384,9 @@ int qlb_swing_leg_torques_host(qlb_context* ctx, size_t B, const double* q, cons
  * An all-zero equality column is treated as absent (the reference's callers pass one).
  * Out: x[n][B]; cost[B] (NULL ok; +inf when infeasible); status[B]: 0 ok, 1 infeasible, 2 G not positive
  * definite or non-finite input, 3 iteration limit; active[B] (NULL ok): bit i = inequality i is in the
- * final working set.  Goldfarb-Idnani with the reference's pivoting rules: same optimum, same working set. */
+ * final working set.  One warp per problem: a dual active-set iteration on the Gram matrix of the whitened
+ * constraint normals (csrc/qlb_qp_dense.cuh); it brings in the most violated constraint first, like the reference,
+ * so optimum and working set agree with the reference's solver on non-degenerate problems. */
 int qlb_qp_dense(qlb_context* ctx, size_t B, int n, int m, int p, const double* G, const double* g0,
                  const double* CE, const double* ce0, const double* CI, const double* ci0, double* x,
                  double* cost, uint32_t* status, uint32_t* active, void* stream);

@@ -373,3 +373,72 @@ def swing_leg_torques(model: dict, model_arr, q, qd, qdd, ptarget=None, vtarget=
                 tau = tau + J.T @ (np.asarray(kp) * ep + np.asarray(kd) * ev)
             out[sl, i] = tau
     return out
+
+
+# ---------------------------------------------------------------- contact state machine (numpy restatement)
+LIMB_INIT, LIMB_STANCE_NORMAL, LIMB_STANCE_SLIPPING, LIMB_STANCE_LOST_CONTACT, LIMB_SWING_NORMAL, LIMB_SWING_LATE_LIFTOFF, \
+    LIMB_SWING_EARLY_TOUCHDOWN, LIMB_SWING_BUMPED_INTO_OBSTACLE, LIMB_SWING_LATELY_TOUCHDOWN = range(9)
+
+
+def contact_fsm(desired, footstep, contact, phase, limb_state):
+    """RosBalanceController::footContactsCallback (ros_balance_controller.cpp:1086-1140), one robot after the other,
+    written as the nested ifs of the reference; then the support-leg decision of update() (:242-366).
+    desired / footstep / contact: uint8 masks [B]; phase [4,B]; limb_state [4,B] previous states.
+    Returns (new limb_state [4,B], stance mask [B])."""
+    B = desired.shape[0]
+    out = np.array(limb_state, dtype=np.uint8, copy=True)
+    stance = np.zeros(B, dtype=np.uint8)
+    for i in range(B):
+        for k in range(4):
+            is_contact = bool((contact[i] >> k) & 1)
+            is_footstep = bool((footstep[i] >> k) & 1) if footstep is not None else True
+            if not (desired[i] >> k) & 1:                      # limbs_desired_state == SwingNormal
+                out[k, i] = LIMB_SWING_NORMAL
+                if is_footstep:
+                    if phase[k, i] > 0.5:
+                        if is_contact:
+                            out[k, i] = LIMB_SWING_EARLY_TOUCHDOWN
+                    elif phase[k, i] > 0.2:
+                        if is_contact:
+                            out[k, i] = LIMB_SWING_BUMPED_INTO_OBSTACLE
+            else:                                              # limbs_desired_state == StanceNormal
+                if not is_footstep:
+                    out[k, i] = LIMB_STANCE_NORMAL
+                else:
+                    if is_contact:
+                        out[k, i] = LIMB_STANCE_NORMAL
+                    elif phase[k, i] < 0.1:
+                        out[k, i] = LIMB_SWING_LATELY_TOUCHDOWN
+                    if phase[k, i] > 0.5:
+                        if not is_contact:
+                            out[k, i] = LIMB_STANCE_LOST_CONTACT
+            if out[k, i] in (LIMB_STANCE_NORMAL, LIMB_SWING_EARLY_TOUCHDOWN, LIMB_INIT):
+                stance[i] |= 1 << k
+    return out, stance
+
+
+def friction_margins(grf, quat, mask, mu, normals=None, fmin=10.0):
+    """Per state: min over stance legs of min(mu fn - |f.t1|, mu fn - |f.t2|) / (mu fn), and min fn - F_min, with the
+    friction frame of ContactForceDistribution.cpp:286-309."""
+    B = grf.shape[1]
+    margin = np.zeros(B); minn = np.zeros(B)
+    for i in range(B):
+        w, x, y, z = quat[:, i]
+        R = np.array([[w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                      [2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z]])
+        best, bestn = np.inf, np.inf
+        for k in range(4):
+            if not (mask[i] >> k) & 1:
+                continue
+            nw = normals[3 * k:3 * k + 3, i] if normals is not None else np.array([0.0, 0.0, 1.0])
+            n = R.T @ nw
+            t1 = np.cross(n, R.T @ np.array([0.0, 1.0, 0.0])); t1 /= np.linalg.norm(t1)
+            t2 = np.cross(n, t1); t2 /= np.linalg.norm(t2)
+            f = grf[3 * k:3 * k + 3, i]
+            fn = f @ n
+            slack = min(mu[k, i] * fn - abs(f @ t1), mu[k, i] * fn - abs(f @ t2))
+            best = min(best, slack / max(mu[k, i] * fn, 1e-300)); bestn = min(bestn, fn - fmin)
+        if mask[i] & 0xF:
+            margin[i], minn[i] = best, bestn
+    return margin, minn

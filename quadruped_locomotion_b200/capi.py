@@ -51,7 +51,7 @@ EXPORTS = (
     "qlb_solve_wrench", "qlb_solve_wrench_host", "qlb_solve_state", "qlb_solve_state_host",
     "qlb_solve_wrench_f32", "qlb_solve_wrench_f32_host", "qlb_solve_state_f32", "qlb_solve_state_f32_host",
     "qlb_default_swing_params", "qlb_set_limb_dynamics", "qlb_swing_leg_torques", "qlb_swing_leg_torques_host",
-    "qlb_set_f32_core", "qlb_set_pipeline", "qlb_generate_states", "qlb_generate_states_f32", "qlb_solve_records", "qlb_solve_records_host", "qlb_stats_allreduce", "qlb_leg_kinematics", "qlb_pack_robot_states", "qlb_feet_in_world", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
+    "qlb_set_f32_core", "qlb_set_pipeline", "qlb_generate_states", "qlb_generate_states_f32", "qlb_solve_records", "qlb_solve_records_host", "qlb_stats_allreduce", "qlb_params_set_key", "qlb_params_get_key", "qlb_params_num_keys", "qlb_params_key", "qlb_params_from_yaml", "qlb_swing_leg_torques_from_queue", "qlb_contact_fsm", "qlb_friction_margins", "qlb_leg_kinematics", "qlb_pack_robot_states", "qlb_feet_in_world", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
     "qlb_last_cuda_error", "qlb_abi_version",
 )
 
@@ -116,6 +116,14 @@ def load() -> C.CDLL:
     lib.qlb_solve_state_f32_host.argtypes = [_vp, C.c_size_t] + [_vp] * 13
     lib.qlb_set_f32_core.argtypes = [_vp, C.c_int]
     lib.qlb_set_pipeline.argtypes = [_vp, C.c_int]
+    lib.qlb_params_set_key.argtypes = [C.POINTER(Params), C.c_char_p, C.c_double]
+    lib.qlb_params_get_key.argtypes = [C.POINTER(Params), C.c_char_p, C.POINTER(C.c_double)]
+    lib.qlb_params_key.argtypes = [C.c_int]
+    lib.qlb_params_key.restype = C.c_char_p
+    lib.qlb_params_from_yaml.argtypes = [C.POINTER(Params), C.c_char_p, C.POINTER(C.c_char_p)]
+    lib.qlb_swing_leg_torques_from_queue.argtypes = [_vp, C.c_size_t, _vp, _vp, _vp, C.c_double, _vp, _vp, C.POINTER(SwingParams), _vp, _vp]
+    lib.qlb_contact_fsm.argtypes = [_vp, C.c_size_t] + [_vp] * 7
+    lib.qlb_friction_margins.argtypes = [_vp, C.c_size_t] + [_vp] * 8
     lib.qlb_stats_allreduce.argtypes = [_vp, _vp, C.POINTER(Stats), _vp]
     lib.qlb_solve_records.argtypes = [_vp, C.c_size_t, _vp, _vp, _vp]
     lib.qlb_solve_records_host.argtypes = [_vp, C.c_size_t, _vp, _vp]
@@ -149,6 +157,16 @@ def default_params() -> Params:
     if rc != 0:
         raise RuntimeError("qlb_default_params failed")
     return p
+
+
+def params_from_yaml(text: str, base: Params | None = None):
+    """(Params, first missing key or None) from the text of a controller_gains.yaml-style file."""
+    p = base if base is not None else default_params()
+    miss = C.c_char_p()
+    n = load().qlb_params_from_yaml(C.byref(p), text.encode(), C.byref(miss))
+    if n < 0:
+        raise RuntimeError("qlb_params_from_yaml failed")
+    return p, (miss.value.decode() if miss.value else None)
 
 
 def leg_models(model: dict | str = "quadruped_model"):
@@ -311,6 +329,22 @@ class Solver:
         rc = self.lib.qlb_swing_leg_torques(self._ctx, q.shape[1], _ptr(q), _ptr(qd), _ptr(qdd), _ptr(ptarget), _ptr(vtarget),
                                             C.byref(params), _ptr(tau), stream if stream is not None else None)
         self._check(rc, "qlb_swing_leg_torques")
+
+    def swing_leg_torques_from_queue(self, q, qd_back, qd_front, period, ptarget, vtarget, params: SwingParams, tau, stream=None):
+        rc = self.lib.qlb_swing_leg_torques_from_queue(self._ctx, q.shape[1], _ptr(q), _ptr(qd_back), _ptr(qd_front), float(period),
+                                                       _ptr(ptarget), _ptr(vtarget), C.byref(params), _ptr(tau),
+                                                       stream if stream is not None else None)
+        self._check(rc, "qlb_swing_leg_torques_from_queue")
+
+    def contact_fsm(self, desired, footstep, contact, phase, limb_state, stance=None, stream=None):
+        rc = self.lib.qlb_contact_fsm(self._ctx, desired.shape[0], _ptr(desired), _ptr(footstep), _ptr(contact), _ptr(phase),
+                                      _ptr(limb_state), _ptr(stance), stream if stream is not None else None)
+        self._check(rc, "qlb_contact_fsm")
+
+    def friction_margins(self, grf, quat, mask, mu, normals, margin, min_normal=None, stream=None):
+        rc = self.lib.qlb_friction_margins(self._ctx, grf.shape[1], _ptr(grf), _ptr(quat), _ptr(mask), _ptr(mu), _ptr(normals),
+                                           _ptr(margin), _ptr(min_normal), stream if stream is not None else None)
+        self._check(rc, "qlb_friction_margins")
 
     def swing_leg_torques_host(self, q, qd, qdd, ptarget, vtarget, params: SwingParams, tau):
         rc = self.lib.qlb_swing_leg_torques_host(self._ctx, q.shape[1], _ptr(q), _ptr(qd), _ptr(qdd), _ptr(ptarget), _ptr(vtarget),

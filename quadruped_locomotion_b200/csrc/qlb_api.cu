@@ -63,6 +63,8 @@ struct qlb_context {
   double* d_out = nullptr;
   uint8_t* d_mask = nullptr;
   uint32_t* d_flags = nullptr;
+  unsigned char* d_qp = nullptr;    // staging of qlb_qp_dense_host
+  size_t qp_bytes = 0;
   unsigned char* d_rec = nullptr;   // record staging of qlb_solve_records_host: kPipe x cap x (216 + 248) bytes
   size_t rec_cap = 0;
   size_t cap = 0;
@@ -427,6 +429,146 @@ int qlb_default_params(qlb_params* p) {
   return QLB_OK;
 }
 
+// ---- parameters from the reference's own keys (ROS parameter paths / controller_gains.yaml)
+namespace {
+struct ParamKey { const char* path; int group; int index; };
+// group 0: wrench_weights[i]; 1: ground_force_weight; 2: friction_default; 3: min_normal_force;
+// 4/5/6: kp/kd/kff translation[i]; 7/8/9: kp/kd/kff rotation[i]
+const ParamKey kParamKeys[] = {
+    {"/balance_controller/contact_force_distribution/weights/force/heading", 0, 0},
+    {"/balance_controller/contact_force_distribution/weights/force/lateral", 0, 1},
+    {"/balance_controller/contact_force_distribution/weights/force/vertical", 0, 2},
+    {"/balance_controller/contact_force_distribution/weights/torque/roll", 0, 3},
+    {"/balance_controller/contact_force_distribution/weights/torque/pitch", 0, 4},
+    {"/balance_controller/contact_force_distribution/weights/torque/yaw", 0, 5},
+    {"/balance_controller/contact_force_distribution/weights/regularizer/value", 1, 0},
+    {"/balance_controller/contact_force_distribution/constraints/friction_coefficient", 2, 0},
+    {"/balance_controller/contact_force_distribution/constraints/minimal_normal_force", 3, 0},
+    {"/balance_controller/virtual_model_controller/heading/kp", 4, 0}, {"/balance_controller/virtual_model_controller/heading/kd", 5, 0},
+    {"/balance_controller/virtual_model_controller/heading/kff", 6, 0}, {"/balance_controller/virtual_model_controller/lateral/kp", 4, 1},
+    {"/balance_controller/virtual_model_controller/lateral/kd", 5, 1}, {"/balance_controller/virtual_model_controller/lateral/kff", 6, 1},
+    {"/balance_controller/virtual_model_controller/vertical/kp", 4, 2}, {"/balance_controller/virtual_model_controller/vertical/kd", 5, 2},
+    {"/balance_controller/virtual_model_controller/vertical/kff", 6, 2}, {"/balance_controller/virtual_model_controller/roll/kp", 7, 0},
+    {"/balance_controller/virtual_model_controller/roll/kd", 8, 0}, {"/balance_controller/virtual_model_controller/roll/kff", 9, 0},
+    {"/balance_controller/virtual_model_controller/pitch/kp", 7, 1}, {"/balance_controller/virtual_model_controller/pitch/kd", 8, 1},
+    {"/balance_controller/virtual_model_controller/pitch/kff", 9, 1}, {"/balance_controller/virtual_model_controller/yaw/kp", 7, 2},
+    {"/balance_controller/virtual_model_controller/yaw/kd", 8, 2}, {"/balance_controller/virtual_model_controller/yaw/kff", 9, 2},
+};
+constexpr int kNumParamKeys = (int)(sizeof(kParamKeys) / sizeof(kParamKeys[0]));
+}  // namespace
+
+int qlb_params_set_key(qlb_params* p, const char* key, double value) {
+  if (!p || !key) return QLB_ERR_INVALID_ARGUMENT;
+  for (int k = 0; k < kNumParamKeys; k++) {
+    if (std::strcmp(key, kParamKeys[k].path) != 0) continue;
+    const int i = kParamKeys[k].index;
+    switch (kParamKeys[k].group) {
+      case 0: p->wrench_weights[i] = value; break;
+      case 1: p->ground_force_weight = value; break;
+      case 2: p->friction_default = value; break;
+      case 3: p->min_normal_force = value; break;
+      case 4: p->kp_translation[i] = value; break;
+      case 5: p->kd_translation[i] = value; break;
+      case 6: p->kff_translation[i] = value; break;
+      case 7: p->kp_rotation[i] = value; break;
+      case 8: p->kd_rotation[i] = value; break;
+      default: p->kff_rotation[i] = value; break;
+    }
+    return k;   // index of the key (>= 0)
+  }
+  return QLB_ERR_INVALID_ARGUMENT;
+}
+
+int qlb_params_get_key(const qlb_params* p, const char* key, double* value) {
+  if (!p || !key || !value) return QLB_ERR_INVALID_ARGUMENT;
+  for (int k = 0; k < kNumParamKeys; k++) {
+    if (std::strcmp(key, kParamKeys[k].path) != 0) continue;
+    const int i = kParamKeys[k].index;
+    switch (kParamKeys[k].group) {
+      case 0: *value = p->wrench_weights[i]; break;
+      case 1: *value = p->ground_force_weight; break;
+      case 2: *value = p->friction_default; break;
+      case 3: *value = p->min_normal_force; break;
+      case 4: *value = p->kp_translation[i]; break;
+      case 5: *value = p->kd_translation[i]; break;
+      case 6: *value = p->kff_translation[i]; break;
+      case 7: *value = p->kp_rotation[i]; break;
+      case 8: *value = p->kd_rotation[i]; break;
+      default: *value = p->kff_rotation[i]; break;
+    }
+    return k;
+  }
+  return QLB_ERR_INVALID_ARGUMENT;
+}
+
+int qlb_params_num_keys(void) { return kNumParamKeys; }
+const char* qlb_params_key(int index) { return (index >= 0 && index < kNumParamKeys) ? kParamKeys[index].path : nullptr; }
+
+// A YAML subset is enough for the reference's parameter files: nested mappings by indentation, `key: scalar` leaves,
+// comments and blank lines.  Every leaf becomes a parameter path "/a/b/c" and goes through qlb_params_set_key;
+// unknown paths are ignored (the files also configure other controllers).
+int qlb_params_from_yaml(qlb_params* p, const char* text, const char** first_missing) {
+  if (!p || !text) return QLB_ERR_INVALID_ARGUMENT;
+  bool seen[kNumParamKeys] = {};
+  struct Level { int indent; size_t len; };
+  Level stack[32];
+  int depth = 0;
+  char path[512];
+  size_t plen = 0;
+  const char* c = text;
+  while (*c) {
+    const char* eol = c;
+    while (*eol && *eol != '\n') eol++;
+    int indent = 0;
+    const char* t = c;
+    while (t < eol && *t == ' ') { indent++; t++; }
+    const char* hash = t;
+    while (hash < eol && *hash != '#') hash++;
+    const char* end = hash;
+    while (end > t && (end[-1] == ' ' || end[-1] == '\t' || end[-1] == '\r')) end--;
+    if (end > t && *t != '-') {
+      const char* colon = t;
+      while (colon < end && *colon != ':') colon++;
+      if (colon < end) {
+        while (depth > 0 && stack[depth - 1].indent >= indent) depth--;
+        plen = depth > 0 ? stack[depth - 1].len : 0;
+        const size_t klen = (size_t)(colon - t);
+        if (plen + 1 + klen + 1 < sizeof path && depth < 32) {
+          path[plen] = '/';
+          std::memcpy(path + plen + 1, t, klen);
+          const size_t nlen = plen + 1 + klen;
+          path[nlen] = 0;
+          const char* v = colon + 1;
+          while (v < end && *v == ' ') v++;
+          if (v < end) {
+            char buf[64];
+            const size_t vl = (size_t)(end - v) < sizeof buf - 1 ? (size_t)(end - v) : sizeof buf - 1;
+            std::memcpy(buf, v, vl);
+            buf[vl] = 0;
+            char* stop = nullptr;
+            const double val = std::strtod(buf, &stop);
+            if (stop != buf) {
+              const int k = qlb_params_set_key(p, path, val);
+              if (k >= 0) seen[k] = true;
+            }
+          } else {
+            stack[depth].indent = indent; stack[depth].len = nlen; depth++;
+          }
+        }
+      }
+    }
+    c = *eol ? eol + 1 : eol;
+  }
+  int found = 0;
+  const char* miss = nullptr;
+  for (int k = 0; k < kNumParamKeys; k++) {
+    if (seen[k]) found++;
+    else if (!miss) miss = kParamKeys[k].path;
+  }
+  if (first_missing) *first_missing = miss;
+  return found;
+}
+
 int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const qlb_params* params, int device,
                size_t max_batch) {
   if (!out || !legs) return QLB_ERR_INVALID_ARGUMENT;
@@ -509,7 +651,7 @@ int qlb_destroy(qlb_context* ctx) {
     if (ctx->pipe[i]) { cudaStreamSynchronize(ctx->pipe[i]); cudaStreamDestroy(ctx->pipe[i]); }
   cudaFree(ctx->d_model); cudaFree(ctx->d_params); cudaFree(ctx->d_counter); cudaFree(ctx->d_stats);
   cudaFree(ctx->d_model_f); cudaFree(ctx->d_params_f); cudaFree(ctx->d_limb);
-  cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags); cudaFree(ctx->d_rec);
+  cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags); cudaFree(ctx->d_rec); cudaFree(ctx->d_qp);
   for (int i = 0; i < 8; i++) cudaFree(ctx->d_list[i]);
   for (int i = 0; i < 8; i++)
     if (ctx->slot_done[i]) cudaEventDestroy(ctx->slot_done[i]);
@@ -852,6 +994,60 @@ int qlb_swing_leg_torques(qlb_context* ctx, size_t B, const double* q, const dou
   return QLB_OK;
 }
 
+int qlb_swing_leg_torques_from_queue(qlb_context* ctx, size_t B, const double* q, const double* qd_back, const double* qd_front,
+                                     double period, const double* foot_target_position, const double* foot_target_velocity,
+                                     const qlb_swing_params* params, double* tau, void* stream) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (!ctx->have_limb) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!q || !qd_back || !qd_front || !params || !tau || !(period > 0.0)) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  SwingArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.B = B; a.q = q; a.qd = qd_back; a.qdd = nullptr; a.qd_front = qd_front; a.inv_window = 1.0 / (10.0 * period);
+  a.ptarget = foot_target_position; a.vtarget = foot_target_velocity; a.tau = tau;
+  for (int c = 0; c < 3; c++) { a.gravity[c] = params->gravity[c]; a.kp[c] = params->kp[c]; a.kd[c] = params->kd[c]; }
+  a.acc_scale = params->acceleration_scale;
+  a.dyn = ctx->d_limb; a.model = ctx->d_model;
+  const unsigned long long total = (unsigned long long)B * 4ull;
+  const unsigned long long blocks = (total + 127) / 128;
+  if (blocks > 0x7fffffffull) return QLB_ERR_BATCH_TOO_LARGE;
+  qlb_swing_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return QLB_OK;
+}
+
+int qlb_contact_fsm(qlb_context* ctx, size_t B, const uint8_t* desired_stance_mask, const uint8_t* footstep_mask,
+                    const uint8_t* contact_mask, const double* phase, uint8_t* limb_state, uint8_t* stance_mask, void* stream) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!desired_stance_mask || !contact_mask || !phase || !limb_state) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  const unsigned long long blocks = ((unsigned long long)B + 255) / 256;
+  if (blocks > 0x7fffffffull) return QLB_ERR_BATCH_TOO_LARGE;
+  qlb_contact_fsm_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(B, desired_stance_mask, footstep_mask,
+                                                                                         contact_mask, phase, limb_state, stance_mask);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return QLB_OK;
+}
+
+int qlb_friction_margins(qlb_context* ctx, size_t B, const double* grf, const double* quat_wxyz, const uint8_t* stance_mask,
+                         const double* mu, const double* normals_world, double* margin, double* min_normal, void* stream) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!grf || !quat_wxyz || !stance_mask || !margin) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  const unsigned long long blocks = ((unsigned long long)B + 255) / 256;
+  if (blocks > 0x7fffffffull) return QLB_ERR_BATCH_TOO_LARGE;
+  qlb_friction_margin_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(B, grf, quat_wxyz, stance_mask, mu,
+                                                                                             normals_world, ctx->d_params, margin, min_normal);
+  QLB_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return QLB_OK;
+}
+
 // HOST pointers: staged through the context's pipeline buffers in chunks, on the context stream; synchronises.
 int qlb_swing_leg_torques_host(qlb_context* ctx, size_t B, const double* q, const double* qd, const double* qdd,
                                const double* foot_target_position, const double* foot_target_velocity,
@@ -1090,10 +1286,11 @@ int qlb_qp_dense(qlb_context* ctx, size_t B, int n, int m, int p, const double* 
   QpDenseArgs a;
   a.B = B; a.n = n; a.m = m; a.p = p; a.G = G; a.g0 = g0; a.CE = CE; a.ce0 = ce0; a.CI = CI; a.ci0 = ci0;
   a.x = x; a.cost = cost; a.status = status; a.active = active;
-  const unsigned threads = 64;
-  const unsigned long long blocks = (B + threads - 1) / threads;
-  if (blocks > 0x7fffffffull) return QLB_ERR_BATCH_TOO_LARGE;
-  qlb_qp_dense_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  // one warp per problem, four problems per CTA, grid-stride over the batch
+  unsigned long long blocks = (B + kQpWarpsPerCta - 1) / kQpWarpsPerCta;
+  const unsigned long long cap = (unsigned long long)ctx->sm_count * 8ull;
+  if (blocks > cap) blocks = cap;
+  qlb_qp_dense_kernel<<<(unsigned)blocks, 32 * kQpWarpsPerCta, 0, static_cast<cudaStream_t>(stream)>>>(a);
   QLB_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
   return QLB_OK;
@@ -1109,12 +1306,20 @@ int qlb_qp_dense_host(qlb_context* ctx, size_t B, int n, int m, int p, const dou
   DeviceGuard guard(ctx->device);
   cudaStream_t st = ctx->stream;
   const size_t nin = (size_t)(n * n + n + n * p + p + n * m + m) * B, nout = (size_t)(n + 1) * B;
-  double* d_in = nullptr; double* d_out = nullptr; uint32_t* d_u = nullptr;
-  if (cudaMalloc(&d_in, nin * sizeof(double)) != cudaSuccess || cudaMalloc(&d_out, nout * sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&d_u, 2 * B * sizeof(uint32_t)) != cudaSuccess) {
-    cudaFree(d_in); cudaFree(d_out); cudaFree(d_u); cudaGetLastError();
-    return QLB_ERR_ALLOC;
+  // staging owned by the context, grown on demand (a controller calls this every tick with the same shape)
+  const size_t need = (nin + nout) * sizeof(double) + 2 * B * sizeof(uint32_t);
+  if (ctx->qp_bytes < need) {
+    QLB_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(ctx->d_qp);
+    ctx->d_qp = nullptr; ctx->qp_bytes = 0;
+    size_t cap = 4096;
+    while (cap < need) cap *= 2;
+    if (cudaMalloc(&ctx->d_qp, cap) != cudaSuccess) { cudaGetLastError(); return QLB_ERR_ALLOC; }
+    ctx->qp_bytes = cap;
   }
+  double* d_in = reinterpret_cast<double*>(ctx->d_qp);
+  double* d_out = d_in + nin;
+  uint32_t* d_u = reinterpret_cast<uint32_t*>(d_out + nout);
   double* dG = d_in; double* dg = dG + (size_t)n * n * B; double* dCE = dg + (size_t)n * B; double* dce = dCE + (size_t)n * p * B;
   double* dCI = dce + (size_t)p * B; double* dci = dCI + (size_t)n * m * B;
   int rc = QLB_OK;
@@ -1133,7 +1338,6 @@ int qlb_qp_dense_host(qlb_context* ctx, size_t B, int n, int m, int p, const dou
   }
   if (cudaStreamSynchronize(st) != cudaSuccess && rc == QLB_OK) rc = QLB_ERR_CUDA;
   if (rc == QLB_ERR_CUDA) cuda_fail(ctx, cudaGetLastError(), "qlb_qp_dense_host");
-  cudaFree(d_in); cudaFree(d_out); cudaFree(d_u);
   return rc;
 }
 

@@ -219,6 +219,98 @@ __global__ void __launch_bounds__(256) qlb_stats_kernel(unsigned long long B, co
     atomicMax(reinterpret_cast<unsigned long long*>(&out[threadIdx.x]), (unsigned long long)__double_as_longlong(sh[threadIdx.x]));
 }
 
+// Batched per-leg contact state machine: RosBalanceController::footContactsCallback
+// (balance_controller/src/ros_controller/ros_balance_controller.cpp:1086-1140) and the support-leg decision that
+// update() derives from the limb state (:242-366).  One thread per state, the four legs in sequence.
+//   desired   bit k = the plan says leg k is a stance leg (limbs_desired_state == StanceNormal, else SwingNormal)
+//   footstep  bit k = is_footstep_ (the leg takes part in contact supervision)
+//   contact   bit k = measured foot contact (FootContacts.is_contact)
+//   phase     [4][B] the phase of the leg's current stance or swing (st_phase / sw_phase, :979-1077)
+//   limb_state[4][B] in: previous state, out: new state (qlb_limb_state values = StateSwitcher::States order)
+//   stance    [B] out: bit k = leg k is a support leg for the force distribution
+// (The reference advances its limb index only at the end of the loop body, so a `continue` makes the next foot
+// overwrite the same limb; the per-limb rules below are the evident intent.)
+__global__ void __launch_bounds__(256) qlb_contact_fsm_kernel(unsigned long long B, const uint8_t* __restrict__ desired,
+                                                              const uint8_t* __restrict__ footstep, const uint8_t* __restrict__ contact,
+                                                              const double* __restrict__ phase, uint8_t* __restrict__ limb_state,
+                                                              uint8_t* __restrict__ stance) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const unsigned des = desired[i], fs = footstep ? footstep[i] : 0xFu, con = contact[i];
+  unsigned mask = 0u;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const bool d = (des >> k) & 1u, f = (fs >> k) & 1u, c = (con >> k) & 1u;
+    const double ph = phase[(size_t)k * B + i];
+    unsigned st = limb_state[(size_t)k * B + i];
+    if (!d) {
+      st = QLB_LIMB_SWING_NORMAL;
+      if (f) {
+        if (ph > 0.5) { if (c) st = QLB_LIMB_SWING_EARLY_TOUCHDOWN; }
+        else if (ph > 0.2) { if (c) st = QLB_LIMB_SWING_BUMPED_INTO_OBSTACLE; }
+      }
+    } else {
+      if (!f) {
+        st = QLB_LIMB_STANCE_NORMAL;
+      } else {
+        if (c) st = QLB_LIMB_STANCE_NORMAL;
+        else if (ph < 0.1) st = QLB_LIMB_SWING_LATELY_TOUCHDOWN;
+        if (ph > 0.5 && !c) st = QLB_LIMB_STANCE_LOST_CONTACT;
+      }
+    }
+    limb_state[(size_t)k * B + i] = (uint8_t)st;
+    const bool support = st == QLB_LIMB_STANCE_NORMAL || st == QLB_LIMB_SWING_EARLY_TOUCHDOWN || st == QLB_LIMB_INIT;
+    mask |= (support ? 1u : 0u) << k;
+  }
+  if (stance) stance[i] = (uint8_t)mask;
+}
+
+// Friction margins of a solved batch: for every state the smallest slack of the friction-pyramid and minimal-force
+// rows over its stance legs, relative to the normal force - how far the planned motion stays from slipping (0 = a
+// friction row is active, negative = infeasible answer).  What a preview of a planned motion reads next to the
+// forces (the rows are those of ContactForceDistribution.cpp:210-336).  One thread per state.
+__global__ void __launch_bounds__(256) qlb_friction_margin_kernel(unsigned long long B, const double* __restrict__ grf,
+                                                                  const double* __restrict__ quat, const uint8_t* __restrict__ mask,
+                                                                  const double* __restrict__ mu, const double* __restrict__ normals,
+                                                                  const DeviceParams* __restrict__ prm, double* __restrict__ margin,
+                                                                  double* __restrict__ min_normal) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const double w = quat[i], x = quat[B + i], y = quat[2 * B + i], z = quat[3 * B + i];
+  const double R[9] = {w * w + x * x - y * y - z * z, 2.0 * (x * y - w * z), 2.0 * (x * z + w * y),
+                       2.0 * (x * y + w * z), w * w - x * x + y * y - z * z, 2.0 * (y * z - w * x),
+                       2.0 * (x * z - w * y), 2.0 * (y * z + w * x), w * w - x * x - y * y + z * z};
+  const unsigned m = mask[i];
+  double best = 1e300, bestn = 1e300;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (!((m >> k) & 1u)) continue;
+    double nw[3] = {0.0, 0.0, 1.0};
+    if (normals) { nw[0] = normals[(size_t)(3 * k) * B + i]; nw[1] = normals[(size_t)(3 * k + 1) * B + i]; nw[2] = normals[(size_t)(3 * k + 2) * B + i]; }
+    double n[3], t1[3], t2[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) n[c] = R[c] * nw[0] + R[3 + c] * nw[1] + R[6 + c] * nw[2];   // R_wb n_world
+    const double ey[3] = {R[3], R[4], R[5]};
+    t1[0] = n[1] * ey[2] - n[2] * ey[1]; t1[1] = n[2] * ey[0] - n[0] * ey[2]; t1[2] = n[0] * ey[1] - n[1] * ey[0];
+    double rn = rsqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+    t1[0] *= rn; t1[1] *= rn; t1[2] *= rn;
+    t2[0] = n[1] * t1[2] - n[2] * t1[1]; t2[1] = n[2] * t1[0] - n[0] * t1[2]; t2[2] = n[0] * t1[1] - n[1] * t1[0];
+    rn = rsqrt(t2[0] * t2[0] + t2[1] * t2[1] + t2[2] * t2[2]);
+    t2[0] *= rn; t2[1] *= rn; t2[2] *= rn;
+    const double f[3] = {grf[(size_t)(3 * k) * B + i], grf[(size_t)(3 * k + 1) * B + i], grf[(size_t)(3 * k + 2) * B + i]};
+    const double fn = f[0] * n[0] + f[1] * n[1] + f[2] * n[2];
+    const double f1 = f[0] * t1[0] + f[1] * t1[1] + f[2] * t1[2];
+    const double f2 = f[0] * t2[0] + f[1] * t2[1] + f[2] * t2[2];
+    const double muk = mu ? mu[(size_t)k * B + i] : prm->mu_default;
+    const double slack = fmin(muk * fn - fabs(f1), muk * fn - fabs(f2));
+    const double rel = slack / fmax(muk * fn, 1e-300);
+    best = fmin(best, rel);
+    bestn = fmin(bestn, fn - prm->fmin);
+  }
+  margin[i] = (m & 0xFu) ? best : 0.0;
+  if (min_normal) min_normal[i] = (m & 0xFu) ? bestn : 0.0;
+}
+
 // FP64 FMA throughput probe: the roofline denominator for this path (SURVEY.md 8d asks for a measured
 // figure; MEASURED_PEAKS.json only has HBM and bf16).  8 independent DFMA chains per thread.
 __global__ void __launch_bounds__(256) qlb_fp64_peak_kernel(double* __restrict__ sink, int iters, double seed) {

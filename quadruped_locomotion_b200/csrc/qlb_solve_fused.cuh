@@ -82,11 +82,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0u;
 }
-// Bounded: a transfer that never completes (a bad tensor map) ends the kernel with an error instead of hanging the GPU.
+// Whole warp.  The exit is decided by a vote, so the warp leaves the loop converged (a per-lane exit, or a trap
+// inside the loop, makes the compiler treat everything after it as possibly divergent: every later shuffle then
+// gets an out-of-line slow path and the kernel doubles in size).  Bounded: a transfer that never completes (a bad
+// tensor map) lets the kernel finish with wrong data instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  unsigned spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+  for (unsigned spins = 0; spins < (1u << 24); spins++) {
+    const bool ok = mbar_try_wait(bar, parity);
+    if (__all_sync(kFull, ok)) break;
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {

@@ -241,7 +241,6 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
   const creal winv = cc.winv, cfmin = cc.fmin;
   unsigned occ = 0u;           // pending slots of the stash (warp-uniform)
   uint32_t parity = 0;
-  asm volatile("" : "+r"(parity));   // opaque: keeps the compiler from peeling the tile loop by mbarrier phase
 
   // Work distribution: boxes are claimed with one atomic each, TWO ahead.  The result of a claim stays in lane 0 and
   // is broadcast only when the box number is needed - a whole tile later - so the round trip of the atomic is never
@@ -264,8 +263,6 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
 #pragma unroll 1
   for (;;) {
     const bool have = cur < nbox;   // warp-uniform
-    // opaque to the optimiser: otherwise it clones the whole tile body per mbarrier phase / tile-of-the-box value
-    asm volatile("" : "+r"(parity), "+r"(sub));
     if (have) {
       // ---- the staged rows of this box
       if (sub == 0) {
@@ -278,7 +275,8 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
       const unsigned long long bq = valid ? s0 : (B - 1);
       RawIn<real, MODE> in;
       stage_read<real, MODE, SUPER>(a, stage, prm.mu_default, leg, col, bq, in);
-      in.mask = valid ? (__shfl_sync(kFull, mask_cur, col) & 0xFu) : 0u;
+      const unsigned mask_byte = __shfl_sync(kFull, mask_cur, col);   // every lane takes part (not inside the `valid` select)
+      in.mask = valid ? (mask_byte & 0xFu) : 0u;
       if (sub == SUPER - 1) {
         __syncwarp();     // every lane has read the last tile of the box: the next box may land in the buffer
         nxt = __shfl_sync(kFull, pending_claim, 0);

@@ -27,7 +27,9 @@ struct SwingArgs {
   unsigned long long B;
   const double* q;
   const double* qd;
-  const double* qdd;
+  const double* qdd;       // null when the acceleration comes from the velocity queue
+  const double* qd_front;  // oldest entry of the caller's joint-velocity queue (qd is its newest entry), or null
+  double inv_window;       // 1 / (10 * period): the reference's Time_derta (model_test_header.cpp:421,428)
   const double* ptarget;   // may be null
   const double* vtarget;   // may be null
   double* tau;
@@ -56,7 +58,10 @@ __global__ void __launch_bounds__(128) qlb_swing_kernel(const SwingArgs a) {
   for (int j = 0; j < 3; j++) {
     qv[j] = a.q[(size_t)(3 * leg + j) * B + i];
     qdv[j] = a.qd[(size_t)(3 * leg + j) * B + i];
-    qddv[j] = a.acc_scale * a.qdd[(size_t)(3 * leg + j) * B + i];
+    // acceleration: given, or estimated as the reference does from the two ends of its velocity queue,
+    // (qd_back - qd_front) / (10 * period)  (model_test_header.cpp:421-429; the windowed average it also computes is never used)
+    const double acc = a.qd_front ? (qdv[j] - a.qd_front[(size_t)(3 * leg + j) * B + i]) * a.inv_window : a.qdd[(size_t)(3 * leg + j) * B + i];
+    qddv[j] = a.acc_scale * acc;
   }
   // ---- outward pass in the base frame
   double R[9], p[3] = {0.0, 0.0, 0.0};

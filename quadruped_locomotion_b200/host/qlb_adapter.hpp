@@ -19,6 +19,8 @@
 #include <array>
 #include <map>
 #include <memory>
+#include <utility>
+#include <vector>
 #include <stdexcept>
 #include <string>
 
@@ -91,6 +93,51 @@ class State {
   LocalAngularVelocity ang_vel_{{0, 0, 0}}, t_ang_vel_{{0, 0, 0}};
 };
 
+// Stand-in for the ROS parameter server behind ros::NodeHandle::hasParam / getParam, which the reference's
+// loadParameters() functions query key by key (ContactForceDistribution.cpp:818-886, VirtualModelController.cpp:
+// 429-548).  Keys are the reference's parameter paths; loadYaml() takes the text of a file laid out like
+// balance_controller/config/controller_gains.yaml.
+class ParameterServer {
+ public:
+  bool hasParam(const std::string& key) const { return values_.count(key) != 0; }
+  bool getParam(const std::string& key, double& value) const {
+    auto it = values_.find(key);
+    if (it == values_.end()) return false;
+    value = it->second;
+    return true;
+  }
+  void setParam(const std::string& key, double value) { values_[key] = value; }
+  void deleteParam(const std::string& key) { values_.erase(key); }
+  void clear() { values_.clear(); }
+  // every `a: {b: {c: number}}` leaf of the text becomes "/a/b/c"
+  void loadYaml(const std::string& text) {
+    std::vector<std::pair<int, std::string>> stack;
+    size_t pos = 0;
+    while (pos <= text.size()) {
+      size_t eol = text.find('\n', pos);
+      if (eol == std::string::npos) eol = text.size();
+      std::string line = text.substr(pos, eol - pos);
+      pos = eol + 1;
+      const size_t hash = line.find('#');
+      if (hash != std::string::npos) line.erase(hash);
+      while (!line.empty() && (line.back() == ' ' || line.back() == '\r' || line.back() == '\t')) line.pop_back();
+      size_t indent = 0;
+      while (indent < line.size() && line[indent] == ' ') indent++;
+      const size_t colon = line.find(':', indent);
+      if (line.size() == indent || colon == std::string::npos) continue;
+      while (!stack.empty() && stack.back().first >= (int)indent) stack.pop_back();
+      const std::string key = (stack.empty() ? std::string() : stack.back().second) + "/" + line.substr(indent, colon - indent);
+      size_t v = colon + 1;
+      while (v < line.size() && line[v] == ' ') v++;
+      if (v >= line.size()) { stack.emplace_back((int)indent, key); continue; }
+      try { values_[key] = std::stod(line.substr(v)); } catch (...) {}
+    }
+  }
+
+ private:
+  std::map<std::string, double> values_;
+};
+
 // Shared owner of one qlb_context (one GPU).  The reference constructs ContactForceDistribution and
 // VirtualModelController around one shared free_gait::State (ros_balance_controller.cpp:73-74); here
 // they additionally share the device context.
@@ -100,17 +147,38 @@ class Device {
     qlb_default_params(&params_);
     const int rc = qlb_create(&ctx_, legs, &params_, device, 1);
     if (rc != QLB_OK) throw std::runtime_error(std::string("qlb_create: ") + qlb_strerror(rc));
+    // the parameter server starts with the values of the reference's controller_gains.yaml (the library defaults),
+    // as after `rosparam load`; parameters().clear() gives an empty server
+    for (int k = 0; k < qlb_params_num_keys(); k++) {
+      double v = 0.0;
+      if (qlb_params_get_key(&params_, qlb_params_key(k), &v) >= 0) server_.setParam(qlb_params_key(k), v);
+    }
   }
   ~Device() { qlb_destroy(ctx_); }
   Device(const Device&) = delete;
   Device& operator=(const Device&) = delete;
   qlb_context* ctx() { return ctx_; }
   qlb_params& params() { return params_; }
+  ParameterServer& parameters() { return server_; }
   bool commit() { return qlb_set_params(ctx_, &params_) == QLB_OK; }
+  // getParam for a list of keys, as the reference's loadParameters() does: false as soon as one is missing
+  bool loadKeys(const char* prefix) {
+    for (int k = 0; k < qlb_params_num_keys(); k++) {
+      const std::string key = qlb_params_key(k);
+      if (key.compare(0, std::string(prefix).size(), prefix) != 0) continue;
+      double v = 0.0;
+      if (!server_.getParam(key, v)) { missing_ = key; return false; }
+      qlb_params_set_key(&params_, key.c_str(), v);
+    }
+    return true;
+  }
+  const std::string& missingParameter() const { return missing_; }
 
  private:
   qlb_context* ctx_ = nullptr;
   qlb_params params_;
+  ParameterServer server_;
+  std::string missing_;
 };
 
 class ContactForceDistributionBase {
@@ -139,9 +207,12 @@ class ContactForceDistribution : public ContactForceDistributionBase {
     for (int l = 0; l < 4; l++) legInfos_[static_cast<LimbEnum>(l)] = LegInfo();
   }
 
-  // ContactForceDistribution::loadParameters (ContactForceDistribution.cpp:818-886): the values of
-  // controller_gains.yaml are the library defaults; setters below stand in for the ROS parameter server.
+  // ContactForceDistribution::loadParameters (ContactForceDistribution.cpp:818-886): the nine keys under
+  // /balance_controller/contact_force_distribution are read from the parameter server; a missing key makes it fail
+  // (isParametersLoaded_ stays false and computeForceDistribution refuses to run), like the reference.
   bool loadParameters() override {
+    isParametersLoaded_ = false;
+    if (!device_->loadKeys("/balance_controller/contact_force_distribution/")) return false;
     for (auto& kv : legInfos_) kv.second.frictionCoefficient_ = device_->params().friction_default;
     isParametersLoaded_ = device_->commit();
     return isParametersLoaded_;
@@ -165,24 +236,43 @@ class ContactForceDistribution : public ContactForceDistributionBase {
     for (int i = 0; i < 12; i++) q[i] = jq[i];
     for (int i = 0; i < 4; i++) quat[i] = robot_state_->getOrientationBaseToWorld()[i];
     for (int i = 0; i < 3; i++) { wrench[i] = F[i]; wrench[3 + i] = T[i]; }
-    int nstance = 0;
+    mask = prepareLegLoading();
     for (int l = 0; l < 4; l++) {
       const LimbEnum limb = static_cast<LimbEnum>(l);
-      LegInfo& info = legInfos_[limb];
-      const bool stance = robot_state_->isSupportLeg(limb);  // prepareLegLoading, CFD.cpp:138-166
-      info.isPartOfForceDistribution_ = stance;
-      info.isLoadConstraintActive_ = stance;
-      info.indexInStanceLegList_ = stance ? nstance : 0;
-      info.startIndexInVectorX_ = 3 * info.indexInStanceLegList_;
-      info.desiredContactForce_ = {0, 0, 0};  // resetOptimization, CFD.cpp:580-596
-      if (stance) { mask |= (1u << l); nstance++; }
-      mu[l] = info.frictionCoefficient_;
+      mu[l] = legInfos_[limb].frictionCoefficient_;
       for (int a = 0; a < 3; a++) normals[3 * l + a] = robot_state_->getSurfaceNormal(limb)[a];
     }
     double grf[12], tau[12], net[6];
     uint32_t flags = 0;
     const int rc = qlb_solve_wrench_host(device_->ctx(), 1, q, quat, wrench, &mask, mu, normals, grf, tau, &flags, net);
     if (rc != QLB_OK) return false;
+    return applyResult(grf, tau, net, flags);
+  }
+
+  // prepareLegLoading + resetOptimization for the current stance flags (CFD.cpp:138-166,580-596); returns the mask
+  uint8_t prepareLegLoading() {
+    uint8_t mask = 0;
+    int nstance = 0;
+    isForceDistributionComputed_ = false;
+    for (int l = 0; l < 4; l++) {
+      const LimbEnum limb = static_cast<LimbEnum>(l);
+      LegInfo& info = legInfos_[limb];
+      const bool stance = robot_state_->isSupportLeg(limb);
+      info.isPartOfForceDistribution_ = stance;
+      info.isLoadConstraintActive_ = stance;
+      info.indexInStanceLegList_ = stance ? nstance : 0;
+      info.startIndexInVectorX_ = 3 * info.indexInStanceLegList_;
+      info.desiredContactForce_ = {0, 0, 0};
+      info.activeRows_ = 0;
+      if (stance) { mask |= (1u << l); nstance++; }
+    }
+    return mask;
+  }
+
+  // What a solve leaves behind in the reference: LegInfo forces, joint efforts in the shared State, the net wrench
+  // and the computed flag (CFD.cpp:496-514,516-578,614-625).  Also used by VirtualModelController::compute, whose
+  // reference version calls computeForceDistribution itself (VMC.cpp:99).
+  bool applyResult(const double* grf, const double* tau, const double* net, uint32_t flags) {
     const unsigned status = (flags & QLB_FLAG_STATUS_MASK) >> QLB_FLAG_STATUS_SHIFT;
     lastFlags_ = flags;
     // the reference returns false (and keeps stale efforts) when the solver fails (CFD.cpp:490-494)
@@ -236,7 +326,13 @@ class VirtualModelController : public MotionControllerBase {
                          std::shared_ptr<ContactForceDistribution> cfd)
       : device_(std::move(device)), robot_state_(std::move(robot_state)), cfd_(std::move(cfd)) {}
 
-  bool loadParameters() override { loaded_ = device_->commit(); return loaded_; }  // VMC.cpp:429-548
+  // VirtualModelController::loadParameters (VMC.cpp:429-548): the eighteen gains under /balance_controller/virtual_model_controller
+  bool loadParameters() override {
+    loaded_ = false;
+    if (!device_->loadKeys("/balance_controller/virtual_model_controller/")) return false;
+    loaded_ = device_->commit();
+    return loaded_;
+  }
   void setProportionalGainTranslation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kp_translation[i] = k[i]; }
   void setDerivativeGainTranslation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kd_translation[i] = k[i]; }
   void setFeedforwardGainTranslation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kff_translation[i] = k[i]; }
@@ -257,9 +353,9 @@ class VirtualModelController : public MotionControllerBase {
       ttwist[a] = s.getTargetLinearVelocityBaseInWorldFrame()[a]; ttwist[3 + a] = s.getTargetAngularVelocityBaseInBaseFrame()[a];
     }
     for (int i = 0; i < 4; i++) { pose[3 + i] = s.getOrientationBaseToWorld()[i]; tpose[3 + i] = s.getTargetOrientationBaseToWorld()[i]; }
+    mask = cfd_->prepareLegLoading();   // also resets the distribution's state before anything can fail
     for (int l = 0; l < 4; l++) {
       const LimbEnum limb = static_cast<LimbEnum>(l);
-      if (s.isSupportLeg(limb)) mask |= (1u << l);
       mu[l] = cfd_->getFrictionCoefficient(limb);
       for (int a = 0; a < 3; a++) normals[3 * l + a] = s.getSurfaceNormal(limb)[a];
     }
@@ -269,18 +365,13 @@ class VirtualModelController : public MotionControllerBase {
                                         &flags, net, wrench);
     if (rc != QLB_OK) return false;
     for (int a = 0; a < 3; a++) { virtualForceInBaseFrame_[a] = wrench[a]; virtualTorqueInBaseFrame_[a] = wrench[3 + a]; }
-    const unsigned status = (flags & QLB_FLAG_STATUS_MASK) >> QLB_FLAG_STATUS_SHIFT;
-    if (status != QLB_STATE_OK && status != QLB_STATE_NO_STANCE) return false;
-    for (int l = 0; l < 4; l++) {
-      const LimbEnum limb = static_cast<LimbEnum>(l);
-      auto& info = cfd_->legInfos_[limb];
-      info.isPartOfForceDistribution_ = s.isSupportLeg(limb);
-      info.desiredContactForce_ = {0, 0, 0};
-      if (!info.isPartOfForceDistribution_) continue;
-      info.desiredContactForce_ = {-grf[3 * l], -grf[3 * l + 1], -grf[3 * l + 2]};
-      robot_state_->setJointEffortsForLimb(limb, {tau[3 * l], tau[3 * l + 1], tau[3 * l + 2]});
-    }
-    return true;
+    // the reference's compute() ends in contactForceDistribution_->computeForceDistribution(F, T) (VMC.cpp:99): the
+    // shared distribution object sees the result exactly as if it had been called
+    return cfd_->applyResult(grf, tau, net, flags);
+  }
+  // VMC.cpp:288-300: what the distribution actually achieved
+  bool getDistributedVirtualForceAndTorqueInBaseFrame(Force& netForce, Torque& netTorque) const {
+    return cfd_->getNetForceAndTorqueOnBase(netForce, netTorque);
   }
   const Force& getDesiredVirtualForceInBaseFrame() const { return virtualForceInBaseFrame_; }
   const Torque& getDesiredVirtualTorqueInBaseFrame() const { return virtualTorqueInBaseFrame_; }

@@ -14,6 +14,7 @@
 // Eigen::MatrixXd / VectorXd (rows(), cols(), operator()(i,j)).
 #pragma once
 
+#include <cmath>
 #include <cstdint>
 #include <memory>
 #include <vector>
@@ -100,4 +101,77 @@ class QuadraticProblemSolver {
 };
 
 }  // namespace qp_solver
+
+// Mirror of sqp_solver::SequenceQuadraticProblemSolver::minimize (qp_solver/src/sequencequadraticproblemsolver.cpp:
+// 18-102): linearise the problem at the current parameters, solve the QP for the step dp on the GPU entry, apply it with
+// the parameterisation's plus(), stop when |dp| < tolerance or after max_iteration steps.  The problem types are
+// template parameters with the reference's method names:
+//   Objective   : public qp_solver::QuadraticObjectiveFunction + getLocalHessian(H, params), getLocalGradient(G, params),
+//                 computeValue(cost, params)
+//   Constraints : public qp_solver::LinearFunctionConstraints + getLocalInequalityConstraintJacobian(A, params),
+//                 getInequalityConstraintMaxValues(b_max), getInequalityConstraintValues(b, params)
+//   Params      : getLocalSize(), getParams(), plus(result, p, dp), setParams(result)
+//                 (the reference's PoseParameterization rebuilds its Pose from `result`, :71)
+// Like the reference, every QP carries a zero equality column (:28-29,45-46), which the GPU entry treats as absent.
+namespace sqp_solver {
+
+template <class Objective, class Constraints, class Params>
+class SequenceQuadraticProblemSolver {
+ public:
+  SequenceQuadraticProblemSolver(std::shared_ptr<qp_solver::QuadraticProblemSolver> quadratic_solver, double tolerance, int max_iteration)
+      : quadratic_solver_(std::move(quadratic_solver)), tolerance_(tolerance), max_iteration_(max_iteration) {}
+
+  bool minimize(Objective& objective, Constraints& constraints, Params& params) {
+    const int n = params.getLocalSize();
+    Matrix H, A, Aeq(n, 1);
+    Vector G, b, b_max, beq(1, 0.0);
+    auto linearise = [&]() {
+      objective.getLocalHessian(H, params);
+      objective.getLocalGradient(G, params);
+      constraints.getLocalInequalityConstraintJacobian(A, params);
+      constraints.getInequalityConstraintMaxValues(b_max);
+      constraints.getInequalityConstraintValues(b, params);
+      for (size_t i = 0; i < b.size(); i++) b[i] = b_max[i] - b[i];
+      objective.setGlobalHessian(H);
+      objective.setLinearTerm(G);
+      constraints.setGlobalInequalityConstraintJacobian(A);
+      constraints.setInequalityConstraintMaxValues(b);
+      constraints.setGlobalEqualityConstraintJacobian(Aeq.setZero());
+      constraints.setEqualityConstraintMaxValues(beq);
+    };
+    linearise();
+    Vector result = params.getParams();
+    iterations_ = 0;
+    status_ = 0;
+    while (iterations_ < max_iteration_) {
+      iterations_++;
+      Vector dp(n, 0.0);
+      quadratic_solver_->minimize(objective, constraints, dp);
+      status_ = quadratic_solver_->status();
+      if (status_ != 0) break;               // the reference carries on with whatever the solver left in dp
+      params.plus(result, result, dp);
+      params.setParams(result);
+      objective.computeValue(cost_, params);
+      double norm2 = 0.0;
+      for (double v : dp) norm2 += v * v;
+      step_norm_ = std::sqrt(norm2);
+      if (step_norm_ < tolerance_) break;
+      linearise();
+    }
+    return true;   // the reference always returns true (:101)
+  }
+  int iterations() const { return iterations_; }
+  int status() const { return status_; }
+  double cost() const { return cost_; }
+  double lastStepNorm() const { return step_norm_; }
+
+ private:
+  std::shared_ptr<qp_solver::QuadraticProblemSolver> quadratic_solver_;
+  double tolerance_;
+  int max_iteration_;
+  int iterations_ = 0, status_ = 0;
+  double cost_ = 0.0, step_norm_ = 0.0;
+};
+
+}  // namespace sqp_solver
 }  // namespace qlb_host
