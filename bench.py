@@ -172,6 +172,106 @@ def cpu_reference(st, steps: int, warmup: int, sample: int):
     return sample / t1, info
 
 
+def run_sweep(args, rank, local_rank, world, dev, warmup):
+    """BASELINE config C5: the Monte-Carlo robustness sweep (2^14 nominal states x 2^10 perturbations of base attitude,
+    friction and wrench scale), sharded by instance over the ranks.  The states are GENERATED ON THE DEVICE
+    (qlb_generate_states, bit-identical to synth.make_states), solved, and reduced to qlb_stats on the device: one step
+    moves nothing over PCIe but 248 bytes of statistics, and the ranks exchange nothing but those (NCCL all-reduce).
+    `value` = solve only (states resident); `e2e` = generate + solve + statistics + all-reduce per step."""
+    import torch
+    import torch.distributed as dist
+    from quadruped_locomotion_b200 import capi, dist as qdist
+    B = args.batch if args.batch != BATCH_PER_GPU else (1 << 21)
+    solver = capi.Solver(MODEL, device=local_rank)
+    stream = torch.cuda.current_stream()
+    f64 = lambda n: torch.empty((n, B), dtype=torch.float64, device=dev)  # noqa: E731
+    q, quat, wrench, mu, grf, tau, net = f64(12), f64(4), f64(6), f64(4), f64(12), f64(12), f64(6)
+    mask = torch.empty(B, dtype=torch.uint8, device=dev)
+    flags = torch.empty(B, dtype=torch.int32, device=dev)
+
+    def generate():
+        solver.generate_states("C5", B, start=rank * B, q=q, quat=quat, wrench=wrench, mask=mask, mu=mu, stream=stream.cuda_stream)
+
+    def solve():
+        solver.solve_wrench(q, quat, wrench, mask, mu, None, grf, tau, flags, net, stream=stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(stream)
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    generate()
+    for _ in range(warmup):
+        solve()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = solver.launches
+    ms_step = timed(solve, args.steps)
+    launches = solver.launches - launches0
+    ms_gen = timed(generate, max(3, args.steps // 4))
+
+    stats_holder = {}
+
+    def sweep_step():
+        generate()
+        solve()
+        s = torch.from_numpy(solver.batch_stats(flags, wrench, net, stream=stream.cuda_stream)).to(dev)
+        qdist.allreduce_stats(s)
+        stats_holder["s"] = s.cpu().numpy()
+
+    for _ in range(2):
+        sweep_step()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sweep_step()
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    sd = qdist.stats_dict(stats_holder["s"])
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": world * B / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (generated on the device)",
+            "config": {"workload": "C5: Monte-Carlo robustness sweep, perturbed base attitude / friction / wrench scale, "
+                                   f"{world * B} samples, FP64, model quadruped_model.urdf", "states_per_gpu": B,
+                       "global_batch": world * B, "parallelism": f"instance-sharded x{world}, no data-path collective",
+                       "l2_policy": "inputs+outputs exceed the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": capi.STATS_NUM * 8, "steps": e2e_steps,
+                    "api": "qlb_generate_states + qlb_solve_wrench + qlb_batch_stats + all-reduce of the statistics: nothing "
+                           "but 248 bytes per rank leaves the device"},
+            "gpu_launches": int(launches), "generate_ms_per_step": ms_gen,
+            "stats": {"count": sd["count"], "ok": sd["ok"], "infeasible": sd["infeasible"], "bad_input": sd["bad_input"],
+                      "max_iter": sd["max_iter"], "mean_solver_rounds": sd["mean_iterations"],
+                      "max_solver_rounds": sd["max_iterations"], "mean_wrench_err": sd["mean_wrench_err"],
+                      "max_wrench_err": sd["max_wrench_err"], "active_row_hist": sd["active_hist"]},
+        }
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,6 +321,13 @@ def main():
         # stderr, the level itself is left alone so that the communicator lines stay visible to the caller
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+
+    if args.config.upper() == "C5":
+        run_sweep(args, rank, local_rank, world, dev, warmup)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- inputs: this rank's contiguous slice of the global synthetic batch (no inter-GPU traffic)
     st = synth.make_states(args.config, B, start=rank * B)
@@ -286,23 +393,48 @@ def main():
     def e2e_step():
         solver.solve_wrench_host(h["q"], h["quat"], h["wrench"], h["mask"], h["mu"], None, h_grf, h_tau, h_flags, h_net)
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
     e2e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+
+    def time_host(fn):
+        """Wall time of e2e_steps calls of a host-pointer entry (each call synchronises), max over ranks."""
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    e2e_s = time_host(e2e_step)
     h2d = B * ((12 + 4 + 6 + 4) * 8 + 1)
     d2h = B * ((12 + 12 + 6) * 8 + 4)
     # the e2e result must be the device result
     assert torch.equal(h_grf, grf.cpu()) and torch.equal(h_flags, flags.cpu())
+
+    # the same through the array-of-structs entry: one contiguous block per direction and chunk
+    rec_np = capi.wrench_records(st)
+    h_rec = torch.from_numpy(rec_np.view(np.uint8).reshape(-1)).pin_memory()
+    h_res = torch.empty(B * capi.RESULT_RECORD_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+
+    def e2e_rec_step():
+        solver.solve_records_host(h_rec, h_res)
+
+    e2e_rec_s = time_host(e2e_rec_step)
+    res_np = h_res.numpy().view(capi.RESULT_RECORD_DTYPE)
+    assert np.array_equal(res_np["grf"].T, h_grf.numpy()) and np.array_equal(res_np["flags"], h_flags.numpy().view(np.uint32))
+    h2d_rec, d2h_rec = B * capi.WRENCH_RECORD_DTYPE.itemsize, B * capi.RESULT_RECORD_DTYPE.itemsize
+    e2e_soa = {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": e2e_steps, "api": "qlb_solve_wrench_host (SoA arrays in pinned host memory, copies inside the timed region)"}
+    e2e_aos = {"value": world * B * e2e_steps / e2e_rec_s, "unit": UNIT, "h2d_bytes_per_step": h2d_rec,
+               "d2h_bytes_per_step": d2h_rec, "steps": e2e_steps,
+               "api": "qlb_solve_records_host (qlb_wrench_record[] / qlb_result_record[] in pinned host memory, one 1-D copy per "
+                      "chunk and direction, copies inside the timed region)"}
+    e2e_best, e2e_other = (e2e_aos, e2e_soa) if e2e_aos["value"] >= e2e_soa["value"] else (e2e_soa, e2e_aos)
+    e2e_best = dict(e2e_best, other_entry=e2e_other)
 
     # ---- the FP32 twin (BASELINE config C4) on the same states: device-resident and end to end
     d32 = {k: (v.float() if v.dtype == torch.float64 else v) for k, v in d.items()}
@@ -336,17 +468,7 @@ def main():
         solver.solve_wrench_host(h32["q"], h32["quat"], h32["wrench"], h32["mask"], h32["mu"], None, h_grf32, h_tau32,
                                  h_flags, h_net32)
 
-    for _ in range(2):
-        e2e_step32()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step32()
-    torch.cuda.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s32 = float(t.item())
+    e2e_s32 = time_host(e2e_step32)
     f32_err = float(((grf32.double() - grf).abs().amax(0) / grf.abs().amax(0).clamp(min=1.0)).median().item())
 
     clocks = sampler.stop() if rank == 0 else None
@@ -404,9 +526,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": bench_config(B, world),
             "clocks": clocks,
-            "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "qlb_solve_wrench_host (pinned host buffers, copies inside the timed region)"},
+            "e2e": e2e_best,
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_info,

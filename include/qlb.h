@@ -296,6 +296,30 @@ int qlb_pack_robot_states(qlb_context* ctx, size_t B, const qlb_robot_state_reco
 int qlb_feet_in_world(qlb_context* ctx, size_t B, const double* q, const double* base_pose,
                       double* feet_world, void* stream);
 
+/* ---- preview of a planned motion --------------------------------------------------------
+ * One sample of the preview: what StateBatchComputer::computeEndEffectorTrajectories collects
+ * (free_gait_core/src/executor/StateBatchComputer.cpp:64-77) plus what the controller would command at that sample. */
+typedef struct qlb_preview_record {
+  double feet_world[12];   /* foot positions in the world frame, leg-major */
+  double grf[12];          /* ground-reaction forces in base frame (zero for swing legs) */
+  double tau[12];          /* joint torques of the stance legs */
+  double netwrench[6];     /* achieved net wrench */
+  double wrench[6];        /* the virtual wrench that was distributed (gravity compensation + feed-forward terms) */
+  double friction_margin;  /* qlb_friction_margins */
+  double min_normal_slack; /* min over stance legs of n.f - F_min */
+  uint32_t flags;          /* result word of the solve */
+  uint32_t reserved;
+} qlb_preview_record;      /* 408 bytes */
+
+/* The whole plan in one call, HOST pointers: records[B] = the states of a StateBatch (one per time sample, as
+ * BatchExecutor::processInThread collects them at 10 ms steps, BatchExecutor.cpp:69-83) -> preview[B].
+ * Each sample is taken as both feedback and target of the virtual model controller (perfect tracking), so the
+ * distributed wrench is the controller's gravity compensation plus its feed-forward terms.  mu[4] = friction
+ * coefficient per leg for every sample, or NULL -> params.friction_default.  Device work per chunk: record packer,
+ * feet-in-world kernel, fused solve (state mode), friction-margin kernel, result packer.  Synchronises. */
+int qlb_preview_plan_host(qlb_context* ctx, size_t B, const qlb_robot_state_record* records, const double mu[4],
+                          qlb_preview_record* preview);
+
 /* ---- swing-leg torques ----------------------------------------------------------
  * Rigid-body table of one limb: three bodies on z-axis revolute joints (the link behind the fixed foot
  * joint merged into the third), as a rigid-body-dynamics URDF reader builds it from the per-leg URDFs that

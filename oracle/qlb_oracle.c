@@ -567,7 +567,8 @@ static int qo_solve_one(const qo_qp* qp, int solver, qo_external_solver ext, int
   *iters = 0;
   if (solver == QO_SOLVER_GI) {
     const double f = qo_goldfarb_idnani(n, m, 0, qp->G, qp->g0, NULL, NULL, qp->D, qp->d, x, active, u, iters);
-    if (!isfinite(f)) status = 4;
+    if (isinf(f) && f > 0.0) status = 5;       /* the solver's "infeasible" return (QuadProg++.cc:340-344) */
+    else if (!isfinite(f)) status = 4;
     if (status == 0 && nsolves == 2) {
       /* addDesiredLegLoadConstraints: second solve with C = I, c = x1 (CFD.cpp:369-381,120) */
       double CE[QO_MAX_N * QO_MAX_N] = {0}, ce0[QO_MAX_N], x2[QO_MAX_N], u2[QO_MAX_M];
@@ -593,7 +594,8 @@ static int qo_solve_one(const qo_qp* qp, int solver, qo_external_solver ext, int
   } else {
     for (int rep = 0; rep < nsolves; rep++) {
       const double f = ext(n, m, qp->G, qp->g0, qp->D, qp->d, x);
-      if (!isfinite(f)) status = 4;
+      if (isinf(f) && f > 0.0) status = 5;
+      else if (!isfinite(f)) status = 4;
     }
     if (status == 0) qo_classify(qp, x, active, u);
   }

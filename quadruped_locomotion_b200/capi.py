@@ -51,7 +51,7 @@ EXPORTS = (
     "qlb_solve_wrench", "qlb_solve_wrench_host", "qlb_solve_state", "qlb_solve_state_host",
     "qlb_solve_wrench_f32", "qlb_solve_wrench_f32_host", "qlb_solve_state_f32", "qlb_solve_state_f32_host",
     "qlb_default_swing_params", "qlb_set_limb_dynamics", "qlb_swing_leg_torques", "qlb_swing_leg_torques_host",
-    "qlb_set_f32_core", "qlb_set_pipeline", "qlb_generate_states", "qlb_generate_states_f32", "qlb_solve_records", "qlb_solve_records_host", "qlb_stats_allreduce", "qlb_params_set_key", "qlb_params_get_key", "qlb_params_num_keys", "qlb_params_key", "qlb_params_from_yaml", "qlb_swing_leg_torques_from_queue", "qlb_contact_fsm", "qlb_friction_margins", "qlb_leg_kinematics", "qlb_pack_robot_states", "qlb_feet_in_world", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
+    "qlb_set_f32_core", "qlb_set_pipeline", "qlb_generate_states", "qlb_generate_states_f32", "qlb_solve_records", "qlb_solve_records_host", "qlb_stats_allreduce", "qlb_preview_plan_host", "qlb_params_set_key", "qlb_params_get_key", "qlb_params_num_keys", "qlb_params_key", "qlb_params_from_yaml", "qlb_swing_leg_torques_from_queue", "qlb_contact_fsm", "qlb_friction_margins", "qlb_leg_kinematics", "qlb_pack_robot_states", "qlb_feet_in_world", "qlb_qp_dense", "qlb_qp_dense_host", "qlb_batch_stats", "qlb_measure_fp64_peak", "qlb_launch_count", "qlb_strerror",
     "qlb_last_cuda_error", "qlb_abi_version",
 )
 
@@ -77,6 +77,12 @@ WRENCH_RECORD_DTYPE = np.dtype([("q", "<f8", 12), ("quat_wxyz", "<f8", 4), ("wre
 RESULT_RECORD_DTYPE = np.dtype([("grf", "<f8", 12), ("tau", "<f8", 12), ("netwrench", "<f8", 6), ("flags", "<u4"),
                                 ("reserved", "<u4")])
 assert WRENCH_RECORD_DTYPE.itemsize == 216 and RESULT_RECORD_DTYPE.itemsize == 248
+
+
+PREVIEW_RECORD_DTYPE = np.dtype([("feet_world", "<f8", 12), ("grf", "<f8", 12), ("tau", "<f8", 12), ("netwrench", "<f8", 6),
+                                 ("wrench", "<f8", 6), ("friction_margin", "<f8"), ("min_normal_slack", "<f8"), ("flags", "<u4"),
+                                 ("reserved", "<u4")])
+assert PREVIEW_RECORD_DTYPE.itemsize == 408
 
 
 def wrench_records(states: dict) -> np.ndarray:
@@ -116,6 +122,7 @@ def load() -> C.CDLL:
     lib.qlb_solve_state_f32_host.argtypes = [_vp, C.c_size_t] + [_vp] * 13
     lib.qlb_set_f32_core.argtypes = [_vp, C.c_int]
     lib.qlb_set_pipeline.argtypes = [_vp, C.c_int]
+    lib.qlb_preview_plan_host.argtypes = [_vp, C.c_size_t, _vp, C.POINTER(C.c_double * 4), _vp]
     lib.qlb_params_set_key.argtypes = [C.POINTER(Params), C.c_char_p, C.c_double]
     lib.qlb_params_get_key.argtypes = [C.POINTER(Params), C.c_char_p, C.POINTER(C.c_double)]
     lib.qlb_params_key.argtypes = [C.c_int]
@@ -376,6 +383,15 @@ class Solver:
                 _ptr(ttwist), _ptr(mask), _ptr(mu), _ptr(normals), _ptr(grf), _ptr(tau),
                 _ptr(flags), _ptr(netwrench), _ptr(wrench_out))
         self._check(rc, "qlb_solve_state_host")
+
+    def preview_plan_host(self, records: np.ndarray, mu=None) -> np.ndarray:
+        """records: numpy array of RECORD_DTYPE (the states of a planned motion) -> array of PREVIEW_RECORD_DTYPE."""
+        B = records.shape[0]
+        out = np.zeros(B, dtype=PREVIEW_RECORD_DTYPE)
+        mu_arr = (C.c_double * 4)(*[float(v) for v in mu]) if mu is not None else None
+        rc = self.lib.qlb_preview_plan_host(self._ctx, B, _ptr(records), C.byref(mu_arr) if mu_arr is not None else None, _ptr(out))
+        self._check(rc, "qlb_preview_plan_host")
+        return out
 
     def solve_records_host(self, records, results):
         """records: B qlb_wrench_record (numpy structured array or pinned torch uint8 tensor), results: B

@@ -63,6 +63,8 @@ struct qlb_context {
   double* d_out = nullptr;
   uint8_t* d_mask = nullptr;
   uint32_t* d_flags = nullptr;
+  unsigned char* d_prev = nullptr;  // staging of qlb_preview_plan_host
+  size_t prev_cap = 0;
   unsigned char* d_qp = nullptr;    // staging of qlb_qp_dense_host
   size_t qp_bytes = 0;
   unsigned char* d_rec = nullptr;   // record staging of qlb_solve_records_host: kPipe x cap x (216 + 248) bytes
@@ -651,7 +653,7 @@ int qlb_destroy(qlb_context* ctx) {
     if (ctx->pipe[i]) { cudaStreamSynchronize(ctx->pipe[i]); cudaStreamDestroy(ctx->pipe[i]); }
   cudaFree(ctx->d_model); cudaFree(ctx->d_params); cudaFree(ctx->d_counter); cudaFree(ctx->d_stats);
   cudaFree(ctx->d_model_f); cudaFree(ctx->d_params_f); cudaFree(ctx->d_limb);
-  cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags); cudaFree(ctx->d_rec); cudaFree(ctx->d_qp);
+  cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_mask); cudaFree(ctx->d_flags); cudaFree(ctx->d_rec); cudaFree(ctx->d_qp); cudaFree(ctx->d_prev);
   for (int i = 0; i < 8; i++) cudaFree(ctx->d_list[i]);
   for (int i = 0; i < 8; i++)
     if (ctx->slot_done[i]) cudaEventDestroy(ctx->slot_done[i]);
@@ -1162,6 +1164,59 @@ int qlb_solve_records_host(qlb_context* ctx, size_t B, const qlb_wrench_record* 
   rc = records_host_chunks(ctx, B, records, results);
   for (int i = 0; i < kPipe; i++)
     if (cudaStreamSynchronize(ctx->pipe[i]) != cudaSuccess && rc == QLB_OK) rc = cuda_fail(ctx, cudaGetLastError(), "cudaStreamSynchronize");
+  return rc;
+}
+
+int qlb_preview_plan_host(qlb_context* ctx, size_t B, const qlb_robot_state_record* records, const double mu[4],
+                          qlb_preview_record* preview) {
+  if (!ctx) return QLB_ERR_NOT_INITIALISED;
+  if (B == 0) return QLB_OK;
+  if (!records || !preview) return QLB_ERR_INVALID_ARGUMENT;
+  DeviceGuard guard(ctx->device);
+  int rc = ensure_capacity(ctx, B);
+  if (rc != QLB_OK) return rc;
+  const size_t cap = ctx->cap;
+  // per state: the input record, the result record, and SoA rows for feet (12), friction coefficients (4), margins (2)
+  const size_t per_state = sizeof(qlb_robot_state_record) + sizeof(qlb_preview_record) + 18 * sizeof(double);
+  if (ctx->prev_cap < cap) {
+    QLB_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(ctx->d_prev);
+    ctx->d_prev = nullptr; ctx->prev_cap = 0;
+    if (cudaMalloc(&ctx->d_prev, cap * per_state) != cudaSuccess) { cudaGetLastError(); return QLB_ERR_ALLOC; }
+    ctx->prev_cap = cap;
+  }
+  cudaStream_t st = ctx->stream;
+  qlb_robot_state_record* d_rec = reinterpret_cast<qlb_robot_state_record*>(ctx->d_prev);
+  qlb_preview_record* d_res = reinterpret_cast<qlb_preview_record*>(ctx->d_prev + cap * sizeof(qlb_robot_state_record));
+  double* extra = reinterpret_cast<double*>(ctx->d_prev + cap * (sizeof(qlb_robot_state_record) + sizeof(qlb_preview_record)));
+  double* feet = extra; double* dmu = extra + 12 * cap; double* margin = extra + 16 * cap; double* minn = extra + 17 * cap;
+  double* din = ctx->d_in; double* dout = ctx->d_out;
+  double* q = din; double* pose = din + 12 * cap; double* twist = din + 19 * cap; double* nrm = din + 25 * cap;
+  double* grf = dout; double* tau = dout + 12 * cap; double* net = dout + 24 * cap; double* wout = dout + 30 * cap;
+  for (size_t b0 = 0; b0 < B && rc == QLB_OK; b0 += cap) {
+    const size_t n = (B - b0 < cap) ? (B - b0) : cap;
+    if (cudaMemcpyAsync(d_rec, records + b0, n * sizeof(qlb_robot_state_record), cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = QLB_ERR_CUDA; break; }
+    rc = qlb_pack_robot_states(ctx, n, d_rec, q, pose, twist, ctx->d_mask, nrm, st);
+    if (rc == QLB_OK) rc = qlb_feet_in_world(ctx, n, q, pose, feet, st);
+    if (rc == QLB_OK && mu) {
+      qlb_fill_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, 4, dmu, mu[0], mu[1], mu[2], mu[3]);
+      ctx->launches++;
+    }
+    // the planned state is feedback AND target: zero tracking error
+    if (rc == QLB_OK) rc = solve_state_t<double>(ctx, n, q, pose, twist, pose, twist, ctx->d_mask, mu ? dmu : nullptr, nrm, grf, tau,
+                                                  ctx->d_flags, net, wout, st);
+    if (rc == QLB_OK) rc = qlb_friction_margins(ctx, n, grf, pose + 3 * n, ctx->d_mask, mu ? dmu : nullptr, nrm, margin, minn, st);
+    if (rc == QLB_OK) {
+      qlb_pack_preview_kernel<<<(unsigned)((n + kPrevTile - 1) / kPrevTile), kPrevTile, 0, st>>>(n, feet, grf, tau, net, wout, margin, minn,
+                                                                                             ctx->d_flags, d_res);
+      ctx->launches++;
+      if (cudaGetLastError() != cudaSuccess) rc = QLB_ERR_CUDA;
+    }
+    if (rc == QLB_OK && cudaMemcpyAsync(preview + b0, d_res, n * sizeof(qlb_preview_record), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = QLB_ERR_CUDA;
+    // the staging is reused by the next chunk
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == QLB_OK) rc = QLB_ERR_CUDA;
+  }
+  if (rc == QLB_ERR_CUDA) cuda_fail(ctx, cudaGetLastError(), "qlb_preview_plan_host");
   return rc;
 }
 

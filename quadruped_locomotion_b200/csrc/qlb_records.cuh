@@ -72,4 +72,45 @@ __global__ void __launch_bounds__(kRecTile) qlb_pack_results_kernel(unsigned lon
   }
 }
 
+// preview of a planned motion: SoA results -> qlb_preview_record[]
+constexpr int kPrevWords = (int)(sizeof(qlb_preview_record) / 8);   // 51
+constexpr int kPrevTile = 64;   // 64 records x 53 words = 27 KB of shared memory
+static_assert(sizeof(qlb_preview_record) == 408, "record layout is part of the ABI");
+__global__ void __launch_bounds__(kPrevTile) qlb_pack_preview_kernel(unsigned long long B, const double* __restrict__ feet,
+                                                                    const double* __restrict__ grf, const double* __restrict__ tau,
+                                                                    const double* __restrict__ net, const double* __restrict__ wrench,
+                                                                    const double* __restrict__ margin, const double* __restrict__ minn,
+                                                                    const uint32_t* __restrict__ flags, qlb_preview_record* __restrict__ rec) {
+  __shared__ double tile[kPrevTile * (kPrevWords + 2)];   // row stride 53 words
+  const unsigned long long base = (unsigned long long)blockIdx.x * kPrevTile;
+  const unsigned long long left = B - base;
+  const int n = left < (unsigned long long)kPrevTile ? (int)left : kPrevTile;
+  const int t = threadIdx.x;
+  if (t < n) {
+    double* r = tile + t * (kPrevWords + 2);
+    const unsigned long long i = base + t;
+#pragma unroll
+    for (int a = 0; a < 12; a++) { r[a] = feet[(size_t)a * B + i]; r[12 + a] = grf[(size_t)a * B + i]; r[24 + a] = tau[(size_t)a * B + i]; }
+#pragma unroll
+    for (int a = 0; a < 6; a++) { r[36 + a] = net[(size_t)a * B + i]; r[42 + a] = wrench[(size_t)a * B + i]; }
+    r[48] = margin[i]; r[49] = minn[i];
+    r[50] = __longlong_as_double((long long)(unsigned long long)flags[i]);
+  }
+  __syncthreads();
+  double* dst = reinterpret_cast<double*>(rec + base);
+  for (int v = threadIdx.x; v < n * kPrevWords; v += kPrevTile) {
+    const int r = v / kPrevWords, c = v - r * kPrevWords;
+    dst[v] = tile[r * (kPrevWords + 2) + c];
+  }
+}
+
+// one value per leg for every state of a batch (the friction coefficient of a preview)
+__global__ void __launch_bounds__(256) qlb_fill_rows_kernel(unsigned long long B, int rows, double* __restrict__ dst, double v0, double v1,
+                                                            double v2, double v3) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const double v[4] = {v0, v1, v2, v3};
+  for (int r = 0; r < rows; r++) dst[(size_t)r * B + i] = v[r & 3];
+}
+
 }  // namespace qlb

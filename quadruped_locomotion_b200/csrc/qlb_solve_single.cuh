@@ -242,23 +242,35 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
   unsigned occ = 0u;           // pending slots of the stash (warp-uniform)
   uint32_t parity = 0;
 
-  // Work distribution: boxes are claimed with one atomic each, TWO ahead.  The result of a claim stays in lane 0 and
-  // is broadcast only when the box number is needed - a whole tile later - so the round trip of the atomic is never
-  // waited for.  The stance masks of a box (one byte per state) are fetched by one coalesced load a box ahead.
-  auto claim_raw = [&]() {
+  // Work distribution: the first three quarters of the boxes are split evenly and contiguously over the warps of
+  // the grid (no atomics, no latency); the last quarter is claimed dynamically, one atomic per box, issued a whole
+  // box ahead - its result stays in lane 0 and is broadcast only when the box number is needed - so warps that
+  // drew cheap states take more of it.  The stance masks of a box (one byte per state) are fetched by one
+  // coalesced load a box ahead.
+  const unsigned long long nwarps = (unsigned long long)gridDim.x * (kQuadThreads / 32);
+  const unsigned long long gwarp = (unsigned long long)blockIdx.x * (kQuadThreads / 32) + warp;
+  const unsigned long long share = (nbox - nbox / 4) / nwarps;     // static boxes per warp
+  const unsigned long long dyn_base = share * nwarps;              // first dynamically claimed box
+  unsigned long long taken = 0;                                    // boxes this warp has started
+  auto claim_raw = [&](const bool doit) {
     unsigned long long b = 0;
-    if (lane == 0) b = atomicAdd(a.counter, 1ull);
+    if (lane == 0 && doit) b = atomicAdd(a.counter, 1ull);
     return b;
   };
   auto mask_bytes = [&](const unsigned long long box) -> unsigned {
     const unsigned long long s = box * (unsigned long long)kCols + lane;
     return (lane < kCols && box < nbox && s < B) ? (unsigned)a.mask[s] : 0u;
   };
-  unsigned long long cur = __shfl_sync(kFull, claim_raw(), 0);
+  unsigned long long pending_claim = claim_raw(share <= 1);
+  unsigned long long cur;
+  {
+    const unsigned long long dyn = __shfl_sync(kFull, pending_claim, 0);
+    cur = share > 0 ? gwarp * share : dyn_base + dyn;
+    if (share == 0) pending_claim = claim_raw(true);
+  }
   if (cur < nbox) stage_issue<real, MODE, SUPER, TMA>(a, maps, cur, stage, bar, lane);
   unsigned mask_cur = mask_bytes(cur), mask_nxt = 0u;
   unsigned long long nxt = 0;
-  unsigned long long pending_claim = claim_raw();
   int sub = 0;                 // tile of the current box
 #pragma unroll 1
   for (;;) {
@@ -279,10 +291,13 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
       in.mask = valid ? (mask_byte & 0xFu) : 0u;
       if (sub == SUPER - 1) {
         __syncwarp();     // every lane has read the last tile of the box: the next box may land in the buffer
-        nxt = __shfl_sync(kFull, pending_claim, 0);
+        taken++;
+        const unsigned long long dyn = __shfl_sync(kFull, pending_claim, 0);   // every lane, whichever branch is taken below
+        nxt = taken < share ? gwarp * share + taken : dyn_base + dyn;
+        // the claim for the box after `nxt`: needed once the static share is used up
+        pending_claim = claim_raw(taken + 1 >= share);
         if (nxt < nbox) stage_issue<real, MODE, SUPER, TMA>(a, maps, nxt, stage, bar, lane);
         mask_nxt = mask_bytes(nxt);
-        pending_claim = claim_raw();
       }
       // ---- kinematics and QP data; the Jacobian goes straight into the slot this quad would keep
       const int slot = nth_set_bit(~occ & ((1u << CAP) - 1u), quad);

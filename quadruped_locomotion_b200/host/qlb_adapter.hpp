@@ -217,10 +217,14 @@ class ContactForceDistribution : public ContactForceDistributionBase {
     isParametersLoaded_ = device_->commit();
     return isParametersLoaded_;
   }
-  void setVirtualForceWeights(const std::array<double, 6>& w) { for (int i = 0; i < 6; i++) device_->params().wrench_weights[i] = w[i]; }
-  void setGroundForceWeight(double w) { device_->params().ground_force_weight = w; }
-  void setMinimalNormalGroundForce(double f) { device_->params().min_normal_force = f; }
-  void setFrictionCoefficient(double mu) { device_->params().friction_default = mu; }
+  // the setters stand in for `rosparam set`: they write the parameter server, loadParameters() picks the values up
+  void setVirtualForceWeights(const std::array<double, 6>& w) {
+    static const char* const names[6] = {"force/heading", "force/lateral", "force/vertical", "torque/roll", "torque/pitch", "torque/yaw"};
+    for (int i = 0; i < 6; i++) device_->parameters().setParam(std::string("/balance_controller/contact_force_distribution/weights/") + names[i], w[i]);
+  }
+  void setGroundForceWeight(double w) { device_->parameters().setParam("/balance_controller/contact_force_distribution/weights/regularizer/value", w); }
+  void setMinimalNormalGroundForce(double f) { device_->parameters().setParam("/balance_controller/contact_force_distribution/constraints/minimal_normal_force", f); }
+  void setFrictionCoefficient(double mu) { device_->parameters().setParam("/balance_controller/contact_force_distribution/constraints/friction_coefficient", mu); }
   double getGroundForceWeight() const { return device_->params().ground_force_weight; }
   double getMinimalNormalGroundForce() const { return device_->params().min_normal_force; }
   double getVirtualForceWeight(int index) const { return device_->params().wrench_weights[index]; }
@@ -333,12 +337,12 @@ class VirtualModelController : public MotionControllerBase {
     loaded_ = device_->commit();
     return loaded_;
   }
-  void setProportionalGainTranslation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kp_translation[i] = k[i]; }
-  void setDerivativeGainTranslation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kd_translation[i] = k[i]; }
-  void setFeedforwardGainTranslation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kff_translation[i] = k[i]; }
-  void setProportionalGainRotation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kp_rotation[i] = k[i]; }
-  void setDerivativeGainRotation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kd_rotation[i] = k[i]; }
-  void setFeedforwardGainRotation(const Vector3& k) { for (int i = 0; i < 3; i++) device_->params().kff_rotation[i] = k[i]; }
+  void setProportionalGainTranslation(const Vector3& k) { setGains("kp", {"heading", "lateral", "vertical"}, k); }
+  void setDerivativeGainTranslation(const Vector3& k) { setGains("kd", {"heading", "lateral", "vertical"}, k); }
+  void setFeedforwardGainTranslation(const Vector3& k) { setGains("kff", {"heading", "lateral", "vertical"}, k); }
+  void setProportionalGainRotation(const Vector3& k) { setGains("kp", {"roll", "pitch", "yaw"}, k); }
+  void setDerivativeGainRotation(const Vector3& k) { setGains("kd", {"roll", "pitch", "yaw"}, k); }
+  void setFeedforwardGainRotation(const Vector3& k) { setGains("kff", {"roll", "pitch", "yaw"}, k); }
   void setGravityCompensationForcePercentage(double p) { device_->params().gravity_compensation_percentage = p; }  // VMC.cpp:655
 
   bool compute() override {
@@ -372,6 +376,10 @@ class VirtualModelController : public MotionControllerBase {
   // VMC.cpp:288-300: what the distribution actually achieved
   bool getDistributedVirtualForceAndTorqueInBaseFrame(Force& netForce, Torque& netTorque) const {
     return cfd_->getNetForceAndTorqueOnBase(netForce, netTorque);
+  }
+  void setGains(const char* gain, const std::array<const char*, 3>& axes, const Vector3& k) {   // `rosparam set`, see loadParameters
+    for (int i = 0; i < 3; i++)
+      device_->parameters().setParam(std::string("/balance_controller/virtual_model_controller/") + axes[i] + "/" + gain, k[i]);
   }
   const Force& getDesiredVirtualForceInBaseFrame() const { return virtualForceInBaseFrame_; }
   const Torque& getDesiredVirtualTorqueInBaseFrame() const { return virtualTorqueInBaseFrame_; }

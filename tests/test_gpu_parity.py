@@ -189,6 +189,79 @@ def test_bad_inputs_are_flagged_and_isolated(solver, oracle, models):
     assert np.array_equal(out["flags"][ok], clean["flags"][ok])
 
 
+def test_negative_friction_is_infeasible_and_zero_friction_is_solved(solver, oracle, models):
+    """mu < 0 on a stance leg: QLB_STATE_INFEASIBLE (5) like the oracle (the reference's solver returns +inf), outputs
+    zero, neighbours untouched.  mu = 0: a frictionless contact is a valid QP (tangential force zero)."""
+    st = synth.make_states("C3", 96, start=5)
+    st["mask"][:] = 0xF
+    clean = solver.solve_wrench_numpy(st)
+    st["mu"][1, 7] = -0.2
+    st["mu"][:, 40] = -1.0
+    st["mu"][3, 60] = 0.0
+    ref = _oracle(oracle, models["quadruped_model"], st)
+    out = solver.solve_wrench_numpy(st)
+    status = (out["flags"] >> 24) & 7
+    for i in (7, 40):
+        assert status[i] == 5 and ((ref["flags"][i] >> 24) & 7) == 5
+        assert not out["grf"][:, i].any() and not out["tau"][:, i].any()
+    assert status[60] == 0
+    assert rel_err(out["grf"][:, 60:61], ref["grf"][:, 60:61]).max() <= TIGHT
+    ok = np.ones(96, bool); ok[[7, 40, 60]] = False
+    assert np.array_equal(out["grf"][:, ok], clean["grf"][:, ok]) and np.array_equal(out["flags"][ok], clean["flags"][ok])
+    # a swing leg's friction coefficient is never looked at
+    st2 = synth.make_states("C2", 64)
+    st2["mu"][0] = np.where((st2["mask"] & 1) == 0, -5.0, st2["mu"][0])
+    out2 = solver.solve_wrench_numpy(st2)
+    assert (((out2["flags"] >> 24) & 7) == 0).all()
+
+
+@pytest.mark.parametrize("fmin", [0.0, -25.0])
+def test_nonpositive_minimal_force(solver, oracle, models, fmin):
+    """F_min = 0 and F_min < 0 (which acts as 0: the friction rows imply n.f >= 0).  Forces against the oracle run
+    with the same F_min; active bits only where the oracle's margin says the active set is well defined (a leg that
+    is unloaded completely sits at the apex of its pyramid, a degenerate vertex)."""
+    st = synth.make_states("C5", 8192, start=999)
+    p = solver.get_params()
+    try:
+        p2 = solver.get_params()
+        p2.min_normal_force = fmin
+        solver.set_params(p2)
+        op = oracle.default_params()
+        op.fmin = fmin
+        ref = _oracle(oracle, models["quadruped_model"], st, params=op)
+        out = solver.solve_wrench_numpy(st)
+        assert (((out["flags"] >> 24) & 7) == 0).all()
+        assert rel_err(out["grf"], ref["grf"]).max() <= 1e-8 and rel_err(out["tau"], ref["tau"]).max() <= 1e-8
+        if fmin == 0.0:
+            mism = ((out["flags"] ^ ref["flags"]) & capi.FLAG_PARITY_MASK) != 0
+            assert (ref["margin"][mism] < 1e-6).all()
+    finally:
+        solver.set_params(p)
+
+
+def test_parameter_bounds_are_enforced(solver):
+    """Weights outside [1e-12, 1e12], a negative default friction coefficient, NaN: qlb_set_params refuses them."""
+    for field, val in (("ground_force_weight", 0.0), ("ground_force_weight", 1e13), ("friction_default", -0.1),
+                       ("min_normal_force", float("nan")), ("ground_force_weight", float("nan"))):
+        p = solver.get_params()
+        setattr(p, field, val)
+        with pytest.raises(RuntimeError):
+            solver.set_params(p)
+    p = solver.get_params()
+    p.wrench_weights[2] = 1e-13
+    with pytest.raises(RuntimeError):
+        solver.set_params(p)
+    assert solver.get_params().ground_force_weight == 1e-4   # the context keeps its parameters
+
+
+def test_huge_joint_angles_are_bad_input(solver):
+    st = synth.make_states("C3", 16)
+    st["q"][5, 3] = 3e9
+    out = solver.solve_wrench_numpy(st)
+    status = (out["flags"] >> 24) & 7
+    assert status[3] == 4 and (np.delete(status, 3) == 0).all() and np.isfinite(out["grf"]).all()
+
+
 def test_full_size_properties(solver, oracle, models):
     """BASELINE size (2^20): size-independent properties on the whole batch + oracle parity on a slice."""
     B = 1 << 20

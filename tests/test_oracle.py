@@ -184,3 +184,28 @@ def test_vmc_gravity_only(oracle):
     w2 = oracle.vmc_wrench(pose, np.zeros(6), np.concatenate([pose[:3], tq]), np.zeros(6))
     assert abs(np.linalg.norm(w2[3:] - w[3:]) - 0.1 * 4000) < 0.1 * 10000  # rotated into the base frame
     assert np.linalg.norm(w2[3:] - w[3:]) > 100
+
+
+def test_negative_friction_is_reported_infeasible(oracle, models):
+    """mu < 0 on a stance leg with F_min > 0: no force satisfies mu n.f >= |t.f| and n.f >= F_min.  The reference's
+    solver returns +inf (QuadProg++.cc:340-344); the oracle reports state status 5 and zero outputs."""
+    from quadruped_locomotion_b200 import synth
+    st = synth.make_states("C3", 64)
+    st["mask"][:] = 0xF
+    st["mu"][2, ::2] = -0.3
+    r = oracle.solve_wrench_batch(models["quadruped_model"], st["q"], st["quat"], st["wrench"], st["mask"], mu=st["mu"])
+    status = (r["flags"] >> 24) & 7
+    assert (status[::2] == 5).all() and (status[1::2] == 0).all()
+    assert not r["grf"][:, ::2].any() and not r["tau"][:, ::2].any()
+
+
+def test_nonpositive_minimal_force_is_equivalent_to_zero(oracle, models):
+    """F_min <= 0 with mu > 0: the friction rows already imply n.f >= 0, so the optimum equals the one for F_min = 0
+    (what the GPU path solves after clamping F_min)."""
+    from quadruped_locomotion_b200 import synth
+    st = synth.make_states("C5", 256)
+    p0 = oracle.default_params(); p0.fmin = 0.0
+    pm = oracle.default_params(); pm.fmin = -25.0
+    a = oracle.solve_wrench_batch(models["quadruped_model"], st["q"], st["quat"], st["wrench"], st["mask"], mu=st["mu"], params=p0)
+    b = oracle.solve_wrench_batch(models["quadruped_model"], st["q"], st["quat"], st["wrench"], st["mask"], mu=st["mu"], params=pm)
+    assert np.abs(a["grf"] - b["grf"]).max() <= 1e-8 * np.abs(a["grf"]).max()

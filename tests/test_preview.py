@@ -88,3 +88,29 @@ def test_preview_of_a_planned_motion(qlb_built, oracle, models):
     mism = ((fl ^ ref["flags"]) & capi.FLAG_PARITY_MASK) != 0
     assert not (mism & (ref["margin"] > 1e-6)).any()
     s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1, 300, 150001])
+def test_preview_plan_one_call(qlb_built, oracle, models, B):
+    """qlb_preview_plan_host: the composition of the test above as ONE call on array-of-structs records, plus friction
+    margins (several pipeline chunks at the largest size)."""
+    rec, st = _records(B, seed=9, cfg="C5")
+    s = capi.Solver("quadruped_model")
+    mu = (0.5, 0.6, 0.7, 0.8)
+    out = s.preview_plan_host(rec, mu=mu)
+    M = models["quadruped_model"]
+    p = oracle.pack_robot_states(rec)
+    n = min(B, 300)
+    fw = oracle.feet_in_world(M, p["q"][:, :n], p["pose"][:, :n])
+    assert np.abs(out["feet_world"][:n].T - fw).max() <= 1e-12
+    wref = np.stack([oracle.vmc_wrench(p["pose"][:, i], p["twist"][:, i], p["pose"][:, i], p["twist"][:, i]) for i in range(n)], axis=1)
+    assert rel_err(out["wrench"][:n].T, wref).max() <= 1e-11
+    mu_a = np.tile(np.array(mu)[:, None], (1, n))
+    ref = oracle.solve_wrench_batch(M, p["q"][:, :n], p["pose"][3:, :n], wref, p["mask"][:n], mu=mu_a, normals=p["normals"][:, :n])
+    assert rel_err(out["grf"][:n].T, ref["grf"]).max() <= 1e-9 and rel_err(out["tau"][:n].T, ref["tau"]).max() <= 1e-9
+    m, mn = oracle.friction_margins(ref["grf"], p["pose"][3:, :n], p["mask"][:n], mu_a, p["normals"][:, :n])
+    np.testing.assert_allclose(out["friction_margin"][:n], m, atol=1e-8)
+    np.testing.assert_allclose(out["min_normal_slack"][:n], mn, atol=1e-7)
+    assert (out["reserved"] == 0).all() and (((out["flags"] >> 24) & 7) <= 1).all()
+    s.close()
