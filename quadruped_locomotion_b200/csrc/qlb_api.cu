@@ -295,6 +295,18 @@ bool make_map(CUtensorMap* m, const T* ptr, unsigned long long B, int rows) {
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// rank-1 tensor map of the stance masks (one byte per state), boxes of `cols` states
+bool make_mask_map(CUtensorMap* m, const uint8_t* ptr, unsigned long long B, int cols) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t gdim[1] = {(cuuint64_t)B};
+  const cuuint64_t gstride[1] = {0};
+  const cuuint32_t box[1] = {(cuuint32_t)cols};
+  const cuuint32_t estr[1] = {1u};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, const_cast<uint8_t*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // the fused kernel (qlb_solve_single.cuh) + the interior-point kernel for the states its rounds could not verify
 // (normally none: it finds an empty list and returns)
 template <typename T, typename C, int MODE>
@@ -311,6 +323,7 @@ int launch_single(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int
   std::memset(&maps, 0, sizeof maps);
   for (int s = 0; s < SG::kNumSeg && tma; s++)
     if (src[s] && !make_map<T>(&maps.seg[s], src[s], a.B, SG::rows(s))) tma = false;
+  if (tma && (SG::kCols < 16 || !aligned16(a.mask) || !make_mask_map(&maps.mask, a.mask, a.B, SG::kCols))) tma = false;
   const unsigned long long ntiles = (a.B + 7) / 8;
   const unsigned long long want = (ntiles + 3) / 4;
   const int bps = ctx->blocks_per_sm_single[sizeof(T) == 4 ? 1 : 0][MODE][tma ? 1 : 0];

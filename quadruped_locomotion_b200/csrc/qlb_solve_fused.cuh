@@ -54,13 +54,15 @@ struct Staging {
   __host__ __device__ static constexpr int offset(int s) {
     return s == 0 ? 0 : s == 1 ? kO1 : s == 2 ? kO2 : s == 3 ? kO3 : s == 4 ? kO4 : s == 5 ? kO5 : kO6;
   }
-  static constexpr int kBytes = (MODE == 1) ? kO6 : kO4;
+  static constexpr int kMaskOff = (MODE == 1) ? kO6 : kO4;     // the stance masks of the box: one byte per state
+  static constexpr int kBytes = kMaskOff + 128;
   static constexpr int kSegMu = (MODE == 1) ? 5 : 3;
 };
 
 // Tensor maps of the input arrays of one call (built on the host, qlb_api.cu), in Staging segment order.
 struct alignas(64) FusedMaps {
   CUtensorMap seg[6];
+  CUtensorMap mask;    // rank 1, uint8, boxes of 8 SUPER states
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -96,6 +98,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const CUtensorMap* map, int c0, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(bar) : "memory");
+}
+// four bytes, of which only `valid` (0..4) are read from global memory; the rest is zero-filled
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, int valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid) : "memory");
+}
 __device__ __forceinline__ void cp_async_elem(uint32_t dst, const double* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -130,11 +140,13 @@ __device__ __forceinline__ void stage_issue(const SolveArgsT<real>& a, const Fus
 #pragma unroll
       for (int s = 0; s < SG::kNumSeg; s++)
         if (src[s] != nullptr) bytes += SG::rows(s) * SG::kRow;
+      bytes += SG::kCols;   // the stance masks
       mbar_expect_tx(bar, bytes);
       const uint32_t dst = smem_u32(stage);
 #pragma unroll
       for (int s = 0; s < SG::kNumSeg; s++)
         if (src[s] != nullptr) tma_load_2d(dst + SG::offset(s), &maps.seg[s], (int)(box * (unsigned long long)SG::kCols), 0, bar);
+      tma_load_1d(dst + SG::kMaskOff, &maps.mask, (int)(box * (unsigned long long)SG::kCols), bar);
     }
   } else {
     const unsigned long long B = a.B;
@@ -151,6 +163,18 @@ __device__ __forceinline__ void stage_issue(const SolveArgsT<real>& a, const Fus
         const int r = r0 + lane / SG::kCols;
         if (r < SG::rows(s)) cp_async_elem(dst + (r * SG::kCols + col) * (int)sizeof(real), src[s] + (size_t)r * B + bx);
       }
+    }
+    // stance masks: four bytes per lane when the array is word-aligned (bytes past the end of the batch are not read),
+    // else byte by byte (synchronous; only for callers with an odd mask pointer)
+    const unsigned long long m0 = box * (unsigned long long)SG::kCols;
+    if ((reinterpret_cast<uintptr_t>(a.mask) & 3u) == 0) {
+      if (lane < SG::kCols / 4) {
+        const unsigned long long first = m0 + 4ull * lane;
+        const int valid = first >= B ? 0 : (B - first < 4 ? (int)(B - first) : 4);
+        cp_async_4(smem_u32(stage) + SG::kMaskOff + 4 * lane, a.mask + (valid ? first : 0), valid);
+      }
+    } else if (lane < SG::kCols) {
+      stage[SG::kMaskOff + lane] = (m0 + lane < B) ? a.mask[m0 + lane] : (unsigned char)0;
     }
     cp_async_commit();
   }
@@ -175,6 +199,7 @@ __device__ __forceinline__ void stage_read(const SolveArgsT<real>& a, const unsi
 #pragma unroll
     for (int r = 0; r < 6; r++) in.b[r] = at(2, r);
   }
+  in.mask = (unsigned)stage[SG::kMaskOff + col] & 0xFu;
   in.mu = (a.mu != nullptr) ? at(SG::kSegMu, leg) : mu_default;
   in.nw[0] = real(0.0); in.nw[1] = real(0.0); in.nw[2] = real(1.0);
   if (a.normals != nullptr) {

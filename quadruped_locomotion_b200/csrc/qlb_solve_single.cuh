@@ -24,7 +24,7 @@ namespace qlb {
 #ifndef QLB_FUSED_MIN_CTAS
 #define QLB_FUSED_MIN_CTAS 3
 #endif
-constexpr int kSingleSmemBudget = 75 * 1024;   // per CTA: three CTAs per SM (228 KB, 1 KB reserved per CTA)
+constexpr int kSingleSmemBudget = (228 / QLB_FUSED_MIN_CTAS - 1) * 1024;   // per CTA: QLB_FUSED_MIN_CTAS CTAs per SM (228 KB, 1 KB reserved per CTA)
 
 // ---------------------------------------------------------------------------------------------------------
 // The stash of one warp: CAP entries.  Per-lane planes (element k of the entry in slot s, leg l at
@@ -245,31 +245,28 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
   // Work distribution: the first three quarters of the boxes are split evenly and contiguously over the warps of
   // the grid (no atomics, no latency); the last quarter is claimed dynamically, one atomic per box, issued a whole
   // box ahead - its result stays in lane 0 and is broadcast only when the box number is needed - so warps that
-  // drew cheap states take more of it.  The stance masks of a box (one byte per state) are fetched by one
-  // coalesced load a box ahead.
+  // drew cheap states take more of it.  (The stance masks travel with the staged box: a loop-carried register loaded
+  // from global memory gets spilled right behind its load, which exposes the full latency.)
   const unsigned long long nwarps = (unsigned long long)gridDim.x * (kQuadThreads / 32);
   const unsigned long long gwarp = (unsigned long long)blockIdx.x * (kQuadThreads / 32) + warp;
   const unsigned long long share = (nbox - nbox / 4) / nwarps;     // static boxes per warp
   const unsigned long long dyn_base = share * nwarps;              // first dynamically claimed box
   unsigned long long taken = 0;                                    // boxes this warp has started
-  auto claim_raw = [&](const bool doit) {
-    unsigned long long b = 0;
-    if (lane == 0 && doit) b = atomicAdd(a.counter, 1ull);
+  auto claim_raw = [&](const bool doit) -> unsigned {   // 32 bits: the value is carried through the whole tile body
+    unsigned b = 0;
+    if (lane == 0 && doit) b = atomicAdd(reinterpret_cast<unsigned*>(a.counter), 1u);
     return b;
   };
-  auto mask_bytes = [&](const unsigned long long box) -> unsigned {
-    const unsigned long long s = box * (unsigned long long)kCols + lane;
-    return (lane < kCols && box < nbox && s < B) ? (unsigned)a.mask[s] : 0u;
-  };
-  unsigned long long pending_claim = claim_raw(share <= 1);
+  unsigned pending_claim = claim_raw(share <= 1);
   unsigned long long cur;
   {
-    const unsigned long long dyn = __shfl_sync(kFull, pending_claim, 0);
-    cur = share > 0 ? gwarp * share : dyn_base + dyn;
+    // (box numbers go through a broadcast from lane 0 even when every lane computes the same value: the compiler
+    // then knows they are warp-uniform; a box number derived from threadIdx would make it treat the whole tile body
+    // as divergent code and give every shuffle an out-of-line slow path)
+    cur = __shfl_sync(kFull, share > 0 ? gwarp * share : dyn_base + (unsigned long long)pending_claim, 0);
     if (share == 0) pending_claim = claim_raw(true);
   }
   if (cur < nbox) stage_issue<real, MODE, SUPER, TMA>(a, maps, cur, stage, bar, lane);
-  unsigned mask_cur = mask_bytes(cur), mask_nxt = 0u;
   unsigned long long nxt = 0;
   int sub = 0;                 // tile of the current box
 #pragma unroll 1
@@ -287,17 +284,14 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
       const unsigned long long bq = valid ? s0 : (B - 1);
       RawIn<real, MODE> in;
       stage_read<real, MODE, SUPER>(a, stage, prm.mu_default, leg, col, bq, in);
-      const unsigned mask_byte = __shfl_sync(kFull, mask_cur, col);   // every lane takes part (not inside the `valid` select)
-      in.mask = valid ? (mask_byte & 0xFu) : 0u;
+      if (!valid) in.mask = 0u;
       if (sub == SUPER - 1) {
         __syncwarp();     // every lane has read the last tile of the box: the next box may land in the buffer
         taken++;
-        const unsigned long long dyn = __shfl_sync(kFull, pending_claim, 0);   // every lane, whichever branch is taken below
-        nxt = taken < share ? gwarp * share + taken : dyn_base + dyn;
+        nxt = __shfl_sync(kFull, taken < share ? gwarp * share + taken : dyn_base + (unsigned long long)pending_claim, 0);
         // the claim for the box after `nxt`: needed once the static share is used up
         pending_claim = claim_raw(taken + 1 >= share);
         if (nxt < nbox) stage_issue<real, MODE, SUPER, TMA>(a, maps, nxt, stage, bar, lane);
-        mask_nxt = mask_bytes(nxt);
       }
       // ---- kinematics and QP data; the Jacobian goes straight into the slot this quad would keep
       const int slot = nth_set_bit(~occ & ((1u << CAP) - 1u), quad);
@@ -342,7 +336,7 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
       }
       occ |= __reduce_or_sync(kFull, hard ? (1u << slot) : 0u);
       __syncwarp();
-      if (++sub == SUPER) { sub = 0; cur = nxt; mask_cur = mask_nxt; }
+      if (++sub == SUPER) { sub = 0; cur = nxt; }
     }
     // one call site (the code of the round phase exists once): after a tile when the stash is full enough, and
     // once more when the boxes are exhausted, until the stash is empty
