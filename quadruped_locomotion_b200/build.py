@@ -45,12 +45,14 @@ def build_host_demo(force: bool = False, verbose: bool = False, which: str = "ti
     """Compile a C++ adapter demo (host code only, links libqlb.so)."""
     exe = os.path.join(PKG, "host", which)
     src = exe + ".cpp"
-    hdrs = [os.path.join(PKG, "host", h) for h in ("qlb_adapter.hpp", "qlb_qp_adapter.hpp")]
+    hdrs = [os.path.join(PKG, "host", h) for h in ("qlb_adapter.hpp", "qlb_qp_adapter.hpp", "qlb_batch_adapter.hpp")]
     build()
     if not force and os.path.exists(exe) and os.path.getmtime(exe) > max([os.path.getmtime(f) for f in [src, LIB] + hdrs]):
         return exe
     cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(PKG, "host"),
            "-o", exe, src, "-L" + PKG, "-lqlb", "-Wl,-rpath," + PKG, "-Wl,-rpath,/usr/local/cuda/lib64"]
+    if which == "nccl_demo":   # the multi-GPU demo talks to the CUDA runtime and NCCL itself
+        cmd += ["-I/usr/local/cuda/include", "-L/usr/local/cuda/lib64", "-lcudart", "-lnccl", "-pthread"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
@@ -63,3 +65,5 @@ if __name__ == "__main__":
     print(build_host_demo(force=True, verbose=True))
     print(build_host_demo(force=True, verbose=True, which="qp_demo"))
     print(build_host_demo(force=True, verbose=True, which="swing_demo"))
+    for extra_demo in ("params_demo", "batch_demo", "nccl_demo"):
+        print(build_host_demo(force=True, verbose=True, which=extra_demo))

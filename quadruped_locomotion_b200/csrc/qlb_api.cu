@@ -325,16 +325,17 @@ int launch_single(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int
     if (src[s] && !make_map<T>(&maps.seg[s], src[s], a.B, SG::rows(s))) tma = false;
   if (tma && (SG::kCols < 16 || !aligned16(a.mask) || !make_mask_map(&maps.mask, a.mask, a.B, SG::kCols))) tma = false;
   const unsigned long long ntiles = (a.B + 7) / 8;
-  const unsigned long long want = (ntiles + 3) / 4;
+  const unsigned long long want = (ntiles + kFusedWarps - 1) / kFusedWarps;
   const int bps = ctx->blocks_per_sm_single[sizeof(T) == 4 ? 1 : 0][MODE][tma ? 1 : 0];
   const unsigned long long cap = (unsigned long long)ctx->sm_count * bps;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  if (tma) qlb_single_kernel<T, C, MODE, QLB_SUPER, true><<<grid, kQuadThreads, FL::kTotal, st>>>(a, maps);
-  else qlb_single_kernel<T, C, MODE, QLB_SUPER, false><<<grid, kQuadThreads, FL::kTotal, st>>>(a, maps);
+  if (tma) qlb_single_kernel<T, C, MODE, QLB_SUPER, true><<<grid, kFusedThreads, FL::kTotal, st>>>(a, maps);
+  else qlb_single_kernel<T, C, MODE, QLB_SUPER, false><<<grid, kFusedThreads, FL::kTotal, st>>>(a, maps);
   QLB_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
   const unsigned long long capq = (unsigned long long)ctx->sm_count * bps_ipm;
-  qlb_quad_kernel<T, C, MODE, 2><<<(unsigned)(want < capq ? want : capq), kQuadThreads, 0, st>>>(a);
+  const unsigned long long wantq = (ntiles + 3) / 4;
+  qlb_quad_kernel<T, C, MODE, 2><<<(unsigned)(wantq < capq ? wantq : capq), kQuadThreads, 0, st>>>(a);
   QLB_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
   QLB_CUDA(ctx, cudaEventRecord(ctx->slot_done[ctx->last_slot], st));
@@ -350,8 +351,8 @@ bool prepare_single_kernels(qlb_context* ctx) {
       cudaFuncSetAttribute(qlb_single_kernel<T, C, MODE, QLB_SUPER, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
       cudaFuncSetAttribute(qlb_single_kernel<T, C, MODE, QLB_SUPER, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
     return false;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out[0], qlb_single_kernel<T, C, MODE, QLB_SUPER, false>, kQuadThreads, FL::kTotal) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out[1], qlb_single_kernel<T, C, MODE, QLB_SUPER, true>, kQuadThreads, FL::kTotal) != cudaSuccess)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out[0], qlb_single_kernel<T, C, MODE, QLB_SUPER, false>, kFusedThreads, FL::kTotal) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out[1], qlb_single_kernel<T, C, MODE, QLB_SUPER, true>, kFusedThreads, FL::kTotal) != cudaSuccess)
     return false;
   return out[0] >= 1 && out[1] >= 1;
 }

@@ -22,8 +22,13 @@
 namespace qlb {
 
 #ifndef QLB_FUSED_MIN_CTAS
-#define QLB_FUSED_MIN_CTAS 3
+#define QLB_FUSED_MIN_CTAS 2     // measured on B200 (2^20 C3 states): 2 x 4 warps 0.613 ms, 3 x 4 warps 0.667 ms - with eight
+#endif                           // warps per SM nothing spills (238 registers) and the instruction cache misses less
+#ifndef QLB_FUSED_THREADS
+#define QLB_FUSED_THREADS 128
 #endif
+constexpr int kFusedThreads = QLB_FUSED_THREADS;
+constexpr int kFusedWarps = kFusedThreads / 32;
 constexpr int kSingleSmemBudget = (228 / QLB_FUSED_MIN_CTAS - 1) * 1024;   // per CTA: QLB_FUSED_MIN_CTAS CTAs per SM (228 KB, 1 KB reserved per CTA)
 
 // ---------------------------------------------------------------------------------------------------------
@@ -50,12 +55,12 @@ struct FusedLayout {
     return ((kStashLane * 4 * c * (int)sizeof(creal) + 12 * 4 * c * (int)sizeof(real) + 6 * c * (int)sizeof(creal) + 16 * c) + 15) & ~15;
   }
   static constexpr int warp_bytes(int c) { return (kStage + stash_bytes(c) + 127) & ~127; }
-  static constexpr int cap_for(int c) { return (kStatic + kFixed + 4 * warp_bytes(c) <= kSingleSmemBudget || c <= 8) ? c : cap_for(c - 1); }
+  static constexpr int cap_for(int c) { return (kStatic + kFixed + kFusedWarps * warp_bytes(c) <= kSingleSmemBudget || c <= 8) ? c : cap_for(c - 1); }
   static constexpr int kCap = cap_for(15);
   static_assert(kCap >= 10, "stash too small");
   static_assert(stash_bytes(kCap) == StashLayout<real, creal, kCap>::kBytes, "layout mismatch");
   static constexpr int kWarpBytes = warp_bytes(kCap);
-  static constexpr int kTotal = kFixed + 4 * kWarpBytes;   // dynamic shared memory of the kernel
+  static constexpr int kTotal = kFixed + kFusedWarps * kWarpBytes;   // dynamic shared memory of the kernel
   static_assert(kStatic + kTotal <= kSingleSmemBudget, "shared memory budget");
 };
 
@@ -205,7 +210,7 @@ __device__ __forceinline__ void round_phase(const SolveArgsT<real>& a, const Cor
 
 // ---------------------------------------------------------------------------------------------------------
 template <typename real, typename creal, int MODE, int SUPER, bool TMA>
-__global__ void __launch_bounds__(kQuadThreads, QLB_FUSED_MIN_CTAS)
+__global__ void __launch_bounds__(kFusedThreads, QLB_FUSED_MIN_CTAS)
 qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps maps) {
   using FL = FusedLayout<real, creal, MODE, SUPER>;
   constexpr int CAP = FL::kCap;
@@ -242,13 +247,14 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
   unsigned occ = 0u;           // pending slots of the stash (warp-uniform)
   uint32_t parity = 0;
 
-  // Work distribution: the first three quarters of the boxes are split evenly and contiguously over the warps of
-  // the grid (no atomics, no latency); the last quarter is claimed dynamically, one atomic per box, issued a whole
+  // Work distribution: the first three quarters of the boxes are dealt out to the warps of the grid round robin
+  // (box b to warp b mod #warps: no atomics, no latency, and neighbouring boxes - whose states are correlated in a
+  // sweep of perturbations around nominal states - go to different warps); the last quarter is claimed dynamically, one atomic per box, issued a whole
   // box ahead - its result stays in lane 0 and is broadcast only when the box number is needed - so warps that
   // drew cheap states take more of it.  (The stance masks travel with the staged box: a loop-carried register loaded
   // from global memory gets spilled right behind its load, which exposes the full latency.)
-  const unsigned long long nwarps = (unsigned long long)gridDim.x * (kQuadThreads / 32);
-  const unsigned long long gwarp = (unsigned long long)blockIdx.x * (kQuadThreads / 32) + warp;
+  const unsigned long long nwarps = (unsigned long long)gridDim.x * kFusedWarps;
+  const unsigned long long gwarp = (unsigned long long)blockIdx.x * kFusedWarps + warp;
   const unsigned long long share = (nbox - nbox / 4) / nwarps;     // static boxes per warp
   const unsigned long long dyn_base = share * nwarps;              // first dynamically claimed box
   unsigned long long taken = 0;                                    // boxes this warp has started
@@ -263,7 +269,7 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
     // (box numbers go through a broadcast from lane 0 even when every lane computes the same value: the compiler
     // then knows they are warp-uniform; a box number derived from threadIdx would make it treat the whole tile body
     // as divergent code and give every shuffle an out-of-line slow path)
-    cur = __shfl_sync(kFull, share > 0 ? gwarp * share : dyn_base + (unsigned long long)pending_claim, 0);
+    cur = __shfl_sync(kFull, share > 0 ? gwarp : dyn_base + (unsigned long long)pending_claim, 0);
     if (share == 0) pending_claim = claim_raw(true);
   }
   if (cur < nbox) stage_issue<real, MODE, SUPER, TMA>(a, maps, cur, stage, bar, lane);
@@ -288,7 +294,7 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
       if (sub == SUPER - 1) {
         __syncwarp();     // every lane has read the last tile of the box: the next box may land in the buffer
         taken++;
-        nxt = __shfl_sync(kFull, taken < share ? gwarp * share + taken : dyn_base + (unsigned long long)pending_claim, 0);
+        nxt = __shfl_sync(kFull, taken < share ? gwarp + taken * nwarps : dyn_base + (unsigned long long)pending_claim, 0);
         // the claim for the box after `nxt`: needed once the static share is used up
         pending_claim = claim_raw(taken + 1 >= share);
         if (nxt < nbox) stage_issue<real, MODE, SUPER, TMA>(a, maps, nxt, stage, bar, lane);

