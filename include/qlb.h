@@ -113,7 +113,9 @@ typedef enum qlb_state_status {
   QLB_STATE_NO_STANCE = 1,     /* no leg in stance: nothing solved, outputs zero (CFD.cpp:127-132) */
   QLB_STATE_MAX_ITER = 2,      /* iteration limit hit; forces are the last iterate */
   QLB_STATE_UNVERIFIED = 3,    /* converged, but the active-set polish failed its KKT check */
-  QLB_STATE_BAD_INPUT = 4,     /* NaN/Inf input or degenerate surface normal; outputs zero */
+  QLB_STATE_BAD_INPUT = 4,     /* NaN/Inf input, degenerate surface normal, a joint angle beyond 1e6 rad, or a base
+                                  quaternion / stance-leg surface normal that is not a unit vector (|v|^2 off by more than
+                                  1e-5; smaller deviations - FP32 rounding - are renormalised); outputs zero */
   QLB_STATE_INFEASIBLE = 5     /* a stance leg has a negative friction coefficient while F_min > 0: no force satisfies
                                   mu n.f >= |t.f| and n.f >= F_min; outputs zero (QuadProg++ returns +inf, QuadProg++.cc:340-344) */
 } qlb_state_status;

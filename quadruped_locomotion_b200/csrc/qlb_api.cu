@@ -136,6 +136,14 @@ void build_device_model(const qlb_leg_model legs[QLB_NUM_LEGS], DeviceModel* m) 
     double acc = 0.0;
     for (int j = 3; j >= 0; j--) { acc += legs[l].link_mass[j]; m->msuf[l][j] = acc; }
   }
+  // joints whose fixed transform is trivial on every leg (the knee of both shipped models has rpy = 0, the thigh xyz = 0)
+  for (int j = 0; j < 4; j++) {
+    bool ri = true, xz = true;
+    for (int l = 0; l < 4; l++)
+      for (int a = 0; a < 3; a++) { ri = ri && legs[l].joint_rpy[j][a] == 0.0; xz = xz && legs[l].joint_xyz[j][a] == 0.0; }
+    m->rot_ident[j] = ri ? 1.0 : 0.0;
+    m->xyz_zero[j] = xz ? 1.0 : 0.0;
+  }
 }
 
 void build_device_params(const qlb_params* p, DeviceParams* d) {
@@ -313,9 +321,8 @@ template <typename T, typename C, int MODE>
 int launch_single(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int bps_ipm) {
   using SG = Staging<T, MODE, QLB_SUPER>;
   using FL = FusedLayout<T, C, MODE, QLB_SUPER>;
-  const T* src[6];
-  if (MODE == 1) { src[0] = a.q; src[1] = a.pose; src[2] = a.twist; src[3] = a.tpose; src[4] = a.ttwist; src[5] = a.mu; }
-  else { src[0] = a.q; src[1] = a.quat; src[2] = a.wrench; src[3] = a.mu; src[4] = nullptr; src[5] = nullptr; }
+  const T* src[SG::kNumSeg];
+  for (int s = 0; s < SG::kNumSeg; s++) src[s] = SG::source(a, s);
   bool tma = ctx->use_tma && a.B >= 64 && a.B < 0x7fffff00ull && ((a.B * sizeof(T)) % 16 == 0);
   for (int s = 0; s < SG::kNumSeg && tma; s++)
     if (src[s] && !aligned16(src[s])) tma = false;

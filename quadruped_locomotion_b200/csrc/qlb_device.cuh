@@ -58,8 +58,11 @@ __device__ __forceinline__ float fast_rsqrt(float x) {
 // sin and cos for joint angles (|x| up to ~1e4 rad; URDF limits are +-3 rad): two-constant Cody-Waite
 // reduction by pi/2 and the fdlibm kernel polynomials.  No slow path, no local memory.
 __device__ __forceinline__ void sincos_small(double x, double* sn, double* cs) {
-  const double kd = rint(x * 6.36619772367581382433e-01);  // x * 2/pi
-  const int k = (int)kd;
+  // nearest multiple of pi/2 by the add-magic-constant trick: the low word of x 2/pi + 1.5 2^52 is the integer k
+  // (no FP64 round / convert instructions, which run at a fraction of the FMA rate)
+  const double km = fma(x, 6.36619772367581382433e-01, 6755399441055744.0);
+  const int k = __double2loint(km);
+  const double kd = km - 6755399441055744.0;
   double r = fma(-kd, 1.57079632673412561417e+00, x);
   r = fma(-kd, 6.07710050650619224932e-11, r);
   const double z = r * r;
@@ -77,11 +80,33 @@ __device__ __forceinline__ void sincos_small(double x, double* sn, double* cs) {
   const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
   const double s0 = (k & 1) ? cr : sr;
   const double c0 = (k & 1) ? sr : cr;
-  *sn = (k & 2) ? -s0 : s0;
-  *cs = ((k + 1) & 2) ? -c0 : c0;
+  // quadrant signs: flip the sign bit in the high word (one logic operation each)
+  *sn = __hiloint2double(__double2hiint(s0) ^ ((k & 2) << 30), __double2loint(s0));
+  *cs = __hiloint2double(__double2hiint(c0) ^ (((k + 1) & 2) << 30), __double2loint(c0));
 }
 
-__device__ __forceinline__ void sincos_small(float x, float* sn, float* cs) { sincosf(x, sn, cs); }
+// FP32 twin (|x| <= 1e6, the bound the callers check): three-constant Cody-Waite reduction, minimax polynomials on
+// [-pi/4, pi/4]; ~1 ulp for joint-range arguments.  No slow path, no local memory (sincosf carries a Payne-Hanek
+// branch with a stack frame).
+__device__ __forceinline__ void sincos_small(float x, float* sn, float* cs) {
+  const float km = fmaf(x, 6.36619772e-01f, 12582912.0f);   // 1.5 2^23: the low bits of the sum hold the integer k
+  const int k = __float_as_int(km);
+  const float kf = km - 12582912.0f;
+  float r = fmaf(-kf, 1.57079601e+00f, x);
+  r = fmaf(-kf, 3.13916473e-07f, r);
+  r = fmaf(-kf, 5.39030253e-15f, r);
+  const float z = r * r;
+  float ps = fmaf(z, -1.95152959e-04f, 8.33216087e-03f);
+  ps = fmaf(z, ps, -1.66666546e-01f);
+  const float sr = fmaf(z * r, ps, r);
+  float pc = fmaf(z, 2.44331571e-05f, -1.38873163e-03f);
+  pc = fmaf(z, pc, 4.16666457e-02f);
+  const float cr = fmaf(z * z, pc, fmaf(-0.5f, z, 1.0f));
+  const float s0 = (k & 1) ? cr : sr;
+  const float c0 = (k & 1) ? sr : cr;
+  *sn = __int_as_float(__float_as_int(s0) ^ ((k & 2) << 30));
+  *cs = __int_as_float(__float_as_int(c0) ^ (((k + 1) & 2) << 30));
+}
 
 // T = double for the FP64 entry points, float for their _f32 twins (the context keeps both copies).
 template <typename T>
@@ -91,6 +116,8 @@ struct DeviceModelT {
   T mass[4][4];     // link masses
   T com[4][4][3];   // link COM in link frame (the foot link's is pre-rotated by rot[leg][3])
   T msuf[4][4];     // suffix sums of mass: msuf[leg][c] = sum_{l>=c} mass[leg][l]
+  T rot_ident[4];   // 1 when <origin rpy> of joint j is zero on all four legs (the chain product skips the fixed rotation),
+  T xyz_zero[4];    // 1 when <origin xyz> of joint j is zero on all four legs; else 0.  Same for every lane: uniform branches
 };
 using DeviceModel = DeviceModelT<double>;
 

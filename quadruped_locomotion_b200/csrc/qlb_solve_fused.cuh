@@ -40,28 +40,36 @@ struct Staging {
   static constexpr int kCols = 8 * SUPER;                                       // states per box
   static constexpr int kRow = kCols * (int)sizeof(real);                        // bytes of one row of a box
   __host__ __device__ static constexpr int align(int x) { return (x + 127) & ~127; }   // TMA destinations: 128-byte aligned
-  // wrench mode: q, quat, wrench, mu;  state mode: q, pose, twist, tpose, ttwist, mu.  (Per-leg surface normals, when
-  // the caller passes them, are read straight from global memory: the rare case does not take staging space.)
-  static constexpr int kNumSeg = (MODE == 1) ? 6 : 4;
+  // wrench mode: q, quat, wrench, mu, normals;  state mode: q, pose, twist, tpose, ttwist, mu, normals.  (Arrays the
+  // caller does not pass - mu, normals - are skipped: no transfer, the space stays unused.)
+  static constexpr int kNumSeg = (MODE == 1) ? 7 : 5;
   __host__ __device__ static constexpr int rows(int s) {
-    return (MODE == 1) ? (s == 0 ? 12 : s == 1 ? 7 : s == 2 ? 6 : s == 3 ? 7 : s == 4 ? 6 : 4)
-                       : (s == 0 ? 12 : s == 1 ? 4 : s == 2 ? 6 : 4);
+    return (MODE == 1) ? (s == 0 ? 12 : s == 1 ? 7 : s == 2 ? 6 : s == 3 ? 7 : s == 4 ? 6 : s == 5 ? 4 : 12)
+                       : (s == 0 ? 12 : s == 1 ? 4 : s == 2 ? 6 : s == 3 ? 4 : 12);
   }
   // (closed form, no recursion: a recursive constexpr function called with a run-time-looking argument is compiled
   // as a real recursive device function - found in the SASS as CALL/RET, 29 % of all executed instructions)
   static constexpr int kO1 = align(rows(0) * kRow), kO2 = kO1 + align(rows(1) * kRow), kO3 = kO2 + align(rows(2) * kRow),
-                       kO4 = kO3 + align(rows(3) * kRow), kO5 = kO4 + align(rows(4) * kRow), kO6 = kO5 + align(rows(5) * kRow);
+                       kO4 = kO3 + align(rows(3) * kRow), kO5 = kO4 + align(rows(4) * kRow),
+                       kO6 = kO5 + align((MODE == 1 ? rows(5) : 0) * kRow), kO7 = kO6 + align((MODE == 1 ? rows(6) : 0) * kRow);
   __host__ __device__ static constexpr int offset(int s) {
-    return s == 0 ? 0 : s == 1 ? kO1 : s == 2 ? kO2 : s == 3 ? kO3 : s == 4 ? kO4 : s == 5 ? kO5 : kO6;
+    return s == 0 ? 0 : s == 1 ? kO1 : s == 2 ? kO2 : s == 3 ? kO3 : s == 4 ? kO4 : s == 5 ? kO5 : s == 6 ? kO6 : kO7;
   }
-  static constexpr int kMaskOff = (MODE == 1) ? kO6 : kO4;     // the stance masks of the box: one byte per state
+  static constexpr int kMaskOff = (MODE == 1) ? kO7 : kO5;     // the stance masks of the box: one byte per state
   static constexpr int kBytes = kMaskOff + 128;
   static constexpr int kSegMu = (MODE == 1) ? 5 : 3;
+  static constexpr int kSegNrm = kSegMu + 1;
+  // the global array behind segment s (nullptr: not passed)
+  template <typename Args>
+  __host__ __device__ static const real* source(const Args& a, const int s) {
+    if (MODE == 1) return s == 0 ? a.q : s == 1 ? a.pose : s == 2 ? a.twist : s == 3 ? a.tpose : s == 4 ? a.ttwist : s == 5 ? a.mu : a.normals;
+    return s == 0 ? a.q : s == 1 ? a.quat : s == 2 ? a.wrench : s == 3 ? a.mu : a.normals;
+  }
 };
 
 // Tensor maps of the input arrays of one call (built on the host, qlb_api.cu), in Staging segment order.
 struct alignas(64) FusedMaps {
-  CUtensorMap seg[6];
+  CUtensorMap seg[7];
   CUtensorMap mask;    // rank 1, uint8, boxes of 8 SUPER states
 };
 
@@ -131,9 +139,9 @@ template <typename real, int MODE, int SUPER, bool TMA>
 __device__ __forceinline__ void stage_issue(const SolveArgsT<real>& a, const FusedMaps& maps, const unsigned long long box,
                                             unsigned char* stage, const uint32_t bar, const int lane) {
   using SG = Staging<real, MODE, SUPER>;
-  const real* src[6];
-  if (MODE == 1) { src[0] = a.q; src[1] = a.pose; src[2] = a.twist; src[3] = a.tpose; src[4] = a.ttwist; src[5] = a.mu; }
-  else { src[0] = a.q; src[1] = a.quat; src[2] = a.wrench; src[3] = a.mu; src[4] = nullptr; src[5] = nullptr; }
+  const real* src[SG::kNumSeg];
+#pragma unroll
+  for (int s = 0; s < SG::kNumSeg; s++) src[s] = SG::source(a, s);
   if (TMA) {
     if (lane == 0) {
       uint32_t bytes = 0;
@@ -204,7 +212,7 @@ __device__ __forceinline__ void stage_read(const SolveArgsT<real>& a, const unsi
   in.nw[0] = real(0.0); in.nw[1] = real(0.0); in.nw[2] = real(1.0);
   if (a.normals != nullptr) {
 #pragma unroll
-    for (int c = 0; c < 3; c++) in.nw[c] = __ldg(a.normals + (size_t)(3 * leg + c) * a.B + bq);
+    for (int c = 0; c < 3; c++) in.nw[c] = at(SG::kSegNrm, 3 * leg + c);
   }
 }
 
@@ -235,6 +243,8 @@ __device__ __forceinline__ void dbas_round(RoundState<creal>& q, const creal* b,
   const creal (&At)[3][6] = q.At;
   const int a0 = q.a0, sg1 = q.sg1, sg2 = q.sg2;
   // ---- reduced columns of the equality-constrained QP for the working set
+  // (a slot that is not free gets the weight al = 0: its column needs no masking - it enters the system and the
+  // recovery of y+ only through al - and the columns of a swing leg are zero anyway)
   creal v[3][6], al[3], r6[6];
   {
     const creal q1 = sg1 * mu, q2 = sg2 * mu;
@@ -247,10 +257,10 @@ __device__ __forceinline__ void dbas_round(RoundState<creal>& q, const creal* b,
 #pragma unroll
     for (int r = 0; r < 6; r++) {
       const creal cn = fma(q2, At[2][r], fma(q1, At[1][r], At[0][r]));
-      v[0][r] = fn ? cn : creal(0.0);
-      v[1][r] = f1 ? At[1][r] : creal(0.0);
-      v[2][r] = f2 ? At[2][r] : creal(0.0);
-      r6[r] = ((leg == 0 && active) ? b[r * bstride] : creal(0.0)) - pin * cn;
+      v[0][r] = cn;
+      v[1][r] = At[1][r];
+      v[2][r] = At[2][r];
+      r6[r] = fma(-pin, cn, (leg == 0 && active) ? b[r * bstride] : creal(0.0));
     }
   }
   // ---- the 6x6 system, summed over the quad

@@ -282,10 +282,13 @@ __device__ __forceinline__ void load_model_to_smem(const DeviceModelT<real>* src
 }
 
 // Everything from the raw inputs of one state (lane = leg `leg`) up to the QP data.
-template <typename real, int MODE>
+// creal: the type of the QP data (friction frame, wrench map, desired wrench).  With FP32 inputs and the FP64 solver
+// core the frame is built in FP64 from the FP32 quaternion and normal, so that it is orthonormal to FP64 rounding and
+// the solver may use the identities that rest on Q Q' = I; the leg kinematics (the bulk of the work) stay in `real`.
+template <typename real, int MODE, typename creal = real>
 __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const DeviceParamsT<real>& prm, const RawIn<real, MODE>& in,
                                            const unsigned long long bq, const bool valid, const bool write_wout,
-                                           const int leg, LegSetup<real>& L, real* const jgp, const int jgs) {
+                                           const int leg, LegSetup<creal>& L, real* const jgp, const int jgs) {
   // jgp / jgs: where this lane parks its leg's Jacobian (9) and gravity torques (3): element k at jgp[k * jgs]
   const unsigned long long B = a.B;
 #if QLB_SMEM_MODEL
@@ -304,7 +307,7 @@ __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const Devi
     // joint angles beyond 1e6 rad are outside the range of the argument reduction (and NaN / Inf fail the comparison)
     bool bad = !(fabs(qj[0]) <= real(1e6) && fabs(qj[1]) <= real(1e6) && fabs(qj[2]) <= real(1e6));
     real quat[4];
-    real (&b)[6] = L.b;
+    real b[6];
     if (MODE == 1) {
       // virtual model controller prologue (VirtualModelController.cpp:104-268), redundantly on the quad
       const real (&pose)[MODE == 1 ? 7 : 1] = in.pose;
@@ -362,28 +365,45 @@ __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const Devi
 #pragma unroll
       for (int r = 0; r < 6; r++) { b[r] = in.b[r]; bad |= !isfinite(b[r]); }
     }
-    const real mu = L.mu = in.mu;
-    const real nw[3] = {in.nw[0], in.nw[1], in.nw[2]};
+#pragma unroll
+    for (int r = 0; r < 6; r++) L.b[r] = (creal)b[r];
+    const real mu = in.mu;
+    L.mu = (creal)mu;
 
     // ---------------- base rotation, friction frame (CFD.cpp:223,237,286-309), gravity in base frame (:518-519)
-    real E[3][3];  // E[0] = n, E[1] = t1, E[2] = t2 in base frame
+    // The contact coordinates rest on an orthonormal frame: the quaternion and the normal must be unit vectors.
+    // Rounding-level deviations (FP32 inputs, a sloppy normalisation) are removed here; anything beyond 1e-5 is
+    // refused as bad input (the reference would silently scale the normal force bound and the friction coefficient).
+    creal E[3][3];  // E[0] = n, E[1] = t1, E[2] = t2 in base frame
     real gb[3];
     {
-      const real w = quat[0], x = quat[1], y = quat[2], z = quat[3];
-      real R[9];
-      R[0] = w * w + x * x - y * y - z * z; R[1] = real(2.0) * (x * y - w * z); R[2] = real(2.0) * (x * z + w * y);
-      R[3] = real(2.0) * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = real(2.0) * (y * z - w * x);
-      R[6] = real(2.0) * (x * z - w * y); R[7] = real(2.0) * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
+      creal w = (creal)quat[0], x = (creal)quat[1], y = (creal)quat[2], z = (creal)quat[3];
+      creal nv[3] = {(creal)in.nw[0], (creal)in.nw[1], (creal)in.nw[2]};
+      const creal qn = w * w + x * x + y * y + z * z, nn = nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2];
+      bad |= !(fabs(qn - creal(1.0)) <= creal(1e-5)) || (alive && !(fabs(nn - creal(1.0)) <= creal(1e-5)));
+      if (sizeof(real) != sizeof(creal) || fabs(qn - creal(1.0)) > creal(1e-14)) {
+        const creal sq = fast_rsqrt(qn);
+        w *= sq; x *= sq; y *= sq; z *= sq;
+      }
+      if (sizeof(real) != sizeof(creal) || fabs(nn - creal(1.0)) > creal(1e-14)) {
+        const creal sn = fast_rsqrt(nn);
+        nv[0] *= sn; nv[1] *= sn; nv[2] *= sn;
+      }
+      const creal (&nw)[3] = nv;
+      creal R[9];
+      R[0] = w * w + x * x - y * y - z * z; R[1] = creal(2.0) * (x * y - w * z); R[2] = creal(2.0) * (x * z + w * y);
+      R[3] = creal(2.0) * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = creal(2.0) * (y * z - w * x);
+      R[6] = creal(2.0) * (x * z - w * y); R[7] = creal(2.0) * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         E[0][c] = R[c] * nw[0] + R[3 + c] * nw[1] + R[6 + c] * nw[2];
-        gb[c] = -prm.gravity * R[6 + c];
+        gb[c] = -prm.gravity * (real)R[6 + c];
       }
-      const real ey[3] = {R[3], R[4], R[5]};
+      const creal ey[3] = {R[3], R[4], R[5]};
       E[1][0] = E[0][1] * ey[2] - E[0][2] * ey[1];
       E[1][1] = E[0][2] * ey[0] - E[0][0] * ey[2];
       E[1][2] = E[0][0] * ey[1] - E[0][1] * ey[0];
-      real rn = fast_rsqrt(E[1][0] * E[1][0] + E[1][1] * E[1][1] + E[1][2] * E[1][2]);
+      creal rn = fast_rsqrt(E[1][0] * E[1][0] + E[1][1] * E[1][1] + E[1][2] * E[1][2]);
 #pragma unroll
       for (int c = 0; c < 3; c++) E[1][c] *= rn;
       E[2][0] = E[0][1] * E[1][2] - E[0][2] * E[1][1];
@@ -412,10 +432,12 @@ __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const Devi
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         if (j > 0) {
-          const real x0 = QLB_MDL(mdl.xyz[leg][j][0]), x1 = QLB_MDL(mdl.xyz[leg][j][1]), x2 = QLB_MDL(mdl.xyz[leg][j][2]);
+          if (QLB_MDL(mdl.xyz_zero[j]) == real(0.0)) {
+            const real x0 = QLB_MDL(mdl.xyz[leg][j][0]), x1 = QLB_MDL(mdl.xyz[leg][j][1]), x2 = QLB_MDL(mdl.xyz[leg][j][2]);
 #pragma unroll
-          for (int c = 0; c < 3; c++) p[c] += R[3 * c] * x0 + R[3 * c + 1] * x1 + R[3 * c + 2] * x2;
-          if (j < 3) {
+            for (int c = 0; c < 3; c++) p[c] += R[3 * c] * x0 + R[3 * c + 1] * x1 + R[3 * c + 2] * x2;
+          }
+          if (j < 3 && QLB_MDL(mdl.rot_ident[j]) == real(0.0)) {
             real Rj[9], T[9];
 #pragma unroll
             for (int e = 0; e < 9; e++) Rj[e] = QLB_MDL(mdl.rot[leg][j][e]);
@@ -465,15 +487,18 @@ __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const Devi
     }
 
     // ---------------- the leg's block of the wrench map in contact coordinates: A_k = [E'; (r x e_c)] (6 x 3)
-    real (&At)[3][6] = L.At;  // At[c] = column of slot c (0 = normal, 1, 2 = tangents)
+    creal (&At)[3][6] = L.At;  // At[c] = column of slot c (0 = normal, 1, 2 = tangents)
+    const creal footc[3] = {(creal)foot[0], (creal)foot[1], (creal)foot[2]};
+    // (a swing leg: zero force rows; its torque rows r x 0 vanish without a second select unless the foot position is
+    // not finite, which the joint-angle check above has already turned into status BAD_INPUT)
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      At[c][0] = alive ? E[c][0] : real(0.0);
-      At[c][1] = alive ? E[c][1] : real(0.0);
-      At[c][2] = alive ? E[c][2] : real(0.0);
-      At[c][3] = alive ? foot[1] * E[c][2] - foot[2] * E[c][1] : real(0.0);
-      At[c][4] = alive ? foot[2] * E[c][0] - foot[0] * E[c][2] : real(0.0);
-      At[c][5] = alive ? foot[0] * E[c][1] - foot[1] * E[c][0] : real(0.0);
+      At[c][0] = alive ? E[c][0] : creal(0.0);
+      At[c][1] = alive ? E[c][1] : creal(0.0);
+      At[c][2] = alive ? E[c][2] : creal(0.0);
+      At[c][3] = footc[1] * At[c][2] - footc[2] * At[c][1];
+      At[c][4] = footc[2] * At[c][0] - footc[0] * At[c][2];
+      At[c][5] = footc[0] * At[c][1] - footc[1] * At[c][0];
     }
     // Jacobian and gravity torques are only needed again for the outputs: park them in shared memory
 #pragma unroll
@@ -483,18 +508,18 @@ __device__ __forceinline__ void quad_setup(const SolveArgsT<real>& a, const Devi
       jgp[(9 + j) * jgs] = gtau[j];
     }
 #pragma unroll
-    for (int c = 0; c < 3; c++) { L.nrm[c] = E[0][c]; L.foot[c] = foot[c]; }
+    for (int c = 0; c < 3; c++) { L.nrm[c] = E[0][c]; L.foot[c] = footc[c]; }
     float gsc = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      real g = real(0.0);
+      creal g = creal(0.0);
 #pragma unroll
-      for (int r = 0; r < 6; r++) g = fma(At[c][r] * prm.S[r], b[r], g);
+      for (int r = 0; r < 6; r++) g = fma(At[c][r] * (creal)prm.S[r], L.b[r], g);
       gsc = fmaxf(gsc, fabsf((float)g));
     }
     L.gscale = fmaxf(1.f, quad_max(gsc));
-    L.c0 = fmax(fmax(real(2.0) * prm.fmin, (b[0] * E[0][0] + b[1] * E[0][1] + b[2] * E[0][2]) * (ns > 0 ? real(1.0) / ns : real(0.0))),
-                           prm.fmin + real(1.0));
+    L.c0 = fmax(fmax(creal(2.0) * (creal)prm.fmin, (L.b[0] * E[0][0] + L.b[1] * E[0][1] + L.b[2] * E[0][2]) * (ns > 0 ? creal(1.0) / ns : creal(0.0))),
+                           (creal)prm.fmin + creal(1.0));
     L.rm = ns > 0 ? 1.f / (5.f * ns) : 0.f;
 
 }
@@ -572,7 +597,9 @@ __device__ __forceinline__ void quad_output(const SolveArgsT<real>& a, const Leg
 // Whole warp (quad shuffles).  Out: y (contact coordinates), t (solution of the 6x6 system; A x = b - S^-1 t),
 // status (0 ok / 1 no stance / 4 bad), hard (some row is violated: the state needs active-set rounds),
 // pat (first pattern: every violated row active, 5 bits per leg, OR-ed over the quad).
-template <typename real, typename creal>
+// FRAME_EXACT: the friction frames are orthonormal to the rounding of creal (built in creal by quad_setup), which the
+// short form of the system below relies on.
+template <typename real, typename creal, bool FRAME_EXACT = (sizeof(real) == sizeof(creal))>
 __device__ __forceinline__ void quad_first_solve(const LegSetup<creal>& L, const creal* sinv, const creal winv, const creal cfmin,
                                                  const int leg, creal (&y)[3], creal (&t)[6], int& status, bool& hard,
                                                  unsigned& pat_out) {
@@ -584,7 +611,7 @@ __device__ __forceinline__ void quad_first_solve(const LegSetup<creal>& L, const
   // unconstrained minimiser through the 6x6 system: (S^-1 + A~ A~'/w) t = b,  y = A~' t / w
   const creal al = alive ? winv : creal(0.0);
   bool pd;
-  if (Tol<creal>::refine || sizeof(real) != sizeof(creal)) {
+  if (Tol<creal>::refine || !FRAME_EXACT) {
     // FP32 core: generic assembly + iterative refinement through the factors.  FP32 interface with the FP64
     // core: generic assembly as well - the system must be built from the same rounded A~ that recovers y.
     creal N[21], rdg[6];
@@ -1270,6 +1297,8 @@ __global__ void __launch_bounds__(kQuadThreads, STAGE == 1 ? QLB_QUAD_MIN_CTAS :
   __shared__ CoreConst<creal> cc;
   __shared__ CoreConst<double> cc64;  // in-kernel rescue of the FP32 core
   __shared__ real jg[12][kQuadThreads];  // per thread: Jacobian (9) and gravity torques (3) of its leg
+  // a list pass with an empty list (the usual case for the interior-point pass behind the fused kernel): nothing to set up
+  if (STAGE != 0 && __ldcg(STAGE == 1 ? a.list_count : a.list2_count) == 0u) return;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.params);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&prm);

@@ -22,14 +22,25 @@
 namespace qlb {
 
 #ifndef QLB_FUSED_MIN_CTAS
-#define QLB_FUSED_MIN_CTAS 2     // measured on B200 (2^20 C3 states): 2 x 4 warps 0.613 ms, 3 x 4 warps 0.667 ms - with eight
-#endif                           // warps per SM nothing spills (238 registers) and the instruction cache misses less
+#define QLB_FUSED_MIN_CTAS 2     // FP64 arrays.  Measured on B200 (2^20 C3 states): 2 x 4 warps 0.613 ms, 3 x 4 warps 0.667 ms - with
+#endif                           // eight warps per SM nothing spills (213 registers) and the instruction fetch stalls less
+#ifndef QLB_FUSED_MIN_CTAS_F32
+#define QLB_FUSED_MIN_CTAS_F32 3 // FP32 arrays: the kinematics need half the registers, nothing spills at 168: 0.518 ms against 0.630 ms
+#endif
 #ifndef QLB_FUSED_THREADS
 #define QLB_FUSED_THREADS 128
 #endif
+#ifndef QLB_STASH_CAP
+#define QLB_STASH_CAP 22         // stash slots per warp (as many as the shared-memory budget allows, at most this)
+#endif
+#ifndef QLB_ROUND_LOW
+#define QLB_ROUND_LOW 8          // the round phase runs until fewer than this many states are pending: all eight quads
+#endif                           // stay busy, and the phases are long (a warp stays in one half of the code for a while)
 constexpr int kFusedThreads = QLB_FUSED_THREADS;
 constexpr int kFusedWarps = kFusedThreads / 32;
-constexpr int kSingleSmemBudget = (228 / QLB_FUSED_MIN_CTAS - 1) * 1024;   // per CTA: QLB_FUSED_MIN_CTAS CTAs per SM (228 KB, 1 KB reserved per CTA)
+template <typename real> constexpr int fused_min_ctas() { return sizeof(real) == 4 ? QLB_FUSED_MIN_CTAS_F32 : QLB_FUSED_MIN_CTAS; }
+// shared memory per CTA: fused_min_ctas CTAs per SM (228 KB, 1 KB reserved per CTA)
+template <typename real> constexpr int fused_smem_budget() { return (228 / fused_min_ctas<real>() - 1) * 1024; }
 
 // ---------------------------------------------------------------------------------------------------------
 // The stash of one warp: CAP entries.  Per-lane planes (element k of the entry in slot s, leg l at
@@ -55,13 +66,13 @@ struct FusedLayout {
     return ((kStashLane * 4 * c * (int)sizeof(creal) + 12 * 4 * c * (int)sizeof(real) + 6 * c * (int)sizeof(creal) + 16 * c) + 15) & ~15;
   }
   static constexpr int warp_bytes(int c) { return (kStage + stash_bytes(c) + 127) & ~127; }
-  static constexpr int cap_for(int c) { return (kStatic + kFixed + kFusedWarps * warp_bytes(c) <= kSingleSmemBudget || c <= 8) ? c : cap_for(c - 1); }
-  static constexpr int kCap = cap_for(15);
+  static constexpr int cap_for(int c) { return (kStatic + kFixed + kFusedWarps * warp_bytes(c) <= fused_smem_budget<real>() || c <= 8) ? c : cap_for(c - 1); }
+  static constexpr int kCap = cap_for(QLB_STASH_CAP);
   static_assert(kCap >= 10, "stash too small");
   static_assert(stash_bytes(kCap) == StashLayout<real, creal, kCap>::kBytes, "layout mismatch");
   static constexpr int kWarpBytes = warp_bytes(kCap);
   static constexpr int kTotal = kFixed + kFusedWarps * kWarpBytes;   // dynamic shared memory of the kernel
-  static_assert(kStatic + kTotal <= kSingleSmemBudget, "shared memory budget");
+  static_assert(kStatic + kTotal <= fused_smem_budget<real>(), "shared memory budget");
 };
 
 template <typename real, typename creal, int CAP>
@@ -210,12 +221,13 @@ __device__ __forceinline__ void round_phase(const SolveArgsT<real>& a, const Cor
 
 // ---------------------------------------------------------------------------------------------------------
 template <typename real, typename creal, int MODE, int SUPER, bool TMA>
-__global__ void __launch_bounds__(kFusedThreads, QLB_FUSED_MIN_CTAS)
+__global__ void __launch_bounds__(kFusedThreads, fused_min_ctas<real>())
 qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps maps) {
   using FL = FusedLayout<real, creal, MODE, SUPER>;
   constexpr int CAP = FL::kCap;
   constexpr int Q = 4 * CAP;
-  constexpr int kRunMin = CAP - 7;            // a tile needs eight free slots: the round phase runs down to CAP - 8 pending
+  constexpr int kRunMin = CAP - 7;            // a tile needs eight free slots: the round phase starts at CAP - 7 pending ...
+  constexpr int kRunLow = QLB_ROUND_LOW < kRunMin ? QLB_ROUND_LOW : kRunMin;   // ... and runs until fewer than this are left
   constexpr int kCols = 8 * SUPER;
   extern __shared__ __align__(128) unsigned char smem[];
   DeviceParamsT<real>& prm = *reinterpret_cast<DeviceParamsT<real>*>(smem);
@@ -302,16 +314,12 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
       // ---- kinematics and QP data; the Jacobian goes straight into the slot this quad would keep
       const int slot = nth_set_bit(~occ & ((1u << CAP) - 1u), quad);
       LegSetup<creal> L;
-      {
-        LegSetup<real> L0;
-        quad_setup<real, MODE>(a, prm, in, bq, valid, true, leg, L0, ws.sj + 4 * slot + leg, Q);
-        widen_setup(L0, L);
-      }
+      quad_setup<real, MODE, creal>(a, prm, in, bq, valid, true, leg, L, ws.sj + 4 * slot + leg, Q);
       int status;
       creal y[3], t[6];
       bool hard;
       unsigned pat;
-      quad_first_solve<real, creal>(L, cc.sinv, winv, cfmin, leg, y, t, status, hard, pat);
+      quad_first_solve<real, creal, true>(L, cc.sinv, winv, cfmin, leg, y, t, status, hard, pat);
       hard = hard && valid;
       creal net[6];
 #pragma unroll
@@ -347,7 +355,7 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
     // one call site (the code of the round phase exists once): after a tile when the stash is full enough, and
     // once more when the boxes are exhausted, until the stash is empty
     const int pending = __popc(occ);
-    if (have ? (pending >= kRunMin) : (pending > 0)) round_phase<real, creal, CAP>(a, cc, ws, occ, !have, kRunMin, lane, leg, quad);
+    if (have ? (pending >= kRunMin) : (pending > 0)) round_phase<real, creal, CAP>(a, cc, ws, occ, !have, kRunLow, lane, leg, quad);
     if (!have) break;
   }
 }

@@ -269,6 +269,31 @@ def test_huge_joint_angles_are_bad_input(solver):
     assert status[3] == 4 and (np.delete(status, 3) == 0).all() and np.isfinite(out["grf"]).all()
 
 
+def test_unit_vector_contract_of_quaternion_and_normals(solver, oracle, models):
+    """The contact coordinates need a unit base quaternion and unit surface normals (QLB_STATE_BAD_INPUT in
+    include/qlb.h): deviations at rounding level are renormalised - the result is the oracle's for the exact unit
+    vectors - and anything beyond 1e-5 in |v|^2 is refused, neighbours untouched."""
+    st = synth.make_states("C3", 64, start=77)
+    st["mask"][:] = 0xF
+    ref = _oracle(oracle, models["quadruped_model"], st)
+    clean = solver.solve_wrench_numpy(st)
+    pert = {k: v.copy() for k, v in st.items()}
+    pert["quat"][:, 5] *= 1.0 + 2e-7           # what an FP32 round trip does to a unit quaternion
+    pert["normals"][:, 9] *= 1.0 - 1.5e-7
+    pert["quat"][:, 20] *= 1.01                # not a rotation any more
+    pert["normals"][3:6, 33] *= 0.9            # leg 1's normal is not a unit vector
+    out = solver.solve_wrench_numpy(pert)
+    status = (out["flags"] >> 24) & 7
+    assert status[20] == 4 and status[33] == 4 and not out["grf"][:, [20, 33]].any()
+    ok = np.ones(64, bool); ok[[20, 33]] = False
+    assert (status[ok] == 0).all()
+    sc = np.maximum(1.0, np.abs(ref["grf"]).max(0))
+    assert (np.abs(out["grf"] - ref["grf"]).max(0) / sc)[ok].max() <= 1e-9
+    assert np.array_equal(out["flags"][ok] & 0xFFFFFF, ref["flags"][ok] & 0xFFFFFF)
+    same = ok.copy(); same[[5, 9]] = False
+    assert np.array_equal(out["grf"][:, same], clean["grf"][:, same])
+
+
 def test_full_size_properties(solver, oracle, models):
     """BASELINE size (2^20): size-independent properties on the whole batch + oracle parity on a slice."""
     B = 1 << 20

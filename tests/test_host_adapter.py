@@ -93,7 +93,8 @@ def test_state_batch_preview_of_a_plan(qlb_built):
     assert r.returncode == 0, r.stderr
     out = json.loads(r.stdout)
     assert out["samples"] == 400 and out["stances"] == 8       # the first stance + seven support changes
-    np.testing.assert_allclose(out["fz"], [499.8] * 3, rtol=1e-9)   # the gravity compensation is distributed
+    np.testing.assert_allclose(out["fz"], [499.8] * 3, rtol=1e-3)   # the gravity compensation is distributed (the force
+    # regulariser of the QP keeps the total a fraction of a newton below the commanded weight)
     assert 0.0 < out["min_margin"] <= 1.0
     # LF foot: under the hip at the start, carried 0.2 m forward by the base at the end
     assert abs(out["lf_last"][0] - out["lf_first"][0] - 0.05 * 3.99) < 1e-9 and abs(out["lf_first"][2]) < 0.05
@@ -106,5 +107,5 @@ def test_stats_allreduce_through_the_c_abi(qlb_built):
     demo = build.build_host_demo(which="nccl_demo")
     r = subprocess.run([demo, "20000"], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
-    f = r.stdout.split()
-    assert f[-1] == "AGREE" and float(f[3]) == 20000.0 * int(f[1]) and float(f[5]) == float(f[3])
+    f = r.stdout.strip().splitlines()[-1].split()      # (NCCL may print its version line first)
+    assert f[0] == "gpus" and f[-1] == "AGREE" and float(f[3]) == 20000.0 * int(f[1]) and float(f[5]) == float(f[3])
