@@ -47,6 +47,7 @@ struct qlb_context {
   int blocks_per_sm_first_m[2] = {0, 0};
   int pipeline = QLB_PIPELINE_FUSED;   // qlb_set_pipeline
   int blocks_per_sm_single[2][2][2] = {};   // [interface type: 0 double, 1 float][MODE][TMA]
+  int fused_bps_cap = 0;                    // experiments (env QLB_FUSED_BPS): fewer CTAs of the fused kernel per SM
   bool use_tma = true;    // fused pipeline: stage the inputs with the TMA unit when the arrays allow it
   bool f32_pure = false;  // qlb_set_f32_core: FP32 solver core with in-kernel FP64 rescue, or FP64 core for every state
   unsigned long long* d_counter = nullptr;
@@ -135,14 +136,6 @@ void build_device_model(const qlb_leg_model legs[QLB_NUM_LEGS], DeviceModel* m) 
     for (int a = 0; a < 3; a++) m->com[l][3][a] = R3[3 * a] * c3[0] + R3[3 * a + 1] * c3[1] + R3[3 * a + 2] * c3[2];
     double acc = 0.0;
     for (int j = 3; j >= 0; j--) { acc += legs[l].link_mass[j]; m->msuf[l][j] = acc; }
-  }
-  // joints whose fixed transform is trivial on every leg (the knee of both shipped models has rpy = 0, the thigh xyz = 0)
-  for (int j = 0; j < 4; j++) {
-    bool ri = true, xz = true;
-    for (int l = 0; l < 4; l++)
-      for (int a = 0; a < 3; a++) { ri = ri && legs[l].joint_rpy[j][a] == 0.0; xz = xz && legs[l].joint_xyz[j][a] == 0.0; }
-    m->rot_ident[j] = ri ? 1.0 : 0.0;
-    m->xyz_zero[j] = xz ? 1.0 : 0.0;
   }
 }
 
@@ -333,7 +326,8 @@ int launch_single(qlb_context* ctx, SolveArgsT<T>& a, cudaStream_t st, const int
   if (tma && (SG::kCols < 16 || !aligned16(a.mask) || !make_mask_map(&maps.mask, a.mask, a.B, SG::kCols))) tma = false;
   const unsigned long long ntiles = (a.B + 7) / 8;
   const unsigned long long want = (ntiles + kFusedWarps - 1) / kFusedWarps;
-  const int bps = ctx->blocks_per_sm_single[sizeof(T) == 4 ? 1 : 0][MODE][tma ? 1 : 0];
+  int bps = ctx->blocks_per_sm_single[sizeof(T) == 4 ? 1 : 0][MODE][tma ? 1 : 0];
+  if (ctx->fused_bps_cap > 0 && bps > ctx->fused_bps_cap) bps = ctx->fused_bps_cap;
   const unsigned long long cap = (unsigned long long)ctx->sm_count * bps;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   if (tma) qlb_single_kernel<T, C, MODE, QLB_SUPER, true><<<grid, kFusedThreads, FL::kTotal, st>>>(a, maps);
@@ -656,6 +650,7 @@ int qlb_create(qlb_context** out, const qlb_leg_model legs[QLB_NUM_LEGS], const 
     cudaGetLastError();
     return fail(QLB_ERR_CUDA);
   }
+  if (const char* e = std::getenv("QLB_FUSED_BPS")) ctx->fused_bps_cap = std::atoi(e);
   if (const char* e = std::getenv("QLB_PIPELINE")) {   // experiments: three_pass | fused | fused_notma
     if (!std::strcmp(e, "three_pass")) ctx->pipeline = QLB_PIPELINE_THREE_PASS;
 

@@ -116,8 +116,6 @@ struct DeviceModelT {
   T mass[4][4];     // link masses
   T com[4][4][3];   // link COM in link frame (the foot link's is pre-rotated by rot[leg][3])
   T msuf[4][4];     // suffix sums of mass: msuf[leg][c] = sum_{l>=c} mass[leg][l]
-  T rot_ident[4];   // 1 when <origin rpy> of joint j is zero on all four legs (the chain product skips the fixed rotation),
-  T xyz_zero[4];    // 1 when <origin xyz> of joint j is zero on all four legs; else 0.  Same for every lane: uniform branches
 };
 using DeviceModel = DeviceModelT<double>;
 

@@ -269,6 +269,19 @@ def test_huge_joint_angles_are_bad_input(solver):
     assert status[3] == 4 and (np.delete(status, 3) == 0).all() and np.isfinite(out["grf"]).all()
 
 
+def test_results_do_not_depend_on_the_launch_geometry(qlb_built, monkeypatch):
+    """The fused kernel is persistent: how many boxes a warp takes - and with it how often hard states are parked in
+    the shared-memory stash and resumed - depends on the number of resident CTAs.  The optimum does not: one CTA per SM
+    (QLB_FUSED_BPS=1, read when the context is created) gives the same forces and the same flags as the default."""
+    st = synth.make_states("C5", 65536, start=3)
+    ref = capi.Solver("quadruped_model").solve_wrench_numpy(st)
+    monkeypatch.setenv("QLB_FUSED_BPS", "1")
+    out = capi.Solver("quadruped_model").solve_wrench_numpy(st)
+    assert np.array_equal(out["flags"] & 0xFFFFFF, ref["flags"] & 0xFFFFFF)
+    sc = np.maximum(1.0, np.abs(ref["grf"]).max(0))
+    assert (np.abs(out["grf"] - ref["grf"]).max(0) / sc).max() <= 1e-10
+
+
 def test_unit_vector_contract_of_quaternion_and_normals(solver, oracle, models):
     """The contact coordinates need a unit base quaternion and unit surface normals (QLB_STATE_BAD_INPUT in
     include/qlb.h): deviations at rounding level are renormalised - the result is the oracle's for the exact unit
