@@ -52,6 +52,29 @@ def bench_config(B: int, world: int) -> dict:
 NCU_RECORD = os.path.join(ROOT, "profiles", "r2_final_ncu.json")   # written by tools/ncu_summary.py from the committed capture
 
 
+_JSON_FD = None   # the process's real stdout once emit_only_json_on_stdout() has moved fd 1 to stderr
+
+
+def emit_only_json_on_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too - NCCL writes its version line to stdout at
+    NCCL_DEBUG=VERSION, a level at which it ignores NCCL_DEBUG_FILE - so fd 1 is pointed at stderr for the rest of the
+    process (nothing is hidden, the NCCL_DEBUG level is the caller's) and the JSON line goes out through the saved fd."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def print_json_line(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def load_ncu_record():
     """DRAM traffic and executed-pipe figures of one solve call on 2^20 C3 states, from the committed ncu capture
     (a run under the profiler is never a bench value; the bench reports these next to its own timing)."""
@@ -269,7 +292,7 @@ def run_sweep(args, rank, local_rank, world, dev, warmup):
                       "max_solver_rounds": sd["max_iterations"], "mean_wrench_err": sd["mean_wrench_err"],
                       "max_wrench_err": sd["max_wrench_err"], "active_row_hist": sd["active_hist"]},
         }
-        print(json.dumps(line), flush=True)
+        print_json_line(line)
 
 
 def main():
@@ -304,7 +327,7 @@ def main():
                 "data": "synthetic", "config": bench_config(B, args.gpus),
                 "cpu_baseline": info, "gpu_launches": 0,
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        print_json_line(line)
         return
 
     import torch
@@ -320,6 +343,7 @@ def main():
         # the contract is ONE JSON line on stdout: NCCL's log (whatever NCCL_DEBUG level the caller chose) goes to
         # stderr, the level itself is left alone so that the communicator lines stay visible to the caller
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        emit_only_json_on_stdout()
         dist.init_process_group("nccl", device_id=dev)
 
     if args.config.upper() == "C5":
@@ -498,7 +522,7 @@ def main():
             "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
             "traffic": tw.get("dram_bytes") * (B / float(1 << 20)) if tw.get("dram_bytes") else None,
-            "kernel": "one solve call = qlb_fused_kernel<double,double,0,true> (TMA-staged inputs, kinematics, QP data, "
+            "kernel": "one solve call = qlb_single_kernel<double,double,0,2,true> (TMA-staged inputs, kinematics, QP data, "
                       "unconstrained minimiser, active-set rounds from a shared-memory stash) + qlb_quad_kernel<..,2> "
                       "(interior-point fallback, normally an empty list)",
             "note": "frac is ALGORITHMIC: FP64 FLOP by the fixed accounting of SURVEY 8d (30k/21k/12k per 4/3/2-stance QP, an "
@@ -534,14 +558,14 @@ def main():
                     "e2e": {"value": world * B * e2e_steps / e2e_s32, "unit": UNIT,
                             "h2d_bytes_per_step": B * ((12 + 4 + 6 + 4) * 4 + 1), "d2h_bytes_per_step": B * ((12 + 12 + 6) * 4 + 4)},
                     "median_rel_force_diff_vs_f64": f32_err,
-                    "note": "qlb_solve_wrench_f32[_host], default core: FP32 interface and kinematics, FP64 solver core; "
+                    "note": "qlb_solve_wrench_f32[_host], default core: FP32 arrays and leg kinematics, friction frame + QP in FP64; "
                             "stated tolerance in include/qlb.h and tests/test_gpu_parity.py"},
             "stats": {"ok": sd["ok"], "max_iter": sd["max_iter"], "unverified": sd["unverified"],
                       "mean_solver_rounds": sd["mean_iterations"], "max_solver_rounds": sd["max_iterations"],
                       "mean_wrench_err": sd["mean_wrench_err"], "allreduce_ms": allreduce_ms,
                       "algorithmic_flop_total": flop_total},
         }
-        print(json.dumps(line), flush=True)
+        print_json_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

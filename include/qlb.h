@@ -212,10 +212,13 @@ int qlb_solve_state_host(qlb_context* ctx, size_t B, const double* q, const doub
 
 /* FP32 twins (SURVEY 8b "_f32 suffix", BASELINE config C4): the same entry points with float arrays -
  * half the HBM / PCIe bytes.  Two solver cores, chosen per context with qlb_set_f32_core:
- *   QLB_F32_CORE_FP64 (default): FP32 interface and kinematics, FP64 solver core.  The only error left is
- *     the rounding of the inputs and outputs.  STATED TOLERANCE: forces within 2e-3 relative of the FP64
- *     result (scale max(1,|f|_inf); measured 5e-4), torques within 4e-3 (measured 1.2e-3); status and
- *     contact bits exact; active-row bits exact on states whose active set is decided by a margin above 1e-3.
+ *   QLB_F32_CORE_FP64 (default): FP32 arrays and leg kinematics (sincos, chain product, Jacobian, gravity torques);
+ *     the friction frame is built in FP64 from the FP32 quaternion and normal (renormalised) and the QP is solved in
+ *     FP64.  The only error left is the rounding of inputs, kinematics and outputs.  STATED TOLERANCE: forces within
+ *     5e-4 relative of the FP64 result (scale max(1,|f|_inf); measured 8e-5 on C3, 9e-7 on C2, 5e-6 on C5), torques
+ *     within 1e-3 (measured 1.5e-4); status and contact bits exact; active-row bits exact on states whose active set
+ *     is decided by a margin above 1e-3 (measured: exact on every test state).  1.12x the FP64 throughput
+ *     device-resident, 1.57x end to end.
  *   QLB_F32_CORE_FP32: FP32 arithmetic throughout (the 6x6 systems with one step of iterative refinement,
  *     active-set rounds, interior point); states the FP32 core cannot verify are solved again by the FP64
  *     core inside the same kernel, so every status is the FP64 one.  About 1.2x the throughput.  STATED

@@ -601,9 +601,9 @@ __device__ __forceinline__ void quad_output(const SolveArgsT<real>& a, const Leg
 // Whole warp (quad shuffles).  Out: y (contact coordinates), t (solution of the 6x6 system; A x = b - S^-1 t),
 // status (0 ok / 1 no stance / 4 bad), hard (some row is violated: the state needs active-set rounds),
 // pat (first pattern: every violated row active, 5 bits per leg, OR-ed over the quad).
-// FRAME_EXACT: the friction frames are orthonormal to the rounding of creal (built in creal by quad_setup), which the
-// short form of the system below relies on.
-template <typename real, typename creal, bool FRAME_EXACT = (sizeof(real) == sizeof(creal))>
+// (The friction frames are orthonormal to the rounding of creal - quad_setup builds them in creal - which the short
+// form of the system below relies on.)
+template <typename real, typename creal>
 __device__ __forceinline__ void quad_first_solve(const LegSetup<creal>& L, const creal* sinv, const creal winv, const creal cfmin,
                                                  const int leg, creal (&y)[3], creal (&t)[6], int& status, bool& hard,
                                                  unsigned& pat_out) {
@@ -615,9 +615,8 @@ __device__ __forceinline__ void quad_first_solve(const LegSetup<creal>& L, const
   // unconstrained minimiser through the 6x6 system: (S^-1 + A~ A~'/w) t = b,  y = A~' t / w
   const creal al = alive ? winv : creal(0.0);
   bool pd;
-  if (Tol<creal>::refine || !FRAME_EXACT) {
-    // FP32 core: generic assembly + iterative refinement through the factors.  FP32 interface with the FP64
-    // core: generic assembly as well - the system must be built from the same rounded A~ that recovers y.
+  if (Tol<creal>::refine) {
+    // FP32 core: generic assembly + iterative refinement through the factors.
     creal N[21], rdg[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) {
@@ -761,11 +760,7 @@ __global__ void __launch_bounds__(kQuadThreads, QLB_FIRST_MIN_CTAS) qlb_quad_fir
     const bool valid = slot < B;
     const unsigned long long bq = valid ? slot : (B - 1);
     LegSetup<creal> L;
-    {
-      LegSetup<real> L0;
-      quad_setup<real, MODE>(a, prm, in, bq, valid, true, leg, L0, &jg[0][threadIdx.x], kQuadThreads);
-      widen_setup(L0, L);
-    }
+    quad_setup<real, MODE, creal>(a, prm, in, bq, valid, true, leg, L, &jg[0][threadIdx.x], kQuadThreads);
     int status;
     creal y[3], t[6];
     bool hard;
@@ -1244,11 +1239,9 @@ __device__ __forceinline__ void quad_batch(const SolveArgsT<real>& a, const Devi
   constexpr bool kRescue = Tol<creal>::rescue && (STAGE == 1 || STAGE == 2);
   LegSetup<creal> L;
   {
-    LegSetup<real> L0;
     RawIn<real, MODE> in;
     quad_load<real, MODE>(a, prm.mu_default, bq, valid, leg, in);
-    quad_setup<real, MODE>(a, prm, in, bq, valid, STAGE == 0, leg, L0, &jg[0][threadIdx.x], kQuadThreads);
-    widen_setup(L0, L);
+    quad_setup<real, MODE, creal>(a, prm, in, bq, valid, STAGE == 0, leg, L, &jg[0][threadIdx.x], kQuadThreads);
   }
   creal y[3];
   int a0, sg1, sg2, status, it;

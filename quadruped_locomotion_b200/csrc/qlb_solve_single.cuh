@@ -257,7 +257,8 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
   }
   __syncthreads();
   const unsigned long long B = a.B;
-  const unsigned long long nbox = (B + kCols - 1) / kCols;
+  const unsigned Bu = (unsigned)B;
+  const unsigned nbox = (unsigned)((B + kCols - 1) / kCols);   // box numbers are 32-bit (B < 2^32): fewer loop-carried registers
   const creal winv = cc.winv, cfmin = cc.fmin;
   unsigned occ = 0u;           // pending slots of the stash (warp-uniform)
   uint32_t parity = 0;
@@ -268,27 +269,27 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
   // box ahead - its result stays in lane 0 and is broadcast only when the box number is needed - so warps that
   // drew cheap states take more of it.  (The stance masks travel with the staged box: a loop-carried register loaded
   // from global memory gets spilled right behind its load, which exposes the full latency.)
-  const unsigned long long nwarps = (unsigned long long)gridDim.x * kFusedWarps;
-  const unsigned long long gwarp = (unsigned long long)blockIdx.x * kFusedWarps + warp;
-  const unsigned long long share = (nbox - nbox / 4) / nwarps;     // static boxes per warp
-  const unsigned long long dyn_base = share * nwarps;              // first dynamically claimed box
-  unsigned long long taken = 0;                                    // boxes this warp has started
+  const unsigned nwarps = gridDim.x * kFusedWarps;
+  const unsigned gwarp = blockIdx.x * kFusedWarps + warp;
+  const unsigned share = (nbox - nbox / 4) / nwarps;     // static boxes per warp
+  const unsigned dyn_base = share * nwarps;              // first dynamically claimed box
+  unsigned taken = 0;                                    // boxes this warp has started
   auto claim_raw = [&](const bool doit) -> unsigned {   // 32 bits: the value is carried through the whole tile body
     unsigned b = 0;
     if (lane == 0 && doit) b = atomicAdd(reinterpret_cast<unsigned*>(a.counter), 1u);
     return b;
   };
   unsigned pending_claim = claim_raw(share <= 1);
-  unsigned long long cur;
+  unsigned cur;
   {
     // (box numbers go through a broadcast from lane 0 even when every lane computes the same value: the compiler
     // then knows they are warp-uniform; a box number derived from threadIdx would make it treat the whole tile body
     // as divergent code and give every shuffle an out-of-line slow path)
-    cur = __shfl_sync(kFull, share > 0 ? gwarp : dyn_base + (unsigned long long)pending_claim, 0);
+    cur = __shfl_sync(kFull, share > 0 ? gwarp : dyn_base + pending_claim, 0);
     if (share == 0) pending_claim = claim_raw(true);
   }
   if (cur < nbox) stage_issue<real, MODE, SUPER, TMA>(a, maps, cur, stage, bar, lane);
-  unsigned long long nxt = 0;
+  unsigned nxt = 0;
   int sub = 0;                 // tile of the current box
 #pragma unroll 1
   for (;;) {
@@ -300,16 +301,16 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
         else { cp_async_wait_all(); __syncwarp(); }
       }
       const int col = sub * 8 + quad;
-      const unsigned long long s0 = cur * (unsigned long long)kCols + col;
-      const bool valid = s0 < B;
-      const unsigned long long bq = valid ? s0 : (B - 1);
+      const unsigned s0 = cur * kCols + col;      // state numbers fit in 32 bits as well
+      const bool valid = s0 < Bu;
+      const unsigned bq = valid ? s0 : (Bu - 1u);
       RawIn<real, MODE> in;
       stage_read<real, MODE, SUPER>(a, stage, prm.mu_default, leg, col, bq, in);
       if (!valid) in.mask = 0u;
       if (sub == SUPER - 1) {
         __syncwarp();     // every lane has read the last tile of the box: the next box may land in the buffer
         taken++;
-        nxt = __shfl_sync(kFull, taken < share ? gwarp + taken * nwarps : dyn_base + (unsigned long long)pending_claim, 0);
+        nxt = __shfl_sync(kFull, taken < share ? gwarp + taken * nwarps : dyn_base + pending_claim, 0);
         // the claim for the box after `nxt`: needed once the static share is used up
         pending_claim = claim_raw(taken + 1 >= share);
         if (nxt < nbox) stage_issue<real, MODE, SUPER, TMA>(a, maps, nxt, stage, bar, lane);
@@ -322,7 +323,7 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
       creal y[3], t[6];
       bool hard;
       unsigned pat;
-      quad_first_solve<real, creal, true>(L, cc.sinv, winv, cfmin, leg, y, t, status, hard, pat);
+      quad_first_solve<real, creal>(L, cc.sinv, winv, cfmin, leg, y, t, status, hard, pat);
       hard = hard && valid;
       creal net[6];
 #pragma unroll

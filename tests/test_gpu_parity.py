@@ -459,7 +459,8 @@ F32_NET = 1e-2          # achieved wrench A x, relative
 F32_FEAS = 1e-4         # constraint violation / force scale
 F32_OBJ = 1e-4          # (f(x32) - f(x*)) / max(1, |f(x*)|); measured 9e-6
 F32_SAME_FLAGS = 0.95   # fraction of states with identical active-row bits
-MIXED_TOL = 2e-3        # FP32 interface + FP64 core: input / output rounding only (measured 5e-4 forces, 1.2e-3 torques)
+MIXED_TOL = 5e-4        # FP32 arrays + kinematics, frame and QP in FP64: rounding of inputs, kinematics, outputs (measured 8e-5 forces,
+                        # 1.5e-4 torques on C3; round 1, with the frame in FP32: 5e-4 / 1.2e-3)
 
 
 def _f32_checks(out, ref, oracle, M, st, nsample=256):
@@ -573,7 +574,7 @@ def test_f32_state_mode_follows_fp64(solver):
     assert np.array_equal((o32["flags"] >> 24) & 7, (o64["flags"] >> 24) & 7)
     e = rel_err(o32["grf"].astype(np.float64), o64["grf"])
     print("f32 state mode vs f64: median %.2e p99 %.2e max %.2e" % (np.median(e), np.percentile(e, 99), e.max()))
-    assert e.max() <= 5 * MIXED_TOL
+    assert e.max() <= 1e-2    # state mode: the virtual wrench itself is computed in FP32 (gains up to 1e4 on FP32 errors)
 
 
 def test_concurrent_streams_do_not_share_launch_slots(solver, oracle, models):
