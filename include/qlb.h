@@ -179,8 +179,9 @@ int qlb_get_params(const qlb_context* ctx, qlb_params* params);
  *        flags[B] result word (see above);
  *        netwrench[6][B] achieved A x (getNetForceAndTorqueOnBase), or NULL.
  * Calls of one context may be in flight on different streams at the same time (the context keeps eight
- * sets of work counters and index lists and orders a ninth call behind the first); the host entry points
- * and the setters are not re-entrant. */
+ * sets of work counters and index lists and orders a ninth call behind the first).  A context may be shared by
+ * several host threads: every entry point holds the context's lock while it enqueues its work (the *_host entry
+ * points until they return), so concurrent calls are serialised on the host and overlap on the device. */
 int qlb_solve_wrench(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz,
                      const double* wrench, const uint8_t* stance_mask, const double* mu,
                      const double* normals_world, double* grf, double* tau, uint32_t* flags,
@@ -255,7 +256,7 @@ int qlb_solve_state_f32_host(qlb_context* ctx, size_t B, const float* q, const f
  *     itself from the stash) - followed by the interior-point kernel for states the rounds could not verify
  *     (normally none).
  *   QLB_PIPELINE_THREE_PASS: the round-1 organisation (first / active-set / interior-point kernels over
- *     compacted index lists in HBM).  Always used by the FP32 solver core. */
+ *     compacted index lists in HBM), kept for comparison.  Always used by the FP32 solver core. */
 #define QLB_PIPELINE_FUSED 0
 #define QLB_PIPELINE_THREE_PASS 1
 int qlb_set_pipeline(qlb_context* ctx, int pipeline);

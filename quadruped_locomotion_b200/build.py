@@ -53,6 +53,8 @@ def build_host_demo(force: bool = False, verbose: bool = False, which: str = "ti
            "-o", exe, src, "-L" + PKG, "-lqlb", "-Wl,-rpath," + PKG, "-Wl,-rpath,/usr/local/cuda/lib64"]
     if which == "nccl_demo":   # the multi-GPU demo talks to the CUDA runtime and NCCL itself
         cmd += ["-I/usr/local/cuda/include", "-L/usr/local/cuda/lib64", "-lcudart", "-lnccl", "-pthread"]
+    if which == "threads_demo":
+        cmd += ["-I/usr/local/cuda/include", "-L/usr/local/cuda/lib64", "-lcudart", "-pthread"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
@@ -65,5 +67,5 @@ if __name__ == "__main__":
     print(build_host_demo(force=True, verbose=True))
     print(build_host_demo(force=True, verbose=True, which="qp_demo"))
     print(build_host_demo(force=True, verbose=True, which="swing_demo"))
-    for extra_demo in ("params_demo", "batch_demo", "nccl_demo"):
+    for extra_demo in ("params_demo", "batch_demo", "nccl_demo", "threads_demo"):
         print(build_host_demo(force=True, verbose=True, which=extra_demo))

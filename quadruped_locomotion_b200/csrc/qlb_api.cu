@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "qlb.h"
@@ -47,6 +48,7 @@ struct qlb_context {
   int blocks_per_sm_first_m[2] = {0, 0};
   int pipeline = QLB_PIPELINE_FUSED;   // qlb_set_pipeline
   int blocks_per_sm_single[2][2][2] = {};   // [interface type: 0 double, 1 float][MODE][TMA]
+  std::recursive_mutex mu;                  // calls on one context from several host threads are serialised (QLB_GUARD)
   int fused_bps_cap = 0;                    // experiments (env QLB_FUSED_BPS): fewer CTAs of the fused kernel per SM
   bool use_tma = true;    // fused pipeline: stage the inputs with the TMA unit when the arrays allow it
   bool f32_pure = false;  // qlb_set_f32_core: FP32 solver core with in-kernel FP64 rescue, or FP64 core for every state
@@ -101,6 +103,13 @@ int cuda_fail(qlb_context* ctx, cudaError_t e, const char* what) {
   if (ctx) std::snprintf(ctx->last_error, sizeof ctx->last_error, "%s: %s", what, cudaGetErrorString(e));
   return QLB_ERR_CUDA;
 }
+// Every entry point that touches the state of a context (launch slots, staging buffers, parameter blocks) holds the
+// context's lock while it enqueues its work: one context may be shared by several host threads.  Device work stays
+// asynchronous (the lock covers the enqueue, not the execution); the *_host entry points hold it until they return.
+#define QLB_GUARD(ctx) \
+  std::unique_lock<std::recursive_mutex> qlb_guard_; \
+  if ((ctx) != nullptr) qlb_guard_ = std::unique_lock<std::recursive_mutex>((ctx)->mu)
+
 #define QLB_CUDA(ctx, call)                                   \
   do {                                                        \
     cudaError_t e__ = (call);                                 \
@@ -679,6 +688,7 @@ int qlb_destroy(qlb_context* ctx) {
 }
 
 int qlb_set_params(qlb_context* ctx, const qlb_params* params) {
+  QLB_GUARD(ctx);
   if (!ctx || !params) return QLB_ERR_INVALID_ARGUMENT;
   if (!params_ok(params)) return QLB_ERR_INVALID_ARGUMENT;
   DeviceGuard guard(ctx->device);
@@ -701,6 +711,7 @@ int qlb_get_params(const qlb_context* ctx, qlb_params* params) {
 }
 
 int qlb_set_f32_core(qlb_context* ctx, int core) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (core != QLB_F32_CORE_FP32 && core != QLB_F32_CORE_FP64) return QLB_ERR_INVALID_ARGUMENT;
   ctx->f32_pure = (core == QLB_F32_CORE_FP32);
@@ -708,6 +719,7 @@ int qlb_set_f32_core(qlb_context* ctx, int core) {
 }
 
 int qlb_set_pipeline(qlb_context* ctx, int pipeline) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (pipeline != QLB_PIPELINE_FUSED && pipeline != QLB_PIPELINE_THREE_PASS) return QLB_ERR_INVALID_ARGUMENT;
   ctx->pipeline = pipeline;
@@ -866,17 +878,20 @@ int solve_state_host_t(qlb_context* ctx, size_t B, const T* q, const T* base_pos
 int qlb_solve_wrench(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz, const double* wrench,
                      const uint8_t* stance_mask, const double* mu, const double* normals_world, double* grf,
                      double* tau, uint32_t* flags, double* netwrench, void* stream) {
+  QLB_GUARD(ctx);
   return solve_wrench_t<double>(ctx, B, q, quat_wxyz, wrench, stance_mask, mu, normals_world, grf, tau, flags, netwrench, stream);
 }
 int qlb_solve_wrench_f32(qlb_context* ctx, size_t B, const float* q, const float* quat_wxyz, const float* wrench,
                          const uint8_t* stance_mask, const float* mu, const float* normals_world, float* grf, float* tau,
                          uint32_t* flags, float* netwrench, void* stream) {
+  QLB_GUARD(ctx);
   return solve_wrench_t<float>(ctx, B, q, quat_wxyz, wrench, stance_mask, mu, normals_world, grf, tau, flags, netwrench, stream);
 }
 int qlb_solve_state(qlb_context* ctx, size_t B, const double* q, const double* base_pose, const double* base_twist,
                     const double* target_pose, const double* target_twist, const uint8_t* stance_mask,
                     const double* mu, const double* normals_world, double* grf, double* tau, uint32_t* flags,
                     double* netwrench, double* wrench_out, void* stream) {
+  QLB_GUARD(ctx);
   return solve_state_t<double>(ctx, B, q, base_pose, base_twist, target_pose, target_twist, stance_mask, mu, normals_world, grf,
                                tau, flags, netwrench, wrench_out, stream);
 }
@@ -884,23 +899,27 @@ int qlb_solve_state_f32(qlb_context* ctx, size_t B, const float* q, const float*
                         const float* target_pose, const float* target_twist, const uint8_t* stance_mask, const float* mu,
                         const float* normals_world, float* grf, float* tau, uint32_t* flags, float* netwrench,
                         float* wrench_out, void* stream) {
+  QLB_GUARD(ctx);
   return solve_state_t<float>(ctx, B, q, base_pose, base_twist, target_pose, target_twist, stance_mask, mu, normals_world, grf,
                               tau, flags, netwrench, wrench_out, stream);
 }
 int qlb_solve_wrench_host(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz, const double* wrench,
                           const uint8_t* stance_mask, const double* mu, const double* normals_world, double* grf,
                           double* tau, uint32_t* flags, double* netwrench) {
+  QLB_GUARD(ctx);
   return solve_wrench_host_t<double>(ctx, B, q, quat_wxyz, wrench, stance_mask, mu, normals_world, grf, tau, flags, netwrench);
 }
 int qlb_solve_wrench_f32_host(qlb_context* ctx, size_t B, const float* q, const float* quat_wxyz, const float* wrench,
                               const uint8_t* stance_mask, const float* mu, const float* normals_world, float* grf, float* tau,
                               uint32_t* flags, float* netwrench) {
+  QLB_GUARD(ctx);
   return solve_wrench_host_t<float>(ctx, B, q, quat_wxyz, wrench, stance_mask, mu, normals_world, grf, tau, flags, netwrench);
 }
 int qlb_solve_state_host(qlb_context* ctx, size_t B, const double* q, const double* base_pose, const double* base_twist,
                          const double* target_pose, const double* target_twist, const uint8_t* stance_mask,
                          const double* mu, const double* normals_world, double* grf, double* tau, uint32_t* flags,
                          double* netwrench, double* wrench_out) {
+  QLB_GUARD(ctx);
   return solve_state_host_t<double>(ctx, B, q, base_pose, base_twist, target_pose, target_twist, stance_mask, mu, normals_world,
                                     grf, tau, flags, netwrench, wrench_out);
 }
@@ -908,12 +927,14 @@ int qlb_solve_state_f32_host(qlb_context* ctx, size_t B, const float* q, const f
                              const float* target_pose, const float* target_twist, const uint8_t* stance_mask, const float* mu,
                              const float* normals_world, float* grf, float* tau, uint32_t* flags, float* netwrench,
                              float* wrench_out) {
+  QLB_GUARD(ctx);
   return solve_state_host_t<float>(ctx, B, q, base_pose, base_twist, target_pose, target_twist, stance_mask, mu, normals_world,
                                    grf, tau, flags, netwrench, wrench_out);
 }
 
 int qlb_leg_kinematics(qlb_context* ctx, size_t B, const double* q, const double* quat_wxyz, double* foot, double* jac,
                        double* gravity_tau, void* stream) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
   if (!q) return QLB_ERR_INVALID_ARGUMENT;
@@ -931,6 +952,7 @@ int qlb_leg_kinematics(qlb_context* ctx, size_t B, const double* q, const double
 
 int qlb_pack_robot_states(qlb_context* ctx, size_t B, const qlb_robot_state_record* records, double* q, double* base_pose,
                           double* base_twist, uint8_t* stance_mask, double* normals_world, void* stream) {
+  QLB_GUARD(ctx);
   static_assert(sizeof(qlb_robot_state_record) == 304, "record layout is part of the ABI");
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
@@ -946,6 +968,7 @@ int qlb_pack_robot_states(qlb_context* ctx, size_t B, const qlb_robot_state_reco
 }
 
 int qlb_feet_in_world(qlb_context* ctx, size_t B, const double* q, const double* base_pose, double* feet_world, void* stream) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
   if (!q || !base_pose || !feet_world) return QLB_ERR_INVALID_ARGUMENT;
@@ -970,6 +993,7 @@ int qlb_default_swing_params(qlb_swing_params* p) {
 }
 
 int qlb_set_limb_dynamics(qlb_context* ctx, const qlb_limb_dynamics legs[QLB_NUM_LEGS]) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (!legs) return QLB_ERR_INVALID_ARGUMENT;
   DeviceGuard guard(ctx->device);
@@ -992,6 +1016,7 @@ int qlb_set_limb_dynamics(qlb_context* ctx, const qlb_limb_dynamics legs[QLB_NUM
 int qlb_swing_leg_torques(qlb_context* ctx, size_t B, const double* q, const double* qd, const double* qdd,
                           const double* foot_target_position, const double* foot_target_velocity,
                           const qlb_swing_params* params, double* tau, void* stream) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (!ctx->have_limb) return QLB_ERR_NOT_INITIALISED;   // qlb_set_limb_dynamics first
   if (B == 0) return QLB_OK;
@@ -1015,6 +1040,7 @@ int qlb_swing_leg_torques(qlb_context* ctx, size_t B, const double* q, const dou
 int qlb_swing_leg_torques_from_queue(qlb_context* ctx, size_t B, const double* q, const double* qd_back, const double* qd_front,
                                      double period, const double* foot_target_position, const double* foot_target_velocity,
                                      const qlb_swing_params* params, double* tau, void* stream) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (!ctx->have_limb) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
@@ -1038,6 +1064,7 @@ int qlb_swing_leg_torques_from_queue(qlb_context* ctx, size_t B, const double* q
 
 int qlb_contact_fsm(qlb_context* ctx, size_t B, const uint8_t* desired_stance_mask, const uint8_t* footstep_mask,
                     const uint8_t* contact_mask, const double* phase, uint8_t* limb_state, uint8_t* stance_mask, void* stream) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
   if (!desired_stance_mask || !contact_mask || !phase || !limb_state) return QLB_ERR_INVALID_ARGUMENT;
@@ -1053,6 +1080,7 @@ int qlb_contact_fsm(qlb_context* ctx, size_t B, const uint8_t* desired_stance_ma
 
 int qlb_friction_margins(qlb_context* ctx, size_t B, const double* grf, const double* quat_wxyz, const uint8_t* stance_mask,
                          const double* mu, const double* normals_world, double* margin, double* min_normal, void* stream) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
   if (!grf || !quat_wxyz || !stance_mask || !margin) return QLB_ERR_INVALID_ARGUMENT;
@@ -1070,6 +1098,7 @@ int qlb_friction_margins(qlb_context* ctx, size_t B, const double* grf, const do
 int qlb_swing_leg_torques_host(qlb_context* ctx, size_t B, const double* q, const double* qd, const double* qdd,
                                const double* foot_target_position, const double* foot_target_velocity,
                                const qlb_swing_params* params, double* tau) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (!ctx->have_limb) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
@@ -1143,6 +1172,7 @@ int records_host_chunks(qlb_context* ctx, size_t B, const qlb_wrench_record* in,
 }  // namespace
 
 int qlb_solve_records(qlb_context* ctx, size_t B, const qlb_wrench_record* records, qlb_result_record* results, void* stream) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
   if (!records || !results) return QLB_ERR_INVALID_ARGUMENT;
@@ -1161,6 +1191,7 @@ int qlb_solve_records(qlb_context* ctx, size_t B, const qlb_wrench_record* recor
 }
 
 int qlb_solve_records_host(qlb_context* ctx, size_t B, const qlb_wrench_record* records, qlb_result_record* results) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
   if (!records || !results) return QLB_ERR_INVALID_ARGUMENT;
@@ -1185,6 +1216,7 @@ int qlb_solve_records_host(qlb_context* ctx, size_t B, const qlb_wrench_record* 
 
 int qlb_preview_plan_host(qlb_context* ctx, size_t B, const qlb_robot_state_record* records, const double mu[4],
                           qlb_preview_record* preview) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (B == 0) return QLB_OK;
   if (!records || !preview) return QLB_ERR_INVALID_ARGUMENT;
@@ -1256,6 +1288,7 @@ int generate_common(qlb_context* ctx, int config, size_t B, uint64_t start, uint
 
 int qlb_generate_states(qlb_context* ctx, int config, size_t B, uint64_t start, uint64_t seed, double* q, double* quat_wxyz,
                         double* wrench, uint8_t* stance_mask, double* mu, double* normals_world, void* stream) {
+  QLB_GUARD(ctx);
   GenArgs g;
   std::memset(&g, 0, sizeof g);
   g.q = q; g.quat = quat_wxyz; g.wrench = wrench; g.mask = stance_mask; g.mu = mu; g.normals = normals_world;
@@ -1264,6 +1297,7 @@ int qlb_generate_states(qlb_context* ctx, int config, size_t B, uint64_t start, 
 
 int qlb_generate_states_f32(qlb_context* ctx, int config, size_t B, uint64_t start, uint64_t seed, float* q, float* quat_wxyz,
                             float* wrench, uint8_t* stance_mask, float* mu, float* normals_world, void* stream) {
+  QLB_GUARD(ctx);
   GenArgs g;
   std::memset(&g, 0, sizeof g);
   g.q32 = q; g.quat32 = quat_wxyz; g.wrench32 = wrench; g.mask = stance_mask; g.mu32 = mu; g.normals32 = normals_world;
@@ -1272,6 +1306,7 @@ int qlb_generate_states_f32(qlb_context* ctx, int config, size_t B, uint64_t sta
 
 int qlb_batch_stats(qlb_context* ctx, size_t B, const uint32_t* flags, const double* wrench, const double* netwrench,
                     qlb_stats* stats_out, void* stream) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (!flags || !stats_out) return QLB_ERR_INVALID_ARGUMENT;
   DeviceGuard guard(ctx->device);
@@ -1280,7 +1315,7 @@ int qlb_batch_stats(qlb_context* ctx, size_t B, const uint32_t* flags, const dou
   if (B > 0) {
     const unsigned threads = 256;
     unsigned long long blocks = (B + threads - 1) / threads;
-    const unsigned long long cap = (unsigned long long)ctx->sm_count * 8ull;
+    const unsigned long long cap = (unsigned long long)ctx->sm_count * 8ull;   // resident in one wave: a grid-stride loop per thread
     if (blocks > cap) blocks = cap;
     qlb_stats_kernel<<<(unsigned)blocks, threads, 0, st>>>(B, flags, wrench, netwrench, ctx->d_params, ctx->d_stats);
     QLB_CUDA(ctx, cudaGetLastError());
@@ -1320,6 +1355,7 @@ const NcclApi& nccl_api() {
 }  // namespace
 
 int qlb_stats_allreduce(qlb_context* ctx, void* nccl_comm, qlb_stats* stats, void* stream) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (!nccl_comm || !stats) return QLB_ERR_INVALID_ARGUMENT;
   const NcclApi& nccl = nccl_api();
@@ -1349,6 +1385,7 @@ int qlb_stats_allreduce(qlb_context* ctx, void* nccl_comm, qlb_stats* stats, voi
 int qlb_qp_dense(qlb_context* ctx, size_t B, int n, int m, int p, const double* G, const double* g0, const double* CE,
                  const double* ce0, const double* CI, const double* ci0, double* x, double* cost, uint32_t* status,
                  uint32_t* active, void* stream) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (n < 1 || n > kQpMaxN || m < 0 || m > kQpMaxM || p < 0 || p > kQpMaxP) return QLB_ERR_INVALID_ARGUMENT;
   if (B == 0) return QLB_OK;
@@ -1370,6 +1407,7 @@ int qlb_qp_dense(qlb_context* ctx, size_t B, int n, int m, int p, const double* 
 int qlb_qp_dense_host(qlb_context* ctx, size_t B, int n, int m, int p, const double* G, const double* g0,
                       const double* CE, const double* ce0, const double* CI, const double* ci0, double* x, double* cost,
                       uint32_t* status, uint32_t* active) {
+  QLB_GUARD(ctx);
   if (!ctx) return QLB_ERR_NOT_INITIALISED;
   if (n < 1 || n > kQpMaxN || m < 0 || m > kQpMaxM || p < 0 || p > kQpMaxP) return QLB_ERR_INVALID_ARGUMENT;
   if (B == 0) return QLB_OK;
@@ -1413,6 +1451,7 @@ int qlb_qp_dense_host(qlb_context* ctx, size_t B, int n, int m, int p, const dou
 }
 
 int qlb_measure_fp64_peak(qlb_context* ctx, double* tflops_out) {
+  QLB_GUARD(ctx);
   if (!ctx || !tflops_out) return QLB_ERR_INVALID_ARGUMENT;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = ctx->stream;

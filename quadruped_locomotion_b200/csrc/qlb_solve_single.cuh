@@ -59,7 +59,9 @@ struct StashLayout {
 template <typename real, typename creal, int MODE, int SUPER>
 struct FusedLayout {
   // fixed part: parameter block, solver constants, one mbarrier per warp (the leg-model table is a static array)
-  static constexpr int kFixed = ((((int)sizeof(DeviceParamsT<real>) + 15) & ~15) + (((int)sizeof(CoreConst<creal>) + 15) & ~15) + 64 + 127) & ~127;
+  static constexpr int kCtlWords = 8;   // per warp: loop-control words that are read once per box (kept out of the registers)
+  static constexpr int kFixed = ((((int)sizeof(DeviceParamsT<real>) + 15) & ~15) + (((int)sizeof(CoreConst<creal>) + 15) & ~15) + 64 +
+                                 kFusedWarps * kCtlWords * 4 + 127) & ~127;
   static constexpr int kStatic = (int)sizeof(DeviceModelT<double>) + 128;
   static constexpr int kStage = Staging<real, MODE, SUPER>::kBytes;
   static constexpr int stash_bytes(int c) {
@@ -235,8 +237,10 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
   extern __shared__ __align__(128) unsigned char smem[];
   DeviceParamsT<real>& prm = *reinterpret_cast<DeviceParamsT<real>*>(smem);
   CoreConst<creal>& cc = *reinterpret_cast<CoreConst<creal>*>(smem + ((sizeof(DeviceParamsT<real>) + 15) & ~15));
-  static_assert(((sizeof(DeviceParamsT<real>) + 15) & ~15) + sizeof(CoreConst<creal>) + 64 <= FL::kFixed, "fixed part");
+  static_assert(((sizeof(DeviceParamsT<real>) + 15) & ~15) + sizeof(CoreConst<creal>) + 64 + kFusedWarps * FL::kCtlWords * 4 <= FL::kFixed, "fixed part");
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + FL::kFixed - 64);
+  volatile unsigned* ctl = reinterpret_cast<volatile unsigned*>(smem + FL::kFixed - 64 - kFusedWarps * FL::kCtlWords * 4) +
+                           (threadIdx.x >> 5) * FL::kCtlWords;   // [0] share [1] dyn_base [2] taken [3] nbox [4] B
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int leg = lane & 3, quad = lane >> 2;
   unsigned char* wbase = smem + FL::kFixed + warp * FL::kWarpBytes;
@@ -256,12 +260,11 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
     }
   }
   __syncthreads();
-  const unsigned long long B = a.B;
-  const unsigned Bu = (unsigned)B;
-  const unsigned nbox = (unsigned)((B + kCols - 1) / kCols);   // box numbers are 32-bit (B < 2^32): fewer loop-carried registers
-  const creal winv = cc.winv, cfmin = cc.fmin;
+  // Box and state numbers are 32-bit (B < 2^32), and what the loop needs only once per box - its share of the boxes,
+  // how many it has taken, the totals - lives in shared-memory control words, not in loop-carried registers: the FP32
+  // twin runs with 168 registers and spilled exactly these to local memory (long-scoreboard stalls behind a small L1).
+  const unsigned nbox = (unsigned)((a.B + kCols - 1) / kCols);
   unsigned occ = 0u;           // pending slots of the stash (warp-uniform)
-  uint32_t parity = 0;
 
   // Work distribution: the first three quarters of the boxes are dealt out to the warps of the grid round robin
   // (box b to warp b mod #warps: no atomics, no latency, and neighbouring boxes - whose states are correlated in a
@@ -273,7 +276,9 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
   const unsigned gwarp = blockIdx.x * kFusedWarps + warp;
   const unsigned share = (nbox - nbox / 4) / nwarps;     // static boxes per warp
   const unsigned dyn_base = share * nwarps;              // first dynamically claimed box
-  unsigned taken = 0;                                    // boxes this warp has started
+  // [2]: boxes started, [5]: tile of the current box, [6]: phase bit of the staging barrier
+  if (lane == 0) { ctl[0] = share; ctl[1] = dyn_base; ctl[2] = 0u; ctl[3] = nbox; ctl[4] = (unsigned)a.B; ctl[5] = 0u; ctl[6] = 0u; }
+  __syncwarp();
   auto claim_raw = [&](const bool doit) -> unsigned {   // 32 bits: the value is carried through the whole tile body
     unsigned b = 0;
     if (lane == 0 && doit) b = atomicAdd(reinterpret_cast<unsigned*>(a.counter), 1u);
@@ -290,18 +295,22 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
   }
   if (cur < nbox) stage_issue<real, MODE, SUPER, TMA>(a, maps, cur, stage, bar, lane);
   unsigned nxt = 0;
-  int sub = 0;                 // tile of the current box
 #pragma unroll 1
   for (;;) {
-    const bool have = cur < nbox;   // warp-uniform
+    // (control words go through a broadcast: the compiler must see warp-uniform values in everything that steers the loop)
+    const bool have = cur < __shfl_sync(kFull, ctl[3], 0);
     if (have) {
+      const int sub = (int)__shfl_sync(kFull, ctl[5], 0);   // tile of the current box
       // ---- the staged rows of this box
       if (sub == 0) {
-        if (TMA) { mbar_wait(bar, parity); parity ^= 1u; }
-        else { cp_async_wait_all(); __syncwarp(); }
+        if (TMA) {
+          const uint32_t parity = __shfl_sync(kFull, ctl[6], 0);
+          mbar_wait(bar, parity);
+          if (lane == 0) ctl[6] = parity ^ 1u;
+        } else { cp_async_wait_all(); __syncwarp(); }
       }
       const int col = sub * 8 + quad;
-      const unsigned s0 = cur * kCols + col;      // state numbers fit in 32 bits as well
+      const unsigned s0 = cur * kCols + col, Bu = ctl[4];
       const bool valid = s0 < Bu;
       const unsigned bq = valid ? s0 : (Bu - 1u);
       RawIn<real, MODE> in;
@@ -309,11 +318,12 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
       if (!valid) in.mask = 0u;
       if (sub == SUPER - 1) {
         __syncwarp();     // every lane has read the last tile of the box: the next box may land in the buffer
-        taken++;
-        nxt = __shfl_sync(kFull, taken < share ? gwarp + taken * nwarps : dyn_base + pending_claim, 0);
+        const unsigned taken = __shfl_sync(kFull, ctl[2], 0) + 1u, shr = __shfl_sync(kFull, ctl[0], 0);
+        if (lane == 0) ctl[2] = taken;
+        nxt = __shfl_sync(kFull, taken < shr ? blockIdx.x * kFusedWarps + warp + taken * (gridDim.x * kFusedWarps) : ctl[1] + pending_claim, 0);
         // the claim for the box after `nxt`: needed once the static share is used up
-        pending_claim = claim_raw(taken + 1 >= share);
-        if (nxt < nbox) stage_issue<real, MODE, SUPER, TMA>(a, maps, nxt, stage, bar, lane);
+        pending_claim = claim_raw(taken + 1 >= shr);
+        if (nxt < __shfl_sync(kFull, ctl[3], 0)) stage_issue<real, MODE, SUPER, TMA>(a, maps, nxt, stage, bar, lane);
       }
       // ---- kinematics and QP data; the Jacobian goes straight into the slot this quad would keep
       const int slot = nth_set_bit(~occ & ((1u << CAP) - 1u), quad);
@@ -323,7 +333,7 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
       creal y[3], t[6];
       bool hard;
       unsigned pat;
-      quad_first_solve<real, creal>(L, cc.sinv, winv, cfmin, leg, y, t, status, hard, pat);
+      quad_first_solve<real, creal>(L, cc.sinv, cc.winv, cc.fmin, leg, y, t, status, hard, pat);
       hard = hard && valid;
       creal net[6];
 #pragma unroll
@@ -354,7 +364,8 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
       }
       occ |= __reduce_or_sync(kFull, hard ? (1u << slot) : 0u);
       __syncwarp();
-      if (++sub == SUPER) { sub = 0; cur = nxt; }
+      if (lane == 0) ctl[5] = (sub + 1 == SUPER) ? 0u : (unsigned)(sub + 1);
+      if (sub + 1 == SUPER) cur = nxt;
     }
     // one call site (the code of the round phase exists once): after a tile when the stash is full enough, and
     // once more when the boxes are exhausted, until the stash is empty

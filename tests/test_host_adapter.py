@@ -109,3 +109,14 @@ def test_stats_allreduce_through_the_c_abi(qlb_built):
     assert r.returncode == 0, r.stdout + r.stderr
     f = r.stdout.strip().splitlines()[-1].split()      # (NCCL may print its version line first)
     assert f[0] == "gpus" and f[-1] == "AGREE" and float(f[3]) == 20000.0 * int(f[1]) and float(f[5]) == float(f[3])
+
+
+@pytest.mark.gpu
+def test_one_context_shared_by_host_threads(qlb_built):
+    """Four host threads call qlb_solve_wrench_host on ONE context at the same time (include/qlb.h: every entry point holds
+    the context's lock while it enqueues): the bits of a serial run."""
+    demo = build.build_host_demo(which="threads_demo")
+    r = subprocess.run([demo, "4", "20000"], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    f = r.stdout.strip().splitlines()[-1].split()
+    assert f[-1] == "SAME" and int(f[3]) == 80000 and int(f[5]) == 80000
