@@ -21,21 +21,25 @@
 
 namespace qlb {
 
+// Launch shape: ONE CTA of twelve warps per SM (168 registers, three warps per scheduler).  Measured on 2^20 C3 states:
+//   2 CTAs x 4 warps (194 registers)  0.576 ms      3 CTAs x 4 warps  0.550 ms      1 CTA x 12 warps  0.490 ms
+//   2 CTAs x 5 warps                  0.640 ms (schedulers loaded 3-3-2-2, spills)
+// (while the kernel still spilled at 168 registers, two CTAs of four warps were the fastest: 0.613 against 0.667 ms)
 #ifndef QLB_FUSED_MIN_CTAS
-#define QLB_FUSED_MIN_CTAS 2     // FP64 arrays.  Measured on B200 (2^20 C3 states): 2 x 4 warps 0.613 ms, 3 x 4 warps 0.667 ms - with
-#endif                           // eight warps per SM nothing spills (213 registers) and the instruction fetch stalls less
+#define QLB_FUSED_MIN_CTAS 1
+#endif
 #ifndef QLB_FUSED_MIN_CTAS_F32
-#define QLB_FUSED_MIN_CTAS_F32 3 // FP32 arrays: the kinematics need half the registers, nothing spills at 168: 0.518 ms against 0.630 ms
+#define QLB_FUSED_MIN_CTAS_F32 1
 #endif
 #ifndef QLB_FUSED_THREADS
-#define QLB_FUSED_THREADS 128
+#define QLB_FUSED_THREADS 384
 #endif
 #ifndef QLB_STASH_CAP
 #define QLB_STASH_CAP 22         // stash slots per warp (as many as the shared-memory budget allows, at most this)
 #endif
 #ifndef QLB_ROUND_LOW
 #define QLB_ROUND_LOW 8          // the round phase runs until fewer than this many states are pending: all eight quads
-#endif                           // stay busy, and the phases are long (a warp stays in one half of the code for a while)
+#endif                           // stay busy
 constexpr int kFusedThreads = QLB_FUSED_THREADS;
 constexpr int kFusedWarps = kFusedThreads / 32;
 template <typename real> constexpr int fused_min_ctas() { return sizeof(real) == 4 ? QLB_FUSED_MIN_CTAS_F32 : QLB_FUSED_MIN_CTAS; }
@@ -45,7 +49,13 @@ template <typename real> constexpr int fused_smem_budget() { return (228 / fused
 // ---------------------------------------------------------------------------------------------------------
 // The stash of one warp: CAP entries.  Per-lane planes (element k of the entry in slot s, leg l at
 // plane[k * 4 CAP + 4 s + l]) and a per-entry header.
-constexpr int kStashLane = 19;   // friction frame / force rows of the wrench map (9), foot (3), mu, y (3), u (3)
+// The entry is kept small - the number of slots decides how full the quads of a round phase run (measured on 2^20 C3
+// states, two CTAs of four warps: 12 slots 0.629 ms, 16 slots 0.573 ms, 22 slots 0.576 ms).  Per leg: normal and first
+// tangent of the friction frame (6; the second tangent is rebuilt from them when the entry is loaded), foot (3), mu,
+// y (3), u (3).  (Going further - the tangents rebuilt from the normal and the base frame's y axis, the multipliers as
+// FP32: 16 slots instead of 14 - measured no gain for FP64 arrays and 4 % loss for FP32 arrays, which have room anyway.)
+constexpr int kStashLane = 16;
+constexpr int kSlFoot = 6, kSlMu = 9, kSlY = 10, kSlU = 13;
 template <typename real, typename creal, int CAP>
 struct StashLayout {
   static constexpr int kQ = 4 * CAP;
@@ -60,7 +70,8 @@ template <typename real, typename creal, int MODE, int SUPER>
 struct FusedLayout {
   // fixed part: parameter block, solver constants, one mbarrier per warp (the leg-model table is a static array)
   static constexpr int kCtlWords = 8;   // per warp: loop-control words that are read once per box (kept out of the registers)
-  static constexpr int kFixed = ((((int)sizeof(DeviceParamsT<real>) + 15) & ~15) + (((int)sizeof(CoreConst<creal>) + 15) & ~15) + 64 +
+  static constexpr int kBarBytes = (kFusedWarps * 8 + 63) & ~63;   // one mbarrier per warp
+  static constexpr int kFixed = ((((int)sizeof(DeviceParamsT<real>) + 15) & ~15) + (((int)sizeof(CoreConst<creal>) + 15) & ~15) + kBarBytes +
                                  kFusedWarps * kCtlWords * 4 + 127) & ~127;
   static constexpr int kStatic = (int)sizeof(DeviceModelT<double>) + 128;
   static constexpr int kStage = Staging<real, MODE, SUPER>::kBytes;
@@ -110,13 +121,23 @@ __device__ __forceinline__ void stash_load(const WarpStash<real, creal, CAP>& ws
   creal foot[3];
 #pragma unroll
   for (int c = 0; c < 3; c++) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) q.At[c][k] = ws.sl[(3 * c + k) * Q + e];
-    foot[c] = ws.sl[(9 + c) * Q + e];
+    q.At[0][c] = ws.sl[c * Q + e];
+    q.At[1][c] = ws.sl[(3 + c) * Q + e];
+    foot[c] = ws.sl[(kSlFoot + c) * Q + e];
   }
-  q.mu = ws.sl[12 * Q + e];
+  {
+    // second tangent t2 = n x t1, normalised - the operations of quad_setup (CFD.cpp:306-309); a swing leg's rows are zero
+    creal t2[3];
+    t2[0] = q.At[0][1] * q.At[1][2] - q.At[0][2] * q.At[1][1];
+    t2[1] = q.At[0][2] * q.At[1][0] - q.At[0][0] * q.At[1][2];
+    t2[2] = q.At[0][0] * q.At[1][1] - q.At[0][1] * q.At[1][0];
+    const creal rn = q.alive ? fast_rsqrt(t2[0] * t2[0] + t2[1] * t2[1] + t2[2] * t2[2]) : creal(0.0);
 #pragma unroll
-  for (int c = 0; c < 3; c++) { q.y[c] = ws.sl[(13 + c) * Q + e]; q.u[c] = ws.sl[(16 + c) * Q + e]; }
+    for (int c = 0; c < 3; c++) q.At[2][c] = t2[c] * rn;
+  }
+  q.mu = ws.sl[kSlMu * Q + e];
+#pragma unroll
+  for (int c = 0; c < 3; c++) { q.y[c] = ws.sl[(kSlY + c) * Q + e]; q.u[c] = ws.sl[(kSlU + c) * Q + e]; }
   // torque rows of the wrench map: r x e_c (zero for a swing leg: its force rows are stored as zero)
 #pragma unroll
   for (int c = 0; c < 3; c++) {
@@ -139,7 +160,7 @@ __device__ __forceinline__ void stash_save(const WarpStash<real, creal, CAP>& ws
   if (doit) {
     const int e = 4 * slot + leg;
 #pragma unroll
-    for (int c = 0; c < 3; c++) { ws.sl[(13 + c) * Q + e] = q.y[c]; ws.sl[(16 + c) * Q + e] = q.u[c]; }
+    for (int c = 0; c < 3; c++) { ws.sl[(kSlY + c) * Q + e] = q.y[c]; ws.sl[(kSlU + c) * Q + e] = q.u[c]; }
     if (leg == 0) ws.sh[CAP + slot] = q.mask | (pat << 4) | ((unsigned)q.rounds << 24);
   }
 }
@@ -237,9 +258,9 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
   extern __shared__ __align__(128) unsigned char smem[];
   DeviceParamsT<real>& prm = *reinterpret_cast<DeviceParamsT<real>*>(smem);
   CoreConst<creal>& cc = *reinterpret_cast<CoreConst<creal>*>(smem + ((sizeof(DeviceParamsT<real>) + 15) & ~15));
-  static_assert(((sizeof(DeviceParamsT<real>) + 15) & ~15) + sizeof(CoreConst<creal>) + 64 + kFusedWarps * FL::kCtlWords * 4 <= FL::kFixed, "fixed part");
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + FL::kFixed - 64);
-  volatile unsigned* ctl = reinterpret_cast<volatile unsigned*>(smem + FL::kFixed - 64 - kFusedWarps * FL::kCtlWords * 4) +
+  static_assert(((sizeof(DeviceParamsT<real>) + 15) & ~15) + sizeof(CoreConst<creal>) + FL::kBarBytes + kFusedWarps * FL::kCtlWords * 4 <= FL::kFixed, "fixed part");
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + FL::kFixed - FL::kBarBytes);
+  volatile unsigned* ctl = reinterpret_cast<volatile unsigned*>(smem + FL::kFixed - FL::kBarBytes - kFusedWarps * FL::kCtlWords * 4) +
                            (threadIdx.x >> 5) * FL::kCtlWords;   // [0] share [1] dyn_base [2] taken [3] nbox [4] B
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int leg = lane & 3, quad = lane >> 2;
@@ -347,12 +368,12 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
 #pragma unroll
         for (int c = 0; c < 3; c++) {
 #pragma unroll
-          for (int k = 0; k < 3; k++) ws.sl[(3 * c + k) * Q + e] = L.At[c][k];
-          ws.sl[(9 + c) * Q + e] = L.foot[c];
-          ws.sl[(13 + c) * Q + e] = y[c];
-          ws.sl[(16 + c) * Q + e] = creal(0.0);
+          for (int k = 0; k < 2; k++) ws.sl[(3 * k + c) * Q + e] = L.At[k][c];
+          ws.sl[(kSlFoot + c) * Q + e] = L.foot[c];
+          ws.sl[(kSlY + c) * Q + e] = y[c];
+          ws.sl[(kSlU + c) * Q + e] = creal(0.0);
         }
-        ws.sl[12 * Q + e] = L.mu;
+        ws.sl[kSlMu * Q + e] = L.mu;
         // lane `leg` stores components leg and leg + 4 (no dynamic register indexing)
         ws.sb[leg * CAP + slot] = (leg == 0) ? L.b[0] : (leg == 1 ? L.b[1] : (leg == 2 ? L.b[2] : L.b[3]));
         if (leg < 2) ws.sb[(4 + leg) * CAP + slot] = (leg == 0) ? L.b[4] : L.b[5];
