@@ -218,8 +218,8 @@ int qlb_solve_state_host(qlb_context* ctx, size_t B, const double* q, const doub
  *     FP64.  The only error left is the rounding of inputs, kinematics and outputs.  STATED TOLERANCE: forces within
  *     5e-4 relative of the FP64 result (scale max(1,|f|_inf); measured 8e-5 on C3, 9e-7 on C2, 5e-6 on C5), torques
  *     within 1e-3 (measured 1.5e-4); status and contact bits exact; active-row bits exact on states whose active set
- *     is decided by a margin above 1e-3 (measured: exact on every test state).  1.12x the FP64 throughput
- *     device-resident, 1.57x end to end.
+ *     is decided by a margin above 1e-3 (measured: exact on every test state).  Device-resident throughput as FP64
+ *     (both kernels are bound by the FP64 solve), 1.55x end to end (half the PCIe bytes).
  *   QLB_F32_CORE_FP32: FP32 arithmetic throughout (the 6x6 systems with one step of iterative refinement,
  *     active-set rounds, interior point); states the FP32 core cannot verify are solved again by the FP64
  *     core inside the same kernel, so every status is the FP64 one.  About 1.2x the throughput.  STATED

@@ -2,16 +2,16 @@
 # multi-GPU record run (run with gpurun --gpus N): C3 bench and the C5 sweep under torchrun on all N GPUs, the C++ NCCL
 # statistics demo, and the pinned-copy bandwidth with 1, 2 and N ranks copying at once (the end-to-end limiter)
 N=${1:-8}
-O=gpurun_out/exp18_n$N; mkdir -p $O
+O=gpurun_out/exp43_n$N; mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 nvidia-smi topo -m > $O/topo.txt 2>&1
-timeout 600 $TR bench.py --gpus $N --steps 20 --warmup 3 > $O/bench_n$N.json 2> $O/bench_n$N.err
+timeout 240 $TR bench.py --gpus $N --steps 20 --warmup 3 > $O/bench_n$N.json 2> $O/bench_n$N.err
 python -c "
 import json; d=json.load(open('$O/bench_n$N.json')); print('C3 n=%d value %.4g ms %.4f e2e %.4g f32 %.4g' % (d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['f32']['value']))"
-timeout 600 $TR bench.py --config C5 --gpus $N --steps 10 --warmup 3 > $O/bench_c5_n$N.json 2> $O/bench_c5_n$N.err
+timeout 240 $TR bench.py --config C5 --gpus $N --steps 10 --warmup 3 > $O/bench_c5_n$N.json 2> $O/bench_c5_n$N.err
 python -c "
 import json; d=json.load(open('$O/bench_c5_n$N.json')); print('C5 n=%d value %.4g ms %.4f e2e %.4g states %d' % (d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['global_batch']))"
-timeout 300 python tools/pcie_check.py > $O/pcie_1.json 2> $O/pcie.err
+timeout 120 python tools/pcie_check.py > $O/pcie_1.json 2> $O/pcie.err
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/pcie_check.py > $O/pcie_2.json 2>> $O/pcie.err
 if [ $N -gt 2 ]; then timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 tools/pcie_check.py > $O/pcie_$N.json 2>> $O/pcie.err; fi
 cat $O/pcie_*.json | cut -c1-400
