@@ -220,15 +220,15 @@ int qlb_solve_state_host(qlb_context* ctx, size_t B, const double* q, const doub
  *     within 1e-3 (measured 1.5e-4); status and contact bits exact; active-row bits exact on states whose active set
  *     is decided by a margin above 1e-3 (measured: exact on every test state).  Device-resident throughput as FP64
  *     (both kernels are bound by the FP64 solve), 1.55x end to end (half the PCIe bytes).
- *   QLB_F32_CORE_FP32: FP32 arithmetic throughout (the 6x6 systems with one step of iterative refinement,
- *     active-set rounds, interior point); states the FP32 core cannot verify are solved again by the FP64
- *     core inside the same kernel, so every status is the FP64 one.  About 1.2x the throughput.  STATED
- *     TOLERANCE (tests/test_gpu_parity.py, measured on C2/C3): the QP Hessian has condition number ~1e5
- *     (W = 1e-4 against S|a|^2 ~ 10), so the weakly determined internal-force directions carry errors of
- *     order cond * eps: relative force error median 2e-7 on full-rank stances and 2e-4 on two-leg stances,
- *     99 % of states below 2e-2, worst observed 5e-2 (more on states driven far into their friction limits);
- *     the achieved wrench A x agrees to 1e-2, every constraint holds to 1e-4 of the force scale, the objective
- *     is within 1e-4 relative of the optimum; contact bits exact, active-row bits equal on >= 95 % of states.
+ *   QLB_F32_CORE_FP32: FP32 arithmetic throughout (the round-1 three-pass kernels: 6x6 systems with one step of
+ *     iterative refinement, active-set rounds, interior point; states the FP32 core cannot verify are solved again by
+ *     the FP64 core inside the same kernel, so every status is the FP64 one).  Kept for comparison: since round 2 it is
+ *     both slower and less accurate than the default.  STATED TOLERANCE (tests/test_gpu_parity.py, measured on C2/C3):
+ *     the QP Hessian has condition number ~1e5 (W = 1e-4 against S|a|^2 ~ 10), so the weakly determined internal-force
+ *     directions carry errors of order cond * eps: relative force error median 2e-7 on full-rank stances and 2e-4 on
+ *     two-leg stances, 99 % of states below 2e-2, worst observed 5e-2; the achieved wrench A x agrees to 1e-2, every
+ *     constraint holds to 1e-4 of the force scale, the objective is within 1e-4 relative of the optimum; contact bits
+ *     exact, active-row bits equal on >= 95 % of states.
  * Status values and layouts are unchanged. */
 int qlb_solve_wrench_f32(qlb_context* ctx, size_t B, const float* q, const float* quat_wxyz,
                          const float* wrench, const uint8_t* stance_mask, const float* mu,

@@ -269,6 +269,35 @@ def test_huge_joint_angles_are_bad_input(solver):
     assert status[3] == 4 and (np.delete(status, 3) == 0).all() and np.isfinite(out["grf"]).all()
 
 
+def test_tma_staging_and_cp_async_staging_agree(qlb_built):
+    """The fused kernel stages its input rows with TMA tensor boxes when the arrays are 16-byte aligned and with
+    cp.async otherwise (include/qlb.h takes any pointer).  The same states through both paths - the second time from
+    arrays that start 8 bytes off a 16-byte boundary, stance masks 1 byte off - give the same bits."""
+    B = 4096
+    st = synth.make_states("C3", B, start=123)
+    dev = torch.device("cuda:0")
+    s = capi.Solver("quadruped_model")
+
+    def run(shift):
+        def put(a):
+            flat = torch.empty(a.size + shift, dtype=torch.from_numpy(a).dtype, device=dev)
+            view = flat[shift:].view(a.shape)
+            view.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+            return view
+        d = {k: put(v) for k, v in st.items()}
+        assert all((t.data_ptr() % 16 == 0) == (shift == 0) for k, t in d.items() if k != "mask")
+        grf = torch.zeros((12, B), dtype=torch.float64, device=dev); tau = torch.zeros_like(grf)
+        net = torch.zeros((6, B), dtype=torch.float64, device=dev); flags = torch.zeros(B, dtype=torch.int32, device=dev)
+        s.solve_wrench(d["q"], d["quat"], d["wrench"], d["mask"], d["mu"], d["normals"], grf, tau, flags, net)
+        torch.cuda.synchronize()
+        return grf.cpu().numpy(), tau.cpu().numpy(), flags.cpu().numpy(), net.cpu().numpy()
+
+    a, b = run(0), run(1)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert ((a[2].view(np.uint32) >> 24) & 7 == 0).all()
+
+
 def test_results_do_not_depend_on_the_launch_geometry(qlb_built, monkeypatch):
     """The fused kernel is persistent: how many boxes a warp takes - and with it how often hard states are parked in
     the shared-memory stash and resumed - depends on the number of resident CTAs.  The optimum does not: one CTA per SM
