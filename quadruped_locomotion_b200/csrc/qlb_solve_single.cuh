@@ -34,6 +34,9 @@ namespace qlb {
 #ifndef QLB_FUSED_THREADS
 #define QLB_FUSED_THREADS 384
 #endif
+#ifndef QLB_DYNAMIC_PART
+#define QLB_DYNAMIC_PART 4       // one box in this many is claimed dynamically (the rest is dealt out statically)
+#endif
 #ifndef QLB_STASH_CAP
 #define QLB_STASH_CAP 22         // stash slots per warp (as many as the shared-memory budget allows, at most this)
 #endif
@@ -295,7 +298,7 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
   // from global memory gets spilled right behind its load, which exposes the full latency.)
   const unsigned nwarps = gridDim.x * kFusedWarps;
   const unsigned gwarp = blockIdx.x * kFusedWarps + warp;
-  const unsigned share = (nbox - nbox / 4) / nwarps;     // static boxes per warp
+  const unsigned share = (nbox - nbox / QLB_DYNAMIC_PART) / nwarps;     // static boxes per warp
   const unsigned dyn_base = share * nwarps;              // first dynamically claimed box
   // [2]: boxes started, [5]: tile of the current box, [6]: phase bit of the staging barrier
   if (lane == 0) { ctl[0] = share; ctl[1] = dyn_base; ctl[2] = 0u; ctl[3] = nbox; ctl[4] = (unsigned)a.B; ctl[5] = 0u; ctl[6] = 0u; }
