@@ -6,15 +6,18 @@
 //                rows of 8 QLB_SUPER states are staged in shared memory by the TMA unit (one cp.async.bulk.tensor box
 //                per input array, completion on a per-warp mbarrier) while the previous box is computed.
 //                Kinematics, friction frames, wrench map, the unconstrained minimiser.  States whose minimiser is
-//                feasible (72 % of config C3) are finished.  The record of a "hard" state - friction frame, foot
-//                position, Jacobian, gravity torques, the minimiser - goes into one of the warp's CAP stash slots
-//                (the Jacobian of every state of the tile is written straight into the slot its quad would keep).
-//   round phase  entered when the stash holds a warp's worth of hard states: each quad takes one and runs rounds of
+//                feasible (72 % of config C3) are finished.  The record of a "hard" state - normal and first tangent
+//                of the friction frame, foot position, Jacobian, gravity torques, the minimiser - goes into one of the
+//                warp's CAP stash slots (the Jacobian of every state of the tile is written straight into the slot its
+//                quad would keep, which is why a tile needs eight free slots).
+//   round phase  entered when fewer than eight slots are free: each quad takes a pending state and runs rounds of
 //                the dual block active-set method (qlb_solve_fused.cuh); a quad that finishes writes its outputs and
 //                takes the next pending slot, so the eight quads stay busy whatever the number of rounds their states
-//                need (measured: 93 % of the quad-rounds executed are useful); when fewer than CAP - 7 states are left
-//                the unfinished ones are written back (iterate, multipliers, working set) and the warp fetches tiles
-//                again.
+//                need (measured: 93 % of the quad-rounds executed are useful); when fewer than min(CAP - 7,
+//                QLB_ROUND_LOW) states are left the unfinished ones are written back (iterate, multipliers, working
+//                set) and the warp fetches tiles again.
+// Launch: one CTA of twelve warps per SM, 168 registers, 222 KB of shared memory (staging buffer, stash and loop-control
+// words per warp; parameters, solver constants, leg model and one mbarrier per warp per CTA).
 #pragma once
 
 #include "qlb_solve_fused.cuh"
@@ -292,8 +295,8 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
 
   // Work distribution: the first three quarters of the boxes are dealt out to the warps of the grid round robin
   // (box b to warp b mod #warps: no atomics, no latency, and neighbouring boxes - whose states are correlated in a
-  // sweep of perturbations around nominal states - go to different warps); the last quarter is claimed dynamically, one atomic per box, issued a whole
-  // box ahead - its result stays in lane 0 and is broadcast only when the box number is needed - so warps that
+  // sweep of perturbations around nominal states - go to different warps); the last quarter is claimed dynamically,
+  // one atomic per box, issued a whole box ahead - its result stays in lane 0 and is broadcast only when the box number is needed - so warps that
   // drew cheap states take more of it.  (The stance masks travel with the staged box: a loop-carried register loaded
   // from global memory gets spilled right behind its load, which exposes the full latency.)
   const unsigned nwarps = gridDim.x * kFusedWarps;
