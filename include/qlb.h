@@ -3,7 +3,8 @@
  *
  * One call solves B independent robot states.  For every state the library runs, fused in
  * sm_100a kernels that keep everything between the input state and the outputs on chip
- * (three launches per call: most states finish in the first, the rest on compacted lists),
+ * (one persistent kernel per call - inputs staged by TMA, the states that need active-set rounds
+ * parked in shared memory - plus a fallback kernel that normally finds nothing to do),
  * the hot path of the reference's balance_controller:
  *
  *   leg forward kinematics + foot Jacobians + gravity torques
