@@ -37,6 +37,9 @@ __device__ __forceinline__ double full_rcp(double x) {
 }
 __device__ __forceinline__ float full_rcp(float x) { return rcp_approx(x); }
 
+// (A single third-order step - r (1 + e/2 + 3 e^2/8), e = 1 - x r^2, five operations instead of seven, and the same for
+// the reciprocal - is as accurate and was measured: the shorter code makes the register allocator spill two values in
+// the fused kernel, 0.510 ms against 0.490 ms.  Kept as two Newton steps.)
 // 1/sqrt(x) to FP64 rounding: FP32 seed (one MUFU.RSQ) + two Newton steps in FP64.  x must be a
 // normal FP32-range number (pivots of the KKT matrices are 1e-4 .. 1e16); x <= 0 gives NaN.
 __device__ __forceinline__ double fast_rsqrt(double x) {
