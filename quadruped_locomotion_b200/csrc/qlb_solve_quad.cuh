@@ -544,6 +544,13 @@ __device__ __forceinline__ void widen_setup(const LegSetup<real>& s, LegSetup<cr
   d.gscale = s.gscale; d.rm = s.rm; d.mask = s.mask; d.ns = s.ns; d.alive = s.alive; d.qbad = s.qbad; d.qinf = s.qinf;
 }
 
+// value number `leg` of four, as two levels of selects (no divergent branches)
+template <typename T>
+__device__ __forceinline__ T sel4(const int leg, const T v0, const T v1, const T v2, const T v3) {
+  const T lo = (leg & 1) ? v1 : v0, hi = (leg & 1) ? v3 : v2;
+  return (leg & 2) ? hi : lo;
+}
+
 // Forces in base frame, joint torques, net wrench, flags word of one finished state.
 template <typename real, typename creal, typename jreal>
 __device__ __forceinline__ void quad_output(const SolveArgsT<real>& a, const LegSetup<creal>& L, creal (&y)[3], const int a0, const int sg1,
@@ -563,10 +570,13 @@ __device__ __forceinline__ void quad_output(const SolveArgsT<real>& a, const Leg
     if (valid) {
 #pragma unroll
       for (int c = 0; c < 3; c++) a.grf[(size_t)(3 * leg + c) * B + bq] = (real)f[c];
+      // (the Jacobian slot is read by every lane - it is a valid address whatever the state - and the select comes
+      // last: no divergent branch around the loads)
 #pragma unroll
-      for (int j = 0; j < 3; j++)
-        a.tau[(size_t)(3 * leg + j) * B + bq] = (real)(
-            live ? (creal)jgp[(9 + j) * jgs] - ((creal)jgp[(3 * j) * jgs] * f[0] + (creal)jgp[(3 * j + 1) * jgs] * f[1] + (creal)jgp[(3 * j + 2) * jgs] * f[2]) : creal(0.0));
+      for (int j = 0; j < 3; j++) {
+        const creal tq = (creal)jgp[(9 + j) * jgs] - ((creal)jgp[(3 * j) * jgs] * f[0] + (creal)jgp[(3 * j + 1) * jgs] * f[1] + (creal)jgp[(3 * j + 2) * jgs] * f[2]);
+        a.tau[(size_t)(3 * leg + j) * B + bq] = (real)(live ? tq : creal(0.0));
+      }
     }
     if (a.netwrench) {
       // A x = sum over legs of A_k y_k (CFD.cpp:614-625)
@@ -579,8 +589,8 @@ __device__ __forceinline__ void quad_output(const SolveArgsT<real>& a, const Leg
       }
       if (valid) {
         // leg k writes components k and k+4 (k < 2)
-        a.netwrench[(size_t)leg * B + bq] = (real)((leg == 0) ? nwv[0] : (leg == 1 ? nwv[1] : (leg == 2 ? nwv[2] : nwv[3])));
-        if (leg < 2) a.netwrench[(size_t)(4 + leg) * B + bq] = (real)((leg == 0) ? nwv[4] : nwv[5]);
+        a.netwrench[(size_t)leg * B + bq] = (real)sel4(leg, nwv[0], nwv[1], nwv[2], nwv[3]);
+        if (leg < 2) a.netwrench[(size_t)(4 + leg) * B + bq] = (real)((leg & 1) ? nwv[5] : nwv[4]);
       }
     }
     {

@@ -321,20 +321,23 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
     if (share == 0) pending_claim = claim_raw(true);
   }
   if (cur < nbox) stage_issue<real, MODE, SUPER, TMA>(a, maps, cur, stage, bar, lane);
+  if (lane == 0) ctl[5] = (cur < nbox) ? 0x200u : 0u;
+  __syncwarp();
   unsigned nxt = 0;
 #pragma unroll 1
   for (;;) {
     // (control words go through a broadcast: the compiler must see warp-uniform values in everything that steers the loop)
-    const bool have = cur < __shfl_sync(kFull, ctl[3], 0);
+    // ONE control word steers the step (one shared-memory read and one broadcast in front of the tile, not three):
+    // bits 0-7 tile of the current box, bit 8 phase of the staging barrier, bit 9 "there is a current box"
+    const unsigned cw = __shfl_sync(kFull, ctl[5], 0);
+    const bool have = (cw & 0x200u) != 0u;
     if (have) {
-      const int sub = (int)__shfl_sync(kFull, ctl[5], 0);   // tile of the current box
-      // ---- the staged rows of this box
+      const int sub = (int)(cw & 0xffu);
+      const unsigned cw_wait = (sub == 0 && TMA) ? (cw ^ 0x100u) : cw;   // the wait below consumes one barrier phase
+      if (sub + 1 < SUPER && lane == 0) ctl[5] = cw_wait + 1u;           // (the last tile of a box writes the word below)
       if (sub == 0) {
-        if (TMA) {
-          const uint32_t parity = __shfl_sync(kFull, ctl[6], 0);
-          mbar_wait(bar, parity);
-          if (lane == 0) ctl[6] = parity ^ 1u;
-        } else { cp_async_wait_all(); __syncwarp(); }
+        if (TMA) mbar_wait(bar, (cw >> 8) & 1u);
+        else { cp_async_wait_all(); __syncwarp(); }
       }
       const int col = sub * 8 + quad;
       const unsigned s0 = cur * kCols + col, Bu = ctl[4];
@@ -350,7 +353,9 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
         nxt = __shfl_sync(kFull, taken < shr ? blockIdx.x * kFusedWarps + warp + taken * (gridDim.x * kFusedWarps) : ctl[1] + pending_claim, 0);
         // the claim for the box after `nxt`: needed once the static share is used up
         pending_claim = claim_raw(taken + 1 >= shr);
-        if (nxt < __shfl_sync(kFull, ctl[3], 0)) stage_issue<real, MODE, SUPER, TMA>(a, maps, nxt, stage, bar, lane);
+        const bool more = nxt < __shfl_sync(kFull, ctl[3], 0);
+        if (lane == 0) ctl[5] = (cw_wait & 0x100u) | (more ? 0x200u : 0u);
+        if (more) stage_issue<real, MODE, SUPER, TMA>(a, maps, nxt, stage, bar, lane);
       }
       // ---- kinematics and QP data; the Jacobian goes straight into the slot this quad would keep
       const int slot = nth_set_bit(~occ & ((1u << CAP) - 1u), quad);
@@ -381,8 +386,8 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
         }
         ws.sl[kSlMu * Q + e] = L.mu;
         // lane `leg` stores components leg and leg + 4 (no dynamic register indexing)
-        ws.sb[leg * CAP + slot] = (leg == 0) ? L.b[0] : (leg == 1 ? L.b[1] : (leg == 2 ? L.b[2] : L.b[3]));
-        if (leg < 2) ws.sb[(4 + leg) * CAP + slot] = (leg == 0) ? L.b[4] : L.b[5];
+        ws.sb[leg * CAP + slot] = sel4(leg, L.b[0], L.b[1], L.b[2], L.b[3]);
+        if (leg < 2) ws.sb[(4 + leg) * CAP + slot] = (leg & 1) ? L.b[5] : L.b[4];
         if (leg == 0) {
           ws.sh[slot] = (unsigned)bq;
           ws.sh[CAP + slot] = L.mask | (pat << 4);
@@ -391,7 +396,6 @@ qlb_single_kernel(const SolveArgsT<real> a, const __grid_constant__ FusedMaps ma
       }
       occ |= __reduce_or_sync(kFull, hard ? (1u << slot) : 0u);
       __syncwarp();
-      if (lane == 0) ctl[5] = (sub + 1 == SUPER) ? 0u : (unsigned)(sub + 1);
       if (sub + 1 == SUPER) cur = nxt;
     }
     // one call site (the code of the round phase exists once): after a tile when the stash is full enough, and
