@@ -1,8 +1,8 @@
 #!/bin/bash
 # record run on one GPU: timing, the whole GPU test suite, bench, launch list, full ncu captures (FP64 and FP32 twin), all configs
-O=gpurun_out/exp42; mkdir -p $O
-bash tools/r2_variants.sh exp42 "main main"
-bash tools/r2_variants.sh exp42f "main" --f32
+O=gpurun_out/${1:-exp70}; mkdir -p $O
+bash tools/r2_variants.sh ${1:-exp70} "main main"
+bash tools/r2_variants.sh ${1:-exp70}f "main" --f32
 timeout 1500 python -m pytest tests -m gpu -x -q --timeout=240 > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
 tail -4 $O/pytest.log
 timeout 400 python bench.py --steps 20 --warmup 3 > $O/bench.json 2> $O/bench.err; python -c "
