@@ -24,7 +24,8 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 // 1/x to ~1e-13 relative: the FP64 seed instruction (MUFU.RCP64H, works on the high word: no conversion to FP32 and
 // back - two quarter-rate instructions less in every dependent chain, 2.6 % of the fused kernel's time - and no FP32
-// range to respect) + two Newton steps
+// range to respect) + two Newton steps.  Measured on B200 over 2^24 arguments in 1e-6 .. 1e18 (tools/seed_accuracy.cu):
+// seed 9.9e-7 relative (1/sqrt: 9.2e-7), after the two steps 2.2e-16 (1/sqrt: 3.2e-16).
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
@@ -41,8 +42,9 @@ __device__ __forceinline__ double full_rcp(double x) {
 __device__ __forceinline__ float full_rcp(float x) { return rcp_approx(x); }
 
 // (A single third-order step - r (1 + e/2 + 3 e^2/8), e = 1 - x r^2, five operations instead of seven, and the same for
-// the reciprocal - is as accurate and was measured: the shorter code makes the register allocator spill two values in
-// the fused kernel, 0.510 ms against 0.490 ms.  Kept as two Newton steps.)
+// the reciprocal - is as accurate (2.7e-16 / 2.2e-16) and was measured twice: with the FP32 seeds the shorter code made
+// the register allocator spill two values in the fused kernel, 0.510 ms against 0.490 ms; with the FP64 seeds nothing
+// spills and it is 0.3 % faster, within the noise.  Kept as two Newton steps.)
 // 1/sqrt(x) to FP64 rounding: FP64 seed (one MUFU.RSQ64H) + two Newton steps.  Any normal FP64 x > 0 (pivots of
 // the KKT matrices are 1e-4 .. 1e16); x <= 0 gives NaN.
 __device__ __forceinline__ double fast_rsqrt(double x) {
