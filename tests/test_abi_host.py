@@ -157,3 +157,17 @@ def test_fused_kernel_has_no_divergence_slow_paths(qlb_built):
         assert v < 4800, (k, v)
     tma = [k for k in fused if k.endswith("Lb1EEEvNS_10SolveArgsTIT_EENS_9FusedMapsE")]
     assert tma and all("UTMALDG" in txt for _ in tma)
+    # the reciprocals and reciprocal square roots of the solver start from the FP64 seed instructions (no conversion to
+    # FP32 and back in the dependent chains), and nothing spills
+    body, name = {}, None
+    for ln in txt.split("\n"):
+        m = re.search(r"Function : (\S+)", ln)
+        if m:
+            name = m.group(1)
+            body[name] = []
+        elif name:
+            body[name].append(ln)
+    for k in fused:
+        sass = "\n".join(body[k])
+        assert "MUFU.RSQ64H" in sass and "MUFU.RCP64H" in sass, k
+        assert not re.search(r"\b(STL|LDL)\b", sass), k
