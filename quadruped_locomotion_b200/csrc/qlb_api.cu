@@ -194,8 +194,9 @@ void narrow_params(const DeviceParams& d, DeviceParamsT<float>* f) {
   f->grav_pct = (float)d.grav_pct;
 }
 
-// The kernels seed reciprocals and reciprocal square roots from FP32 (qlb_device.cuh): weights, their inverses and
-// the pivots built from them must stay inside the FP32 normal range, so the weights are bounded here.
+// The FP32-core kernels seed reciprocals and reciprocal square roots from FP32 (qlb_device.cuh; the FP64 kernels use
+// the FP64 seed instructions and have no such limit): weights, their inverses and the pivots built from them must stay
+// inside the FP32 normal range for that core, so the weights are bounded here for every core alike.
 bool params_ok(const qlb_params* p) {
   const double lo = 1e-12, hi = 1e12;
   if (!(p->ground_force_weight >= lo && p->ground_force_weight <= hi) || !(p->ipm_tolerance > 0.0) || p->ipm_max_iterations < 1)
